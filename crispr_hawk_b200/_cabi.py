@@ -1,0 +1,305 @@
+"""ctypes binding of libhawkscan.so (include/hawkscan.h). No CPU fallback: if the
+library or a CUDA device is missing every entry point raises `HawkLibraryError`."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("HAWKSCAN_LIB", os.path.join(PKG_DIR, "libhawkscan.so"))
+
+HAWK_MAX_PAM = 16
+HAWK_F_UNPHASED = 1
+
+HAWK_OK = 0
+HAWK_EINVAL = -1
+HAWK_ECUDA = -2
+HAWK_ENOMEM = -3
+HAWK_EIUPAC = -4
+HAWK_ECAPACITY = -5
+HAWK_EALLELES = -6
+HAWK_EDUPREF = -7
+
+
+class HawkLibraryError(RuntimeError):
+    """libhawkscan.so is missing, cannot be loaded, or reported a failure."""
+
+    def __init__(self, message: str, code: int = 0):
+        super().__init__(message)
+        self.code = code
+
+
+class HawkParams(C.Structure):
+    _fields_ = [
+        ("pam_len", C.c_int32),
+        ("guide_len", C.c_int32),
+        ("right", C.c_int32),
+        ("flags", C.c_uint32),
+        ("pam_fwd", C.c_uint8 * HAWK_MAX_PAM),
+        ("pam_rc", C.c_uint8 * HAWK_MAX_PAM),
+    ]
+
+
+_P = C.c_void_p
+_I32P = C.POINTER(C.c_int32)
+_I64P = C.POINTER(C.c_int64)
+_U8P = C.POINTER(C.c_uint8)
+_U32P = C.POINTER(C.c_uint32)
+_U64P = C.POINTER(C.c_uint64)
+
+# name -> (restype, argtypes); every symbol include/hawkscan.h declares
+SIGNATURES = {
+    "hawk_abi_version": (C.c_int, []),
+    "hawk_last_error": (C.c_char_p, []),
+    "hawk_strerror": (C.c_char_p, [C.c_int]),
+    "hawk_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "hawk_ctx_destroy": (C.c_int, [_P]),
+    "hawk_ctx_info": (C.c_int, [_P, _I32P, _I64P, _I64P]),
+    "hawk_layout": (C.c_int, [_I32P, C.c_int32, _I64P, _I64P]),
+    "hawk_batch_create": (C.c_int, [_P, _U8P, _I64P, _I32P, C.c_int32, C.POINTER(_P), _I64P]),
+    "hawk_batch_destroy": (C.c_int, [_P]),
+    "hawk_batch_export_nibbles": (C.c_int, [_P, C.c_int32, _U8P, _U8P]),
+    "hawk_batch_set_posmap": (C.c_int, [_P, _I64P, _I32P, _I32P, _U8P]),
+    "hawk_batch_set_alleles": (C.c_int, [_P, _I64P, _I32P, _I64P, _U8P]),
+    "hawk_search": (C.c_int, [_P, _P, C.POINTER(HawkParams), _I32P, _I32P, _U8P, C.POINTER(_P)]),
+    "hawk_pam_search": (C.c_int, [_P, _P, C.POINTER(HawkParams), _I32P, _I32P, C.POINTER(_P)]),
+    "hawk_result_destroy": (C.c_int, [_P]),
+    "hawk_result_info": (C.c_int, [_P, _I64P, _I64P, _I32P, _I64P]),
+    "hawk_result_fetch": (C.c_int, [_P, _I32P, _U8P, _I32P, _I32P, _I32P, _I64P, _U8P]),
+    "hawk_result_fetch_hits": (C.c_int, [_P, C.c_int32, _U64P]),
+    "hawk_pack_dev": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
+    "hawk_scan_plan": (C.c_int64, [_I32P, _I32P, C.c_int32, _I64P]),
+    "hawk_scan_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "hawk_scan_dev": (
+        C.c_int,
+        [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64,
+         C.POINTER(HawkParams), C.c_int32, _P, _P, C.c_int64, C.c_int64, _P, _P],
+    ),  # fmt: skip
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen libhawkscan.so and bind every declared symbol (works without a GPU)."""
+    global _lib
+    with _lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or LIB_PATH
+        if not os.path.exists(p):
+            raise HawkLibraryError(
+                f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(crispr_hawk_b200 has no CPU fallback)"
+            )
+        try:
+            lib = C.CDLL(p)
+        except OSError as e:
+            raise HawkLibraryError(f"cannot load {p}: {e}") from e
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:
+                raise HawkLibraryError(f"{p} does not export {name}") from e
+            fn.restype = res
+            fn.argtypes = args
+        if lib.hawk_abi_version() != 1:
+            raise HawkLibraryError(f"{p}: unexpected ABI version {lib.hawk_abi_version()}")
+        if path is None:
+            _lib = lib
+        return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != HAWK_OK:
+        lib = load_library()
+        msg = lib.hawk_last_error().decode("utf-8", "replace")
+        raise HawkLibraryError(f"{what or 'libhawkscan'}: {msg} [{lib.hawk_strerror(rc).decode()}]", rc)
+
+
+def ptr(arr: Optional[np.ndarray], ctype):
+    if arr is None:
+        return None
+    assert arr.flags["C_CONTIGUOUS"], "array must be contiguous"
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+def make_params(pam_fwd, pam_rc, guide_len: int, right: bool, unphased: bool) -> HawkParams:
+    p = HawkParams()
+    if len(pam_fwd) != len(pam_rc) or not (1 <= len(pam_fwd) <= HAWK_MAX_PAM):
+        raise HawkLibraryError(f"PAM length must be 1..{HAWK_MAX_PAM} (got {len(pam_fwd)})", HAWK_EINVAL)
+    p.pam_len = len(pam_fwd)
+    p.guide_len = int(guide_len)
+    p.right = 1 if right else 0
+    p.flags = HAWK_F_UNPHASED if unphased else 0
+    for i, (a, b) in enumerate(zip(pam_fwd, pam_rc)):
+        p.pam_fwd[i] = int(a)
+        p.pam_rc[i] = int(b)
+    return p
+
+
+class Context:
+    """One device, one stream (hawk_ctx)."""
+
+    _default = {}
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = _P()
+        check(self.lib.hawk_ctx_create(int(device), C.byref(h)), "hawk_ctx_create")
+        self.handle = h
+        self.device = device
+
+    @classmethod
+    def default(cls, device: Optional[int] = None) -> "Context":
+        if device is None:
+            device = int(os.environ.get("HAWKSCAN_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        if device not in cls._default:
+            cls._default[device] = cls(device)
+        return cls._default[device]
+
+    def info(self):
+        sm, tot, free = C.c_int32(), C.c_int64(), C.c_int64()
+        check(self.lib.hawk_ctx_info(self.handle, C.byref(sm), C.byref(tot), C.byref(free)))
+        return {"sm_count": sm.value, "total_mem": tot.value, "free_mem": free.value}
+
+    def close(self):
+        if self.handle:
+            self.lib.hawk_ctx_destroy(self.handle)
+            self.handle = None
+
+
+class Batch:
+    """Packed haplotypes of one region on the device (hawk_batch)."""
+
+    def __init__(self, ctx: Context, ascii_slots: np.ndarray, slot_off: np.ndarray, lens: np.ndarray):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.slot_off = np.ascontiguousarray(slot_off, dtype=np.int64)
+        self.lens = np.ascontiguousarray(lens, dtype=np.int32)
+        self.n_hap = len(self.lens)
+        ascii_slots = np.ascontiguousarray(ascii_slots, dtype=np.uint8)
+        h, bad = _P(), C.c_int64(-1)
+        rc = self.lib.hawk_batch_create(
+            ctx.handle, ptr(ascii_slots, C.c_uint8), ptr(self.slot_off, C.c_int64),
+            ptr(self.lens, C.c_int32), self.n_hap, C.byref(h), C.byref(bad),
+        )  # fmt: skip
+        self.bad_slot = bad.value
+        if rc != HAWK_OK:
+            err = HawkLibraryError(self.lib.hawk_last_error().decode(), rc)
+            err.bad_slot = bad.value
+            raise err
+        self.handle = h
+        self.has_posmap = False
+        self.has_alleles = False
+
+    def export_nibbles(self, hap: int, want_lower: bool = False):
+        n = int(self.lens[hap])
+        nib = np.empty(n, np.uint8)
+        low = np.empty(n, np.uint8) if want_lower else None
+        check(self.lib.hawk_batch_export_nibbles(self.handle, hap, ptr(nib, C.c_uint8), ptr(low, C.c_uint8)))
+        return (nib, low) if want_lower else nib
+
+    def set_posmap(self, seg):
+        check(
+            self.lib.hawk_batch_set_posmap(
+                self.handle, ptr(seg.seg_off, C.c_int64), ptr(seg.seg_rel, C.c_int32),
+                ptr(seg.seg_gen, C.c_int32), ptr(seg.seg_step, C.c_uint8),
+            ),  # fmt: skip
+            "hawk_batch_set_posmap",
+        )
+        self.has_posmap = True
+
+    def set_alleles(self, va):
+        check(
+            self.lib.hawk_batch_set_alleles(
+                self.handle, ptr(va.va_off, C.c_int64), ptr(va.va_idx, C.c_int32),
+                ptr(va.va_ent_off, C.c_int64), ptr(va.va_ref, C.c_uint8),
+            ),  # fmt: skip
+            "hawk_batch_set_alleles",
+        )
+        self.has_alleles = True
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.hawk_batch_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Result:
+    """Guide table / hit lists of one search (hawk_result)."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.handle = lib, handle
+        n, hits, w, bp = C.c_int64(), (C.c_int64 * 2)(), C.c_int32(), C.c_int64()
+        check(lib.hawk_result_info(handle, C.byref(n), hits, C.byref(w), C.byref(bp)))
+        self.n_guides, self.n_hits, self.window, self.scanned_bp = n.value, (hits[0], hits[1]), w.value, bp.value
+
+    def table(self):
+        n, w = self.n_guides, self.window
+        out = {
+            "hap": np.empty(n, np.int32), "strand": np.empty(n, np.uint8), "pos": np.empty(n, np.int32),
+            "start": np.empty(n, np.int32), "stop": np.empty(n, np.int32),
+            "bucket": np.empty(n, np.int64), "text": np.empty((n, w), np.uint8),
+        }  # fmt: skip
+        check(
+            self.lib.hawk_result_fetch(
+                self.handle, ptr(out["hap"], C.c_int32), ptr(out["strand"], C.c_uint8),
+                ptr(out["pos"], C.c_int32), ptr(out["start"], C.c_int32), ptr(out["stop"], C.c_int32),
+                ptr(out["bucket"], C.c_int64), ptr(out["text"], C.c_uint8),
+            ),  # fmt: skip
+            "hawk_result_fetch",
+        )
+        return out
+
+    def hits(self, strand: int) -> np.ndarray:
+        out = np.empty(self.n_hits[strand], np.uint64)
+        check(self.lib.hawk_result_fetch_hits(self.handle, strand, ptr(out, C.c_uint64)))
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.hawk_result_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def search(ctx: Context, batch: Batch, params: HawkParams, scan_start, scan_stop, is_ref) -> Result:
+    a = np.ascontiguousarray(scan_start, dtype=np.int32)
+    b = np.ascontiguousarray(scan_stop, dtype=np.int32)
+    r = np.ascontiguousarray(is_ref, dtype=np.uint8)
+    h = _P()
+    check(
+        ctx.lib.hawk_search(ctx.handle, batch.handle, C.byref(params), ptr(a, C.c_int32),
+                            ptr(b, C.c_int32), ptr(r, C.c_uint8), C.byref(h)),
+        "hawk_search",
+    )  # fmt: skip
+    return Result(ctx.lib, h)
+
+
+def pam_search(ctx: Context, batch: Batch, params: HawkParams, scan_start, scan_stop) -> Result:
+    a = np.ascontiguousarray(scan_start, dtype=np.int32)
+    b = np.ascontiguousarray(scan_stop, dtype=np.int32)
+    h = _P()
+    check(
+        ctx.lib.hawk_pam_search(ctx.handle, batch.handle, C.byref(params), ptr(a, C.c_int32),
+                                ptr(b, C.c_int32), C.byref(h)),
+        "hawk_pam_search",
+    )  # fmt: skip
+    return Result(ctx.lib, h)

@@ -1,0 +1,651 @@
+// api.cu -- C-ABI host layer of libhawkscan: contexts, packed batches, the
+// search pipeline (K2 scan -> rows -> [resolve] -> compaction -> gather ->
+// buckets) and result download. See include/hawkscan.h for the contract.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "hawk_core.h"
+#include "hawk_kernels.h"
+#include "hawk_post.h"
+
+using namespace hawk;
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+int hawk_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int hawk_check_cuda(cudaError_t err, const char* what) {
+  if (err == cudaSuccess) return HAWK_OK;
+  return hawk_fail(err == cudaErrorMemoryAllocation ? HAWK_ENOMEM : HAWK_ECUDA, "%s: %s (%s)", what,
+                   cudaGetErrorString(err), cudaGetErrorName(err));
+}
+
+#define CK(expr)                                   \
+  do {                                             \
+    int _rc = (expr);                              \
+    if (_rc != HAWK_OK) return _rc;                \
+  } while (0)
+#define CKCUDA(expr) CK(hawk_check_cuda((expr), #expr))
+
+extern "C" int hawk_abi_version(void) { return HAWK_ABI_VERSION; }
+extern "C" const char* hawk_last_error(void) { return g_err; }
+extern "C" const char* hawk_strerror(int code) {
+  switch (code) {
+    case HAWK_OK: return "ok";
+    case HAWK_EINVAL: return "invalid argument";
+    case HAWK_ECUDA: return "CUDA failure";
+    case HAWK_ENOMEM: return "out of device memory";
+    case HAWK_EIUPAC: return "non-IUPAC character";
+    case HAWK_ECAPACITY: return "capacity exceeded";
+    case HAWK_EALLELES: return "ambiguity code without variant alleles";
+    case HAWK_EDUPREF: return "duplicate REF guide";
+    default: return "unknown error";
+  }
+}
+
+// ------------------------------------------------------------------ objects
+struct hawk_ctx {
+  int device;
+  cudaStream_t stream;
+  int sm_count;
+};
+
+// device buffer owned through the stream-ordered allocator
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaStream_t st = nullptr;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  int alloc(cudaStream_t s, size_t n, bool zero = false) {
+    release();
+    st = s;
+    bytes = n ? n : 16;
+    cudaError_t e = cudaMallocAsync(&p, bytes, st);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return hawk_check_cuda(e, "cudaMallocAsync");
+    }
+    if (zero) return hawk_check_cuda(cudaMemsetAsync(p, 0, bytes, st), "cudaMemsetAsync");
+    return HAWK_OK;
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, st);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return (T*)p; }
+};
+
+static int upload(cudaStream_t st, DevBuf& b, const void* src, size_t bytes) {
+  CK(b.alloc(st, bytes));
+  if (bytes) CKCUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+  return HAWK_OK;
+}
+
+struct hawk_batch {
+  hawk_ctx* ctx;
+  int32_t n_hap;
+  int64_t total_slots;
+  std::vector<int64_t> slot_off;
+  std::vector<int32_t> len;
+  DevBuf q, v, d_slot_off, d_len;
+  DevBuf seg_off, seg_rel, seg_gen, seg_step;
+  DevBuf va_off, va_idx, va_ent_off, va_ref;
+  bool has_posmap = false, has_alleles = false;
+};
+
+struct hawk_result {
+  hawk_ctx* ctx;
+  int64_t n_guides = 0;
+  int64_t n_hits[2] = {0, 0};
+  int32_t window = 0;
+  int64_t scanned_bp = 0;
+  DevBuf hits[2];
+  DevBuf hap, strand, pos, start, stop, bucket, text;
+};
+
+// ------------------------------------------------------------------ context
+extern "C" int hawk_ctx_create(int device, hawk_ctx** out) {
+  if (!out) return hawk_fail(HAWK_EINVAL, "hawk_ctx_create: null output");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return hawk_fail(HAWK_ECUDA, "hawk_ctx_create: no CUDA device available (%s); libhawkscan has no CPU path",
+                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return hawk_fail(HAWK_EINVAL, "hawk_ctx_create: device %d of %d", device, n);
+  CKCUDA(cudaSetDevice(device));
+  hawk_ctx* c = new (std::nothrow) hawk_ctx();
+  if (!c) return hawk_fail(HAWK_ENOMEM, "hawk_ctx_create: host allocation");
+  c->device = device;
+  cudaDeviceProp prop;
+  CKCUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CKCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  // keep freed blocks cached in the pool: repeated searches reuse them
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = c;
+  return HAWK_OK;
+}
+
+extern "C" int hawk_ctx_destroy(hawk_ctx* c) {
+  if (!c) return HAWK_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return HAWK_OK;
+}
+
+extern "C" int hawk_ctx_info(hawk_ctx* c, int32_t* sm_count, int64_t* total_mem, int64_t* free_mem) {
+  if (!c) return hawk_fail(HAWK_EINVAL, "hawk_ctx_info: null context");
+  CKCUDA(cudaSetDevice(c->device));
+  size_t f = 0, t = 0;
+  CKCUDA(cudaMemGetInfo(&f, &t));
+  if (sm_count) *sm_count = c->sm_count;
+  if (total_mem) *total_mem = (int64_t)t;
+  if (free_mem) *free_mem = (int64_t)f;
+  return HAWK_OK;
+}
+
+// ------------------------------------------------------------------ layout
+extern "C" int hawk_layout(const int32_t* len, int32_t n_hap, int64_t* slot_off, int64_t* total_slots) {
+  if (n_hap < 0 || (n_hap > 0 && (!len || !slot_off)))
+    return hawk_fail(HAWK_EINVAL, "hawk_layout: bad arguments");
+  int64_t off = 0;
+  for (int32_t h = 0; h < n_hap; ++h) {
+    if (len[h] < 0) return hawk_fail(HAWK_EINVAL, "hawk_layout: negative length at %d", h);
+    slot_off[h] = off;
+    off += ((int64_t)len[h] + HAWK_SLOT_ALIGN - 1) / HAWK_SLOT_ALIGN * HAWK_SLOT_ALIGN;
+  }
+  if (slot_off) slot_off[n_hap] = off;
+  if (total_slots) *total_slots = off;
+  return HAWK_OK;
+}
+
+// ------------------------------------------------------------------ batch
+extern "C" int hawk_batch_create(hawk_ctx* c, const uint8_t* ascii, const int64_t* slot_off,
+                                 const int32_t* len, int32_t n_hap, hawk_batch** out,
+                                 int64_t* bad_slot) {
+  if (!c || !out || n_hap < 0 || (n_hap > 0 && (!ascii || !slot_off || !len)))
+    return hawk_fail(HAWK_EINVAL, "hawk_batch_create: bad arguments");
+  CKCUDA(cudaSetDevice(c->device));
+  if (bad_slot) *bad_slot = -1;
+  std::vector<int64_t> expect(n_hap + 1);
+  int64_t total = 0;
+  CK(hawk_layout(len, n_hap, expect.data(), &total));
+  for (int32_t h = 0; h <= n_hap; ++h)
+    if (n_hap && slot_off[h] != expect[h])
+      return hawk_fail(HAWK_EINVAL, "hawk_batch_create: slot_off[%d] does not follow hawk_layout", h);
+  hawk_batch* b = new (std::nothrow) hawk_batch();
+  if (!b) return hawk_fail(HAWK_ENOMEM, "hawk_batch_create: host allocation");
+  b->ctx = c;
+  b->n_hap = n_hap;
+  b->total_slots = total;
+  b->slot_off.assign(expect.begin(), expect.end());
+  b->len.assign(len, len + n_hap);
+  cudaStream_t st = c->stream;
+  int rc = HAWK_OK;
+  DevBuf d_ascii, d_bad;
+  const size_t n_chunks = (size_t)total / HAWK_CHUNK + HAWK_SLACK_CHUNKS;
+  do {
+    if ((rc = b->q.alloc(st, n_chunks * 16, true))) break;
+    if ((rc = b->v.alloc(st, n_chunks * 4, true))) break;
+    if ((rc = upload(st, b->d_slot_off, b->slot_off.data(), (size_t)(n_hap + 1) * 8))) break;
+    if ((rc = upload(st, b->d_len, b->len.data(), (size_t)n_hap * 4))) break;
+    if (total > 0) {
+      if ((rc = upload(st, d_ascii, ascii, (size_t)total))) break;
+      int64_t init = INT64_MAX;
+      if ((rc = upload(st, d_bad, &init, 8))) break;
+      if ((rc = hawk_pack_dev(st, d_ascii.as<uint8_t>(), total, b->q.p, b->v.as<uint32_t>(),
+                              d_bad.as<int64_t>())))
+        break;
+      int64_t bad = INT64_MAX;
+      if ((rc = hawk_check_cuda(cudaMemcpyAsync(&bad, d_bad.p, 8, cudaMemcpyDeviceToHost, st), "bad D2H"))) break;
+      if ((rc = hawk_check_cuda(cudaStreamSynchronize(st), "pack sync"))) break;
+      if (bad != INT64_MAX) {
+        if (bad_slot) *bad_slot = bad;
+        rc = hawk_fail(HAWK_EIUPAC, "non-IUPAC character at slot %lld", (long long)bad);
+        break;
+      }
+    }
+  } while (0);
+  if (rc != HAWK_OK) {
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return HAWK_OK;
+}
+
+extern "C" int hawk_batch_destroy(hawk_batch* b) {
+  if (!b) return HAWK_OK;
+  cudaSetDevice(b->ctx->device);
+  delete b;
+  return HAWK_OK;
+}
+
+extern "C" int hawk_batch_export_nibbles(hawk_batch* b, int32_t hap, uint8_t* nibbles, uint8_t* lower) {
+  if (!b || hap < 0 || hap >= b->n_hap || !nibbles)
+    return hawk_fail(HAWK_EINVAL, "hawk_batch_export_nibbles: bad arguments");
+  CKCUDA(cudaSetDevice(b->ctx->device));
+  cudaStream_t st = b->ctx->stream;
+  int32_t L = b->len[hap];
+  if (L == 0) return HAWK_OK;
+  DevBuf dn, dl;
+  CK(dn.alloc(st, L));
+  if (lower) CK(dl.alloc(st, L));
+  CK(launch_export_nibbles(st, b->q.p, b->v.as<uint32_t>(), b->slot_off[hap] >> 5, L,
+                           dn.as<uint8_t>(), lower ? dl.as<uint8_t>() : nullptr));
+  CKCUDA(cudaMemcpyAsync(nibbles, dn.p, L, cudaMemcpyDeviceToHost, st));
+  if (lower) CKCUDA(cudaMemcpyAsync(lower, dl.p, L, cudaMemcpyDeviceToHost, st));
+  CKCUDA(cudaStreamSynchronize(st));
+  return HAWK_OK;
+}
+
+extern "C" int hawk_batch_set_posmap(hawk_batch* b, const int64_t* seg_off, const int32_t* seg_rel,
+                                     const int32_t* seg_gen, const uint8_t* seg_step) {
+  if (!b || !seg_off) return hawk_fail(HAWK_EINVAL, "hawk_batch_set_posmap: bad arguments");
+  CKCUDA(cudaSetDevice(b->ctx->device));
+  for (int32_t h = 0; h < b->n_hap; ++h) {
+    if (seg_off[h + 1] <= seg_off[h])
+      return hawk_fail(HAWK_EINVAL, "hawk_batch_set_posmap: haplotype %d has no segment", h);
+    if (seg_rel[seg_off[h]] != 0)
+      return hawk_fail(HAWK_EINVAL, "hawk_batch_set_posmap: first segment of haplotype %d must start at 0", h);
+  }
+  cudaStream_t st = b->ctx->stream;
+  size_t n = (size_t)seg_off[b->n_hap];
+  CK(upload(st, b->seg_off, seg_off, (size_t)(b->n_hap + 1) * 8));
+  CK(upload(st, b->seg_rel, seg_rel, n * 4));
+  CK(upload(st, b->seg_gen, seg_gen, n * 4));
+  CK(upload(st, b->seg_step, seg_step, n));
+  CKCUDA(cudaStreamSynchronize(st));
+  b->has_posmap = true;
+  return HAWK_OK;
+}
+
+extern "C" int hawk_batch_set_alleles(hawk_batch* b, const int64_t* va_off, const int32_t* va_idx,
+                                      const int64_t* va_ent_off, const uint8_t* va_ref) {
+  if (!b || !va_off || !va_ent_off) return hawk_fail(HAWK_EINVAL, "hawk_batch_set_alleles: bad arguments");
+  CKCUDA(cudaSetDevice(b->ctx->device));
+  cudaStream_t st = b->ctx->stream;
+  size_t n_sites = (size_t)va_off[b->n_hap];
+  size_t n_ent = (size_t)va_ent_off[n_sites];
+  CK(upload(st, b->va_off, va_off, (size_t)(b->n_hap + 1) * 8));
+  CK(upload(st, b->va_idx, va_idx, n_sites * 4));
+  CK(upload(st, b->va_ent_off, va_ent_off, (n_sites + 1) * 8));
+  CK(upload(st, b->va_ref, va_ref, n_ent));
+  CKCUDA(cudaStreamSynchronize(st));
+  b->has_alleles = true;
+  return HAWK_OK;
+}
+
+// ------------------------------------------------------------------ search
+static BatchView batch_view(const hawk_batch* b, const int32_t* d_a, const int32_t* d_b,
+                            const uint8_t* d_isref) {
+  BatchView B{};
+  B.q = b->q.as<Planes>();
+  B.v = b->v.as<uint32_t>();
+  B.slot_off = b->d_slot_off.as<int64_t>();
+  B.len = b->d_len.as<int32_t>();
+  B.scan_start = d_a;
+  B.scan_stop = d_b;
+  B.is_ref = d_isref;
+  B.n_hap = b->n_hap;
+  B.seg_off = b->seg_off.as<int64_t>();
+  B.seg_rel = b->seg_rel.as<int32_t>();
+  B.seg_gen = b->seg_gen.as<int32_t>();
+  B.seg_step = b->seg_step.as<uint8_t>();
+  B.va_off = b->va_off.as<int64_t>();
+  B.va_idx = b->va_idx.as<int32_t>();
+  B.va_ent_off = b->va_ent_off.as<int64_t>();
+  B.va_ref = b->va_ref.as<uint8_t>();
+  return B;
+}
+
+struct ScanOut {
+  DevBuf hits[2];
+  int64_t n[2] = {0, 0};
+  int64_t scanned_bp = 0;
+};
+
+// run K2 with growing output capacity until everything fits
+static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const int32_t* scan_start,
+                    const int32_t* scan_stop, const uint8_t* is_ref, int raw, DevBuf& d_a,
+                    DevBuf& d_b, DevBuf& d_isref, ScanOut& out) {
+  cudaStream_t st = c->stream;
+  const int32_t n_hap = b->n_hap;
+  std::vector<int64_t> span_off(n_hap + 1);
+  int64_t n_spans = hawk_scan_plan(scan_start, scan_stop, n_hap, span_off.data());
+  int64_t est = 4096;
+  out.scanned_bp = 0;
+  for (int32_t h = 0; h < n_hap; ++h) {
+    int64_t a = scan_start[h] < 0 ? 0 : scan_start[h], e = scan_stop[h];
+    if (e <= a) continue;
+    out.scanned_bp += e - a;
+    est += (raw || is_ref[h]) ? (e - a) / 3 : (e - a) / 48;
+  }
+  CK(upload(st, d_a, scan_start, (size_t)n_hap * 4));
+  CK(upload(st, d_b, scan_stop, (size_t)n_hap * 4));
+  CK(upload(st, d_isref, is_ref, (size_t)n_hap));
+  if (n_spans == 0) return HAWK_OK;
+  DevBuf d_span_off, d_counts, d_ws;
+  CK(upload(st, d_span_off, span_off.data(), (size_t)(n_hap + 1) * 8));
+  CK(d_counts.alloc(st, 32));
+  size_t ws_bytes = hawk_scan_workspace_bytes(n_spans);
+  CK(d_ws.alloc(st, ws_bytes));
+  int64_t cap[2] = {est, est};
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(st, (size_t)cap[s] * 8));
+    CKCUDA(cudaMemsetAsync(d_counts.p, 0, 32, st));
+    CKCUDA(cudaMemsetAsync(d_ws.p, 0, ws_bytes, st));
+    CK(hawk_scan_dev(st, c->sm_count, b->q.p, b->v.as<uint32_t>(), b->d_slot_off.as<int64_t>(),
+                     b->d_len.as<int32_t>(), d_a.as<int32_t>(), d_b.as<int32_t>(),
+                     d_isref.as<uint8_t>(), d_span_off.as<int64_t>(), n_hap, n_spans, params, raw,
+                     out.hits[0].as<uint64_t>(), out.hits[1].as<uint64_t>(), cap[0], cap[1],
+                     d_counts.as<uint64_t>(), d_ws.p));
+    uint64_t counts[4];
+    CKCUDA(cudaMemcpyAsync(counts, d_counts.p, 32, cudaMemcpyDeviceToHost, st));
+    CKCUDA(cudaStreamSynchronize(st));
+    out.n[0] = (int64_t)counts[0];
+    out.n[1] = (int64_t)counts[1];
+    if (out.n[0] <= cap[0] && out.n[1] <= cap[1]) return HAWK_OK;
+    cap[0] = out.n[0] > cap[0] ? out.n[0] : cap[0];
+    cap[1] = out.n[1] > cap[1] ? out.n[1] : cap[1];
+  }
+  return hawk_fail(HAWK_ECAPACITY, "scan output did not fit after resizing");
+}
+
+static int check_scan_args(hawk_ctx* c, hawk_batch* b, const hawk_params* p, const int32_t* a,
+                           const int32_t* e, hawk_result** out) {
+  if (!c || !b || !p || !out || (b->n_hap > 0 && (!a || !e)))
+    return hawk_fail(HAWK_EINVAL, "search: bad arguments");
+  if (b->ctx != c) return hawk_fail(HAWK_EINVAL, "search: batch belongs to another context");
+  if (p->pam_len < 1 || p->pam_len > HAWK_MAX_PAM || p->guide_len < 1)
+    return hawk_fail(HAWK_EINVAL, "search: PAM length must be 1..%d and guide length >= 1", HAWK_MAX_PAM);
+  if (p->pam_len + p->guide_len + 2 * HAWK_GUIDESEQPAD > HAWK_MAX_WINDOW)
+    return hawk_fail(HAWK_EINVAL, "search: guide + PAM window exceeds %d", HAWK_MAX_WINDOW);
+  for (int i = 0; i < p->pam_len; ++i)
+    if (p->pam_fwd[i] < 1 || p->pam_fwd[i] > 15 || p->pam_rc[i] < 1 || p->pam_rc[i] > 15)
+      return hawk_fail(HAWK_EINVAL, "search: PAM nibble %d out of range", i);
+  return HAWK_OK;
+}
+
+extern "C" int hawk_pam_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params,
+                               const int32_t* scan_start, const int32_t* scan_stop,
+                               hawk_result** out) {
+  CK(check_scan_args(c, b, params, scan_start, scan_stop, out));
+  CKCUDA(cudaSetDevice(c->device));
+  hawk_result* r = new (std::nothrow) hawk_result();
+  if (!r) return hawk_fail(HAWK_ENOMEM, "hawk_pam_search: host allocation");
+  r->ctx = c;
+  r->window = params->pam_len + params->guide_len + 2 * HAWK_GUIDESEQPAD;
+  std::vector<uint8_t> isref(b->n_hap, 1);
+  DevBuf d_a, d_b, d_isref;
+  ScanOut so;
+  int rc = run_scan(c, b, params, scan_start, scan_stop, isref.data(), 1, d_a, d_b, d_isref, so);
+  if (rc != HAWK_OK) {
+    delete r;
+    return rc;
+  }
+  for (int s = 0; s < 2; ++s) {
+    r->n_hits[s] = so.n[s];
+    r->hits[s].p = so.hits[s].p;
+    r->hits[s].bytes = so.hits[s].bytes;
+    r->hits[s].st = so.hits[s].st;
+    so.hits[s].p = nullptr;
+  }
+  r->scanned_bp = so.scanned_bp;
+  *out = r;
+  return HAWK_OK;
+}
+
+extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params,
+                           const int32_t* scan_start, const int32_t* scan_stop,
+                           const uint8_t* is_ref, hawk_result** out) {
+  CK(check_scan_args(c, b, params, scan_start, scan_stop, out));
+  if (b->n_hap > 0 && !is_ref) return hawk_fail(HAWK_EINVAL, "hawk_search: is_ref missing");
+  if (!b->has_posmap) return hawk_fail(HAWK_EINVAL, "hawk_search: call hawk_batch_set_posmap first");
+  const bool unphased = (params->flags & HAWK_F_UNPHASED) != 0;
+  if (unphased && !b->has_alleles)
+    return hawk_fail(HAWK_EINVAL, "hawk_search: unphased search needs hawk_batch_set_alleles");
+  CKCUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  int32_t ref_h = -1, n_ref = 0;
+  for (int32_t h = 0; h < b->n_hap; ++h)
+    if (is_ref[h]) {
+      if (ref_h < 0) ref_h = h;
+      ++n_ref;
+    }
+  if (n_ref > 1)
+    return hawk_fail(HAWK_EDUPREF, "hawk_search: %d haplotypes are labelled REF; the reference aborts on "
+                     "the duplicate REF guides this produces (search_guides.py:328-334)", n_ref);
+
+  hawk_result* r = new (std::nothrow) hawk_result();
+  if (!r) return hawk_fail(HAWK_ENOMEM, "hawk_search: host allocation");
+  r->ctx = c;
+  const ScanConst K = make_scan_const(*params, 0);
+  const int W = K.C + 2 * HAWK_GUIDESEQPAD;
+  r->window = W;
+
+  int rc = HAWK_OK;
+  DevBuf d_a, d_b, d_isref, d_refrange, d_err;
+  DevBuf start[2], stop[2], keep[2], kept_excl[2], tile_sums, cnt[2], off[2], text_pre[2], row_hit[2];
+  ScanOut so;
+  do {
+    if ((rc = run_scan(c, b, params, scan_start, scan_stop, is_ref, 0, d_a, d_b, d_isref, so))) break;
+    r->scanned_bp = so.scanned_bp;
+    const BatchView B = batch_view(b, d_a.as<int32_t>(), d_b.as<int32_t>(), d_isref.as<uint8_t>());
+    const int64_t n_hits[2] = {so.n[0], so.n[1]};
+    if ((rc = d_refrange.alloc(st, 32, true))) break;
+    if ((rc = d_err.alloc(st, 4, true))) break;
+    if ((rc = launch_ref_range(st, so.hits[0].as<uint64_t>(), n_hits[0], so.hits[1].as<uint64_t>(),
+                               n_hits[1], ref_h, d_refrange.as<int64_t>())))
+      break;
+    int64_t n_rows[2] = {n_hits[0], n_hits[1]};
+    for (int s = 0; s < 2 && rc == HAWK_OK; ++s) {
+      if ((rc = start[s].alloc(st, (size_t)n_hits[s] * 4))) break;
+      if ((rc = stop[s].alloc(st, (size_t)n_hits[s] * 4))) break;
+      if ((rc = keep[s].alloc(st, (size_t)n_hits[s]))) break;
+      rc = launch_rows(st, B, K, so.hits[s].as<uint64_t>(), n_hits[s], s, ref_h,
+                       d_refrange.as<int64_t>(), unphased ? 0 : 1, start[s].as<int32_t>(),
+                       stop[s].as<int32_t>(), keep[s].as<uint8_t>());
+    }
+    if (rc) break;
+    int64_t max_tiles = scan_tiles(n_hits[0] > n_hits[1] ? n_hits[0] : n_hits[1]);
+    if (unphased) {
+      // resolve_guide: count, scan, write
+      uint64_t totals[2] = {0, 0};
+      if ((rc = tile_sums.alloc(st, (size_t)(max_tiles + 1) * 8))) break;
+      for (int s = 0; s < 2 && rc == HAWK_OK; ++s) {
+        if (n_hits[s] == 0) continue;
+        if ((rc = cnt[s].alloc(st, (size_t)n_hits[s] * 8))) break;
+        if ((rc = off[s].alloc(st, (size_t)n_hits[s] * 8))) break;
+        if ((rc = launch_expand_count(st, B, K, so.hits[s].as<uint64_t>(), n_hits[s], s,
+                                      cnt[s].as<uint64_t>(), d_err.as<int>())))
+          break;
+        if ((rc = exclusive_scan_u64(st, cnt[s].as<uint64_t>(), n_hits[s], off[s].as<uint64_t>(),
+                                     tile_sums.as<uint64_t>())))
+          break;
+        rc = hawk_check_cuda(cudaMemcpyAsync(&totals[s], tile_sums.as<uint64_t>() + scan_tiles(n_hits[s]), 8,
+                                             cudaMemcpyDeviceToHost, st), "expansion total D2H");
+        if (rc) break;
+        rc = hawk_check_cuda(cudaStreamSynchronize(st), "expansion count sync");
+      }
+      if (rc) break;
+      int err = 0;
+      if ((rc = hawk_check_cuda(cudaMemcpyAsync(&err, d_err.p, 4, cudaMemcpyDeviceToHost, st), "err D2H"))) break;
+      if ((rc = hawk_check_cuda(cudaStreamSynchronize(st), "err sync"))) break;
+      if (err == HAWK_EALLELES) {
+        rc = hawk_fail(HAWK_EALLELES, "ambiguity code inside a guide window has no variant_alleles entry");
+        break;
+      }
+      if (err == HAWK_ECAPACITY) {
+        rc = hawk_fail(HAWK_ECAPACITY, "resolve_guide expansion of one hit exceeds %llu strings",
+                       (unsigned long long)HAWK_MAX_EXPANSION);
+        break;
+      }
+      for (int s = 0; s < 2 && rc == HAWK_OK; ++s) {
+        n_rows[s] = (int64_t)totals[s];
+        if (n_rows[s] == 0) continue;
+        if ((rc = text_pre[s].alloc(st, (size_t)n_rows[s] * W))) break;
+        if ((rc = row_hit[s].alloc(st, (size_t)n_rows[s] * 8))) break;
+        if ((rc = keep[s].alloc(st, (size_t)n_rows[s]))) break;
+        rc = launch_expand_write(st, B, K, so.hits[s].as<uint64_t>(), n_hits[s], s,
+                                 off[s].as<uint64_t>(), n_rows[s], ref_h, d_refrange.as<int64_t>(),
+                                 start[s].as<int32_t>(), text_pre[s].as<uint8_t>(),
+                                 row_hit[s].as<int64_t>(), keep[s].as<uint8_t>());
+      }
+      if (rc) break;
+      int64_t t2 = scan_tiles(n_rows[0] > n_rows[1] ? n_rows[0] : n_rows[1]);
+      if (t2 > max_tiles) {
+        max_tiles = t2;
+        if ((rc = tile_sums.alloc(st, (size_t)(max_tiles + 1) * 8))) break;
+      }
+    } else {
+      if ((rc = tile_sums.alloc(st, (size_t)(max_tiles + 1) * 8))) break;
+    }
+    // stable compaction offsets of the surviving rows
+    uint64_t kept_total[2] = {0, 0};
+    for (int s = 0; s < 2 && rc == HAWK_OK; ++s) {
+      if (n_rows[s] == 0) continue;
+      if ((rc = kept_excl[s].alloc(st, (size_t)n_rows[s] * 8))) break;
+      if ((rc = exclusive_scan_u8(st, keep[s].as<uint8_t>(), n_rows[s], kept_excl[s].as<uint64_t>(),
+                                  tile_sums.as<uint64_t>())))
+        break;
+      if ((rc = hawk_check_cuda(cudaMemcpyAsync(&kept_total[s], tile_sums.as<uint64_t>() + scan_tiles(n_rows[s]),
+                                                8, cudaMemcpyDeviceToHost, st), "kept total D2H")))
+        break;
+      rc = hawk_check_cuda(cudaStreamSynchronize(st), "kept sync");
+    }
+    if (rc) break;
+    const int64_t n = (int64_t)(kept_total[0] + kept_total[1]);
+    r->n_guides = n;
+    if ((rc = r->hap.alloc(st, (size_t)n * 4))) break;
+    if ((rc = r->strand.alloc(st, (size_t)n))) break;
+    if ((rc = r->pos.alloc(st, (size_t)n * 4))) break;
+    if ((rc = r->start.alloc(st, (size_t)n * 4))) break;
+    if ((rc = r->stop.alloc(st, (size_t)n * 4))) break;
+    if ((rc = r->bucket.alloc(st, (size_t)n * 8))) break;
+    if ((rc = r->text.alloc(st, (size_t)n * W))) break;
+    if (n > 0) {
+      GatherLaunch g;
+      g.B = B;
+      g.K = K;
+      for (int s = 0; s < 2; ++s) {
+        g.recs[s] = so.hits[s].as<uint64_t>();
+        g.row_hit[s] = unphased ? row_hit[s].as<int64_t>() : nullptr;
+        g.keep[s] = keep[s].as<uint8_t>();
+        g.kept_excl[s] = kept_excl[s].as<uint64_t>();
+        g.text_pre[s] = unphased ? text_pre[s].as<uint8_t>() : nullptr;
+        g.start[s] = start[s].as<int32_t>();
+        g.stop[s] = stop[s].as<int32_t>();
+        g.n_rows[s] = n_rows[s];
+        g.kept_total[s] = kept_total[s];
+      }
+      g.o_hap = r->hap.as<int32_t>();
+      g.o_strand = r->strand.as<uint8_t>();
+      g.o_pos = r->pos.as<int32_t>();
+      g.o_start = r->start.as<int32_t>();
+      g.o_stop = r->stop.as<int32_t>();
+      g.o_text = r->text.as<uint8_t>();
+      if ((rc = launch_gather(st, g))) break;
+      // first-seen bucket ids
+      uint64_t tsize = 1024;
+      while (tsize < (uint64_t)n * 2) tsize <<= 1;
+      DevBuf keys, vals;
+      if ((rc = keys.alloc(st, tsize * 8))) break;
+      if ((rc = vals.alloc(st, tsize * 8))) break;
+      if ((rc = hawk_check_cuda(cudaMemsetAsync(keys.p, 0xFF, tsize * 8, st), "bucket keys memset"))) break;
+      if ((rc = hawk_check_cuda(cudaMemsetAsync(vals.p, 0xFF, tsize * 8, st), "bucket vals memset"))) break;
+      if ((rc = launch_buckets(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n,
+                               keys.as<unsigned long long>(), vals.as<unsigned long long>(), tsize,
+                               r->bucket.as<int64_t>())))
+        break;
+    }
+    if ((rc = hawk_check_cuda(cudaStreamSynchronize(st), "search sync"))) break;
+    for (int s = 0; s < 2; ++s) {
+      r->n_hits[s] = n_hits[s];
+      r->hits[s].p = so.hits[s].p;
+      r->hits[s].bytes = so.hits[s].bytes;
+      r->hits[s].st = so.hits[s].st;
+      so.hits[s].p = nullptr;
+    }
+  } while (0);
+  if (rc != HAWK_OK) {
+    cudaStreamSynchronize(st);
+    delete r;
+    return rc;
+  }
+  *out = r;
+  return HAWK_OK;
+}
+
+extern "C" int hawk_result_destroy(hawk_result* r) {
+  if (!r) return HAWK_OK;
+  cudaSetDevice(r->ctx->device);
+  delete r;
+  return HAWK_OK;
+}
+
+extern "C" int hawk_result_info(hawk_result* r, int64_t* n_guides, int64_t* n_hits, int32_t* window,
+                                int64_t* scanned_bp) {
+  if (!r) return hawk_fail(HAWK_EINVAL, "hawk_result_info: null result");
+  if (n_guides) *n_guides = r->n_guides;
+  if (n_hits) {
+    n_hits[0] = r->n_hits[0];
+    n_hits[1] = r->n_hits[1];
+  }
+  if (window) *window = r->window;
+  if (scanned_bp) *scanned_bp = r->scanned_bp;
+  return HAWK_OK;
+}
+
+extern "C" int hawk_result_fetch(hawk_result* r, int32_t* hap, uint8_t* strand, int32_t* pos,
+                                 int32_t* start, int32_t* stop, int64_t* bucket, uint8_t* text) {
+  if (!r) return hawk_fail(HAWK_EINVAL, "hawk_result_fetch: null result");
+  CKCUDA(cudaSetDevice(r->ctx->device));
+  cudaStream_t st = r->ctx->stream;
+  size_t n = (size_t)r->n_guides;
+  if (n == 0) return HAWK_OK;
+  if (hap) CKCUDA(cudaMemcpyAsync(hap, r->hap.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (strand) CKCUDA(cudaMemcpyAsync(strand, r->strand.p, n, cudaMemcpyDeviceToHost, st));
+  if (pos) CKCUDA(cudaMemcpyAsync(pos, r->pos.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (start) CKCUDA(cudaMemcpyAsync(start, r->start.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (stop) CKCUDA(cudaMemcpyAsync(stop, r->stop.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (bucket) CKCUDA(cudaMemcpyAsync(bucket, r->bucket.p, n * 8, cudaMemcpyDeviceToHost, st));
+  if (text) CKCUDA(cudaMemcpyAsync(text, r->text.p, n * (size_t)r->window, cudaMemcpyDeviceToHost, st));
+  CKCUDA(cudaStreamSynchronize(st));
+  return HAWK_OK;
+}
+
+extern "C" int hawk_result_fetch_hits(hawk_result* r, int32_t strand, uint64_t* hits) {
+  if (!r || strand < 0 || strand > 1) return hawk_fail(HAWK_EINVAL, "hawk_result_fetch_hits: bad arguments");
+  CKCUDA(cudaSetDevice(r->ctx->device));
+  size_t n = (size_t)r->n_hits[strand];
+  if (n == 0) return HAWK_OK;
+  if (!hits) return hawk_fail(HAWK_EINVAL, "hawk_result_fetch_hits: null output");
+  CKCUDA(cudaMemcpyAsync(hits, r->hits[strand].p, n * 8, cudaMemcpyDeviceToHost, r->ctx->stream));
+  CKCUDA(cudaStreamSynchronize(r->ctx->stream));
+  return HAWK_OK;
+}

@@ -1,0 +1,13 @@
+// hawk_kernels.h -- internal declarations shared by the .cu files of libhawkscan
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hawkscan.h"
+
+// chunks per scan span (one CTA iteration): 2048 chunks = 65,536 base slots,
+// two 8 KB hit bitmaps in shared memory
+#define HAWK_SPAN_CHUNKS 2048
+
+int hawk_fail(int code, const char* fmt, ...);
+int hawk_check_cuda(cudaError_t err, const char* what);

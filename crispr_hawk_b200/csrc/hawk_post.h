@@ -1,0 +1,55 @@
+// hawk_post.h -- launch wrappers of post_kernels.cu (internal)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hawk_core.h"
+
+// resolve_guide products above this are refused (the reference would need that
+// many Python strings per hit)
+#define HAWK_MAX_EXPANSION (1ull << 24)
+
+namespace hawk {
+
+struct GatherLaunch {
+  BatchView B;
+  ScanConst K;
+  const uint64_t* recs[2];
+  const int64_t* row_hit[2];
+  const uint8_t* keep[2];
+  const uint64_t* kept_excl[2];
+  const uint8_t* text_pre[2];
+  const int32_t* start[2];
+  const int32_t* stop[2];
+  int64_t n_rows[2];
+  uint64_t kept_total[2];
+  int32_t* o_hap;
+  uint8_t* o_strand;
+  int32_t* o_pos;
+  int32_t* o_start;
+  int32_t* o_stop;
+  uint8_t* o_text;
+};
+
+int64_t scan_tiles(int64_t n);
+int exclusive_scan_u8(cudaStream_t st, const uint8_t* in, int64_t n, uint64_t* out, uint64_t* tile_sums);
+int exclusive_scan_u64(cudaStream_t st, const uint64_t* in, int64_t n, uint64_t* out, uint64_t* tile_sums);
+int launch_ref_range(cudaStream_t st, const uint64_t* r0, int64_t n0, const uint64_t* r1, int64_t n1,
+                     int32_t ref_h, int64_t* out);
+int launch_rows(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* recs,
+                int64_t n, int s, int32_t ref_h, const int64_t* ref_range, int dedup,
+                int32_t* start, int32_t* stop, uint8_t* keep);
+int launch_expand_count(cudaStream_t st, const BatchView& B, const ScanConst& K,
+                        const uint64_t* recs, int64_t n, int s, uint64_t* cnt, int* err);
+int launch_expand_write(cudaStream_t st, const BatchView& B, const ScanConst& K,
+                        const uint64_t* recs, int64_t n_hits, int s, const uint64_t* off,
+                        int64_t n_rows, int32_t ref_h, const int64_t* ref_range,
+                        const int32_t* start, uint8_t* text, int64_t* row_hit, uint8_t* keep);
+int launch_gather(cudaStream_t st, const GatherLaunch& g);
+int launch_buckets(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n,
+                   unsigned long long* keys, unsigned long long* vals, uint64_t table_size,
+                   int64_t* bucket);
+int launch_export_nibbles(cudaStream_t st, const void* q, const uint32_t* v, int64_t chunk0,
+                          int32_t len, uint8_t* nib, uint8_t* lower);
+
+}  // namespace hawk

@@ -1,0 +1,126 @@
+"""GPU replacement of `search_guides.search` (search_guides.py:510-548), same
+signature, same `List[Guide]` (order included).
+
+Division of labour: scan bounds are read from the haplotypes' own position maps
+(host dict lookups, :49-84); PAM matching on both strands, the in-range and
+REF-core filters, unphased IUPAC resolution, genomic start/stop, redundancy
+removal, emission-order merge, bucket ids and window text all run on the GPU
+behind `hawk_search` (include/hawkscan.h); this module turns the returned table
+into `Guide` objects. There is no CPU implementation of the scan here."""
+
+from __future__ import annotations
+
+from time import time
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import _cabi, marshal
+from .encoder import PackedRegion, encode_region
+from .errors import error_class, exception_handler, print_verbosity
+from .guide import guide_class
+from .pam import pam_patterns
+
+GUIDESEQPAD = marshal.GUIDESEQPAD
+
+
+def _packed_for(haplotypes, haplotypes_bits, verbosity: int, debug: bool) -> PackedRegion:
+    if isinstance(haplotypes_bits, PackedRegion) and haplotypes_bits.matches(haplotypes):
+        return haplotypes_bits
+    # bit lists produced elsewhere (e.g. the reference's own encoder) carry no
+    # case plane: pack from the haplotype texts
+    return encode_region(haplotypes, verbosity, debug)
+
+
+def _prepare(pam, region, haplotypes, packed: PackedRegion, guidelen, right, unphased):
+    fwd, rc = pam_patterns(pam)
+    params = _cabi.make_params(fwd, rc, guidelen, right, unphased)
+    bounds = [marshal.scan_bounds(h, region.start, region.stop, len(fwd)) for h in haplotypes]
+    a = np.array([b[0] for b in bounds], dtype=np.int32)
+    b = np.array([b[1] for b in bounds], dtype=np.int32)
+    return params, a, b
+
+
+def _split_hits(recs: np.ndarray, n_hap: int) -> List[List[int]]:
+    hap = (recs >> np.uint64(32)).astype(np.int64)
+    pos = (recs & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    cuts = np.searchsorted(hap, np.arange(n_hap + 1))
+    return [pos[cuts[h] : cuts[h + 1]].tolist() for h in range(n_hap)]
+
+
+def pam_search(pam, region, haplotypes, haplotypes_bits, verbosity: int, debug: bool) -> List[Tuple[List[int], List[int]]]:
+    """search_guides.py:102-131 on the GPU: raw PAM occurrences per haplotype and strand."""
+    packed = _packed_for(haplotypes, haplotypes_bits, verbosity, debug)
+    params, a, b = _prepare(pam, region, haplotypes, packed, 1, False, False)
+    res = _cabi.pam_search(packed.batch.ctx, packed.batch, params, a, b)
+    fwd = _split_hits(res.hits(0), len(haplotypes))
+    rev = _split_hits(res.hits(1), len(haplotypes))
+    res.close()
+    for h, (f, r) in zip(haplotypes, zip(fwd, rev)):
+        print_verbosity(f"Searching PAM occurrences in haplotype {h.samples}", verbosity, 3)
+        print_verbosity(
+            f"Found {len(f) + len(r)} PAM occurrences ({len(f)} on 5'-3'; {len(r)} on 3'-5')", verbosity, 3
+        )
+    return list(zip(fwd, rev))
+
+
+def search_table(pam, region, haplotypes, haplotypes_bits, guidelen: int, right: bool,
+                 variants_present: bool, phased: bool, verbosity: int = 0, debug: bool = False):  # fmt: skip
+    """Run the device pipeline and return (table dict, Result) without building Guides."""
+    packed = _packed_for(haplotypes, haplotypes_bits, verbosity, debug)
+    batch = packed.batch
+    unphased = bool(variants_present and not phased)
+    params, a, b = _prepare(pam, region, haplotypes, packed, guidelen, right, unphased)
+    if not batch.has_posmap:
+        batch.set_posmap(marshal.segment_table(haplotypes))
+    if unphased and not batch.has_alleles:
+        batch.set_alleles(marshal.allele_table(haplotypes))
+    is_ref = np.array([h.samples == "REF" for h in haplotypes], dtype=np.uint8)
+    try:
+        res = _cabi.search(batch.ctx, batch, params, a, b, is_ref)
+    except _cabi.HawkLibraryError as e:
+        if e.code == _cabi.HAWK_EALLELES:
+            # the reference dies with a bare KeyError here (search_guides.py:207-213)
+            raise KeyError("ambiguity code without variant_alleles entry inside a guide window") from e
+        if e.code == _cabi.HAWK_EDUPREF:
+            exception_handler(
+                error_class("CrisprHawkCfdScoreError"),
+                "Duplicate REF guide at position ? CFDon calculation failed",
+                65, debug, e,
+            )  # fmt: skip
+        raise
+    return res.table(), res
+
+
+def search(pam, region, haplotypes, haplotypes_bits, guidelen: int, right: bool,
+           variants_present: bool, phased: bool, verbosity: int, debug: bool) -> list:  # fmt: skip
+    print_verbosity(f"Searching guide candidates in {region.coordinates}", verbosity, 3)
+    if verbosity >= 3:
+        pam_search(pam, region, haplotypes, haplotypes_bits, verbosity, debug)
+    start_t = time()
+    table, res = search_table(pam, region, haplotypes, haplotypes_bits, guidelen, right,
+                              variants_present, phased, verbosity, debug)  # fmt: skip
+    res.close()
+    Guide = guide_class()
+    pamlen = len(pam_patterns(pam)[0])
+    span = guidelen + pamlen
+    # remove_redundant_guides returns buckets in first-seen order, members in emission
+    # order (:306-369): a stable sort of the emission-ordered table by bucket id
+    order = np.argsort(table["bucket"], kind="stable")
+    hap_i, strand, pos = table["hap"], table["strand"], table["pos"]
+    starts, stops = table["start"].tolist(), table["stop"].tolist()
+    texts = table["text"]
+    guides = []
+    for i in order.tolist():
+        h = haplotypes[hap_i[i]]
+        s = int(strand[i])
+        rp = (not right) if s == 1 else bool(right)  # :538
+        pivot = int(pos[i]) if rp else int(pos[i]) - guidelen
+        pm = h.posmap
+        gpm = {j: pm[pivot + j] for j in range(span)}  # retrieve_guide_posmap :283-303
+        guides.append(
+            Guide(starts[i], stops[i], texts[i].tobytes().decode("ascii"), guidelen, pamlen, s,
+                  h.samples, h.variants, h.afs, gpm, debug, rp, h.id)
+        )  # fmt: skip
+    print_verbosity(f"Guides retrieved in {time() - start_t:.2f}s", verbosity, 3)
+    return guides

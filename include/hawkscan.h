@@ -1,0 +1,182 @@
+/*
+ * hawkscan.h -- C-ABI of the B200-native CRISPR-HAWK guide-discovery scan.
+ *
+ * The reference (pinellolab/CRISPR-HAWK v0.2.2) has no FFI; its narrowest seam
+ * for this path is three Python callables invoked from crisprhawk.py
+ * (SURVEY.md 8b). Each entry point below cites the reference interface it
+ * replaces (paths relative to /root/reference/src/crisprhawk). The Python
+ * mirror in crispr_hawk_b200/ binds these with ctypes; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes, no torch/C++ types; every function
+ * returns 0 (HAWK_OK) or a negative HAWK_E* code; hawk_last_error() gives the
+ * message of the calling thread's last failure. Two layers:
+ *   - host layer  (hawk_batch_*, hawk_search*): caller-owned HOST buffers in and
+ *     out, library-owned device buffers behind opaque handles, synchronous.
+ *   - device layer (hawk_*_dev): caller-owned DEVICE buffers and stream (e.g.
+ *     torch tensors), asynchronous, no allocation inside.
+ *
+ * Slot layout (both layers). Haplotype h owns base slots
+ * [slot_off[h], slot_off[h] + len[h]) of one flat slot space; slot_off[h] is a
+ * multiple of HAWK_SLOT_ALIGN; unused slots hold 0. Device planes:
+ *   q  : one uint4 {A,C,G,T} per 32-slot chunk -- the 4-bit IUPAC mask of
+ *        encoder.py:18-34, bit-sliced: bit i of .x/.y/.z/.w is bit 0/1/2/3 of
+ *        the nibble of slot 32*chunk + i (0.5 B per base).
+ *   v  : one uint32 per chunk, bit i = base was lower-case (a variant base,
+ *        haplotype.py:106-121) (0.125 B per base).
+ */
+#ifndef HAWKSCAN_H
+#define HAWKSCAN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HAWK_ABI_VERSION 1
+#define HAWK_SLOT_ALIGN 128 /* bases; haplotypes start on a 64-byte plane boundary */
+#define HAWK_CHUNK 32       /* bases per chunk (one uint4 of planes, one uint32 of case bits) */
+#define HAWK_SLACK_CHUNKS 8 /* readable zero chunks after the last slot */
+#define HAWK_MAX_PAM 16
+#define HAWK_GUIDESEQPAD 10 /* guide.py:21 */
+#define HAWK_MAX_WINDOW 160 /* G + P + 2*PAD upper bound supported on device */
+
+enum {
+  HAWK_OK = 0,
+  HAWK_EINVAL = -1,   /* bad argument */
+  HAWK_ECUDA = -2,    /* CUDA runtime failure */
+  HAWK_ENOMEM = -3,   /* allocation failure */
+  HAWK_EIUPAC = -4,   /* non-IUPAC character (encoder.py:38-44) */
+  HAWK_ECAPACITY = -5,/* caller-provided output capacity too small (dev layer) */
+  HAWK_EALLELES = -6, /* ambiguity code without variant_alleles entry (KeyError, search_guides.py:207-213) */
+  HAWK_EDUPREF = -7   /* two REF guides at one (start, strand) (search_guides.py:328-334) */
+};
+
+/* mode flags of hawk_params.flags */
+#define HAWK_F_UNPHASED 1u /* variants_present and not phased: is_pamhit_valid + resolve_guide (search_guides.py:473-479) */
+
+typedef struct hawk_ctx hawk_ctx;       /* one device, one stream, reusable workspace */
+typedef struct hawk_batch hawk_batch;   /* packed haplotypes of one region, device resident */
+typedef struct hawk_result hawk_result; /* guide table of one search, device resident */
+
+/* Replaces pam.py:127-142 (PAM.encode): caller passes the nibble lists
+ * (`bits_list` of the forward PAM and of its reverse complement). */
+typedef struct hawk_params {
+  int32_t pam_len;                 /* P, 1..HAWK_MAX_PAM */
+  int32_t guide_len;               /* G >= 1 */
+  int32_t right;                   /* --right: guide downstream of the PAM on strand 0 */
+  uint32_t flags;                  /* HAWK_F_* */
+  uint8_t pam_fwd[HAWK_MAX_PAM];   /* IUPAC nibbles of the PAM, 5'->3' */
+  uint8_t pam_rc[HAWK_MAX_PAM];    /* nibbles of its reverse complement (pam.py:63) */
+} hawk_params;
+
+int hawk_abi_version(void);
+const char *hawk_last_error(void);
+const char *hawk_strerror(int code);
+
+/* ---- context ------------------------------------------------------------ */
+int hawk_ctx_create(int device, hawk_ctx **ctx);
+int hawk_ctx_destroy(hawk_ctx *ctx);
+/* SM count etc. for callers sizing grids/benchmarks */
+int hawk_ctx_info(hawk_ctx *ctx, int32_t *sm_count, int64_t *total_mem, int64_t *free_mem);
+
+/* ---- layout helper -------------------------------------------------------
+ * slot_off[0..n_hap]: aligned exclusive prefix of len[]; returns total slots
+ * (multiple of HAWK_SLOT_ALIGN) in *total_slots. */
+int hawk_layout(const int32_t *len, int32_t n_hap, int64_t *slot_off, int64_t *total_slots);
+
+/* ---- host layer ----------------------------------------------------------
+ * hawk_batch_create replaces crisprhawk.py:64-81 (encode_haplotypes) /
+ * encoder.py:48-57 (encode) for a whole region at once: `ascii` is the slot
+ * space filled with the haplotype texts (case preserved, unused slots 0),
+ * total_slots bytes of HOST memory. On a non-IUPAC byte returns HAWK_EIUPAC
+ * and stores its slot index in *bad_slot (the Python mirror turns it into the
+ * reference's CrisprHawkIupacTableError). */
+int hawk_batch_create(hawk_ctx *ctx, const uint8_t *ascii, const int64_t *slot_off,
+                      const int32_t *len, int32_t n_hap, hawk_batch **batch, int64_t *bad_slot);
+int hawk_batch_destroy(hawk_batch *batch);
+/* encoder.encode's return value for one haplotype: one nibble (1..15) per base */
+int hawk_batch_export_nibbles(hawk_batch *batch, int32_t hap, uint8_t *nibbles /* len[hap] */,
+                              uint8_t *lower /* len[hap], may be NULL */);
+
+/* Coordinate maps (haplotype.py:90-104,138-159 `posmap`), run-length encoded:
+ * haplotype h owns segments [seg_off[h], seg_off[h+1]); inside segment k
+ * posmap(i) = seg_gen[k] + seg_step[k] * (i - seg_rel[k]), seg_step in {0,1}. */
+int hawk_batch_set_posmap(hawk_batch *batch, const int64_t *seg_off, const int32_t *seg_rel,
+                          const int32_t *seg_gen, const uint8_t *seg_step);
+
+/* Unphased only (haplotype.py:287-291 `variant_alleles`): haplotype h owns
+ * sites [va_off[h], va_off[h+1]) sorted by va_idx (relative index); site j owns
+ * entries [va_ent_off[j], va_ent_off[j+1]); va_ref[e] = nibble of the entry's
+ * REF allele when it is a single base, else 0. */
+int hawk_batch_set_alleles(hawk_batch *batch, const int64_t *va_off, const int32_t *va_idx,
+                           const int64_t *va_ent_off, const uint8_t *va_ref);
+
+/* Replaces search_guides.py:510-548 (search) up to, not including, the
+ * construction of Python Guide objects. scan_start/scan_stop are the
+ * haplotype-relative bounds of compute_scan_start_stop (:49-84); is_ref[h] =
+ * (samples == "REF"). The result is the guide table in the reference's
+ * emission order (haplotype, strand, position, expansion), already filtered by
+ * is_pamhit_in_range (:395-420), the REF-core filter (:468-471),
+ * is_pamhit_valid + resolve_guide (unphased, :216-257, :372-392) and
+ * remove_redundant_guides (:340-369). */
+int hawk_search(hawk_ctx *ctx, hawk_batch *batch, const hawk_params *params,
+                const int32_t *scan_start, const int32_t *scan_stop, const uint8_t *is_ref,
+                hawk_result **result);
+int hawk_result_destroy(hawk_result *result);
+/* Replaces search_guides.py:102-131 (pam_search): raw PAM occurrences inside
+ * the scan bounds on both strands, no window / REF-core filter. The result
+ * holds hit lists only (n_guides == 0). */
+int hawk_pam_search(hawk_ctx *ctx, hawk_batch *batch, const hawk_params *params,
+                    const int32_t *scan_start, const int32_t *scan_stop, hawk_result **result);
+/* n_guides: rows of the table; n_hits[2]: records per strand in the result's
+ * hit lists (hawk_pam_search: raw PAM hits; hawk_search: hits that survived
+ * the in-range and REF-core filters, before resolution / redundancy removal);
+ * window: characters per row (G + P + 20); scanned_bp: sum of scan_stop -
+ * scan_start, the unit of the haplotype-bp/s metric. */
+int hawk_result_info(hawk_result *result, int64_t *n_guides, int64_t *n_hits, int32_t *window,
+                     int64_t *scanned_bp);
+/* Copy the table to HOST arrays of n_guides rows: haplotype index, strand,
+ * PAM position (haplotype-relative), genomic start/stop
+ * (adjust_guide_position, :260-280), bucket = smallest row index among the
+ * rows sharing the row's (start, strand) key, i.e. buckets ordered by bucket id
+ * are in first-seen order (group_guides_position, :306-337), and the padded
+ * window text (extract_guide_sequence / resolved string), `window` bytes per
+ * row. Any pointer may be NULL. */
+int hawk_result_fetch(hawk_result *result, int32_t *hap, uint8_t *strand, int32_t *pos,
+                      int32_t *start, int32_t *stop, int64_t *bucket, uint8_t *text);
+/* hit list of one strand: packed (hap << 32 | pos), ascending */
+int hawk_result_fetch_hits(hawk_result *result, int32_t strand, uint64_t *hits /* n_hits[strand] */);
+
+/* ---- device layer (asynchronous on `stream`, a cudaStream_t) -------------- */
+/* K1: ASCII slot space -> planes. d_bad: one int64, must hold INT64_MAX on
+ * entry; receives the smallest slot index with a non-IUPAC byte. */
+int hawk_pack_dev(void *stream, const uint8_t *d_ascii, int64_t total_slots, void *d_q,
+                  uint32_t *d_v, int64_t *d_bad);
+
+/* scan plan: host-side span directory for hawk_scan_dev. Returns the number
+ * of spans; span_off (n_hap+1) is filled when non-NULL. */
+int64_t hawk_scan_plan(const int32_t *scan_start, const int32_t *scan_stop, int32_t n_hap,
+                       int64_t *span_off);
+/* bytes of zero-initialised device workspace hawk_scan_dev needs */
+size_t hawk_scan_workspace_bytes(int64_t n_spans);
+
+/* K2: PAM match on both strands + in-range / REF-core filters + ordered
+ * compaction. All d_* are device pointers; per-haplotype arrays have n_hap
+ * entries (d_span_off n_hap+1). d_hits[s] receives (hap << 32 | pos) records
+ * ascending, at most cap[s]; d_counts (uint64[4]) receives the filtered totals
+ * per strand in [0..1] and the raw PAM-hit totals in [2..3]. The workspace
+ * must be zeroed by the caller before every launch. */
+int hawk_scan_dev(void *stream, int32_t sm_count, const void *d_q, const uint32_t *d_v,
+                  const int64_t *d_slot_off, const int32_t *d_len, const int32_t *d_scan_start,
+                  const int32_t *d_scan_stop, const uint8_t *d_is_ref, const int64_t *d_span_off,
+                  int32_t n_hap, int64_t n_spans, const hawk_params *params, int32_t raw_hits,
+                  uint64_t *d_hits_fwd, uint64_t *d_hits_rev, int64_t cap_fwd, int64_t cap_rev,
+                  uint64_t *d_counts, void *d_workspace);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAWKSCAN_H */

@@ -90,3 +90,36 @@ def fixture_objects(case: dict):
     region = FxRegion(case["contig"], case["region_start"], case["region_stop"])
     haps = [FxHap(h) for h in case["haps"]]
     return region, haps
+
+
+def table_to_tuples(table, haps, guidelen, pamlen, right):
+    """Guide table (hawk_result_fetch layout) -> OracleGuide tuples in final order.
+
+    Same host steps as crispr_hawk_b200.search_guides.search, minus object creation."""
+    import numpy as np
+
+    from oracle.hawk_oracle import OracleGuide
+
+    order = np.argsort(table["bucket"], kind="stable")
+    out = []
+    for i in order.tolist():
+        h = haps[int(table["hap"][i])]
+        s = int(table["strand"][i])
+        rp = (not right) if s == 1 else bool(right)
+        pivot = int(table["pos"][i]) - (0 if rp else guidelen)
+        gpm = tuple(h.posmap[pivot + j] for j in range(guidelen + pamlen))
+        out.append(
+            OracleGuide(int(table["start"][i]), int(table["stop"][i]), s,
+                        table["text"][i].tobytes().decode("ascii"), rp, h.samples, h.variants, h.id,
+                        gpm, guidelen, pamlen)
+        )  # fmt: skip
+    return out
+
+
+def split_hits(recs, n_hap):
+    import numpy as np
+
+    hap = (recs >> np.uint64(32)).astype(np.int64)
+    pos = (recs & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    cuts = np.searchsorted(hap, np.arange(n_hap + 1))
+    return [pos[cuts[h] : cuts[h + 1]].tolist() for h in range(n_hap)]

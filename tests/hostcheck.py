@@ -1,0 +1,99 @@
+"""ctypes driver of libhawkcheck.so: the kernels' __host__ __device__ core compiled for
+the CPU (crispr_hawk_b200/csrc/hostcheck.cpp). TEST SUPPORT ONLY."""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from crispr_hawk_b200 import _cabi, build, marshal
+from crispr_hawk_b200.pam import pam_patterns
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = build.build_hostcheck()
+        _lib = C.CDLL(path)
+        _lib.hawkcheck_pack.restype = C.c_int64
+        _lib.hawkcheck_search.restype = C.c_void_p
+        _lib.hawkcheck_n.restype = C.c_int64
+        _lib.hawkcheck_nhits.restype = C.c_int64
+        for f in ("hawkcheck_n", "hawkcheck_err", "hawkcheck_window", "hawkcheck_free"):
+            getattr(_lib, f).argtypes = [C.c_void_p]
+        _lib.hawkcheck_nhits.argtypes = [C.c_void_p, C.c_int]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def pack(texts):
+    buf, off, lens = marshal.stage_ascii(texts)
+    n_chunks = len(buf) // 32 + 8
+    q = np.zeros(n_chunks * 4, np.uint32)
+    v = np.zeros(n_chunks, np.uint32)
+    bad = lib().hawkcheck_pack(_p(buf), C.c_int64(len(buf)), _p(q), _p(v))
+    return q, v, off, lens, bad
+
+
+def unpack_nibbles(q, v, off, lens, h):
+    n = int(lens[h])
+    idx = np.arange(n) + int(off[h])
+    chunk, bit = idx // 32, (idx % 32).astype(np.uint32)
+    planes = q.reshape(-1, 4)
+    nib = np.zeros(n, np.uint8)
+    for k in range(4):
+        nib |= (((planes[chunk, k] >> bit) & 1) << k).astype(np.uint8)
+    low = ((v[chunk] >> bit) & 1).astype(np.uint8)
+    return nib, low
+
+
+def search(pam, region, haps, guidelen, right, variants_present, phased, raw=False):
+    texts = [marshal.hap_text(h) for h in haps]
+    q, v, off, lens, bad = pack(texts)
+    assert bad == -1
+    fwd, rc = pam_patterns(pam)
+    unphased = bool(variants_present and not phased)
+    params = _cabi.make_params(fwd, rc, guidelen, right, unphased)
+    bounds = [marshal.scan_bounds(h, region.start, region.stop, len(fwd)) for h in haps]
+    a = np.array([b[0] for b in bounds], np.int32)
+    b = np.array([b[1] for b in bounds], np.int32)
+    is_ref = np.array([h.samples == "REF" for h in haps], np.uint8)
+    seg = marshal.segment_table(haps)
+    va = marshal.allele_table(haps)
+    L = lib()
+    t = L.hawkcheck_search(
+        _p(q), _p(v), _p(off), _p(lens), _p(a), _p(b), _p(is_ref), C.c_int32(len(haps)),
+        _p(seg.seg_off), _p(seg.seg_rel), _p(seg.seg_gen), _p(seg.seg_step),
+        _p(va.va_off), _p(va.va_idx), _p(va.va_ent_off), _p(va.va_ref),
+        C.byref(params), C.c_int(1 if raw else 0),
+    )  # fmt: skip
+    t = C.c_void_p(t)
+    try:
+        hits = []
+        for s in (0, 1):
+            n = L.hawkcheck_nhits(t, s)
+            arr = np.empty(n, np.uint64)
+            L.hawkcheck_fetch_hits(t, C.c_int(s), _p(arr))
+            hits.append(arr)
+        if raw:
+            return hits
+        err = L.hawkcheck_err(t)
+        if err:
+            raise KeyError(f"hostcheck error {err}")
+        n, w = L.hawkcheck_n(t), L.hawkcheck_window(t)
+        tab = {
+            "hap": np.empty(n, np.int32), "strand": np.empty(n, np.uint8), "pos": np.empty(n, np.int32),
+            "start": np.empty(n, np.int32), "stop": np.empty(n, np.int32),
+            "bucket": np.empty(n, np.int64), "text": np.empty((n, w), np.uint8),
+        }  # fmt: skip
+        L.hawkcheck_fetch(t, _p(tab["hap"]), _p(tab["strand"]), _p(tab["pos"]), _p(tab["start"]),
+                          _p(tab["stop"]), _p(tab["bucket"]), _p(tab["text"]))  # fmt: skip
+        return tab
+    finally:
+        L.hawkcheck_free(t)

@@ -1,0 +1,51 @@
+"""CPU check of the kernels' bit logic: the __host__ __device__ core the CUDA
+kernels are built from (hawk_core.h), compiled for the host, against the golden
+vectors. Covers K1's SWAR packing, the per-chunk scan with fused filters, the
+run-length posmap, REF-core comparison and IUPAC resolution. The block-level
+parts of the kernels need a GPU (tests/test_gpu_parity.py)."""
+
+import numpy as np
+import pytest
+
+from oracle import hawk_oracle as O
+from tests import hostcheck
+from tests.helpers import all_golden_cases, fixture_objects, golden_guides, split_hits, table_to_tuples
+
+CASES = all_golden_cases()
+
+
+def test_pack_matches_oracle_encode():
+    rng = np.random.default_rng(7)
+    alphabet = "ACGTNRYSWKMBDHVacgtnryswkmbdhv"
+    texts = ["".join(rng.choice(list(alphabet), size=n)) for n in (0, 1, 31, 32, 33, 127, 128, 129, 1000)]
+    q, v, off, lens, bad = hostcheck.pack(texts)
+    assert bad == -1
+    for h, t in enumerate(texts):
+        nib, low = hostcheck.unpack_nibbles(q, v, off, lens, h)
+        assert nib.tolist() == O.encode(t)
+        assert low.tolist() == [int(c.islower()) for c in t]
+    # unused slots stay zero
+    used = np.zeros(len(v) * 32, bool)
+    for h, t in enumerate(texts):
+        used[off[h] : off[h] + len(t)] = True
+    planes = q.reshape(-1, 4)
+    for k in range(4):
+        bits = ((planes[:, k][:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1).astype(bool)
+        assert not bits[~used].any()
+
+
+def test_pack_flags_first_invalid_slot():
+    q, v, off, lens, bad = hostcheck.pack(["ACGT" * 50, "ACGTXACGT!"])
+    assert bad == off[1] + 4
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_core_matches_golden(case):
+    region, haps = fixture_objects(case)
+    G, P = case["guidelen"], len(case["pam"])
+    raw = hostcheck.search(case["pam"], region, haps, G, case["right"], case["variants_present"],
+                           case["phased"], raw=True)  # fmt: skip
+    got_hits = [[f, r] for f, r in zip(split_hits(raw[0], len(haps)), split_hits(raw[1], len(haps)))]
+    assert got_hits == case["pam_hits"]
+    tab = hostcheck.search(case["pam"], region, haps, G, case["right"], case["variants_present"], case["phased"])
+    assert table_to_tuples(tab, haps, G, P, case["right"]) == golden_guides(case)
