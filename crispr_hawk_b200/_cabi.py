@@ -62,6 +62,14 @@ SIGNATURES = {
     "hawk_ctx_info": (C.c_int, [_P, _I32P, _I64P, _I64P]),
     "hawk_layout": (C.c_int, [_I32P, C.c_int32, _I64P, _I64P]),
     "hawk_batch_create": (C.c_int, [_P, _U8P, _I64P, _I32P, C.c_int32, C.POINTER(_P), _I64P]),
+    "hawk_batch_create_dev": (C.c_int, [_P, _P, _I64P, _I32P, C.c_int32, C.POINTER(_P), _I64P]),
+    "hawk_batch_repack_dev": (C.c_int, [_P, _P, _I64P]),
+    "hawk_ctx_stream": (C.c_void_p, [_P]),
+    "hawk_ctx_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "hawk_ctx_profile": (C.c_int, [_P, C.POINTER(C.c_double), _I64P]),
+    "hawk_materialize_dev": (
+        C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P],
+    ),
     "hawk_batch_destroy": (C.c_int, [_P]),
     "hawk_batch_export_nibbles": (C.c_int, [_P, C.c_int32, _U8P, _U8P]),
     "hawk_batch_set_posmap": (C.c_int, [_P, _I64P, _I32P, _I32P, _U8P]),
@@ -169,6 +177,20 @@ class Context:
         check(self.lib.hawk_ctx_info(self.handle, C.byref(sm), C.byref(tot), C.byref(free)))
         return {"sm_count": sm.value, "total_mem": tot.value, "free_mem": free.value}
 
+    @property
+    def stream(self) -> int:
+        """cudaStream_t of the context as an integer (for torch.cuda.ExternalStream)."""
+        return int(self.lib.hawk_ctx_stream(self.handle) or 0)
+
+    def set_profiling(self, enabled: bool) -> None:
+        check(self.lib.hawk_ctx_set_profiling(self.handle, 1 if enabled else 0))
+
+    def profile(self):
+        """{'pack'|'scan'|'post': (total ms, launches)} since the last call."""
+        ms, n = (C.c_double * 3)(), (C.c_int64 * 3)()
+        check(self.lib.hawk_ctx_profile(self.handle, ms, n))
+        return {k: (ms[i], n[i]) for i, k in enumerate(("pack", "scan", "post"))}
+
     def close(self):
         if self.handle:
             self.lib.hawk_ctx_destroy(self.handle)
@@ -178,17 +200,26 @@ class Context:
 class Batch:
     """Packed haplotypes of one region on the device (hawk_batch)."""
 
-    def __init__(self, ctx: Context, ascii_slots: np.ndarray, slot_off: np.ndarray, lens: np.ndarray):
+    def __init__(self, ctx: Context, ascii_slots, slot_off: np.ndarray, lens: np.ndarray,
+                 device_ptr: Optional[int] = None):  # fmt: skip
+        """`ascii_slots`: host uint8 array in the slot layout, or None with `device_ptr`
+        = address of the same bytes in device memory (hawk_batch_create_dev)."""
         self.ctx, self.lib = ctx, ctx.lib
         self.slot_off = np.ascontiguousarray(slot_off, dtype=np.int64)
         self.lens = np.ascontiguousarray(lens, dtype=np.int32)
         self.n_hap = len(self.lens)
-        ascii_slots = np.ascontiguousarray(ascii_slots, dtype=np.uint8)
         h, bad = _P(), C.c_int64(-1)
-        rc = self.lib.hawk_batch_create(
-            ctx.handle, ptr(ascii_slots, C.c_uint8), ptr(self.slot_off, C.c_int64),
-            ptr(self.lens, C.c_int32), self.n_hap, C.byref(h), C.byref(bad),
-        )  # fmt: skip
+        if device_ptr is not None:
+            rc = self.lib.hawk_batch_create_dev(
+                ctx.handle, C.c_void_p(device_ptr), ptr(self.slot_off, C.c_int64),
+                ptr(self.lens, C.c_int32), self.n_hap, C.byref(h), C.byref(bad),
+            )  # fmt: skip
+        else:
+            ascii_slots = np.ascontiguousarray(ascii_slots, dtype=np.uint8)
+            rc = self.lib.hawk_batch_create(
+                ctx.handle, ptr(ascii_slots, C.c_uint8), ptr(self.slot_off, C.c_int64),
+                ptr(self.lens, C.c_int32), self.n_hap, C.byref(h), C.byref(bad),
+            )  # fmt: skip
         self.bad_slot = bad.value
         if rc != HAWK_OK:
             err = HawkLibraryError(self.lib.hawk_last_error().decode(), rc)
@@ -197,6 +228,12 @@ class Batch:
         self.handle = h
         self.has_posmap = False
         self.has_alleles = False
+
+    def repack(self, device_ptr: int) -> None:
+        """Re-run K1 from device-resident texts of the same layout (hawk_batch_repack_dev)."""
+        bad = C.c_int64(-1)
+        check(self.lib.hawk_batch_repack_dev(self.handle, C.c_void_p(device_ptr), C.byref(bad)),
+              "hawk_batch_repack_dev")  # fmt: skip
 
     def export_nibbles(self, hap: int, want_lower: bool = False):
         n = int(self.lens[hap])
@@ -246,13 +283,19 @@ class Result:
         check(lib.hawk_result_info(handle, C.byref(n), hits, C.byref(w), C.byref(bp)))
         self.n_guides, self.n_hits, self.window, self.scanned_bp = n.value, (hits[0], hits[1]), w.value, bp.value
 
-    def table(self):
+    def table(self, buffers=None):
+        """Download the guide table. `buffers`: optional dict of preallocated (e.g. pinned)
+        1-D numpy arrays with at least n rows each; views of them are returned."""
         n, w = self.n_guides, self.window
-        out = {
-            "hap": np.empty(n, np.int32), "strand": np.empty(n, np.uint8), "pos": np.empty(n, np.int32),
-            "start": np.empty(n, np.int32), "stop": np.empty(n, np.int32),
-            "bucket": np.empty(n, np.int64), "text": np.empty((n, w), np.uint8),
-        }  # fmt: skip
+        if buffers is not None:
+            out = {k: buffers[k][:n] for k in ("hap", "strand", "pos", "start", "stop", "bucket")}
+            out["text"] = buffers["text"][: n * w].reshape(n, w)
+        else:
+            out = {
+                "hap": np.empty(n, np.int32), "strand": np.empty(n, np.uint8), "pos": np.empty(n, np.int32),
+                "start": np.empty(n, np.int32), "stop": np.empty(n, np.int32),
+                "bucket": np.empty(n, np.int64), "text": np.empty((n, w), np.uint8),
+            }  # fmt: skip
         check(
             self.lib.hawk_result_fetch(
                 self.handle, ptr(out["hap"], C.c_int32), ptr(out["strand"], C.c_uint8),

@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libhawkscan.so")
 CHECK_LIB = os.path.join(PKG, "libhawkcheck.so")
 
-CUDA_SOURCES = ["scan_kernels.cu", "post_kernels.cu", "api.cu"]
+CUDA_SOURCES = ["scan_kernels.cu", "post_kernels.cu", "synth_kernels.cu", "api.cu"]
 HEADERS = ["hawk_core.h", "hawk_kernels.h", "hawk_post.h", "../../include/hawkscan.h"]
 
 
@@ -43,7 +43,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cmd = [
         nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
-        "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-O2,-Wall", "--expt-relaxed-constexpr",
+        "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unknown-pragmas", "--expt-relaxed-constexpr",
         "-o", LIB,
     ] + srcs  # fmt: skip
     if verbose:

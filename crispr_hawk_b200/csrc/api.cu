@@ -61,6 +61,22 @@ struct hawk_ctx {
   int device;
   cudaStream_t stream;
   int sm_count;
+  // optional per-kernel timing (hawk_ctx_set_profiling)
+  bool profiling = false;
+  struct Span { cudaEvent_t a, b; int kind; };
+  std::vector<Span> spans;
+  void mark(int kind, cudaEvent_t* a) {
+    if (!profiling) return;
+    Span s; s.kind = kind;
+    cudaEventCreate(&s.a); cudaEventCreate(&s.b);
+    cudaEventRecord(s.a, stream);
+    spans.push_back(s);
+    *a = s.a;
+  }
+  void close_mark() {
+    if (!profiling || spans.empty()) return;
+    cudaEventRecord(spans.back().b, stream);
+  }
 };
 
 // device buffer owned through the stream-ordered allocator
@@ -184,9 +200,9 @@ extern "C" int hawk_layout(const int32_t* len, int32_t n_hap, int64_t* slot_off,
 }
 
 // ------------------------------------------------------------------ batch
-extern "C" int hawk_batch_create(hawk_ctx* c, const uint8_t* ascii, const int64_t* slot_off,
-                                 const int32_t* len, int32_t n_hap, hawk_batch** out,
-                                 int64_t* bad_slot) {
+static int batch_create_impl(hawk_ctx* c, const uint8_t* ascii, bool ascii_on_device,
+                             const int64_t* slot_off, const int32_t* len, int32_t n_hap,
+                             hawk_batch** out, int64_t* bad_slot) {
   if (!c || !out || n_hap < 0 || (n_hap > 0 && (!ascii || !slot_off || !len)))
     return hawk_fail(HAWK_EINVAL, "hawk_batch_create: bad arguments");
   CKCUDA(cudaSetDevice(c->device));
@@ -209,17 +225,27 @@ extern "C" int hawk_batch_create(hawk_ctx* c, const uint8_t* ascii, const int64_
   DevBuf d_ascii, d_bad;
   const size_t n_chunks = (size_t)total / HAWK_CHUNK + HAWK_SLACK_CHUNKS;
   do {
-    if ((rc = b->q.alloc(st, n_chunks * 16, true))) break;
-    if ((rc = b->v.alloc(st, n_chunks * 4, true))) break;
+    // K1 writes every chunk of the slot space; only the readable slack behind it is zeroed
+    const size_t used = (size_t)total / HAWK_CHUNK;
+    if ((rc = b->q.alloc(st, n_chunks * 16))) break;
+    if ((rc = b->v.alloc(st, n_chunks * 4))) break;
+    if ((rc = hawk_check_cuda(cudaMemsetAsync(b->q.as<uint8_t>() + used * 16, 0, (n_chunks - used) * 16, st), "slack memset"))) break;
+    if ((rc = hawk_check_cuda(cudaMemsetAsync(b->v.as<uint8_t>() + used * 4, 0, (n_chunks - used) * 4, st), "slack memset"))) break;
     if ((rc = upload(st, b->d_slot_off, b->slot_off.data(), (size_t)(n_hap + 1) * 8))) break;
     if ((rc = upload(st, b->d_len, b->len.data(), (size_t)n_hap * 4))) break;
     if (total > 0) {
-      if ((rc = upload(st, d_ascii, ascii, (size_t)total))) break;
+      const uint8_t* src = ascii;
+      if (!ascii_on_device) {
+        if ((rc = upload(st, d_ascii, ascii, (size_t)total))) break;
+        src = d_ascii.as<uint8_t>();
+      }
       int64_t init = INT64_MAX;
       if ((rc = upload(st, d_bad, &init, 8))) break;
-      if ((rc = hawk_pack_dev(st, d_ascii.as<uint8_t>(), total, b->q.p, b->v.as<uint32_t>(),
-                              d_bad.as<int64_t>())))
-        break;
+      cudaEvent_t ev;
+      c->mark(0, &ev);
+      rc = hawk_pack_dev(st, src, total, b->q.p, b->v.as<uint32_t>(), d_bad.as<int64_t>());
+      c->close_mark();
+      if (rc) break;
       int64_t bad = INT64_MAX;
       if ((rc = hawk_check_cuda(cudaMemcpyAsync(&bad, d_bad.p, 8, cudaMemcpyDeviceToHost, st), "bad D2H"))) break;
       if ((rc = hawk_check_cuda(cudaStreamSynchronize(st), "pack sync"))) break;
@@ -235,6 +261,71 @@ extern "C" int hawk_batch_create(hawk_ctx* c, const uint8_t* ascii, const int64_
     return rc;
   }
   *out = b;
+  return HAWK_OK;
+}
+
+extern "C" int hawk_batch_create(hawk_ctx* c, const uint8_t* ascii, const int64_t* slot_off,
+                                 const int32_t* len, int32_t n_hap, hawk_batch** out,
+                                 int64_t* bad_slot) {
+  return batch_create_impl(c, ascii, false, slot_off, len, n_hap, out, bad_slot);
+}
+
+extern "C" int hawk_batch_create_dev(hawk_ctx* c, const uint8_t* d_ascii, const int64_t* slot_off,
+                                     const int32_t* len, int32_t n_hap, hawk_batch** out,
+                                     int64_t* bad_slot) {
+  if ((uintptr_t)d_ascii & 15) return hawk_fail(HAWK_EINVAL, "hawk_batch_create_dev: d_ascii must be 16-byte aligned");
+  return batch_create_impl(c, d_ascii, true, slot_off, len, n_hap, out, bad_slot);
+}
+
+extern "C" int hawk_batch_repack_dev(hawk_batch* b, const uint8_t* d_ascii, int64_t* bad_slot) {
+  if (!b || !d_ascii || ((uintptr_t)d_ascii & 15))
+    return hawk_fail(HAWK_EINVAL, "hawk_batch_repack_dev: bad arguments");
+  hawk_ctx* c = b->ctx;
+  CKCUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  if (bad_slot) *bad_slot = -1;
+  if (b->total_slots == 0) return HAWK_OK;
+  DevBuf d_bad;
+  int64_t init = INT64_MAX;
+  CK(upload(st, d_bad, &init, 8));
+  cudaEvent_t ev;
+  c->mark(0, &ev);
+  int rc = hawk_pack_dev(st, d_ascii, b->total_slots, b->q.p, b->v.as<uint32_t>(), d_bad.as<int64_t>());
+  c->close_mark();
+  CK(rc);
+  int64_t bad = INT64_MAX;
+  CKCUDA(cudaMemcpyAsync(&bad, d_bad.p, 8, cudaMemcpyDeviceToHost, st));
+  CKCUDA(cudaStreamSynchronize(st));
+  if (bad != INT64_MAX) {
+    if (bad_slot) *bad_slot = bad;
+    return hawk_fail(HAWK_EIUPAC, "non-IUPAC character at slot %lld", (long long)bad);
+  }
+  return HAWK_OK;
+}
+
+extern "C" void* hawk_ctx_stream(hawk_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+extern "C" int hawk_ctx_set_profiling(hawk_ctx* c, int32_t enabled) {
+  if (!c) return hawk_fail(HAWK_EINVAL, "hawk_ctx_set_profiling: null context");
+  c->profiling = enabled != 0;
+  return HAWK_OK;
+}
+
+extern "C" int hawk_ctx_profile(hawk_ctx* c, double* ms, int64_t* n) {
+  if (!c || !ms || !n) return hawk_fail(HAWK_EINVAL, "hawk_ctx_profile: bad arguments");
+  CKCUDA(cudaSetDevice(c->device));
+  CKCUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 3; ++i) { ms[i] = 0; n[i] = 0; }
+  for (auto& s : c->spans) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess && s.kind >= 0 && s.kind < 3) {
+      ms[s.kind] += t;
+      n[s.kind] += 1;
+    }
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  c->spans.clear();
   return HAWK_OK;
 }
 
@@ -359,11 +450,15 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
     for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(st, (size_t)cap[s] * 8));
     CKCUDA(cudaMemsetAsync(d_counts.p, 0, 32, st));
     CKCUDA(cudaMemsetAsync(d_ws.p, 0, ws_bytes, st));
-    CK(hawk_scan_dev(st, c->sm_count, b->q.p, b->v.as<uint32_t>(), b->d_slot_off.as<int64_t>(),
+    cudaEvent_t ev;
+    c->mark(1, &ev);
+    int src = hawk_scan_dev(st, c->sm_count, b->q.p, b->v.as<uint32_t>(), b->d_slot_off.as<int64_t>(),
                      b->d_len.as<int32_t>(), d_a.as<int32_t>(), d_b.as<int32_t>(),
                      d_isref.as<uint8_t>(), d_span_off.as<int64_t>(), n_hap, n_spans, params, raw,
                      out.hits[0].as<uint64_t>(), out.hits[1].as<uint64_t>(), cap[0], cap[1],
-                     d_counts.as<uint64_t>(), d_ws.p));
+                     d_counts.as<uint64_t>(), d_ws.p);
+    c->close_mark();
+    CK(src);
     uint64_t counts[4];
     CKCUDA(cudaMemcpyAsync(counts, d_counts.p, 32, cudaMemcpyDeviceToHost, st));
     CKCUDA(cudaStreamSynchronize(st));
@@ -455,6 +550,8 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
   do {
     if ((rc = run_scan(c, b, params, scan_start, scan_stop, is_ref, 0, d_a, d_b, d_isref, so))) break;
     r->scanned_bp = so.scanned_bp;
+    cudaEvent_t ev_post;
+    c->mark(2, &ev_post);
     const BatchView B = batch_view(b, d_a.as<int32_t>(), d_b.as<int32_t>(), d_isref.as<uint8_t>());
     const int64_t n_hits[2] = {so.n[0], so.n[1]};
     if ((rc = d_refrange.alloc(st, 32, true))) break;
@@ -583,6 +680,7 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
                                r->bucket.as<int64_t>())))
         break;
     }
+    c->close_mark();
     if ((rc = hawk_check_cuda(cudaStreamSynchronize(st), "search sync"))) break;
     for (int s = 0; s < 2; ++s) {
       r->n_hits[s] = n_hits[s];

@@ -1,0 +1,117 @@
+"""Device-resident synthetic workloads for bench.py and the large GPU tests.
+
+One `Workload` = one region: the cohort (host), its haplotype texts materialised in
+HBM in the slot layout, the derived flat arrays, and the two ways of running the hot
+path over it: `step_resident` (inputs already in HBM) and `step_host` (everything
+starts and ends in host memory, through the host layer of the C-ABI)."""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import _cabi, marshal, synth
+from .pam import pam_patterns
+
+
+class Workload:
+    def __init__(self, cohort: synth.Cohort, pam: str, guidelen: int, right: bool,
+                 ctx: Optional[_cabi.Context] = None, device: Optional[int] = None):  # fmt: skip
+        import torch
+
+        self.torch = torch
+        self.cohort = cohort
+        self.pam, self.guidelen, self.right = pam, guidelen, right
+        self.device = torch.cuda.current_device() if device is None else device
+        self.ctx = ctx or _cabi.Context.default(self.device)
+        self.d = synth.derive(cohort)
+        self.fwd, self.rc = pam_patterns(pam)
+        self.params = _cabi.make_params(self.fwd, self.rc, guidelen, right, False)
+        self.a, self.b = synth.scan_bounds(cohort, len(self.fwd))
+        self.scanned_bp = int((self.b.astype(np.int64) - self.a).clip(min=0).sum())
+        self.ascii_dev = synth.materialize_device(cohort, self.ctx, self.device)
+        self.batch = None
+
+    # ---- sizes for the roofline (algorithmic bytes) ----
+    def ref_scanned_bp(self) -> int:
+        ref = self.d.is_ref.astype(bool)
+        return int((self.b.astype(np.int64) - self.a)[ref].clip(min=0).sum())
+
+    def scan_algorithmic_bytes(self, n_hits: int) -> float:
+        """0.5 B/bp of planes for REF haplotypes; for the others 0.125 B/bp of case plane
+        plus 0.5 B for every base inside a variant window (2(G+P)-1 bases around each
+        variant base, capped by the scanned length); 8 B per emitted hit record."""
+        ref_bp = self.ref_scanned_bp()
+        alt_bp = self.scanned_bp - ref_bp
+        span = 2 * (self.guidelen + len(self.fwd)) - 1
+        window_bp = min(alt_bp, self.d.variant_bases * span)
+        return 0.5 * ref_bp + 0.125 * alt_bp + 0.5 * window_bp + 8.0 * n_hits
+
+    def pack_algorithmic_bytes(self) -> float:
+        """1 B ASCII read + 0.5 B planes + 0.125 B case bits written per slot."""
+        return 1.625 * self.d.total_slots
+
+    # ---- the hot path, inputs resident in HBM ----
+    def prepare_resident(self) -> None:
+        self.batch = _cabi.Batch(self.ctx, None, self.d.slot_off, self.d.lens, device_ptr=self.ascii_dev.data_ptr())
+        self.batch.set_posmap(self.d.seg)
+
+    def step_resident(self) -> _cabi.Result:
+        """encode (K1) + search (K2 + post-scan pipeline); table stays on the device."""
+        if self.batch is None:
+            self.prepare_resident()
+        self.batch.repack(self.ascii_dev.data_ptr())
+        return _cabi.search(self.ctx, self.batch, self.params, self.a, self.b, self.d.is_ref)
+
+    # ---- the hot path through host buffers ----
+    def host_buffers(self):
+        """Pinned host copies of the inputs and pinned output buffers (allocated once)."""
+        torch = self.torch
+        if not hasattr(self, "_host"):
+            ascii_host = torch.empty(self.d.total_slots, dtype=torch.uint8, pin_memory=True)
+            ascii_host.copy_(self.ascii_dev)
+            torch.cuda.synchronize(self.device)
+            self._host = {"ascii": ascii_host, "out": None}
+        return self._host
+
+    def step_host(self):
+        """Host ASCII in, host guide table out: H2D copy, K1, K2, post, D2H, all inside."""
+        torch = self.torch
+        hb = self.host_buffers()
+        batch = _cabi.Batch(self.ctx, hb["ascii"].numpy(), self.d.slot_off, self.d.lens)
+        batch.set_posmap(self.d.seg)
+        res = _cabi.search(self.ctx, batch, self.params, self.a, self.b, self.d.is_ref)
+        n, w = res.n_guides, res.window
+        if hb["out"] is None or len(hb["out"]["hap"]) < n:
+            cap = int(n * 1.05) + 1024
+            mk = lambda dt, k=1: torch.empty(cap * k, dtype=dt, pin_memory=True).numpy()  # noqa: E731
+            hb["out"] = {"hap": mk(torch.int32), "strand": mk(torch.uint8), "pos": mk(torch.int32),
+                         "start": mk(torch.int32), "stop": mk(torch.int32), "bucket": mk(torch.int64),
+                         "text": mk(torch.uint8, w)}  # fmt: skip
+        table = res.table(hb["out"])
+        h2d = self.d.total_slots + self.d.seg.seg_rel.nbytes * 2 + self.d.seg.seg_step.nbytes + \
+            self.d.seg.seg_off.nbytes + self.a.nbytes * 2 + self.d.is_ref.nbytes + self.d.slot_off.nbytes + self.d.lens.nbytes
+        d2h = n * (4 + 1 + 4 + 4 + 4 + 8 + w)
+        res.close()
+        batch.close()
+        return table, h2d, d2h
+
+    def host_arrays_for_oracle(self, hap_indices):
+        """(ascii slots, slot_off, lens, a, b, is_ref, segments) of a subset of haplotypes,
+        copied to the host, in the form oracle/c_oracle.search takes."""
+        idx = np.asarray(hap_indices)
+        lens = self.d.lens[idx]
+        off, total = marshal.layout(lens)
+        buf = np.zeros(total, np.uint8)
+        for k, h in enumerate(idx):
+            s = int(self.d.slot_off[h])
+            n = int(lens[k])
+            buf[off[k] : off[k] + n] = self.ascii_dev[s : s + n].cpu().numpy()
+        so = self.d.seg.seg_off
+        cnt = (so[idx + 1] - so[idx]).astype(np.int64)
+        seg_off = np.concatenate(([0], np.cumsum(cnt)))
+        take = np.concatenate([np.arange(so[h], so[h + 1]) for h in idx]) if len(idx) else np.zeros(0, np.int64)
+        seg = marshal.SegmentTable(seg_off.astype(np.int64), self.d.seg.seg_rel[take], self.d.seg.seg_gen[take],
+                                   self.d.seg.seg_step[take])  # fmt: skip
+        return buf, off, lens, self.a[idx], self.b[idx], self.d.is_ref[idx], seg

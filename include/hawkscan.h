@@ -150,6 +150,23 @@ int hawk_result_fetch(hawk_result *result, int32_t *hap, uint8_t *strand, int32_
 /* hit list of one strand: packed (hap << 32 | pos), ascending */
 int hawk_result_fetch_hits(hawk_result *result, int32_t strand, uint64_t *hits /* n_hits[strand] */);
 
+/* Same as hawk_batch_create for haplotype texts that already live in DEVICE memory
+ * (slot layout, total_slots bytes, 16-byte aligned): no host copy is made. */
+int hawk_batch_create_dev(hawk_ctx *ctx, const uint8_t *d_ascii, const int64_t *slot_off,
+                          const int32_t *len, int32_t n_hap, hawk_batch **batch, int64_t *bad_slot);
+
+/* Re-run K1 into an existing batch from device-resident texts of the same layout (the
+ * coordinate maps / allele tables attached to the batch are kept). */
+int hawk_batch_repack_dev(hawk_batch *batch, const uint8_t *d_ascii, int64_t *bad_slot);
+
+/* The context's cudaStream_t (so callers can time with events on the stream the kernels
+ * run on) and optional per-kernel timing: with profiling on, every K1 / K2 launch of the
+ * host layer is bracketed by CUDA events; hawk_ctx_profile returns and resets the sums.
+ * ms[0] = K1 pack, ms[1] = K2 scan, ms[2] = post-scan pipeline; n[i] = launches. */
+void *hawk_ctx_stream(hawk_ctx *ctx);
+int hawk_ctx_set_profiling(hawk_ctx *ctx, int32_t enabled);
+int hawk_ctx_profile(hawk_ctx *ctx, double *ms /* [3] */, int64_t *n /* [3] */);
+
 /* ---- device layer (asynchronous on `stream`, a cudaStream_t) -------------- */
 /* K1: ASCII slot space -> planes. d_bad: one int64, must hold INT64_MAX on
  * entry; receives the smallest slot index with a non-IUPAC byte. */
@@ -175,6 +192,19 @@ int hawk_scan_dev(void *stream, int32_t sm_count, const void *d_q, const uint32_
                   int32_t n_hap, int64_t n_spans, const hawk_params *params, int32_t raw_hits,
                   uint64_t *d_hits_fwd, uint64_t *d_hits_rev, int64_t cap_fwd, int64_t cap_rev,
                   uint64_t *d_counts, void *d_workspace);
+
+/* N1 (next row): materialise haplotype texts on the device from the reference text and
+ * per-haplotype sorted, non-overlapping edit lists (haplotype.py:106-121,185-252
+ * conventions: ALT allele characters lower-case; SNV 1 base, insertion anchor + inserted
+ * bases, deletion the 1-base anchor). edit_outpos[e] = haplotype index where edit e's ALT
+ * text starts. Output: the ASCII slot space consumed by hawk_pack_dev. */
+int hawk_materialize_dev(void *stream, const uint8_t *d_ref, int64_t ref_len,
+                         const int64_t *d_edit_off, const int32_t *d_edit_pos,
+                         const int32_t *d_edit_reflen, const int32_t *d_edit_altlen,
+                         const int64_t *d_edit_altoff, const int32_t *d_edit_outpos,
+                         const uint8_t *d_alt_pool, const int64_t *d_slot_off,
+                         const int32_t *d_len, int32_t n_hap, int64_t total_slots,
+                         uint8_t *d_ascii_out);
 
 #ifdef __cplusplus
 }
