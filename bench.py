@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- haplotype-bp scanned per second for the guide-discovery hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2]
+
+One *step* = one pass of the hot path (encode -> PAM scan on both strands -> in-range /
+REF-core filters -> genomic coordinates -> redundancy removal -> guide table) over one
+batch of synthetic haplotypes of the BASELINE.json shape (default: config 2, SpCas9
+NGG / 20 nt, 1 Mb region, 2,504 phased samples -> 5,008 haplotypes + REF).
+
+* `value`  : whole-job haplotype-bp/s, haplotype texts already resident in HBM.
+* `e2e`    : the same through host buffers (pinned ASCII in, guide table out, PCIe copies
+             inside the timed region).
+* `roofline`: the dominant kernel's algorithmic bytes / its CUDA-event duration against the
+             measured HBM copy bandwidth (MEASURED_PEAKS.json).
+* `cpu_baseline`: the C restatement of the reference scan (oracle/, a checker -- never on
+             the product path) on a bounded sample of the same workload, on the host cores.
+
+`--impl reference` times only that CPU arm (all host threads). Under torchrun every rank
+scans its own block of haplotypes of the same region (weak scaling, no data-path
+collective; one NCCL all-reduce of the per-rank guide counts and checksums per step).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "haplotype_bp_scanned_per_s"
+UNIT = "hap-bp/s"
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampling of one GPU during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")  # fmt: skip
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )  # fmt: skip
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_sample(workload: str, n_alt: int, scale: float):
+    """A bounded sample of the workload for the CPU arm: the same region and sites, the
+    first `n_alt` non-reference haplotypes (+ REF), materialised on the host."""
+    from crispr_hawk_b200 import marshal, synth
+
+    k = synth.CONFIGS[workload]
+    c = synth.config_cohort(workload, scale, n_alt_hap=n_alt)
+    d = synth.derive(c)
+    texts = synth.materialize_host(c)
+    buf, off, lens = marshal.stage_ascii(texts)
+    from crispr_hawk_b200.pam import pam_patterns
+
+    fwd, rc = pam_patterns(k["pam"])
+    a, b = synth.scan_bounds(c, len(fwd))
+    bp = int((b.astype(np.int64) - a).clip(min=0).sum())
+    return dict(cohort=c, d=d, texts=texts, buf=buf, off=off, lens=lens, fwd=fwd, rc=rc, a=a, b=b, bp=bp,
+                G=k["guidelen"], right=k["right"], pam=k["pam"])  # fmt: skip
+
+
+def cpu_step(s, threads):
+    from oracle import c_oracle
+
+    t0 = time.perf_counter()
+    enc_bad = 0
+    # encoder.encode over every haplotype (scalar table lookup), then search
+    for h in range(len(s["lens"])):
+        o, n = int(s["off"][h]), int(s["lens"][h])
+        c_oracle.encode_into(s["buf"][o : o + n])
+    out = c_oracle.search(s["buf"], s["off"], s["lens"], s["a"], s["b"], s["d"].is_ref, s["d"].seg,
+                          s["fwd"], s["rc"], s["G"], s["right"], threads=threads)  # fmt: skip
+    dt = time.perf_counter() - t0
+    return dt, len(out["hap"]), enc_bad
+
+
+def python_port_rate(workload: str, scale: float, budget_s: float = 6.0):
+    """The pure-Python restatement (same interpreter-bound cost model as the reference,
+    which is pure Python) on a tiny slice -- context for the C port's number."""
+    from crispr_hawk_b200 import synth
+    from oracle import hawk_oracle as O
+
+    k = synth.CONFIGS[workload]
+    c = synth.make_cohort(20_000, 3, 200, 20, seed=77, snv_frac=k["snv"], ins_frac=k["ins"], max_indel=k["max_indel"])
+    haps = synth.synth_haplotypes(c)
+    a, b = synth.scan_bounds(c, len(k["pam"]))
+    bp = int((b.astype(np.int64) - a).sum())
+    t0 = time.perf_counter()
+    ohaps = [O.OracleHap.from_object(h) for h in haps]
+    n = len(O.search(k["pam"], c.region_start, c.region_stop, ohaps, k["guidelen"], k["right"], True, True))
+    dt = time.perf_counter() - t0
+    return bp / dt, bp, n
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return 0
+    from oracle import c_oracle
+
+    threads = c_oracle.max_threads()
+    # size the sample so one step is a few seconds of CPU work on all threads
+    n_alt = max(threads * 2, 16)
+    s = cpu_sample(args.workload, n_alt, args.scale)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, n, _ = cpu_step(s, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = s["bp"] / (ms / 1e3)
+    sample = f"{n_alt + 1} haplotypes (REF + first {n_alt}) of workload {args.workload} x {s['bp'] // (n_alt + 1)} bp, encode + search, per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, s["bp"], n_alt + 1, sample=True),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU arm: oracle/scan_oracle.c (C restatement of encoder.py + search_guides.py, OpenMP over haplotypes). "
+                "The reference itself is single-threaded pure Python and cannot travel to this box.",
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, scanned_bp, n_hap, sample=False):
+    from crispr_hawk_b200 import synth
+
+    k = synth.CONFIGS[args.workload]
+    return {
+        "workload": f"{args.workload}: {k['pam']} / {k['guidelen']} nt / {'right' if k['right'] else 'left'}, "
+                    f"{int(k['bed_len'] * args.scale):,} bp region, phased, {n_hap} haplotypes per rank"
+                    + (" (CPU sample)" if sample else ""),
+        "haplotypes_per_rank": n_hap, "scanned_bp_per_rank_per_step": scanned_bp,
+        "l2": "inputs exceed L2 (no flush needed)" if scanned_bp > 400e6 else "L2 flushed between steps",
+        "seed": k["seed"],
+    }  # fmt: skip
+
+
+# --------------------------------------------------------------------------- product arm
+def run_product_arm(args, rank, world, local_rank):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from crispr_hawk_b200 import _cabi, synth
+    from crispr_hawk_b200.workload import Workload
+
+    lib = _cabi.load_library()
+    k = synth.CONFIGS[args.workload]
+    n_alt = args.haplotypes or k["n_alt_hap"]
+    cohort = synth.config_cohort(args.workload, args.scale, n_alt_hap=n_alt, hap_block=rank)
+    ctx = _cabi.Context.default(local_rank)
+    wl = Workload(cohort, k["pam"], k["guidelen"], k["right"], ctx, local_rank)
+    wl.prepare_resident()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    flush = None
+    if wl.scanned_bp <= 400e6:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+
+    def barrier():
+        torch.cuda.synchronize(local_rank)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(local_rank)
+
+    tally = torch.zeros(2, dtype=torch.int64, device=f"cuda:{local_rank}")
+
+    def one_step():
+        res = wl.step_resident()
+        n = res.n_guides
+        h = res.n_hits
+        res.close()
+        if dist is not None:  # the only exchange of the timed path: per-rank counts
+            tally[0] = n
+            tally[1] = h[0] + h[1]
+            dist.all_reduce(tally)
+        if flush is not None:
+            flush.fill_(1)
+        return n, h
+
+    torch.cuda.set_stream(stream)  # NCCL / flush work is ordered with the library's stream
+    for _ in range(max(args.warmup, 3)):
+        n_guides, n_hits = one_step()
+    barrier()
+    ctx.set_profiling(True)
+    ctx.profile()
+    sampler = ClockSampler(local_rank).start()
+    launches0 = lib.hawk_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        n_guides, n_hits = one_step()
+    ev1.record(stream)
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = lib.hawk_launch_count() - launches0
+    prof = ctx.profile()
+    ctx.set_profiling(False)
+    # CUDA events on the context's stream (the launching stream); the host layer synchronises
+    # inside a step, so this is ~= the wall time, which is reported beside it
+    step_ms = dev_ms / args.steps
+    t = torch.tensor([step_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    tot = torch.tensor([wl.scanned_bp, n_guides], dtype=torch.int64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    step_ms = float(t.item())
+    total_bp, total_guides = int(tot[0].item()), int(tot[1].item())
+    value = total_bp / (step_ms / 1e3)
+
+    # ---- per-kernel roofline (rank 0's kernels) ----
+    peak, peak_src = measured_peak()
+    hits_total = n_hits[0] + n_hits[1]
+    kernels = {}
+    pack_ms = prof["pack"][0] / max(prof["pack"][1], 1)
+    scan_ms = prof["scan"][0] / max(prof["scan"][1], 1)
+    post_ms = prof["post"][0] / max(prof["post"][1], 1)
+    pack_bytes = wl.pack_algorithmic_bytes()
+    scan_bytes = wl.scan_algorithmic_bytes(hits_total)
+    kernels["pack_kernel"] = {"ms": pack_ms, "algorithmic_bytes": pack_bytes, "gbs": pack_bytes / pack_ms / 1e6 if pack_ms else None,
+                              "launches_per_step": prof["pack"][1] / args.steps}  # fmt: skip
+    kernels["scan_kernel"] = {"ms": scan_ms, "algorithmic_bytes": scan_bytes, "gbs": scan_bytes / scan_ms / 1e6 if scan_ms else None,
+                              "launches_per_step": prof["scan"][1] / args.steps}  # fmt: skip
+    kernels["post_pipeline"] = {"ms": post_ms, "launches_per_step": prof["post"][1] / args.steps}
+    dom = "pack_kernel" if pack_ms >= scan_ms else "scan_kernel"
+    ach = kernels[dom]["gbs"] or 0.0
+    roofline = {
+        "kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
+        "scan_kernel_frac": (kernels["scan_kernel"]["gbs"] or 0.0) / peak,
+        "pack_kernel_frac": (kernels["pack_kernel"]["gbs"] or 0.0) / peak,
+    }  # fmt: skip
+
+    # ---- e2e: host buffers in, host table out ----
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        wl.batch.close()
+        wl.batch = None
+        wl.host_buffers()
+        wl.step_host()  # warm-up (allocates the pinned output buffers)
+        wl.step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            table, h2d, d2h = wl.step_host()
+        torch.cuda.synchronize(local_rank)
+        e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+        te = torch.tensor([e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_ms = float(te.item())
+        e2e = {"value": total_bp / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e_ms, "steps": e2e_steps, "rows_per_step": int(len(table["hap"]))}  # fmt: skip
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import c_oracle
+
+        threads = c_oracle.max_threads()
+        n_cpu = max(threads * 2, 16)
+        s = cpu_sample(args.workload, n_cpu, args.scale)
+        cpu_step(s, threads)
+        reps, acc = 0, 0.0
+        while acc < 8.0 and reps < 20:
+            dt, _, _ = cpu_step(s, threads)
+            acc += dt
+            reps += 1
+        one_dt, _, _ = cpu_step(s, 1) if s["bp"] < 200e6 else (None, None, None)
+        py_rate, py_bp, _ = python_port_rate(args.workload, args.scale)
+        cpu = {
+            "value": s["bp"] * reps / acc, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_cpu + 1} haplotypes (REF + first {n_cpu}) of the same workload, {s['bp']:,} hap-bp per pass, "
+                      f"{reps} passes, encode + search (oracle/scan_oracle.c, OpenMP)",
+            "single_thread_value": (s["bp"] / one_dt) if one_dt else None,
+            "python_port_value": py_rate, "python_port_sample_bp": py_bp,
+        }  # fmt: skip
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, wl.scanned_bp, cohort.n_hap),
+            "guides_per_step": total_guides, "hits_per_step_rank0": hits_total,
+            "device_ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks,
+        }  # fmt: skip
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+# (profiles/); filled in once a capture of this workload exists
+TRAFFIC = {}
+_traffic = os.path.join(ROOT, "profiles", "traffic.json")
+if os.path.exists(_traffic):
+    try:
+        TRAFFIC = json.load(open(_traffic))
+    except Exception:
+        TRAFFIC = {}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the region (debugging only)")
+    ap.add_argument("--haplotypes", type=int, default=0, help="non-REF haplotypes per rank (default: the config's)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    import __graft_entry__ as entry
+
+    if rank == 0 or not os.path.exists(os.path.join(ROOT, "crispr_hawk_b200", "libhawkscan.so")):
+        entry.build()
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+    return run_product_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

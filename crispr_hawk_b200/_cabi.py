@@ -57,6 +57,7 @@ SIGNATURES = {
     "hawk_abi_version": (C.c_int, []),
     "hawk_last_error": (C.c_char_p, []),
     "hawk_strerror": (C.c_char_p, [C.c_int]),
+    "hawk_launch_count": (C.c_int64, []),
     "hawk_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "hawk_ctx_destroy": (C.c_int, [_P]),
     "hawk_ctx_info": (C.c_int, [_P, _I32P, _I64P, _I64P]),

@@ -36,7 +36,34 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found")
 
 
+class _BuildLock:
+    """Serialises concurrent builds (torchrun starts one process per GPU)."""
+
+    def __enter__(self):
+        import fcntl
+
+        self.f = open(os.path.join(PKG, ".build.lock"), "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *a):
+        import fcntl
+
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
+
+
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
+    with _BuildLock():
+        return _build_cuda(force, verbose)
+
+
+def build_hostcheck(force: bool = False) -> str:
+    with _BuildLock():
+        return _build_hostcheck(force)
+
+
+def _build_cuda(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
     deps = srcs + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
     if not force and not _newer(LIB, deps):
@@ -52,7 +79,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-def build_hostcheck(force: bool = False) -> str:
+def _build_hostcheck(force: bool = False) -> str:
     src = os.path.join(CSRC, "hostcheck.cpp")
     deps = [src, os.path.join(CSRC, "hawk_core.h"), os.path.normpath(os.path.join(CSRC, "../../include/hawkscan.h"))]
     if not force and not _newer(CHECK_LIB, deps):

@@ -40,6 +40,11 @@ int hawk_check_cuda(cudaError_t err, const char* what) {
   } while (0)
 #define CKCUDA(expr) CK(hawk_check_cuda((expr), #expr))
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void hawk_note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t hawk_launch_count(void) { return (int64_t)g_launches.load(); }
+
 extern "C" int hawk_abi_version(void) { return HAWK_ABI_VERSION; }
 extern "C" const char* hawk_last_error(void) { return g_err; }
 extern "C" const char* hawk_strerror(int code) {

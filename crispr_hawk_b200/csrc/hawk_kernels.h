@@ -11,3 +11,6 @@
 
 int hawk_fail(int code, const char* fmt, ...);
 int hawk_check_cuda(cudaError_t err, const char* what);
+
+// every kernel launch of the library is counted (bench.py reports it as gpu_launches)
+void hawk_note_launch(int n);

@@ -249,8 +249,11 @@ static int exclusive_scan_impl(cudaStream_t st, const T* in, int64_t n, uint64_t
   int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   if (n_tiles < 1) n_tiles = 1;
   tile_sum_kernel<T><<<(unsigned)n_tiles, SCAN_T, 0, st>>>(in, n, tile_sums);
+  hawk_note_launch(1);
   tile_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, n_tiles);
+  hawk_note_launch(1);
   tile_apply_kernel<T><<<(unsigned)n_tiles, SCAN_T, 0, st>>>(in, n, tile_sums, out);
+  hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "exclusive_scan launch");
 }
 
@@ -389,6 +392,7 @@ __global__ void export_nibbles_kernel(const Planes* __restrict__ q, const uint32
 int launch_ref_range(cudaStream_t st, const uint64_t* r0, int64_t n0, const uint64_t* r1, int64_t n1,
                      int32_t ref_h, int64_t* out) {
   ref_range_kernel<<<1, 32, 0, st>>>(r0, n0, r1, n1, ref_h, out);
+  hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "ref_range_kernel launch");
 }
 
@@ -398,6 +402,7 @@ int launch_rows(cudaStream_t st, const BatchView& B, const ScanConst& K, const u
   if (n <= 0) return HAWK_OK;
   rows_kernel<<<grid_for(n, 128), 128, 0, st>>>(B, K, recs, n, s, ref_h, ref_range, dedup, start,
                                                 stop, keep);
+  hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "rows_kernel launch");
 }
 
@@ -405,6 +410,7 @@ int launch_expand_count(cudaStream_t st, const BatchView& B, const ScanConst& K,
                         const uint64_t* recs, int64_t n, int s, uint64_t* cnt, int* err) {
   if (n <= 0) return HAWK_OK;
   expand_count_kernel<<<grid_for(n, 128), 128, 0, st>>>(B, K, recs, n, s, cnt, err);
+  hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "expand_count_kernel launch");
 }
 
@@ -416,6 +422,7 @@ int launch_expand_write(cudaStream_t st, const BatchView& B, const ScanConst& K,
   expand_write_kernel<<<grid_for(n_rows, 128), 128, 0, st>>>(B, K, recs, n_hits, s, off, n_rows,
                                                             ref_h, ref_range, start, text, row_hit,
                                                             keep);
+  hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "expand_write_kernel launch");
 }
 
@@ -443,6 +450,7 @@ int launch_gather(cudaStream_t st, const GatherLaunch& g) {
   for (int s = 0; s < 2; ++s) {
     if (g.n_rows[s] <= 0) continue;
     gather_kernel<<<grid_for(g.n_rows[s], 128), 128, 0, st>>>(A, s);
+    hawk_note_launch(1);
   }
   return hawk_check_cuda(cudaGetLastError(), "gather_kernel launch");
 }
@@ -453,8 +461,10 @@ int launch_buckets(cudaStream_t st, const int32_t* start, const uint8_t* strand,
   if (n <= 0) return HAWK_OK;
   bucket_insert_kernel<<<grid_for(n, 256), 256, 0, st>>>(start, strand, n, keys, vals,
                                                          table_size - 1);
+  hawk_note_launch(1);
   bucket_lookup_kernel<<<grid_for(n, 256), 256, 0, st>>>(start, strand, n, keys, vals,
                                                          table_size - 1, bucket);
+  hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "bucket kernels launch");
 }
 
@@ -463,6 +473,7 @@ int launch_export_nibbles(cudaStream_t st, const void* q, const uint32_t* v, int
   if (len <= 0) return HAWK_OK;
   export_nibbles_kernel<<<grid_for(len, 256), 256, 0, st>>>((const Planes*)q, v, chunk0, len, nib,
                                                             lower);
+  hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "export_nibbles_kernel launch");
 }
 

@@ -242,6 +242,7 @@ extern "C" int hawk_pack_dev(void* stream, const uint8_t* d_ascii, int64_t total
   if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride: 16 CTAs per SM
   pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       (const uint4*)d_ascii, n_chunks, (uint4*)d_q, d_v, (unsigned long long*)d_bad);
+  hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "pack_kernel launch");
 }
 
@@ -301,5 +302,6 @@ extern "C" int hawk_scan_dev(void* stream, int32_t sm_count, const void* d_q, co
   int64_t blocks = (int64_t)sm_count * 8;  // persistent CTAs, 8 per SM (16 KB smem each)
   if (blocks > n_spans) blocks = n_spans;
   scan_kernel<<<(unsigned)blocks, SCAN_THREADS, 0, (cudaStream_t)stream>>>(A);
+  hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "scan_kernel launch");
 }

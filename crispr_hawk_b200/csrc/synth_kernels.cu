@@ -98,5 +98,6 @@ extern "C" int hawk_materialize_dev(void* stream, const uint8_t* d_ref, int64_t 
                     d_edit_outpos, d_alt_pool, d_slot_off, d_len, n_hap, d_ascii_out};
   int64_t blocks = (n_chunks + 255) / 256;
   materialize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, n_chunks);
+  hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "materialize_kernel launch");
 }

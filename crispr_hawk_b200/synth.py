@@ -51,10 +51,12 @@ class Cohort:
 
 def make_cohort(bed_len: int, n_alt_hap: int, n_sites: int, mean_alts_per_hap: float, seed: int,
                 snv_frac: float = 0.9, ins_frac: float = 0.05, max_indel: int = 10,
-                bed_start: int = 10001) -> Cohort:  # fmt: skip
+                bed_start: int = 10001, hap_block: int = 0) -> Cohort:  # fmt: skip
     """Region of `bed_len` bases, `n_alt_hap` non-reference haplotypes (+ REF as haplotype 0),
     `n_sites` cohort-wide sites on a jittered grid, allele frequencies from a 1/x spectrum
-    scaled so a haplotype carries `mean_alts_per_hap` alternate alleles on average."""
+    scaled so a haplotype carries `mean_alts_per_hap` alternate alleles on average.
+    `hap_block` selects an independent block of haplotypes over the SAME reference and
+    sites (rank r of a multi-GPU run scans block r of the cohort)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     L = bed_len + 2 * PADDING
     ref = _BASES[rng.integers(0, 4, L)]
@@ -94,6 +96,8 @@ def make_cohort(bed_len: int, n_alt_hap: int, n_sites: int, mean_alts_per_hap: f
     af = np.clip(af, 0.0, 0.9)
     hap_off = np.zeros(n_alt_hap + 2, np.int64)
     chunks: List[np.ndarray] = []
+    if hap_block:
+        rng = np.random.Generator(np.random.PCG64([seed, hap_block]))
     for h in range(n_alt_hap):  # row-wise Bernoulli draws keep memory bounded
         carried = np.flatnonzero(rng.random(n_sites) < af).astype(np.int32)
         chunks.append(carried)
@@ -324,10 +328,11 @@ CONFIGS = {
 }  # fmt: skip
 
 
-def config_cohort(name: str, scale: float = 1.0, seed_offset: int = 0, n_alt_hap: Optional[int] = None) -> Cohort:
+def config_cohort(name: str, scale: float = 1.0, seed_offset: int = 0, n_alt_hap: Optional[int] = None,
+                  hap_block: int = 0) -> Cohort:
     k = CONFIGS[name]
     bed_len = max(200, int(k["bed_len"] * scale))
     n_sites = max(1, int(k["n_sites"] * scale))
     mean = k["mean_alts"] * scale
     return make_cohort(bed_len, k["n_alt_hap"] if n_alt_hap is None else n_alt_hap, n_sites, mean,
-                       k["seed"] + seed_offset, k["snv"], k["ins"], k["max_indel"])  # fmt: skip
+                       k["seed"] + seed_offset, k["snv"], k["ins"], k["max_indel"], hap_block=hap_block)  # fmt: skip

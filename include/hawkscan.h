@@ -75,6 +75,8 @@ typedef struct hawk_params {
 int hawk_abi_version(void);
 const char *hawk_last_error(void);
 const char *hawk_strerror(int code);
+/* CUDA kernels launched by this library in this process so far (bench.py's gpu_launches) */
+int64_t hawk_launch_count(void);
 
 /* ---- context ------------------------------------------------------------ */
 int hawk_ctx_create(int device, hawk_ctx **ctx);

@@ -60,6 +60,19 @@ def encode(text: bytes) -> np.ndarray:
     return out
 
 
+_scratch = np.empty(0, np.uint8)
+
+
+def encode_into(buf: np.ndarray) -> None:
+    """oracle_encode of one haplotype text into a reusable scratch buffer (timing only)."""
+    global _scratch
+    if len(_scratch) < len(buf):
+        _scratch = np.empty(len(buf), np.uint8)
+    bad = lib().oracle_encode(_p(buf), C.c_int64(len(buf)), _p(_scratch))
+    if bad >= 0:
+        raise ValueError(f"non-IUPAC character at {bad}")
+
+
 def search(ascii_slots, slot_off, lens, scan_start, scan_stop, is_ref, seg, pam_fwd, pam_rc, G, right,
            threads=1, raw_only=False):  # fmt: skip
     """Returns dict(hap,strand,pos,start,stop,text) in FINAL order + raw hit lists."""

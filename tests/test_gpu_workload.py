@@ -1,0 +1,127 @@
+"""GPU parity at workload scale: device-materialised synthetic cohorts of the BASELINE.json
+shapes through the C-ABI (K1 pack -> K2 scan -> post-scan pipeline) against the C
+restatement of the reference scan (oracle/scan_oracle.c, itself pinned to the reference's
+golden vectors by tests/test_oracle_c.py). Bit-exact: every row, every column, in order."""
+
+import numpy as np
+import pytest
+
+from crispr_hawk_b200 import _cabi, marshal, synth
+from crispr_hawk_b200.workload import Workload
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+COLS = ("hap", "strand", "pos", "start", "stop")
+
+
+def final_order(table):
+    order = np.argsort(table["bucket"], kind="stable")
+    return {k: table[k][order] for k in COLS + ("text",)}
+
+
+def assert_tables_equal(got, want, what=""):
+    assert len(got["hap"]) == len(want["hap"]), f"{what}: row count {len(got['hap'])} != {len(want['hap'])}"
+    for k in COLS:
+        bad = np.flatnonzero(got[k] != want[k])
+        assert len(bad) == 0, f"{what}: column {k} differs first at row {bad[0]}"
+    assert np.array_equal(got["text"], want["text"]), f"{what}: window text differs"
+
+
+def oracle_table(wl, hap_indices, threads=4):
+    buf, off, lens, a, b, is_ref, seg = wl.host_arrays_for_oracle(hap_indices)
+    return c_oracle.search(buf, off, lens, a, b, is_ref, seg, wl.fwd, wl.rc, wl.guidelen, wl.right, threads=threads)
+
+
+def check_bucket_ids(table):
+    """bucket[i] == smallest emission index sharing (start, strand) (group_guides_position)."""
+    key = table["start"].astype(np.int64) * 2 + table["strand"]
+    _, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    assert np.array_equal(table["bucket"], first[inv])
+
+
+def test_device_materialisation_matches_host():
+    c = synth.make_cohort(bed_len=40_000, n_alt_hap=9, n_sites=900, mean_alts_per_hap=120, seed=5,
+                          snv_frac=0.6, ins_frac=0.2, max_indel=7)  # fmt: skip
+    d = synth.derive(c)
+    dev = synth.materialize_device(c).cpu().numpy()
+    texts = synth.materialize_host(c)
+    buf, off, lens = marshal.stage_ascii(texts)
+    assert off.tolist() == d.slot_off.tolist() and lens.tolist() == d.lens.tolist()
+    assert np.array_equal(dev, buf)
+
+
+@pytest.mark.parametrize("name,scale,n_alt", [("c1", 1.0, 20), ("c2", 0.2, 23), ("c3", 0.2, 23), ("c5shard", 0.004, 7)])
+def test_workload_table_matches_c_oracle(name, scale, n_alt):
+    k = synth.CONFIGS[name]
+    c = synth.config_cohort(name, scale, n_alt_hap=n_alt)
+    wl = Workload(c, k["pam"], k["guidelen"], k["right"])
+    res = wl.step_resident()
+    table = res.table()
+    hits = [res.hits(0), res.hits(1)]
+    assert res.scanned_bp == wl.scanned_bp
+    res.close()
+    check_bucket_ids(table)
+    want = oracle_table(wl, np.arange(c.n_hap))
+    assert want["scanned_bp"] == wl.scanned_bp
+    assert_tables_equal(final_order(table), want, name)
+    assert len(table["hap"]) > 100
+    # host-buffer path gives the same table
+    t2, h2d, d2h = wl.step_host()
+    for kcol in COLS + ("bucket",):
+        assert np.array_equal(t2[kcol], table[kcol])
+    assert np.array_equal(t2["text"], table["text"])
+    assert h2d > wl.d.total_slots and d2h == len(table["hap"]) * (25 + wl.guidelen + len(wl.fwd) + 20)
+    # raw pam_search semantics on the same batch
+    raw = _cabi.pam_search(wl.ctx, wl.batch, wl.params, wl.a, wl.b)
+    for s in (0, 1):
+        assert np.array_equal(raw.hits(s), want["hits"][s])
+        # filtered hit list is a subset of the raw one, ascending
+        assert np.all(np.diff(hits[s].astype(np.int64)) > 0)
+        assert np.isin(hits[s], want["hits"][s]).all()
+    raw.close()
+
+
+def test_repeated_steps_are_idempotent():
+    k = synth.CONFIGS["c2"]
+    c = synth.config_cohort("c2", 0.05, n_alt_hap=40)
+    wl = Workload(c, k["pam"], k["guidelen"], k["right"])
+    first = wl.step_resident()
+    t1 = first.table()
+    first.close()
+    for _ in range(3):
+        r = wl.step_resident()
+        t = r.table()
+        r.close()
+        for kcol in COLS + ("bucket",):
+            assert np.array_equal(t[kcol], t1[kcol])
+        assert np.array_equal(t["text"], t1["text"])
+
+
+def test_full_size_config2_properties():
+    """BASELINE.json config 2 at full size (1 Mb x 5,009 haplotypes = 5.0 G hap-bp): the oracle
+    checks a random subset of haplotypes row by row; the whole table is checked through
+    size-independent properties (emission order, bucket ids, REF rows = the REF-only search)."""
+    k = synth.CONFIGS["c2"]
+    c = synth.config_cohort("c2")
+    wl = Workload(c, k["pam"], k["guidelen"], k["right"])
+    res = wl.step_resident()
+    table = res.table()
+    res.close()
+    assert wl.scanned_bp > 5.0e9
+    n = len(table["hap"])
+    assert n > 1e7
+    # emission order: (hap, strand, pos) strictly ascending
+    key = (table["hap"].astype(np.int64) << 33) | (table["strand"].astype(np.int64) << 32) | table["pos"].astype(np.int64)
+    assert np.all(np.diff(key) > 0)
+    check_bucket_ids(table)
+    rng = np.random.default_rng(0)
+    subset = np.sort(np.concatenate(([0], rng.choice(np.arange(1, c.n_hap), 12, replace=False))))
+    want = oracle_table(wl, subset, threads=8)
+    # oracle rows (final order of the subset) -> emission order
+    okey = (want["hap"].astype(np.int64) << 33) | (want["strand"].astype(np.int64) << 32) | want["pos"].astype(np.int64)
+    oo = np.argsort(okey, kind="stable")
+    sel = np.flatnonzero(np.isin(table["hap"], subset))
+    got = {kcol: table[kcol][sel] for kcol in COLS + ("text",)}
+    got["hap"] = np.searchsorted(subset, got["hap"]).astype(np.int32)
+    assert_tables_equal(got, {kcol: want[kcol][oo] for kcol in COLS + ("text",)}, "config 2 subset")
