@@ -7,8 +7,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
 #include <new>
 #include <vector>
+#include <stdlib.h>
 
 #include "hawk_core.h"
 #include "hawk_kernels.h"
@@ -61,11 +63,62 @@ extern "C" const char* hawk_strerror(int code) {
   }
 }
 
+// HAWK_TRACE=1: host-side wall-clock trace of the search pipeline on stderr (debugging aid)
+struct Trace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  Trace() : on(getenv("HAWK_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void tick(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[hawk] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 // ------------------------------------------------------------------ objects
 struct hawk_ctx {
   int device;
   cudaStream_t stream;
   int sm_count;
+  // Device-memory cache: every buffer of the library lives on this one stream, so a freed
+  // block can be handed to the next request without synchronising (stream order protects
+  // it). Avoids the per-search cost of the driver allocator for multi-GB temporaries.
+  struct Block { void* p; size_t bytes; };
+  std::vector<Block> free_blocks;
+  void* take(size_t n, size_t* got) {
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < free_blocks.size(); ++i)
+      if (free_blocks[i].bytes >= n && free_blocks[i].bytes <= 2 * n + (4u << 20) &&
+          (best == (size_t)-1 || free_blocks[i].bytes < free_blocks[best].bytes))
+        best = i;
+    if (best != (size_t)-1) {
+      Block b = free_blocks[best];
+      free_blocks.erase(free_blocks.begin() + best);
+      *got = b.bytes;
+      return b.p;
+    }
+    size_t want = n < (1u << 20) ? ((n + 511) & ~(size_t)511) : ((n + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1));
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {  // give the cached blocks back to the driver and try once more
+      cudaGetLastError();
+      cudaStreamSynchronize(stream);
+      trim();
+      e = cudaMalloc(&p, want);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+    }
+    *got = want;
+    return p;
+  }
+  void give(void* p, size_t bytes) { free_blocks.push_back(Block{p, bytes}); }
+  void trim() {
+    for (auto& b : free_blocks) cudaFree(b.p);
+    free_blocks.clear();
+  }
   // optional per-kernel timing (hawk_ctx_set_profiling)
   bool profiling = false;
   struct Span { cudaEvent_t a, b; int kind; };
@@ -76,7 +129,7 @@ struct hawk_ctx {
     cudaEventCreate(&s.a); cudaEventCreate(&s.b);
     cudaEventRecord(s.a, stream);
     spans.push_back(s);
-    *a = s.a;
+    if (a) *a = s.a;
   }
   void close_mark() {
     if (!profiling || spans.empty()) return;
@@ -84,39 +137,46 @@ struct hawk_ctx {
   }
 };
 
-// device buffer owned through the stream-ordered allocator
+// device buffer owned through the context's block cache
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
-  cudaStream_t st = nullptr;
+  hawk_ctx* ctx = nullptr;
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
-  int alloc(cudaStream_t s, size_t n, bool zero = false) {
+  int alloc(hawk_ctx* c, size_t n, bool zero = false) {
     release();
-    st = s;
-    bytes = n ? n : 16;
-    cudaError_t e = cudaMallocAsync(&p, bytes, st);
-    if (e != cudaSuccess) {
-      p = nullptr;
-      return hawk_check_cuda(e, "cudaMallocAsync");
+    ctx = c;
+    p = c->take(n ? n : 16, &bytes);
+    if (!p) {
+      bytes = 0;
+      return hawk_fail(HAWK_ENOMEM, "out of device memory (%zu bytes requested)", n);
     }
-    if (zero) return hawk_check_cuda(cudaMemsetAsync(p, 0, bytes, st), "cudaMemsetAsync");
+    if (zero) return hawk_check_cuda(cudaMemsetAsync(p, 0, n ? n : 16, c->stream), "cudaMemsetAsync");
     return HAWK_OK;
   }
   void release() {
-    if (p) cudaFreeAsync(p, st);
+    if (p) ctx->give(p, bytes);
     p = nullptr;
     bytes = 0;
+  }
+  void move_from(DevBuf& o) {
+    release();
+    p = o.p;
+    bytes = o.bytes;
+    ctx = o.ctx;
+    o.p = nullptr;
+    o.bytes = 0;
   }
   template <class T>
   T* as() const { return (T*)p; }
 };
 
-static int upload(cudaStream_t st, DevBuf& b, const void* src, size_t bytes) {
-  CK(b.alloc(st, bytes));
-  if (bytes) CKCUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+static int upload(hawk_ctx* c, DevBuf& b, const void* src, size_t bytes) {
+  CK(b.alloc(c, bytes));
+  if (bytes) CKCUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
   return HAWK_OK;
 }
 
@@ -159,12 +219,6 @@ extern "C" int hawk_ctx_create(int device, hawk_ctx** out) {
   CKCUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   CKCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  // keep freed blocks cached in the pool: repeated searches reuse them
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
   *out = c;
   return HAWK_OK;
 }
@@ -173,6 +227,7 @@ extern "C" int hawk_ctx_destroy(hawk_ctx* c) {
   if (!c) return HAWK_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  c->trim();
   cudaStreamDestroy(c->stream);
   delete c;
   return HAWK_OK;
@@ -193,11 +248,11 @@ extern "C" int hawk_ctx_info(hawk_ctx* c, int32_t* sm_count, int64_t* total_mem,
 extern "C" int hawk_layout(const int32_t* len, int32_t n_hap, int64_t* slot_off, int64_t* total_slots) {
   if (n_hap < 0 || (n_hap > 0 && (!len || !slot_off)))
     return hawk_fail(HAWK_EINVAL, "hawk_layout: bad arguments");
-  int64_t off = 0;
+  int64_t off = HAWK_SLOT_GAP;
   for (int32_t h = 0; h < n_hap; ++h) {
     if (len[h] < 0) return hawk_fail(HAWK_EINVAL, "hawk_layout: negative length at %d", h);
     slot_off[h] = off;
-    off += ((int64_t)len[h] + HAWK_SLOT_ALIGN - 1) / HAWK_SLOT_ALIGN * HAWK_SLOT_ALIGN;
+    off += ((int64_t)len[h] + HAWK_SLOT_ALIGN - 1) / HAWK_SLOT_ALIGN * HAWK_SLOT_ALIGN + HAWK_SLOT_GAP;
   }
   if (slot_off) slot_off[n_hap] = off;
   if (total_slots) *total_slots = off;
@@ -232,20 +287,23 @@ static int batch_create_impl(hawk_ctx* c, const uint8_t* ascii, bool ascii_on_de
   do {
     // K1 writes every chunk of the slot space; only the readable slack behind it is zeroed
     const size_t used = (size_t)total / HAWK_CHUNK;
-    if ((rc = b->q.alloc(st, n_chunks * 16))) break;
-    if ((rc = b->v.alloc(st, n_chunks * 4))) break;
+    if ((rc = b->q.alloc(c, n_chunks * 16))) break;
+    if ((rc = b->v.alloc(c, n_chunks * 4))) break;
     if ((rc = hawk_check_cuda(cudaMemsetAsync(b->q.as<uint8_t>() + used * 16, 0, (n_chunks - used) * 16, st), "slack memset"))) break;
     if ((rc = hawk_check_cuda(cudaMemsetAsync(b->v.as<uint8_t>() + used * 4, 0, (n_chunks - used) * 4, st), "slack memset"))) break;
-    if ((rc = upload(st, b->d_slot_off, b->slot_off.data(), (size_t)(n_hap + 1) * 8))) break;
-    if ((rc = upload(st, b->d_len, b->len.data(), (size_t)n_hap * 4))) break;
-    if (total > 0) {
+    if ((rc = upload(c, b->d_slot_off, b->slot_off.data(), (size_t)(n_hap + 1) * 8))) break;
+    if ((rc = upload(c, b->d_len, b->len.data(), (size_t)n_hap * 4))) break;
+    if (!ascii) {  // no haplotypes: the slot space is the leading gap only
+      if ((rc = hawk_check_cuda(cudaMemsetAsync(b->q.p, 0, n_chunks * 16, st), "gap memset"))) break;
+      if ((rc = hawk_check_cuda(cudaMemsetAsync(b->v.p, 0, n_chunks * 4, st), "gap memset"))) break;
+    } else if (total > 0) {
       const uint8_t* src = ascii;
       if (!ascii_on_device) {
-        if ((rc = upload(st, d_ascii, ascii, (size_t)total))) break;
+        if ((rc = upload(c, d_ascii, ascii, (size_t)total))) break;
         src = d_ascii.as<uint8_t>();
       }
       int64_t init = INT64_MAX;
-      if ((rc = upload(st, d_bad, &init, 8))) break;
+      if ((rc = upload(c, d_bad, &init, 8))) break;
       cudaEvent_t ev;
       c->mark(0, &ev);
       rc = hawk_pack_dev(st, src, total, b->q.p, b->v.as<uint32_t>(), d_bad.as<int64_t>());
@@ -292,7 +350,7 @@ extern "C" int hawk_batch_repack_dev(hawk_batch* b, const uint8_t* d_ascii, int6
   if (b->total_slots == 0) return HAWK_OK;
   DevBuf d_bad;
   int64_t init = INT64_MAX;
-  CK(upload(st, d_bad, &init, 8));
+  CK(upload(c, d_bad, &init, 8));
   cudaEvent_t ev;
   c->mark(0, &ev);
   int rc = hawk_pack_dev(st, d_ascii, b->total_slots, b->q.p, b->v.as<uint32_t>(), d_bad.as<int64_t>());
@@ -344,13 +402,14 @@ extern "C" int hawk_batch_destroy(hawk_batch* b) {
 extern "C" int hawk_batch_export_nibbles(hawk_batch* b, int32_t hap, uint8_t* nibbles, uint8_t* lower) {
   if (!b || hap < 0 || hap >= b->n_hap || !nibbles)
     return hawk_fail(HAWK_EINVAL, "hawk_batch_export_nibbles: bad arguments");
-  CKCUDA(cudaSetDevice(b->ctx->device));
-  cudaStream_t st = b->ctx->stream;
+  hawk_ctx* c = b->ctx;
+  CKCUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
   int32_t L = b->len[hap];
   if (L == 0) return HAWK_OK;
   DevBuf dn, dl;
-  CK(dn.alloc(st, L));
-  if (lower) CK(dl.alloc(st, L));
+  CK(dn.alloc(c, L));
+  if (lower) CK(dl.alloc(c, L));
   CK(launch_export_nibbles(st, b->q.p, b->v.as<uint32_t>(), b->slot_off[hap] >> 5, L,
                            dn.as<uint8_t>(), lower ? dl.as<uint8_t>() : nullptr));
   CKCUDA(cudaMemcpyAsync(nibbles, dn.p, L, cudaMemcpyDeviceToHost, st));
@@ -369,12 +428,13 @@ extern "C" int hawk_batch_set_posmap(hawk_batch* b, const int64_t* seg_off, cons
     if (seg_rel[seg_off[h]] != 0)
       return hawk_fail(HAWK_EINVAL, "hawk_batch_set_posmap: first segment of haplotype %d must start at 0", h);
   }
-  cudaStream_t st = b->ctx->stream;
+  hawk_ctx* c = b->ctx;
+  cudaStream_t st = c->stream;
   size_t n = (size_t)seg_off[b->n_hap];
-  CK(upload(st, b->seg_off, seg_off, (size_t)(b->n_hap + 1) * 8));
-  CK(upload(st, b->seg_rel, seg_rel, n * 4));
-  CK(upload(st, b->seg_gen, seg_gen, n * 4));
-  CK(upload(st, b->seg_step, seg_step, n));
+  CK(upload(c, b->seg_off, seg_off, (size_t)(b->n_hap + 1) * 8));
+  CK(upload(c, b->seg_rel, seg_rel, n * 4));
+  CK(upload(c, b->seg_gen, seg_gen, n * 4));
+  CK(upload(c, b->seg_step, seg_step, n));
   CKCUDA(cudaStreamSynchronize(st));
   b->has_posmap = true;
   return HAWK_OK;
@@ -384,13 +444,14 @@ extern "C" int hawk_batch_set_alleles(hawk_batch* b, const int64_t* va_off, cons
                                       const int64_t* va_ent_off, const uint8_t* va_ref) {
   if (!b || !va_off || !va_ent_off) return hawk_fail(HAWK_EINVAL, "hawk_batch_set_alleles: bad arguments");
   CKCUDA(cudaSetDevice(b->ctx->device));
-  cudaStream_t st = b->ctx->stream;
+  hawk_ctx* c = b->ctx;
+  cudaStream_t st = c->stream;
   size_t n_sites = (size_t)va_off[b->n_hap];
   size_t n_ent = (size_t)va_ent_off[n_sites];
-  CK(upload(st, b->va_off, va_off, (size_t)(b->n_hap + 1) * 8));
-  CK(upload(st, b->va_idx, va_idx, n_sites * 4));
-  CK(upload(st, b->va_ent_off, va_ent_off, (n_sites + 1) * 8));
-  CK(upload(st, b->va_ref, va_ref, n_ent));
+  CK(upload(c, b->va_off, va_off, (size_t)(b->n_hap + 1) * 8));
+  CK(upload(c, b->va_idx, va_idx, n_sites * 4));
+  CK(upload(c, b->va_ent_off, va_ent_off, (n_sites + 1) * 8));
+  CK(upload(c, b->va_ref, va_ref, n_ent));
   CKCUDA(cudaStreamSynchronize(st));
   b->has_alleles = true;
   return HAWK_OK;
@@ -425,14 +486,22 @@ struct ScanOut {
   int64_t scanned_bp = 0;
 };
 
-// run K2 with growing output capacity until everything fits
+// run K2 into the staging segments; if a warp's share of the staging capacity overflowed,
+// run it once more with the exact per-warp sizes the first launch counted; then concatenate
+// the segments into exactly-sized hit lists
 static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const int32_t* scan_start,
                     const int32_t* scan_stop, const uint8_t* is_ref, int raw, DevBuf& d_a,
                     DevBuf& d_b, DevBuf& d_isref, ScanOut& out) {
   cudaStream_t st = c->stream;
+  Trace tr;
   const int32_t n_hap = b->n_hap;
   std::vector<int64_t> span_off(n_hap + 1);
-  int64_t n_spans = hawk_scan_plan(scan_start, scan_stop, n_hap, span_off.data());
+  const int64_t n_spans = hawk_scan_plan(scan_start, scan_stop, is_ref, n_hap, raw, 0, span_off.data(), nullptr, nullptr);
+  const int32_t n_units = hawk_scan_units(c->sm_count, n_spans);
+  std::vector<int64_t> unit_span((size_t)n_units + 1);
+  std::vector<double> unit_frac((size_t)n_units + 1);
+  if (n_units > 0)
+    hawk_scan_plan(scan_start, scan_stop, is_ref, n_hap, raw, n_units, span_off.data(), unit_span.data(), unit_frac.data());
   int64_t est = 4096;
   out.scanned_bp = 0;
   for (int32_t h = 0; h < n_hap; ++h) {
@@ -441,39 +510,60 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
     out.scanned_bp += e - a;
     est += (raw || is_ref[h]) ? (e - a) / 3 : (e - a) / 48;
   }
-  CK(upload(st, d_a, scan_start, (size_t)n_hap * 4));
-  CK(upload(st, d_b, scan_stop, (size_t)n_hap * 4));
-  CK(upload(st, d_isref, is_ref, (size_t)n_hap));
+  CK(upload(c, d_a, scan_start, (size_t)n_hap * 4));
+  CK(upload(c, d_b, scan_stop, (size_t)n_hap * 4));
+  CK(upload(c, d_isref, is_ref, (size_t)n_hap));
   if (n_spans == 0) return HAWK_OK;
-  DevBuf d_span_off, d_counts, d_ws;
-  CK(upload(st, d_span_off, span_off.data(), (size_t)(n_hap + 1) * 8));
-  CK(d_counts.alloc(st, 32));
-  size_t ws_bytes = hawk_scan_workspace_bytes(n_spans);
-  CK(d_ws.alloc(st, ws_bytes));
+  DevBuf d_span_off, d_unit_span, d_unit_frac, d_counts, d_ws;
+  CK(upload(c, d_span_off, span_off.data(), (size_t)(n_hap + 1) * 8));
+  CK(upload(c, d_unit_span, unit_span.data(), ((size_t)n_units + 1) * 8));
+  CK(upload(c, d_unit_frac, unit_frac.data(), ((size_t)n_units + 1) * 8));
+  CK(d_counts.alloc(c, 64));
+  tr.tick("scan: plan + uploads");
   int64_t cap[2] = {est, est};
-  for (int attempt = 0; attempt < 3; ++attempt) {
-    for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(st, (size_t)cap[s] * 8));
-    CKCUDA(cudaMemsetAsync(d_counts.p, 0, 32, st));
-    CKCUDA(cudaMemsetAsync(d_ws.p, 0, ws_bytes, st));
+  CK(d_ws.alloc(c, hawk_scan_workspace_bytes(n_spans, n_units, cap[0], cap[1])));
+  int exact = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
     cudaEvent_t ev;
     c->mark(1, &ev);
-    int src = hawk_scan_dev(st, c->sm_count, b->q.p, b->v.as<uint32_t>(), b->d_slot_off.as<int64_t>(),
-                     b->d_len.as<int32_t>(), d_a.as<int32_t>(), d_b.as<int32_t>(),
-                     d_isref.as<uint8_t>(), d_span_off.as<int64_t>(), n_hap, n_spans, params, raw,
-                     out.hits[0].as<uint64_t>(), out.hits[1].as<uint64_t>(), cap[0], cap[1],
-                     d_counts.as<uint64_t>(), d_ws.p);
+    int src = hawk_scan_dev(st, b->q.p, b->v.as<uint32_t>(), b->d_slot_off.as<int64_t>(),
+                            b->d_len.as<int32_t>(), d_a.as<int32_t>(), d_b.as<int32_t>(),
+                            d_isref.as<uint8_t>(), d_span_off.as<int64_t>(), d_unit_span.as<int64_t>(),
+                            d_unit_frac.as<double>(), n_hap, n_spans, n_units, params, raw, exact,
+                            cap[0], cap[1], d_counts.as<uint64_t>(), d_ws.p);
     c->close_mark();
     CK(src);
-    uint64_t counts[4];
-    CKCUDA(cudaMemcpyAsync(counts, d_counts.p, 32, cudaMemcpyDeviceToHost, st));
+    tr.tick("scan: launch");
+    uint64_t counts[8];
+    CKCUDA(cudaMemcpyAsync(counts, d_counts.p, 64, cudaMemcpyDeviceToHost, st));
     CKCUDA(cudaStreamSynchronize(st));
     out.n[0] = (int64_t)counts[0];
     out.n[1] = (int64_t)counts[1];
-    if (out.n[0] <= cap[0] && out.n[1] <= cap[1]) return HAWK_OK;
-    cap[0] = out.n[0] > cap[0] ? out.n[0] : cap[0];
-    cap[1] = out.n[1] > cap[1] ? out.n[1] : cap[1];
+    tr.tick("scan: sync");
+    if (!counts[4] && out.n[0] <= cap[0] && out.n[1] <= cap[1]) break;
+    if (attempt == 1) return hawk_fail(HAWK_ECAPACITY, "scan output did not fit after the exact retry");
+    exact = 1;
+    if (out.n[0] > cap[0] || out.n[1] > cap[1]) {
+      // grow the staging area; the per-unit counts of the first launch move with it
+      const int64_t ncap[2] = {out.n[0] > cap[0] ? out.n[0] : cap[0], out.n[1] > cap[1] ? out.n[1] : cap[1]};
+      DevBuf bigger;
+      CK(bigger.alloc(c, hawk_scan_workspace_bytes(n_spans, n_units, ncap[0], ncap[1])));
+      // everything in front of the staging buffers has the same layout for any capacity
+      const size_t head = hawk_scan_workspace_bytes(n_spans, n_units, 0, 0);
+      CKCUDA(cudaMemcpyAsync(bigger.p, d_ws.p, head, cudaMemcpyDeviceToDevice, st));
+      d_ws.move_from(bigger);
+      cap[0] = ncap[0];
+      cap[1] = ncap[1];
+    }
   }
-  return hawk_fail(HAWK_ECAPACITY, "scan output did not fit after resizing");
+  for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(c, (size_t)(out.n[s] > 0 ? out.n[s] : 1) * 8));
+  c->mark(1, nullptr);
+  int crc = hawk_scan_compact_dev(st, d_unit_frac.as<double>(), n_units, n_spans, exact, cap[0], cap[1], d_ws.p,
+                                  out.hits[0].as<uint64_t>(), out.hits[1].as<uint64_t>(), out.n[0], out.n[1]);
+  c->close_mark();
+  CK(crc);
+  tr.tick("scan: compact launched");
+  return HAWK_OK;
 }
 
 static int check_scan_args(hawk_ctx* c, hawk_batch* b, const hawk_params* p, const int32_t* a,
@@ -510,10 +600,7 @@ extern "C" int hawk_pam_search(hawk_ctx* c, hawk_batch* b, const hawk_params* pa
   }
   for (int s = 0; s < 2; ++s) {
     r->n_hits[s] = so.n[s];
-    r->hits[s].p = so.hits[s].p;
-    r->hits[s].bytes = so.hits[s].bytes;
-    r->hits[s].st = so.hits[s].st;
-    so.hits[s].p = nullptr;
+    r->hits[s].move_from(so.hits[s]);
   }
   r->scanned_bp = so.scanned_bp;
   *out = r;
@@ -553,36 +640,39 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
   DevBuf start[2], stop[2], keep[2], kept_excl[2], tile_sums, cnt[2], off[2], text_pre[2], row_hit[2];
   ScanOut so;
   do {
+    Trace tr;
     if ((rc = run_scan(c, b, params, scan_start, scan_stop, is_ref, 0, d_a, d_b, d_isref, so))) break;
+    tr.tick("run_scan total");
     r->scanned_bp = so.scanned_bp;
     cudaEvent_t ev_post;
     c->mark(2, &ev_post);
     const BatchView B = batch_view(b, d_a.as<int32_t>(), d_b.as<int32_t>(), d_isref.as<uint8_t>());
     const int64_t n_hits[2] = {so.n[0], so.n[1]};
-    if ((rc = d_refrange.alloc(st, 32, true))) break;
-    if ((rc = d_err.alloc(st, 4, true))) break;
+    if ((rc = d_refrange.alloc(c, 32, true))) break;
+    if ((rc = d_err.alloc(c, 4, true))) break;
     if ((rc = launch_ref_range(st, so.hits[0].as<uint64_t>(), n_hits[0], so.hits[1].as<uint64_t>(),
                                n_hits[1], ref_h, d_refrange.as<int64_t>())))
       break;
     int64_t n_rows[2] = {n_hits[0], n_hits[1]};
     for (int s = 0; s < 2 && rc == HAWK_OK; ++s) {
-      if ((rc = start[s].alloc(st, (size_t)n_hits[s] * 4))) break;
-      if ((rc = stop[s].alloc(st, (size_t)n_hits[s] * 4))) break;
-      if ((rc = keep[s].alloc(st, (size_t)n_hits[s]))) break;
+      if ((rc = start[s].alloc(c, (size_t)n_hits[s] * 4))) break;
+      if ((rc = stop[s].alloc(c, (size_t)n_hits[s] * 4))) break;
+      if ((rc = keep[s].alloc(c, (size_t)n_hits[s]))) break;
       rc = launch_rows(st, B, K, so.hits[s].as<uint64_t>(), n_hits[s], s, ref_h,
                        d_refrange.as<int64_t>(), unphased ? 0 : 1, start[s].as<int32_t>(),
                        stop[s].as<int32_t>(), keep[s].as<uint8_t>());
     }
     if (rc) break;
+    tr.tick("post: rows launched");
     int64_t max_tiles = scan_tiles(n_hits[0] > n_hits[1] ? n_hits[0] : n_hits[1]);
     if (unphased) {
       // resolve_guide: count, scan, write
       uint64_t totals[2] = {0, 0};
-      if ((rc = tile_sums.alloc(st, (size_t)(max_tiles + 1) * 8))) break;
+      if ((rc = tile_sums.alloc(c, (size_t)(max_tiles + 1) * 8))) break;
       for (int s = 0; s < 2 && rc == HAWK_OK; ++s) {
         if (n_hits[s] == 0) continue;
-        if ((rc = cnt[s].alloc(st, (size_t)n_hits[s] * 8))) break;
-        if ((rc = off[s].alloc(st, (size_t)n_hits[s] * 8))) break;
+        if ((rc = cnt[s].alloc(c, (size_t)n_hits[s] * 8))) break;
+        if ((rc = off[s].alloc(c, (size_t)n_hits[s] * 8))) break;
         if ((rc = launch_expand_count(st, B, K, so.hits[s].as<uint64_t>(), n_hits[s], s,
                                       cnt[s].as<uint64_t>(), d_err.as<int>())))
           break;
@@ -610,9 +700,9 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
       for (int s = 0; s < 2 && rc == HAWK_OK; ++s) {
         n_rows[s] = (int64_t)totals[s];
         if (n_rows[s] == 0) continue;
-        if ((rc = text_pre[s].alloc(st, (size_t)n_rows[s] * W))) break;
-        if ((rc = row_hit[s].alloc(st, (size_t)n_rows[s] * 8))) break;
-        if ((rc = keep[s].alloc(st, (size_t)n_rows[s]))) break;
+        if ((rc = text_pre[s].alloc(c, (size_t)n_rows[s] * W))) break;
+        if ((rc = row_hit[s].alloc(c, (size_t)n_rows[s] * 8))) break;
+        if ((rc = keep[s].alloc(c, (size_t)n_rows[s]))) break;
         rc = launch_expand_write(st, B, K, so.hits[s].as<uint64_t>(), n_hits[s], s,
                                  off[s].as<uint64_t>(), n_rows[s], ref_h, d_refrange.as<int64_t>(),
                                  start[s].as<int32_t>(), text_pre[s].as<uint8_t>(),
@@ -622,16 +712,16 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
       int64_t t2 = scan_tiles(n_rows[0] > n_rows[1] ? n_rows[0] : n_rows[1]);
       if (t2 > max_tiles) {
         max_tiles = t2;
-        if ((rc = tile_sums.alloc(st, (size_t)(max_tiles + 1) * 8))) break;
+        if ((rc = tile_sums.alloc(c, (size_t)(max_tiles + 1) * 8))) break;
       }
     } else {
-      if ((rc = tile_sums.alloc(st, (size_t)(max_tiles + 1) * 8))) break;
+      if ((rc = tile_sums.alloc(c, (size_t)(max_tiles + 1) * 8))) break;
     }
     // stable compaction offsets of the surviving rows
     uint64_t kept_total[2] = {0, 0};
     for (int s = 0; s < 2 && rc == HAWK_OK; ++s) {
       if (n_rows[s] == 0) continue;
-      if ((rc = kept_excl[s].alloc(st, (size_t)n_rows[s] * 8))) break;
+      if ((rc = kept_excl[s].alloc(c, (size_t)n_rows[s] * 8))) break;
       if ((rc = exclusive_scan_u8(st, keep[s].as<uint8_t>(), n_rows[s], kept_excl[s].as<uint64_t>(),
                                   tile_sums.as<uint64_t>())))
         break;
@@ -642,14 +732,15 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
     }
     if (rc) break;
     const int64_t n = (int64_t)(kept_total[0] + kept_total[1]);
+    tr.tick("post: keep scans + sync");
     r->n_guides = n;
-    if ((rc = r->hap.alloc(st, (size_t)n * 4))) break;
-    if ((rc = r->strand.alloc(st, (size_t)n))) break;
-    if ((rc = r->pos.alloc(st, (size_t)n * 4))) break;
-    if ((rc = r->start.alloc(st, (size_t)n * 4))) break;
-    if ((rc = r->stop.alloc(st, (size_t)n * 4))) break;
-    if ((rc = r->bucket.alloc(st, (size_t)n * 8))) break;
-    if ((rc = r->text.alloc(st, (size_t)n * W))) break;
+    if ((rc = r->hap.alloc(c, (size_t)n * 4))) break;
+    if ((rc = r->strand.alloc(c, (size_t)n))) break;
+    if ((rc = r->pos.alloc(c, (size_t)n * 4))) break;
+    if ((rc = r->start.alloc(c, (size_t)n * 4))) break;
+    if ((rc = r->stop.alloc(c, (size_t)n * 4))) break;
+    if ((rc = r->bucket.alloc(c, (size_t)n * 8))) break;
+    if ((rc = r->text.alloc(c, (size_t)n * W))) break;
     if (n > 0) {
       GatherLaunch g;
       g.B = B;
@@ -676,8 +767,8 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
       uint64_t tsize = 1024;
       while (tsize < (uint64_t)n * 2) tsize <<= 1;
       DevBuf keys, vals;
-      if ((rc = keys.alloc(st, tsize * 8))) break;
-      if ((rc = vals.alloc(st, tsize * 8))) break;
+      if ((rc = keys.alloc(c, tsize * 8))) break;
+      if ((rc = vals.alloc(c, tsize * 8))) break;
       if ((rc = hawk_check_cuda(cudaMemsetAsync(keys.p, 0xFF, tsize * 8, st), "bucket keys memset"))) break;
       if ((rc = hawk_check_cuda(cudaMemsetAsync(vals.p, 0xFF, tsize * 8, st), "bucket vals memset"))) break;
       if ((rc = launch_buckets(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n,
@@ -686,13 +777,12 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
         break;
     }
     c->close_mark();
+    tr.tick("post: gather+buckets launched");
     if ((rc = hawk_check_cuda(cudaStreamSynchronize(st), "search sync"))) break;
+    tr.tick("post: final sync");
     for (int s = 0; s < 2; ++s) {
       r->n_hits[s] = n_hits[s];
-      r->hits[s].p = so.hits[s].p;
-      r->hits[s].bytes = so.hits[s].bytes;
-      r->hits[s].st = so.hits[s].st;
-      so.hits[s].p = nullptr;
+      r->hits[s].move_from(so.hits[s]);
     }
   } while (0);
   if (rc != HAWK_OK) {

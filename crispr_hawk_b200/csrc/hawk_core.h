@@ -9,6 +9,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "../../include/hawkscan.h"
+
 #if defined(__CUDACC__)
 #define HAWK_HD __host__ __device__ __forceinline__
 #define HAWK_UNROLL _Pragma("unroll")
@@ -51,34 +53,106 @@ HAWK_HD uint8_t iupac_entry(uint8_t ch) {
   return (uint8_t)(n | lower);
 }
 
-// K1 inner step: 4 table entries (one per ASCII byte, iupac_entry format) packed in a
-// word -> bit `b` of every entry gathered into 4 consecutive bits.
-// (y & 0x01010101) * 0x01020408 moves bits 0,8,16,24 to bits 24..27; bits 28..31 stay 0.
-HAWK_HD uint32_t gather_entry_bit(uint32_t entries, int b) {
-  return (((entries >> b) & 0x01010101u) * 0x01020408u) >> 24;
+// ---- K1: 32 ASCII bytes -> bit-sliced planes, no table lookups ---------------------
+// (1) an 8x8 bit-matrix transpose per 8 bytes turns the characters into bit planes
+//     b0..b7 (bit i of plane k = bit k of character i);
+// (2) the letter's low five bits index 32-entry truth tables, one per output plane,
+//     evaluated for 32 characters at once with 3-input boolean ops (Shannon expansion
+//     over b4, b3; LOP3 on the GPU).
+
+// 3-input boolean function selected by the 8-bit truth table IMM (index a<<2 | b<<1 | c)
+template <int IMM>
+HAWK_HD uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(IMM));
+  return d;
+#else
+  uint32_t r = 0;
+  for (int i = 0; i < 8; ++i)
+    if (IMM & (1 << i)) r |= ((i & 4) ? a : ~a) & ((i & 2) ? b : ~b) & ((i & 1) ? c : ~c);
+  return r;
+#endif
+}
+
+HAWK_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(a, b, sel);
+#else
+  uint64_t both = ((uint64_t)b << 32) | a;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) r |= (uint32_t)((both >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+  return r;
+#endif
+}
+
+// 8x8 bit-matrix transpose: byte k of the result holds bit k of the eight input bytes
+// (bit i of it comes from input byte i)
+HAWK_HD uint64_t transpose8x8(uint64_t x) {
+  uint64_t t;
+  t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;
+  x ^= t ^ (t << 7);
+  t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull;
+  x ^= t ^ (t << 14);
+  t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull;
+  x ^= t ^ (t << 28);
+  return x;
+}
+
+// truth table over the letter number (ch & 31): bit L set <=> the IUPAC code of letter L
+// contains base `bit` (encoder.py:18-34)
+constexpr uint32_t letter_table(int bit) {
+  uint32_t m = 0;
+  const char letters[] = "ACGTRYSWKMBDHVN";
+  const int codes[] = {1, 2, 4, 8, 5, 10, 6, 9, 12, 3, 14, 13, 11, 7, 15};
+  for (int i = 0; i < 15; ++i)
+    if (codes[i] & (1 << bit)) m |= 1u << (letters[i] & 31);
+  return m;
+}
+
+// f(b4..b0) for 32 characters at once, f given as a 32-entry truth table
+template <uint32_t TABLE>
+HAWK_HD uint32_t table5(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t b4) {
+  uint32_t g0 = lop3<(int)(TABLE & 0xFF)>(b2, b1, b0);
+  uint32_t g1 = lop3<(int)((TABLE >> 8) & 0xFF)>(b2, b1, b0);
+  uint32_t g2 = lop3<(int)((TABLE >> 16) & 0xFF)>(b2, b1, b0);
+  uint32_t g3 = lop3<(int)((TABLE >> 24) & 0xFF)>(b2, b1, b0);
+  uint32_t lo = lop3<0xCA>(b3, g1, g0);  // b3 ? g1 : g0
+  uint32_t hi = lop3<0xCA>(b3, g3, g2);
+  return lop3<0xCA>(b4, hi, lo);
 }
 
 struct PackedChunk {
   uint32_t a, c, g, t, v, invalid;
 };
 
-// 32 ASCII bytes (8 little-endian words) -> plane words; `entry(byte)` is the LUT
-template <class F>
-HAWK_HD PackedChunk pack_chunk(const uint32_t* words, F&& entry) {
-  PackedChunk o{0, 0, 0, 0, 0, 0};
+// 32 ASCII bytes (8 little-endian words) -> plane words. NUL bytes (unused slots) give
+// all-zero bits; any other non-IUPAC byte sets its `invalid` bit.
+HAWK_HD PackedChunk pack_chunk(const uint32_t* words) {
+  uint32_t lo[4], hi[4];
   HAWK_UNROLL
-  for (int k = 0; k < 8; ++k) {
-    uint32_t x = words[k];
-    uint32_t e = (uint32_t)entry(x & 0xFF) | ((uint32_t)entry((x >> 8) & 0xFF) << 8) |
-                 ((uint32_t)entry((x >> 16) & 0xFF) << 16) | ((uint32_t)entry(x >> 24) << 24);
-    int sh = 4 * k;
-    o.a |= gather_entry_bit(e, 0) << sh;
-    o.c |= gather_entry_bit(e, 1) << sh;
-    o.g |= gather_entry_bit(e, 2) << sh;
-    o.t |= gather_entry_bit(e, 3) << sh;
-    o.v |= gather_entry_bit(e, 4) << sh;
-    o.invalid |= gather_entry_bit(e, 7) << sh;
+  for (int g = 0; g < 4; ++g) {
+    uint64_t t = transpose8x8(((uint64_t)words[2 * g + 1] << 32) | words[2 * g]);
+    lo[g] = (uint32_t)t;          // bytes: bit planes 0..3 of characters 8g .. 8g+7
+    hi[g] = (uint32_t)(t >> 32);  // bit planes 4..7
   }
+  uint32_t b[8];
+  HAWK_UNROLL
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t sel = (uint32_t)k | ((uint32_t)(4 + k) << 4);  // byte k of a, byte k of b
+    b[k] = byte_perm(byte_perm(lo[0], lo[1], sel), byte_perm(lo[2], lo[3], sel), 0x5410);
+    b[4 + k] = byte_perm(byte_perm(hi[0], hi[1], sel), byte_perm(hi[2], hi[3], sel), 0x5410);
+  }
+  const uint32_t alpha = ~b[7] & b[6];  // 0x40..0x7F; b5 = lower-case
+  PackedChunk o;
+  o.a = alpha & table5<letter_table(0)>(b[0], b[1], b[2], b[3], b[4]);
+  o.c = alpha & table5<letter_table(1)>(b[0], b[1], b[2], b[3], b[4]);
+  o.g = alpha & table5<letter_table(2)>(b[0], b[1], b[2], b[3], b[4]);
+  o.t = alpha & table5<letter_table(3)>(b[0], b[1], b[2], b[3], b[4]);
+  const uint32_t valid = o.a | o.c | o.g | o.t;
+  const uint32_t nul = ~(b[0] | b[1] | b[2] | b[3] | b[4] | b[5] | b[6] | b[7]);
+  o.v = valid & b[5];
+  o.invalid = ~(valid | nul);
   return o;
 }
 
@@ -113,8 +187,8 @@ HAWK_HD int popc32(uint32_t x) {
 }
 
 // bits i of a 32-slot chunk starting at p0 with lo <= p0 + i < hi
-HAWK_HD uint32_t interval_mask(int64_t lo, int64_t hi, int64_t p0) {
-  int64_t l = lo - p0, h = hi - p0;
+HAWK_HD uint32_t interval_mask(int32_t lo, int32_t hi, int32_t p0) {
+  int32_t l = lo - p0, h = hi - p0;
   if (l < 0) l = 0;
   if (h > 32) h = 32;
   if (h <= l) return 0u;
@@ -133,19 +207,29 @@ HAWK_HD uint32_t select_planes(const Planes& p, uint32_t code) {
   return r;
 }
 
-// search_guides.py:32-46 (match) for the 32 positions of one chunk at once:
-// bit i of the result <=> for every k < P: pattern[k] & nibble(p0 + i + k) != 0.
-// `cur` / `nxt` are the planes of the chunk and of the following chunk (P <= 16
-// never reaches further). Pattern nibbles equal to 15 (N) match every real base.
-HAWK_HD uint32_t match_chunk(const Planes& cur, const Planes& nxt, const uint8_t* pattern, int P) {
-  uint32_t m = 0xFFFFFFFFu;
+// search_guides.py:32-46 (match) for the 32 positions of one chunk at once, both
+// patterns together: bit i of m[s] <=> for every k < P: pat[s][k] & nibble(p0 + i + k) != 0.
+// `cur` / `nxt` are the planes of the chunk and of the following chunk (P <= 16 never
+// reaches further). sel[s][k] = one all-ones / all-zeros word per base of pattern nibble k
+// (branch-free AND-mask plane select); the shifted planes are shared by the two patterns.
+// Pattern nibbles equal to 15 (N) match every real base and are skipped (skip bit k of
+// skip[s]).
+struct PamSelect {
+  uint32_t sel[2][HAWK_MAX_PAM][4];
+  uint32_t skip[2];
+};
+
+HAWK_HD void match_chunk2(const Planes& cur, const Planes& nxt, const PamSelect& S, int P,
+                          uint32_t m[2]) {
+  m[0] = m[1] = 0xFFFFFFFFu;
   for (int k = 0; k < P; ++k) {
-    uint32_t code = pattern[k];
-    if (code == 15u) continue;
-    uint32_t lo = select_planes(cur, code), hi = select_planes(nxt, code);
-    m &= funnel_r(lo, hi, (uint32_t)k);
+    const bool s0 = !((S.skip[0] >> k) & 1u), s1 = !((S.skip[1] >> k) & 1u);
+    if (!(s0 || s1)) continue;
+    const uint32_t a = funnel_r(cur.a, nxt.a, (uint32_t)k), c = funnel_r(cur.c, nxt.c, (uint32_t)k),
+                   g = funnel_r(cur.g, nxt.g, (uint32_t)k), t = funnel_r(cur.t, nxt.t, (uint32_t)k);
+    if (s0) m[0] &= (a & S.sel[0][k][0]) | (c & S.sel[0][k][1]) | (g & S.sel[0][k][2]) | (t & S.sel[0][k][3]);
+    if (s1) m[1] &= (a & S.sel[1][k][0]) | (c & S.sel[1][k][1]) | (g & S.sel[1][k][2]) | (t & S.sel[1][k][3]);
   }
-  return m;
 }
 
 // Per-strand geometry of search_guides.py:134-160, :395-420, :372-392.
@@ -175,6 +259,26 @@ HAWK_HD StrandGeom strand_geom(int G, int P, bool rp, bool unphased, int pad) {
     s.stop_off = P;
   }
   return s;
+}
+
+// Sliding OR over a 96-bit window held in three words (bit 0 = LSB of w0):
+// afterwards bit x of the window = OR of the original bits [x, x + C), for every x with
+// x + C <= 96. Log-doubling, 1 <= C <= 33 (all shifts are < 32).
+HAWK_HD void dilate96_step(uint32_t& w0, uint32_t& w1, uint32_t& w2, uint32_t k) {
+  w0 |= funnel_r(w0, w1, k);
+  w1 |= funnel_r(w1, w2, k);
+  w2 |= w2 >> k;
+}
+HAWK_HD void dilate96(uint32_t& w0, uint32_t& w1, uint32_t& w2, int C) {
+  // after the steps taken so far every bit covers `cover` original bits; C is uniform
+  // over the launch, so these are uniform branches
+  if (C >= 2) dilate96_step(w0, w1, w2, 1);
+  if (C >= 4) dilate96_step(w0, w1, w2, 2);
+  if (C >= 8) dilate96_step(w0, w1, w2, 4);
+  if (C >= 16) dilate96_step(w0, w1, w2, 8);
+  if (C >= 32) dilate96_step(w0, w1, w2, 16);
+  const int cover = C >= 32 ? 32 : C >= 16 ? 16 : C >= 8 ? 8 : C >= 4 ? 4 : C >= 2 ? 2 : 1;
+  if (C > cover) dilate96_step(w0, w1, w2, (uint32_t)(C - cover));
 }
 
 // bit x of a bit-vector stored as 32-bit words, via accessor f(word_index)
@@ -294,7 +398,10 @@ struct ScanConst {
   int32_t right;        // --right
   int32_t unphased;     // HAWK_F_UNPHASED
   int32_t raw;          // 1: pam_search semantics (no in-range / REF-core filter)
+  int32_t small;        // G <= 32 and C <= 33: a guide core reaches at most one case word either side
+  int32_t back, ahead;  // case words before / after a chunk that can hold a core's variant base
   uint8_t pat[2][HAWK_MAX_PAM];  // [0] forward PAM, [1] reverse complement
+  PamSelect sel;                 // plane-select masks of pat
   StrandGeom geom[2];   // per strand (right' = right XOR strand)
 };
 
@@ -306,9 +413,19 @@ HAWK_HD ScanConst make_scan_const(const hawk_params& p, int raw) {
   k.right = p.right ? 1 : 0;
   k.unphased = (p.flags & HAWK_F_UNPHASED) ? 1 : 0;
   k.raw = raw;
+  k.small = (k.G <= 32 && k.C <= 33) ? 1 : 0;
+  k.back = (k.G + 31) >> 5;       // left core starts G bases before the PAM position
+  k.ahead = (31 + k.C - 1) >> 5;  // right core ends C - 1 bases after it
   for (int i = 0; i < HAWK_MAX_PAM; ++i) {
     k.pat[0][i] = p.pam_fwd[i];
     k.pat[1][i] = p.pam_rc[i];
+  }
+  for (int s = 0; s < 2; ++s) {
+    k.sel.skip[s] = 0;
+    for (int i = 0; i < HAWK_MAX_PAM; ++i) {
+      for (int b = 0; b < 4; ++b) k.sel.sel[s][i][b] = ((k.pat[s][i] >> b) & 1) ? 0xFFFFFFFFu : 0u;
+      if (k.pat[s][i] == 15) k.sel.skip[s] |= 1u << i;
+    }
   }
   for (int s = 0; s < 2; ++s)
     k.geom[s] = strand_geom(k.G, k.P, (k.right != 0) != (s == 1), k.unphased != 0, HAWK_GUIDESEQPAD);
@@ -321,7 +438,8 @@ struct HapScan {
   int32_t len, a, b;
   int32_t nchunks;  // chunks holding its bases
   int32_t is_ref;
-  int64_t lo[2], hi[2];  // admissible position interval per strand, [lo, hi)
+  int32_t lo[2], hi[2];  // admissible position interval per strand, [lo, hi)
+  int32_t c_in_lo, c_in_hi;  // chunks [c_in_lo, c_in_hi) lie inside all three intervals
 };
 
 HAWK_HD HapScan load_hap_scan(const BatchView& B, const ScanConst& K, int32_t h) {
@@ -336,49 +454,75 @@ HAWK_HD HapScan load_hap_scan(const BatchView& B, const ScanConst& K, int32_t h)
   H.nchunks = (H.len + 31) >> 5;
   H.is_ref = B.is_ref[h];
   for (int s = 0; s < 2; ++s) {
-    int64_t lo = H.a, hi = H.b;
+    int32_t lo = H.a, hi = H.b;
     if (!K.raw) {
-      int64_t glo = K.geom[s].lo, ghi = (int64_t)H.len - K.geom[s].hi_sub + 1;
+      int32_t glo = K.geom[s].lo, ghi = H.len - K.geom[s].hi_sub + 1;
       if (glo > lo) lo = glo;
       if (ghi < hi) hi = ghi;
     }
     H.lo[s] = lo;
     H.hi[s] = hi;
   }
+  int32_t in_lo = H.a > H.lo[0] ? H.a : H.lo[0], in_hi = H.b < H.hi[0] ? H.b : H.hi[0];
+  if (H.lo[1] > in_lo) in_lo = H.lo[1];
+  if (H.hi[1] < in_hi) in_hi = H.hi[1];
+  H.c_in_lo = in_lo <= 0 ? 0 : (in_lo + 31) >> 5;
+  H.c_in_hi = in_hi <= 0 ? 0 : in_hi >> 5;
   return H;
 }
 
 // The whole per-position work of pam_search + the fused filters for the 32
 // positions of chunk `c` (haplotype-relative) : out[s] = surviving hit bits of
 // strand s, raw[s] = PAM matches inside the scan interval before the filters.
+// `vword(w)` returns case word w of the haplotype (0 outside it); the kernel serves it
+// from the shared-memory tile, the host check from the plane in memory.
+template <class VW>
 HAWK_HD void scan_chunk(const BatchView& B, const ScanConst& K, const HapScan& H, int64_t c,
-                        uint32_t out[2], uint32_t raw[2]) {
-  int64_t p0 = c << 5;
-  uint32_t inscan = interval_mask(H.a, H.b, p0);
+                        VW&& vword, uint32_t out[2], uint32_t raw[2]) {
+  const int32_t p0 = (int32_t)(c << 5);
   out[0] = out[1] = raw[0] = raw[1] = 0;
-  if (!inscan) return;
-  uint32_t cand[2] = {interval_mask(H.lo[0], H.hi[0], p0), interval_mask(H.lo[1], H.hi[1], p0)};
-  auto vword = [&](int64_t w) -> uint32_t {
-    return (w < 0 || w >= H.nchunks) ? 0u : B.v[H.chunk0 + w];
-  };
+  uint32_t inscan = 0xFFFFFFFFu, cand[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+  if (c < H.c_in_lo || c >= H.c_in_hi) {  // boundary chunk of the scan / window intervals
+    inscan = interval_mask(H.a, H.b, p0);
+    if (!inscan) return;
+    cand[0] = interval_mask(H.lo[0], H.hi[0], p0);
+    cand[1] = interval_mask(H.lo[1], H.hi[1], p0);
+  }
   if (!K.raw && !H.is_ref) {
     // search_guides.py:468-471: a non-REF hit survives only if its core holds a
     // variant base; skip the plane loads when no variant bit is in reach.
-    for (int s = 0; s < 2; ++s)
-      if (cand[s]) cand[s] &= core_variant_mask(vword, p0, K.geom[s].c0, K.C);
-    if (!(cand[0] | cand[1])) {
-      // raw counts still need the match when requested; they are only reported
-      // for REF haplotypes / raw mode, so nothing more to do here.
-      return;
+    if (K.small) {
+      uint32_t w0 = vword(c - 1), w1 = vword(c), w2 = vword(c + 1);
+      if (!(w0 | w1 | w2)) return;
+      dilate96(w0, w1, w2, K.C);
+      HAWK_UNROLL
+      for (int s = 0; s < 2; ++s) {
+        // core of position p0 + i starts at window bit 32 + c0 + i (c0 = 0 or -G, G <= 32)
+        uint32_t off = (uint32_t)(32 + K.geom[s].c0);
+        cand[s] &= (off == 32u) ? w1 : funnel_r(w0, w1, off);
+      }
+    } else {
+      for (int s = 0; s < 2; ++s)
+        if (cand[s]) cand[s] &= core_variant_mask(vword, p0, K.geom[s].c0, K.C);
     }
+    if (!(cand[0] | cand[1])) return;
   }
   Planes cur = B.q[H.chunk0 + c], nxt = B.q[H.chunk0 + c + 1];
-  uint32_t mf = match_chunk(cur, nxt, K.pat[0], K.P);
-  uint32_t mr = match_chunk(cur, nxt, K.pat[1], K.P);
-  raw[0] = mf & inscan;
-  raw[1] = mr & inscan;
-  out[0] = mf & cand[0];
-  out[1] = mr & cand[1];
+  uint32_t m[2];
+  match_chunk2(cur, nxt, K.sel, K.P, m);
+  raw[0] = m[0] & inscan;
+  raw[1] = m[1] & inscan;
+  out[0] = m[0] & cand[0];
+  out[1] = m[1] & cand[1];
+}
+
+// same, case words read straight from the batch's plane
+HAWK_HD void scan_chunk(const BatchView& B, const ScanConst& K, const HapScan& H, int64_t c,
+                        uint32_t out[2], uint32_t raw[2]) {
+  auto vword = [&](int64_t w) -> uint32_t {
+    return (w < 0 || w >= H.nchunks) ? 0u : B.v[H.chunk0 + w];
+  };
+  scan_chunk(B, K, H, c, vword, out, raw);
 }
 
 // ---- per-hit row geometry -------------------------------------------------------

@@ -5,9 +5,9 @@
 
 #include "../../include/hawkscan.h"
 
-// chunks per scan span (one CTA iteration): 2048 chunks = 65,536 base slots,
-// two 8 KB hit bitmaps in shared memory
-#define HAWK_SPAN_CHUNKS 2048
+// chunks per scan span (the unit one warp processes at a time): 256 chunks = 8,192 base
+// slots = 1 KB of case words
+#define HAWK_SPAN_CHUNKS 256
 
 int hawk_fail(int code, const char* fmt, ...);
 int hawk_check_cuda(cudaError_t err, const char* what);

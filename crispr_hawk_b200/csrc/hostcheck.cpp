@@ -27,7 +27,7 @@ int64_t hawkcheck_pack(const uint8_t* ascii, int64_t total_slots, uint32_t* q /*
   for (int64_t c = 0; c < total_slots / 32; ++c) {
     uint32_t words[8];
     memcpy(words, ascii + c * 32, 32);
-    PackedChunk o = pack_chunk(words, [](uint32_t b) { return iupac_entry((uint8_t)b); });
+    PackedChunk o = pack_chunk(words);
     q[4 * c + 0] = o.a;
     q[4 * c + 1] = o.c;
     q[4 * c + 2] = o.g;

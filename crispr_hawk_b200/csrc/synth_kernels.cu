@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) materialize_kernel(const __grid_constant_
   for (int i = 0; i < 32; ++i) {
     int64_t j = j0 + i;
     uint8_t ch = 0;
-    if (j < L) {
+    if (j >= 0 && j < L) {
       while (el + 1 < e1 && A.edit_outpos[el + 1] <= j) ++el;
       if (el < e0) {
         ch = A.ref[j];

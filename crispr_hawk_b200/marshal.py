@@ -13,6 +13,7 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 
 SLOT_ALIGN = 128  # HAWK_SLOT_ALIGN
+SLOT_GAP = 128  # HAWK_SLOT_GAP: zero slots before the first and after every haplotype
 CHUNK = 32
 PADDING = 100  # region_constructor.py:21
 GUIDESEQPAD = 10  # guide.py:21
@@ -31,9 +32,9 @@ def hap_text(hap) -> str:
 def layout(lengths: Sequence[int]) -> Tuple[np.ndarray, int]:
     """Aligned exclusive prefix of the haplotype lengths (mirror of hawk_layout)."""
     lens = np.asarray(lengths, dtype=np.int64)
-    padded = (lens + SLOT_ALIGN - 1) // SLOT_ALIGN * SLOT_ALIGN
-    off = np.zeros(len(lens) + 1, dtype=np.int64)
-    np.cumsum(padded, out=off[1:])
+    padded = (lens + SLOT_ALIGN - 1) // SLOT_ALIGN * SLOT_ALIGN + SLOT_GAP
+    off = np.full(len(lens) + 1, SLOT_GAP, dtype=np.int64)
+    off[1:] += np.cumsum(padded)
     return off, int(off[-1])
 
 

@@ -18,7 +18,9 @@
  *
  * Slot layout (both layers). Haplotype h owns base slots
  * [slot_off[h], slot_off[h] + len[h]) of one flat slot space; slot_off[h] is a
- * multiple of HAWK_SLOT_ALIGN; unused slots hold 0. Device planes:
+ * multiple of HAWK_SLOT_ALIGN and every haplotype is preceded and followed by at
+ * least HAWK_SLOT_GAP unused slots (the halo the scan's tiles read); unused slots
+ * hold 0. Device planes:
  *   q  : one uint4 {A,C,G,T} per 32-slot chunk -- the 4-bit IUPAC mask of
  *        encoder.py:18-34, bit-sliced: bit i of .x/.y/.z/.w is bit 0/1/2/3 of
  *        the nibble of slot 32*chunk + i (0.5 B per base).
@@ -37,11 +39,12 @@ extern "C" {
 
 #define HAWK_ABI_VERSION 1
 #define HAWK_SLOT_ALIGN 128 /* bases; haplotypes start on a 64-byte plane boundary */
+#define HAWK_SLOT_GAP 128   /* unused (zero) slots before the first and after every haplotype */
 #define HAWK_CHUNK 32       /* bases per chunk (one uint4 of planes, one uint32 of case bits) */
 #define HAWK_SLACK_CHUNKS 8 /* readable zero chunks after the last slot */
 #define HAWK_MAX_PAM 16
 #define HAWK_GUIDESEQPAD 10 /* guide.py:21 */
-#define HAWK_MAX_WINDOW 160 /* G + P + 2*PAD upper bound supported on device */
+#define HAWK_MAX_WINDOW 148 /* G + P + 2*PAD upper bound supported on device (G + P <= 128) */
 
 enum {
   HAWK_OK = 0,
@@ -85,8 +88,9 @@ int hawk_ctx_destroy(hawk_ctx *ctx);
 int hawk_ctx_info(hawk_ctx *ctx, int32_t *sm_count, int64_t *total_mem, int64_t *free_mem);
 
 /* ---- layout helper -------------------------------------------------------
- * slot_off[0..n_hap]: aligned exclusive prefix of len[]; returns total slots
- * (multiple of HAWK_SLOT_ALIGN) in *total_slots. */
+ * slot_off[0..n_hap]: slot_off[0] = HAWK_SLOT_GAP, slot_off[h+1] = slot_off[h] +
+ * len[h] rounded up to HAWK_SLOT_ALIGN + HAWK_SLOT_GAP; returns total slots
+ * (= slot_off[n_hap], a multiple of HAWK_SLOT_ALIGN) in *total_slots. */
 int hawk_layout(const int32_t *len, int32_t n_hap, int64_t *slot_off, int64_t *total_slots);
 
 /* ---- host layer ----------------------------------------------------------
@@ -175,25 +179,46 @@ int hawk_ctx_profile(hawk_ctx *ctx, double *ms /* [3] */, int64_t *n /* [3] */);
 int hawk_pack_dev(void *stream, const uint8_t *d_ascii, int64_t total_slots, void *d_q,
                   uint32_t *d_v, int64_t *d_bad);
 
-/* scan plan: host-side span directory for hawk_scan_dev. Returns the number
- * of spans; span_off (n_hap+1) is filled when non-NULL. */
-int64_t hawk_scan_plan(const int32_t *scan_start, const int32_t *scan_stop, int32_t n_hap,
-                       int64_t *span_off);
-/* bytes of zero-initialised device workspace hawk_scan_dev needs */
-size_t hawk_scan_workspace_bytes(int64_t n_spans);
+/* Scan plan (host side). A span is 256 chunks (8,192 base slots) of one haplotype; spans
+ * are numbered in (haplotype, position) order and every warp of the persistent scan grid
+ * (a "unit") owns a contiguous span range. hawk_scan_units gives the number of units the
+ * kernel wants for a device with sm_count SMs. hawk_scan_plan fills span_off (n_hap + 1)
+ * and, when unit_span is non-NULL, the balanced assignment of span ranges to n_units
+ * (unit_span, n_units + 1) with each unit's cumulative share of the staging capacity
+ * (unit_frac, n_units + 1, 0..1). is_ref may be NULL; raw_hits as in hawk_scan_dev.
+ * Returns the number of spans. */
+int32_t hawk_scan_units(int32_t sm_count, int64_t n_spans);
+int64_t hawk_scan_plan(const int32_t *scan_start, const int32_t *scan_stop, const uint8_t *is_ref,
+                       int32_t n_hap, int32_t raw_hits, int32_t n_units, int64_t *span_off,
+                       int64_t *unit_span, double *unit_frac);
+/* bytes of device workspace for hawk_scan_dev / hawk_scan_compact_dev (no initialisation
+ * required). cap_* = staging capacity in records; everything in front of the staging
+ * buffers has the same layout for any capacity. */
+size_t hawk_scan_workspace_bytes(int64_t n_spans, int32_t n_units, int64_t cap_fwd, int64_t cap_rev);
 
-/* K2: PAM match on both strands + in-range / REF-core filters + ordered
- * compaction. All d_* are device pointers; per-haplotype arrays have n_hap
- * entries (d_span_off n_hap+1). d_hits[s] receives (hap << 32 | pos) records
- * ascending, at most cap[s]; d_counts (uint64[4]) receives the filtered totals
- * per strand in [0..1] and the raw PAM-hit totals in [2..3]. The workspace
- * must be zeroed by the caller before every launch. */
-int hawk_scan_dev(void *stream, int32_t sm_count, const void *d_q, const uint32_t *d_v,
-                  const int64_t *d_slot_off, const int32_t *d_len, const int32_t *d_scan_start,
-                  const int32_t *d_scan_stop, const uint8_t *d_is_ref, const int64_t *d_span_off,
-                  int32_t n_hap, int64_t n_spans, const hawk_params *params, int32_t raw_hits,
-                  uint64_t *d_hits_fwd, uint64_t *d_hits_rev, int64_t cap_fwd, int64_t cap_rev,
-                  uint64_t *d_counts, void *d_workspace);
+/* K2: PAM match on both strands + in-range / REF-core filters
+ * (search_guides.py:32-131, :395-420, :468-471). All d_* are device pointers;
+ * per-haplotype arrays have n_hap entries; d_span_off / d_unit_span / d_unit_frac are the
+ * uploaded outputs of hawk_scan_plan. Every unit writes its (hap << 32 | pos) records,
+ * ascending, into its own segment of the staging buffers inside the workspace.
+ * d_counts (uint64[8]): [0..1] totals per strand, [2..3] raw PAM-hit totals, [4] != 0 when
+ * a unit's share of the staging capacity overflowed. If a total exceeds its cap or [4] is
+ * set, call again with caps >= the totals and exact_retry = 1 (same workspace, or a larger
+ * one whose head was copied over), which sizes every unit's segment from the first launch's
+ * exact counts. raw_hits = 1 gives pam_search semantics (no window / REF-core filter). */
+int hawk_scan_dev(void *stream, const void *d_q, const uint32_t *d_v, const int64_t *d_slot_off,
+                  const int32_t *d_len, const int32_t *d_scan_start, const int32_t *d_scan_stop,
+                  const uint8_t *d_is_ref, const int64_t *d_span_off, const int64_t *d_unit_span,
+                  const double *d_unit_frac, int32_t n_hap, int64_t n_spans, int32_t n_units,
+                  const hawk_params *params, int32_t raw_hits, int32_t exact_retry, int64_t cap_fwd,
+                  int64_t cap_rev, uint64_t *d_counts, void *d_workspace);
+/* K3: concatenate the staging segments into dense hit lists sorted by (haplotype,
+ * position): d_hits[s] receives min(total[s], out_cap[s]) records. Same n_units / n_spans /
+ * caps / exact_retry / workspace as the hawk_scan_dev call it follows. */
+int hawk_scan_compact_dev(void *stream, const double *d_unit_frac, int32_t n_units, int64_t n_spans,
+                          int32_t exact_retry, int64_t cap_fwd, int64_t cap_rev, void *d_workspace,
+                          uint64_t *d_hits_fwd, uint64_t *d_hits_rev, int64_t out_cap_fwd,
+                          int64_t out_cap_rev);
 
 /* N1 (next row): materialise haplotype texts on the device from the reference text and
  * per-haplotype sorted, non-overlapping edit lists (haplotype.py:106-121,185-252
