@@ -313,6 +313,8 @@ def run_product_arm(args, rank, world, local_rank):
     kernels["scan_kernel"] = {"ms": scan_ms, "algorithmic_bytes": scan_bytes, "gbs": scan_bytes / scan_ms / 1e6 if scan_ms else None,
                               "launches_per_step": prof["scan"][1] / args.steps}  # fmt: skip
     kernels["post_pipeline"] = {"ms": post_ms, "launches_per_step": prof["post"][1] / args.steps}
+    kernels["compact_kernel"] = {"ms": prof["compact"][0] / max(prof["compact"][1], 1),
+                                 "launches_per_step": prof["compact"][1] / args.steps}
     dom = "pack_kernel" if pack_ms >= scan_ms else "scan_kernel"
     ach = kernels[dom]["gbs"] or 0.0
     roofline = {

@@ -78,7 +78,7 @@ SIGNATURES = {
     "hawk_search": (C.c_int, [_P, _P, C.POINTER(HawkParams), _I32P, _I32P, _U8P, C.POINTER(_P)]),
     "hawk_pam_search": (C.c_int, [_P, _P, C.POINTER(HawkParams), _I32P, _I32P, C.POINTER(_P)]),
     "hawk_result_destroy": (C.c_int, [_P]),
-    "hawk_result_info": (C.c_int, [_P, _I64P, _I64P, _I32P, _I64P]),
+    "hawk_result_info": (C.c_int, [_P, _I64P, _I64P, _I32P, _I32P, _I64P]),
     "hawk_result_fetch": (C.c_int, [_P, _I32P, _U8P, _I32P, _I32P, _I32P, _I64P, _U8P]),
     "hawk_result_fetch_hits": (C.c_int, [_P, C.c_int32, _U64P]),
     "hawk_pack_dev": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
@@ -192,9 +192,9 @@ class Context:
 
     def profile(self):
         """{'pack'|'scan'|'post': (total ms, launches)} since the last call."""
-        ms, n = (C.c_double * 3)(), (C.c_int64 * 3)()
+        ms, n = (C.c_double * 4)(), (C.c_int64 * 4)()
         check(self.lib.hawk_ctx_profile(self.handle, ms, n))
-        return {k: (ms[i], n[i]) for i, k in enumerate(("pack", "scan", "post"))}
+        return {k: (ms[i], n[i]) for i, k in enumerate(("pack", "scan", "post", "compact"))}
 
     def close(self):
         if self.handle:
@@ -284,22 +284,23 @@ class Result:
 
     def __init__(self, lib, handle):
         self.lib, self.handle = lib, handle
-        n, hits, w, bp = C.c_int64(), (C.c_int64 * 2)(), C.c_int32(), C.c_int64()
-        check(lib.hawk_result_info(handle, C.byref(n), hits, C.byref(w), C.byref(bp)))
+        n, hits, w, ts, bp = C.c_int64(), (C.c_int64 * 2)(), C.c_int32(), C.c_int32(), C.c_int64()
+        check(lib.hawk_result_info(handle, C.byref(n), hits, C.byref(w), C.byref(ts), C.byref(bp)))
         self.n_guides, self.n_hits, self.window, self.scanned_bp = n.value, (hits[0], hits[1]), w.value, bp.value
+        self.text_stride = ts.value or w.value
 
     def table(self, buffers=None):
         """Download the guide table. `buffers`: optional dict of preallocated (e.g. pinned)
         1-D numpy arrays with at least n rows each; views of them are returned."""
-        n, w = self.n_guides, self.window
+        n, w, ts = self.n_guides, self.window, self.text_stride
         if buffers is not None:
             out = {k: buffers[k][:n] for k in ("hap", "strand", "pos", "start", "stop", "bucket")}
-            out["text"] = buffers["text"][: n * w].reshape(n, w)
+            out["text"] = buffers["text"][: n * ts].reshape(n, ts)
         else:
             out = {
                 "hap": np.empty(n, np.int32), "strand": np.empty(n, np.uint8), "pos": np.empty(n, np.int32),
                 "start": np.empty(n, np.int32), "stop": np.empty(n, np.int32),
-                "bucket": np.empty(n, np.int64), "text": np.empty((n, w), np.uint8),
+                "bucket": np.empty(n, np.int64), "text": np.empty((n, ts), np.uint8),
             }  # fmt: skip
         check(
             self.lib.hawk_result_fetch(
@@ -309,6 +310,7 @@ class Result:
             ),  # fmt: skip
             "hawk_result_fetch",
         )
+        out["text"] = out["text"][:, :w]  # rows are padded to text_stride bytes on the device
         return out
 
     def hits(self, strand: int) -> np.ndarray:

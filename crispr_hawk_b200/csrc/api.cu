@@ -190,13 +190,18 @@ struct hawk_batch {
   DevBuf seg_off, seg_rel, seg_gen, seg_step;
   DevBuf va_off, va_idx, va_ent_off, va_ref;
   bool has_posmap = false, has_alleles = false;
+  // host-side facts about the coordinate maps (hawk_batch_set_posmap)
+  std::vector<int64_t> h_seg_off;
+  std::vector<int32_t> first_gen;   // posmap(0) per haplotype
+  std::vector<uint8_t> linear;      // one step-1 segment
+  int32_t gmin = 0, gmax = -1;      // genomic coordinate range over all haplotypes
 };
 
 struct hawk_result {
   hawk_ctx* ctx;
   int64_t n_guides = 0;
   int64_t n_hits[2] = {0, 0};
-  int32_t window = 0;
+  int32_t window = 0, text_stride = 0;
   int64_t scanned_bp = 0;
   DevBuf hits[2];
   DevBuf hap, strand, pos, start, stop, bucket, text;
@@ -378,10 +383,10 @@ extern "C" int hawk_ctx_profile(hawk_ctx* c, double* ms, int64_t* n) {
   if (!c || !ms || !n) return hawk_fail(HAWK_EINVAL, "hawk_ctx_profile: bad arguments");
   CKCUDA(cudaSetDevice(c->device));
   CKCUDA(cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < 3; ++i) { ms[i] = 0; n[i] = 0; }
+  for (int i = 0; i < 4; ++i) { ms[i] = 0; n[i] = 0; }
   for (auto& s : c->spans) {
     float t = 0;
-    if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess && s.kind >= 0 && s.kind < 3) {
+    if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess && s.kind >= 0 && s.kind < 4) {
       ms[s.kind] += t;
       n[s.kind] += 1;
     }
@@ -431,6 +436,25 @@ extern "C" int hawk_batch_set_posmap(hawk_batch* b, const int64_t* seg_off, cons
   hawk_ctx* c = b->ctx;
   cudaStream_t st = c->stream;
   size_t n = (size_t)seg_off[b->n_hap];
+  b->h_seg_off.assign(seg_off, seg_off + b->n_hap + 1);
+  b->first_gen.resize(b->n_hap);
+  b->linear.resize(b->n_hap);
+  int64_t gmin = INT64_MAX, gmax = INT64_MIN;
+  for (int32_t h = 0; h < b->n_hap; ++h) {
+    const int64_t s0 = seg_off[h], s1 = seg_off[h + 1];
+    b->first_gen[h] = seg_gen[s0];
+    b->linear[h] = (s1 - s0 == 1 && seg_step[s0] == 1) ? 1 : 0;
+    for (int64_t k = s0; k < s1; ++k) {
+      const int64_t rel_end = k + 1 < s1 ? seg_rel[k + 1] : b->len[h];
+      const int64_t lo = seg_gen[k], hi = seg_gen[k] + (seg_step[k] && rel_end > seg_rel[k] ? rel_end - seg_rel[k] - 1 : 0);
+      if (lo < gmin) gmin = lo;
+      if (hi > gmax) gmax = hi;
+    }
+  }
+  if (gmin > gmax) gmin = 0, gmax = -1;
+  if (gmin < INT32_MIN || gmax > INT32_MAX) return hawk_fail(HAWK_EINVAL, "hawk_batch_set_posmap: coordinates exceed 32 bits");
+  b->gmin = (int32_t)gmin;
+  b->gmax = (int32_t)gmax;
   CK(upload(c, b->seg_off, seg_off, (size_t)(b->n_hap + 1) * 8));
   CK(upload(c, b->seg_rel, seg_rel, n * 4));
   CK(upload(c, b->seg_gen, seg_gen, n * 4));
@@ -557,7 +581,7 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
     }
   }
   for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(c, (size_t)(out.n[s] > 0 ? out.n[s] : 1) * 8));
-  c->mark(1, nullptr);
+  c->mark(3, nullptr);
   int crc = hawk_scan_compact_dev(st, d_unit_frac.as<double>(), n_units, n_spans, exact, cap[0], cap[1], d_ws.p,
                                   out.hits[0].as<uint64_t>(), out.hits[1].as<uint64_t>(), out.n[0], out.n[1]);
   c->close_mark();
@@ -607,6 +631,99 @@ extern "C" int hawk_pam_search(hawk_ctx* c, hawk_batch* b, const hawk_params* pa
   return HAWK_OK;
 }
 
+// phased / variant-free pipeline downstream of the scan (table_kernels.cu)
+static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const BatchView& B, ScanOut& so,
+                       int32_t ref_h, hawk_result* r) {
+  cudaStream_t st = c->stream;
+  Trace tr;
+  const int64_t n_hits[2] = {so.n[0], so.n[1]};
+  const uint64_t* recs[2] = {so.hits[0].as<uint64_t>(), so.hits[1].as<uint64_t>()};
+  RefInfo ref{ref_h, 0, 0, 0};
+  DevBuf d_refrange, d_refbm[2], start[2], stop[2], keep[2], blk_cnt[2], blk_base[2], d_tot, d_kb;
+  CK(d_refrange.alloc(c, 32, true));
+  CK(launch_ref_range(st, recs[0], n_hits[0], recs[1], n_hits[1], ref_h, d_refrange.as<int64_t>()));
+  if (ref_h >= 0) {
+    ref.linear = b->linear[ref_h];
+    ref.g0 = b->first_gen[ref_h];
+    ref.len = b->len[ref_h];
+    if (ref.linear) {
+      const size_t words = (size_t)(ref.len + 31) / 32 + 1;
+      for (int s = 0; s < 2; ++s) CK(d_refbm[s].alloc(c, words * 4, true));
+      CK(launch_ref_bitmap(st, recs[0], recs[1], d_refrange.as<int64_t>(), d_refbm[0].as<uint32_t>(),
+                           d_refbm[1].as<uint32_t>()));
+    }
+  }
+  int64_t n_blk[2];
+  CK(d_tot.alloc(c, 16, true));
+  for (int s = 0; s < 2; ++s) {
+    n_blk[s] = row_blocks(n_hits[s]);
+    CK(start[s].alloc(c, (size_t)n_hits[s] * 4));
+    CK(stop[s].alloc(c, (size_t)n_hits[s] * 4));
+    CK(keep[s].alloc(c, (size_t)n_hits[s]));
+    CK(blk_cnt[s].alloc(c, (size_t)(n_blk[s] + 1) * 4));
+    CK(blk_base[s].alloc(c, (size_t)(n_blk[s] + 1) * 8));
+    CK(launch_rows_fast(st, B, K, recs[s], n_hits[s], s, ref, d_refbm[s].as<uint32_t>(), d_refrange.as<int64_t>(),
+                        start[s].as<int32_t>(), stop[s].as<int32_t>(), keep[s].as<uint8_t>(),
+                        blk_cnt[s].as<uint32_t>()));
+    if (n_hits[s] > 0)
+      CK(launch_blk_prefix(st, blk_cnt[s].as<uint32_t>(), n_blk[s], blk_base[s].as<uint64_t>(),
+                           d_tot.as<uint64_t>() + s));
+  }
+  uint64_t kept[2] = {0, 0};
+  CKCUDA(cudaMemcpyAsync(kept, d_tot.p, 16, cudaMemcpyDeviceToHost, st));
+  CKCUDA(cudaStreamSynchronize(st));
+  tr.tick("table: rows + prefix + sync");
+  const int64_t n = (int64_t)(kept[0] + kept[1]);
+  const int W = K.C + 2 * HAWK_GUIDESEQPAD;
+  r->n_guides = n;
+  r->text_stride = (W + 15) / 16 * 16;
+  CK(r->hap.alloc(c, (size_t)n * 4));
+  CK(r->strand.alloc(c, (size_t)n));
+  CK(r->pos.alloc(c, (size_t)n * 4));
+  CK(r->start.alloc(c, (size_t)n * 4));
+  CK(r->stop.alloc(c, (size_t)n * 4));
+  CK(r->bucket.alloc(c, (size_t)n * 8));
+  CK(r->text.alloc(c, (size_t)n * r->text_stride));
+  if (n == 0) return HAWK_OK;
+  CK(d_kb.alloc(c, (size_t)(b->n_hap + 1) * 16));
+  CK(launch_hap_offsets(st, recs[0], recs[1], n_hits[0], n_hits[1], keep[0].as<uint8_t>(), keep[1].as<uint8_t>(),
+                        blk_base[0].as<uint64_t>(), blk_base[1].as<uint64_t>(), kept[0], kept[1], b->n_hap,
+                        d_kb.as<uint64_t>()));
+  // first-seen bucket ids: direct-address table over (start, strand) when the coordinate
+  // range allows it, else the hash table of post_kernels.cu
+  const int64_t key_span = b->gmax >= b->gmin ? ((int64_t)b->gmax - b->gmin + 1) * 2 : 0;
+  const bool direct = key_span > 0 && key_span <= (1ll << 28) && n < 0xFFFFFFFFll;
+  DevBuf key_table;
+  if (direct) {
+    CK(key_table.alloc(c, (size_t)key_span * 4));
+    CKCUDA(cudaMemsetAsync(key_table.p, 0xFF, (size_t)key_span * 4, st));
+  }
+  for (int s = 0; s < 2; ++s)
+    CK(launch_gather_fast(st, B, K, recs[s], keep[s].as<uint8_t>(), blk_base[s].as<uint64_t>(),
+                          start[s].as<int32_t>(), stop[s].as<int32_t>(),
+                          d_kb.as<uint64_t>() + (size_t)(1 - s) * (b->n_hap + 1), n_hits[s], s, r->text_stride,
+                          r->hap.as<int32_t>(), r->strand.as<uint8_t>(), r->pos.as<int32_t>(),
+                          r->start.as<int32_t>(), r->stop.as<int32_t>(), r->text.as<uint8_t>(),
+                          direct ? key_table.as<uint32_t>() : nullptr, b->gmin));
+  if (direct) {
+    CK(launch_bucket_read(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n, key_table.as<uint32_t>(), b->gmin,
+                          r->bucket.as<int64_t>()));
+  } else {
+    uint64_t tsize = 1024;
+    while (tsize < (uint64_t)n * 2) tsize <<= 1;
+    DevBuf keys, vals;
+    CK(keys.alloc(c, tsize * 8));
+    CK(vals.alloc(c, tsize * 8));
+    CKCUDA(cudaMemsetAsync(keys.p, 0xFF, tsize * 8, st));
+    CKCUDA(cudaMemsetAsync(vals.p, 0xFF, tsize * 8, st));
+    CK(launch_buckets(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n, keys.as<unsigned long long>(),
+                      vals.as<unsigned long long>(), tsize, r->bucket.as<int64_t>()));
+    CKCUDA(cudaStreamSynchronize(st));  // keys / vals are released on return
+  }
+  tr.tick("table: gather launched");
+  return HAWK_OK;
+}
+
 extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params,
                            const int32_t* scan_start, const int32_t* scan_stop,
                            const uint8_t* is_ref, hawk_result** out) {
@@ -648,6 +765,17 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
     c->mark(2, &ev_post);
     const BatchView B = batch_view(b, d_a.as<int32_t>(), d_b.as<int32_t>(), d_isref.as<uint8_t>());
     const int64_t n_hits[2] = {so.n[0], so.n[1]};
+    if (!unphased) {
+      if ((rc = search_fast(c, b, K, B, so, ref_h, r))) break;
+      c->close_mark();
+      if ((rc = hawk_check_cuda(cudaStreamSynchronize(st), "search sync"))) break;
+      tr.tick("table: final sync");
+      for (int s = 0; s < 2; ++s) {
+        r->n_hits[s] = n_hits[s];
+        r->hits[s].move_from(so.hits[s]);
+      }
+      break;
+    }
     if ((rc = d_refrange.alloc(c, 32, true))) break;
     if ((rc = d_err.alloc(c, 4, true))) break;
     if ((rc = launch_ref_range(st, so.hits[0].as<uint64_t>(), n_hits[0], so.hits[1].as<uint64_t>(),
@@ -734,13 +862,14 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
     const int64_t n = (int64_t)(kept_total[0] + kept_total[1]);
     tr.tick("post: keep scans + sync");
     r->n_guides = n;
+    r->text_stride = (W + 15) / 16 * 16;
     if ((rc = r->hap.alloc(c, (size_t)n * 4))) break;
     if ((rc = r->strand.alloc(c, (size_t)n))) break;
     if ((rc = r->pos.alloc(c, (size_t)n * 4))) break;
     if ((rc = r->start.alloc(c, (size_t)n * 4))) break;
     if ((rc = r->stop.alloc(c, (size_t)n * 4))) break;
     if ((rc = r->bucket.alloc(c, (size_t)n * 8))) break;
-    if ((rc = r->text.alloc(c, (size_t)n * W))) break;
+    if ((rc = r->text.alloc(c, (size_t)n * r->text_stride))) break;
     if (n > 0) {
       GatherLaunch g;
       g.B = B;
@@ -762,6 +891,7 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
       g.o_start = r->start.as<int32_t>();
       g.o_stop = r->stop.as<int32_t>();
       g.o_text = r->text.as<uint8_t>();
+      g.text_stride = r->text_stride;
       if ((rc = launch_gather(st, g))) break;
       // first-seen bucket ids
       uint64_t tsize = 1024;
@@ -802,7 +932,7 @@ extern "C" int hawk_result_destroy(hawk_result* r) {
 }
 
 extern "C" int hawk_result_info(hawk_result* r, int64_t* n_guides, int64_t* n_hits, int32_t* window,
-                                int64_t* scanned_bp) {
+                                int32_t* text_stride, int64_t* scanned_bp) {
   if (!r) return hawk_fail(HAWK_EINVAL, "hawk_result_info: null result");
   if (n_guides) *n_guides = r->n_guides;
   if (n_hits) {
@@ -810,6 +940,7 @@ extern "C" int hawk_result_info(hawk_result* r, int64_t* n_guides, int64_t* n_hi
     n_hits[1] = r->n_hits[1];
   }
   if (window) *window = r->window;
+  if (text_stride) *text_stride = r->text_stride;
   if (scanned_bp) *scanned_bp = r->scanned_bp;
   return HAWK_OK;
 }
@@ -827,7 +958,7 @@ extern "C" int hawk_result_fetch(hawk_result* r, int32_t* hap, uint8_t* strand, 
   if (start) CKCUDA(cudaMemcpyAsync(start, r->start.p, n * 4, cudaMemcpyDeviceToHost, st));
   if (stop) CKCUDA(cudaMemcpyAsync(stop, r->stop.p, n * 4, cudaMemcpyDeviceToHost, st));
   if (bucket) CKCUDA(cudaMemcpyAsync(bucket, r->bucket.p, n * 8, cudaMemcpyDeviceToHost, st));
-  if (text) CKCUDA(cudaMemcpyAsync(text, r->text.p, n * (size_t)r->window, cudaMemcpyDeviceToHost, st));
+  if (text) CKCUDA(cudaMemcpyAsync(text, r->text.p, n * (size_t)r->text_stride, cudaMemcpyDeviceToHost, st));
   CKCUDA(cudaStreamSynchronize(st));
   return HAWK_OK;
 }

@@ -291,6 +291,7 @@ struct GatherArgs {
   int32_t* o_start;
   int32_t* o_stop;
   uint8_t* o_text;
+  int32_t text_stride;
 };
 
 __device__ __forceinline__ int32_t row_hap(const GatherArgs& A, int t, int64_t row) {
@@ -321,7 +322,8 @@ __global__ void gather_kernel(const __grid_constant__ GatherArgs A, int s) {
   A.o_start[f] = A.start[s][hit];
   A.o_stop[f] = A.stop[s][hit];
   const int W = A.K.C + 2 * HAWK_GUIDESEQPAD;
-  uint8_t* dst = A.o_text + f * W;
+  uint8_t* dst = A.o_text + f * (uint64_t)A.text_stride;
+  for (int j = W; j < A.text_stride; ++j) dst[j] = 0;
   if (A.text_pre[s]) {
     const uint8_t* src = A.text_pre[s] + r * W;
     for (int j = 0; j < W; ++j) dst[j] = src[j];
@@ -447,6 +449,7 @@ int launch_gather(cudaStream_t st, const GatherLaunch& g) {
   A.o_start = g.o_start;
   A.o_stop = g.o_stop;
   A.o_text = g.o_text;
+  A.text_stride = g.text_stride;
   for (int s = 0; s < 2; ++s) {
     if (g.n_rows[s] <= 0) continue;
     gather_kernel<<<grid_for(g.n_rows[s], 128), 128, 0, st>>>(A, s);

@@ -1,0 +1,305 @@
+// table_kernels.cu -- the phased / variant-free guide-table pipeline downstream of the
+// scan (retrieve_guides + remove_redundant_guides, search_guides.py:340-369, :423-507,
+// without the unphased resolve_guide branch, which lives in post_kernels.cu):
+//
+//   ref_bitmap   one bit per REF position and strand that holds a REF guide
+//   rows         per hit: genomic start/stop through the run-length posmap (:260-280), REF
+//                partner by direct lookup (REF coordinates are linear) + upper-cased core
+//                comparison on the nibble planes (:356-369) -> keep flag, kept rows per block
+//   blk_prefix   exclusive prefix of the per-block kept counts (single CTA)
+//   hap_offsets  rows of each strand stream that precede a haplotype (for the emission-order
+//                merge of the two streams, :530-547)
+//   gather       surviving rows -> table columns in emission order, padded window text
+//                rebuilt from the planes (:134-160) with 128-bit stores, first-seen bucket id
+//                of the (start, strand) key by atomicMin on a direct-address table (:306-337)
+//   bucket_read  bucket id column
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hawk_core.h"
+#include "hawk_kernels.h"
+#include "hawk_post.h"
+
+namespace hawk {
+
+constexpr int ROW_T = 256;  // rows per block in rows / gather (the two must agree)
+
+// ---------------------------------------------------------------- REF guide bitmap
+__global__ void ref_bitmap_kernel(const uint64_t* __restrict__ recs0, const uint64_t* __restrict__ recs1,
+                                  const int64_t* __restrict__ ref_range, uint32_t* __restrict__ bm0,
+                                  uint32_t* __restrict__ bm1) {
+  const int s = blockIdx.y;
+  const uint64_t* recs = s ? recs1 : recs0;
+  uint32_t* bm = s ? bm1 : bm0;
+  const int64_t lo = ref_range[2 * s], hi = ref_range[2 * s + 1];
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t pos = (uint32_t)(recs[i] & 0xFFFFFFFFu);
+    atomicOr(&bm[pos >> 5], 1u << (pos & 31));
+  }
+}
+
+// ---------------------------------------------------------------- rows
+struct RowsArgs {
+  BatchView B;
+  ScanConst K;
+  const uint64_t* recs;
+  int64_t n;
+  int32_t s;
+  int32_t ref_h;         // -1: no REF haplotype
+  int32_t ref_linear;    // REF posmap is one step-1 segment: posmap(i) = ref_g0 + i
+  int32_t ref_g0, ref_len;
+  const uint32_t* ref_bm;     // REF guide bitmap of this strand (ref_linear)
+  const int64_t* ref_range;   // REF record range per strand (general REF posmap)
+  int32_t* start;
+  int32_t* stop;
+  uint8_t* keep;
+  uint32_t* blk_cnt;
+};
+
+__global__ void __launch_bounds__(ROW_T) rows_fast_kernel(const __grid_constant__ RowsArgs A) {
+  const int64_t i = (int64_t)blockIdx.x * ROW_T + threadIdx.x;
+  int k = 0;
+  if (i < A.n) {
+    const uint64_t rec = A.recs[i];
+    const int32_t h = (int32_t)(rec >> 32), pos = (int32_t)(rec & 0xFFFFFFFFu);
+    const RowCoords rc = row_coords(A.B, A.K, h, pos, A.s);
+    A.start[i] = rc.start;
+    A.stop[i] = rc.stop;
+    k = 1;
+    if (A.ref_h >= 0 && !A.B.is_ref[h]) {
+      // remove_redundant_guides (:356-369): a non-REF guide whose upper-cased core equals the
+      // REF guide's at the same (start, strand) is dropped
+      int32_t rpivot = -1;
+      if (A.ref_linear) {
+        const int32_t rp = rc.start - A.ref_g0, rpos = rp - A.K.geom[A.s].c0;
+        if (rp >= 0 && rpos >= 0 && rpos < A.ref_len && ((A.ref_bm[rpos >> 5] >> (rpos & 31)) & 1u)) rpivot = rp;
+      } else {
+        const int64_t lo = A.ref_range[2 * A.s], hi = A.ref_range[2 * A.s + 1];
+        const int64_t j = find_ref_partner(A.B, A.K, A.recs, lo, hi, A.ref_h, A.s, rc.start);
+        if (j < hi) {
+          const int32_t rp = (int32_t)(A.recs[j] & 0xFFFFFFFFu) + A.K.geom[A.s].c0;
+          if (posmap_eval(A.B.seg_rel, A.B.seg_gen, A.B.seg_step, A.B.seg_off[A.ref_h], A.B.seg_off[A.ref_h + 1], rp) ==
+              rc.start)
+            rpivot = rp;
+        }
+      }
+      if (rpivot >= 0 &&
+          cores_equal(A.B.q, A.B.slot_off[h] >> 5, rc.pivot, A.B.slot_off[A.ref_h] >> 5, rpivot, A.K.C))
+        k = 0;
+    }
+    A.keep[i] = (uint8_t)k;
+  }
+  const int cnt = __syncthreads_count(k);
+  if (threadIdx.x == 0) A.blk_cnt[blockIdx.x] = (uint32_t)cnt;
+}
+
+// ---------------------------------------------------------------- block prefix (single CTA)
+__global__ void __launch_bounds__(1024) blk_prefix_kernel(const uint32_t* __restrict__ in, int64_t n,
+                                                          uint64_t* __restrict__ out, uint64_t* total) {
+  __shared__ uint64_t part[1024];
+  const int tid = threadIdx.x;
+  const int64_t per = (n + 1023) / 1024;
+  const int64_t lo = (int64_t)tid * per, hi = lo + per < n ? lo + per : n;
+  uint64_t sum = 0;
+  for (int64_t j = lo; j < hi; ++j) sum += in[j];
+  part[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    uint64_t y = tid >= o ? part[tid - o] : 0;
+    __syncthreads();
+    part[tid] += y;
+    __syncthreads();
+  }
+  uint64_t run = part[tid] - sum;
+  for (int64_t j = lo; j < hi; ++j) {
+    out[j] = run;
+    run += in[j];
+  }
+  if (tid == 1023) *total = part[1023];
+}
+
+// ---------------------------------------------------------------- per-haplotype offsets
+// kb[s][h] = kept rows of stream s whose haplotype is < h  (h = 0 .. n_hap)
+__global__ void hap_offsets_kernel(const uint64_t* __restrict__ recs0, const uint64_t* __restrict__ recs1,
+                                   int64_t n0, int64_t n1, const uint8_t* __restrict__ keep0,
+                                   const uint8_t* __restrict__ keep1, const uint64_t* __restrict__ base0,
+                                   const uint64_t* __restrict__ base1, uint64_t total0, uint64_t total1,
+                                   int32_t n_hap, uint64_t* __restrict__ kb) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * (int64_t)(n_hap + 1)) return;
+  const int s = (int)(t / (n_hap + 1));
+  const int32_t h = (int32_t)(t % (n_hap + 1));
+  const uint64_t* recs = s ? recs1 : recs0;
+  const int64_t n = s ? n1 : n0;
+  const uint8_t* keep = s ? keep1 : keep0;
+  const uint64_t* base = s ? base1 : base0;
+  const uint64_t key = (uint64_t)(uint32_t)h << 32;
+  int64_t lo = 0, hi = n;  // first record with haplotype >= h
+  while (lo < hi) {
+    const int64_t m = (lo + hi) >> 1;
+    if (recs[m] < key) lo = m + 1; else hi = m;
+  }
+  uint64_t r;
+  if (lo >= n) {
+    r = s ? total1 : total0;
+  } else {
+    const int64_t b0 = lo / ROW_T * ROW_T;
+    r = base[lo / ROW_T];
+    for (int64_t j = b0; j < lo; ++j) r += keep[j];
+  }
+  kb[(size_t)s * (n_hap + 1) + h] = r;
+}
+
+// ---------------------------------------------------------------- gather
+struct GatherFastArgs {
+  BatchView B;
+  ScanConst K;
+  const uint64_t* recs;
+  const uint8_t* keep;
+  const uint64_t* blk_base;
+  const int32_t* start;
+  const int32_t* stop;
+  const uint64_t* kb_other;  // kb of the other stream, n_hap + 1 entries
+  int64_t n;
+  int32_t s;
+  int32_t text_stride;  // bytes per text row, multiple of 16
+  int32_t* o_hap;
+  uint8_t* o_strand;
+  int32_t* o_pos;
+  int32_t* o_start;
+  int32_t* o_stop;
+  uint8_t* o_text;
+  uint32_t* key_table;  // direct-address first-seen table, or null
+  int32_t key_min;      // smallest genomic coordinate of the batch
+};
+
+// 16 window characters starting at window offset j0 from the plane bits of [o, o + 32)
+__device__ __forceinline__ uint4 window_chars(uint32_t pa, uint32_t pc, uint32_t pg, uint32_t pt, uint32_t pv,
+                                              int i0, int W, int j0) {
+  uint32_t w[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + 4 * q + j;
+      const uint32_t n = ((pa >> i) & 1u) | (((pc >> i) & 1u) << 1) | (((pg >> i) & 1u) << 2) | (((pt >> i) & 1u) << 3);
+      uint32_t ch = (uint32_t)(uint8_t)nibble_letter(n) | (((pv >> i) & 1u) << 5);
+      if (j0 + 4 * q + j >= W) ch = 0;
+      word |= ch << (8 * j);
+    }
+    w[q] = word;
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(ROW_T) gather_fast_kernel(const __grid_constant__ GatherFastArgs A) {
+  __shared__ uint32_t warp_cnt[ROW_T / 32];
+  const int64_t i = (int64_t)blockIdx.x * ROW_T + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool k = i < A.n && A.keep[i];
+  const uint32_t bal = __ballot_sync(0xFFFFFFFFu, k);
+  if (lane == 0) warp_cnt[warp] = __popc(bal);
+  __syncthreads();
+  if (!k) return;
+  uint32_t rank = __popc(bal & ((1u << lane) - 1u));
+  for (int w = 0; w < warp; ++w) rank += warp_cnt[w];
+  const uint64_t rec = A.recs[i];
+  const int32_t h = (int32_t)(rec >> 32), pos = (int32_t)(rec & 0xFFFFFFFFu);
+  // rows of the other stream emitted before this one: haplotype < h (strand 0) or <= h (strand 1)
+  const uint64_t f = A.blk_base[blockIdx.x] + rank + A.kb_other[h + (A.s == 1 ? 1 : 0)];
+  const int32_t st = A.start[i];
+  A.o_hap[f] = h;
+  A.o_strand[f] = (uint8_t)A.s;
+  A.o_pos[f] = pos;
+  A.o_start[f] = st;
+  A.o_stop[f] = A.stop[i];
+  if (A.key_table) atomicMin(&A.key_table[((uint32_t)(st - A.key_min) << 1) | (uint32_t)A.s], (uint32_t)f);
+  // extract_guide_sequence (:134-160): padded window text from planes + case bits
+  const int W = A.K.C + 2 * HAWK_GUIDESEQPAD;
+  const int64_t chunk0 = A.B.slot_off[h] >> 5;
+  const int32_t w0 = pos + A.K.geom[A.s].w0;
+  uint4* dst = reinterpret_cast<uint4*>(A.o_text + f * (uint64_t)A.text_stride);
+  for (int j0 = 0; j0 < A.text_stride; j0 += 32) {
+    const int32_t o = w0 + j0;
+    const uint32_t sh = (uint32_t)(o & 31);
+    const uint4 q0 = *reinterpret_cast<const uint4*>(&A.B.q[chunk0 + (o >> 5)]);
+    const uint4 q1 = *reinterpret_cast<const uint4*>(&A.B.q[chunk0 + (o >> 5) + 1]);
+    const uint32_t v0 = A.B.v[chunk0 + (o >> 5)], v1 = A.B.v[chunk0 + (o >> 5) + 1];
+    const uint32_t pa = funnel_r(q0.x, q1.x, sh), pc = funnel_r(q0.y, q1.y, sh), pg = funnel_r(q0.z, q1.z, sh),
+                   pt = funnel_r(q0.w, q1.w, sh), pv = funnel_r(v0, v1, sh);
+    dst[j0 >> 4] = window_chars(pa, pc, pg, pt, pv, 0, W, j0);
+    if (j0 + 16 < A.text_stride) dst[(j0 >> 4) + 1] = window_chars(pa, pc, pg, pt, pv, 16, W, j0 + 16);
+  }
+}
+
+__global__ void bucket_read_kernel(const int32_t* __restrict__ start, const uint8_t* __restrict__ strand, int64_t n,
+                                   const uint32_t* __restrict__ key_table, int32_t key_min,
+                                   int64_t* __restrict__ bucket) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bucket[i] = (int64_t)key_table[((uint32_t)(start[i] - key_min) << 1) | strand[i]];
+}
+
+// ---------------------------------------------------------------- launch wrappers
+static inline unsigned blocks_for(int64_t n, int t) {
+  int64_t b = (n + t - 1) / t;
+  return (unsigned)(b < 1 ? 1 : b);
+}
+
+int64_t row_blocks(int64_t n) { return (n + ROW_T - 1) / ROW_T; }
+
+int launch_ref_bitmap(cudaStream_t st, const uint64_t* r0, const uint64_t* r1, const int64_t* ref_range,
+                      uint32_t* bm0, uint32_t* bm1) {
+  ref_bitmap_kernel<<<dim3(296, 2), 256, 0, st>>>(r0, r1, ref_range, bm0, bm1);
+  hawk_note_launch(1);
+  return hawk_check_cuda(cudaGetLastError(), "ref_bitmap_kernel launch");
+}
+
+int launch_rows_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* recs, int64_t n,
+                     int s, const RefInfo& ref, const uint32_t* ref_bm, const int64_t* ref_range, int32_t* start,
+                     int32_t* stop, uint8_t* keep, uint32_t* blk_cnt) {
+  if (n <= 0) return HAWK_OK;
+  RowsArgs A{B, K, recs, n, s, ref.h, ref.linear, ref.g0, ref.len, ref_bm, ref_range, start, stop, keep, blk_cnt};
+  rows_fast_kernel<<<blocks_for(n, ROW_T), ROW_T, 0, st>>>(A);
+  hawk_note_launch(1);
+  return hawk_check_cuda(cudaGetLastError(), "rows_fast_kernel launch");
+}
+
+int launch_blk_prefix(cudaStream_t st, const uint32_t* cnt, int64_t n_blk, uint64_t* base, uint64_t* total) {
+  blk_prefix_kernel<<<1, 1024, 0, st>>>(cnt, n_blk, base, total);
+  hawk_note_launch(1);
+  return hawk_check_cuda(cudaGetLastError(), "blk_prefix_kernel launch");
+}
+
+int launch_hap_offsets(cudaStream_t st, const uint64_t* r0, const uint64_t* r1, int64_t n0, int64_t n1,
+                       const uint8_t* k0, const uint8_t* k1, const uint64_t* b0, const uint64_t* b1, uint64_t t0,
+                       uint64_t t1, int32_t n_hap, uint64_t* kb) {
+  const int64_t n = 2 * (int64_t)(n_hap + 1);
+  hap_offsets_kernel<<<blocks_for(n, 128), 128, 0, st>>>(r0, r1, n0, n1, k0, k1, b0, b1, t0, t1, n_hap, kb);
+  hawk_note_launch(1);
+  return hawk_check_cuda(cudaGetLastError(), "hap_offsets_kernel launch");
+}
+
+int launch_gather_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* recs,
+                       const uint8_t* keep, const uint64_t* blk_base, const int32_t* start, const int32_t* stop,
+                       const uint64_t* kb_other, int64_t n, int s, int32_t text_stride, int32_t* o_hap,
+                       uint8_t* o_strand, int32_t* o_pos, int32_t* o_start, int32_t* o_stop, uint8_t* o_text,
+                       uint32_t* key_table, int32_t key_min) {
+  if (n <= 0) return HAWK_OK;
+  GatherFastArgs A{B, K, recs, keep, blk_base, start, stop, kb_other, n, s, text_stride,
+                   o_hap, o_strand, o_pos, o_start, o_stop, o_text, key_table, key_min};
+  gather_fast_kernel<<<blocks_for(n, ROW_T), ROW_T, 0, st>>>(A);
+  hawk_note_launch(1);
+  return hawk_check_cuda(cudaGetLastError(), "gather_fast_kernel launch");
+}
+
+int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n,
+                       const uint32_t* key_table, int32_t key_min, int64_t* bucket) {
+  if (n <= 0) return HAWK_OK;
+  bucket_read_kernel<<<blocks_for(n, 256), 256, 0, st>>>(start, strand, n, key_table, key_min, bucket);
+  hawk_note_launch(1);
+  return hawk_check_cuda(cudaGetLastError(), "bucket_read_kernel launch");
+}
+
+}  // namespace hawk

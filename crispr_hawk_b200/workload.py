@@ -82,7 +82,7 @@ class Workload:
         batch = _cabi.Batch(self.ctx, hb["ascii"].numpy(), self.d.slot_off, self.d.lens)
         batch.set_posmap(self.d.seg)
         res = _cabi.search(self.ctx, batch, self.params, self.a, self.b, self.d.is_ref)
-        n, w = res.n_guides, res.window
+        n, w = res.n_guides, res.text_stride
         if hb["out"] is None or len(hb["out"]["hap"]) < n:
             cap = int(n * 1.05) + 1024
             mk = lambda dt, k=1: torch.empty(cap * k, dtype=dt, pin_memory=True).numpy()  # noqa: E731

@@ -140,17 +140,18 @@ int hawk_pam_search(hawk_ctx *ctx, hawk_batch *batch, const hawk_params *params,
 /* n_guides: rows of the table; n_hits[2]: records per strand in the result's
  * hit lists (hawk_pam_search: raw PAM hits; hawk_search: hits that survived
  * the in-range and REF-core filters, before resolution / redundancy removal);
- * window: characters per row (G + P + 20); scanned_bp: sum of scan_stop -
+ * window: characters per row (G + P + 20); text_stride: bytes per row of the text
+ * column (window rounded up to 16, zero padded); scanned_bp: sum of scan_stop -
  * scan_start, the unit of the haplotype-bp/s metric. */
 int hawk_result_info(hawk_result *result, int64_t *n_guides, int64_t *n_hits, int32_t *window,
-                     int64_t *scanned_bp);
+                     int32_t *text_stride, int64_t *scanned_bp);
 /* Copy the table to HOST arrays of n_guides rows: haplotype index, strand,
  * PAM position (haplotype-relative), genomic start/stop
  * (adjust_guide_position, :260-280), bucket = smallest row index among the
  * rows sharing the row's (start, strand) key, i.e. buckets ordered by bucket id
  * are in first-seen order (group_guides_position, :306-337), and the padded
- * window text (extract_guide_sequence / resolved string), `window` bytes per
- * row. Any pointer may be NULL. */
+ * window text (extract_guide_sequence / resolved string), `text_stride` bytes per
+ * row of which the first `window` are the text. Any pointer may be NULL. */
 int hawk_result_fetch(hawk_result *result, int32_t *hap, uint8_t *strand, int32_t *pos,
                       int32_t *start, int32_t *stop, int64_t *bucket, uint8_t *text);
 /* hit list of one strand: packed (hap << 32 | pos), ascending */
@@ -168,10 +169,11 @@ int hawk_batch_repack_dev(hawk_batch *batch, const uint8_t *d_ascii, int64_t *ba
 /* The context's cudaStream_t (so callers can time with events on the stream the kernels
  * run on) and optional per-kernel timing: with profiling on, every K1 / K2 launch of the
  * host layer is bracketed by CUDA events; hawk_ctx_profile returns and resets the sums.
- * ms[0] = K1 pack, ms[1] = K2 scan, ms[2] = post-scan pipeline; n[i] = launches. */
+ * ms[0] = K1 pack, ms[1] = K2 scan (span table + scan + segment prefix), ms[2] = guide-table
+ * pipeline, ms[3] = K3 segment compaction; n[i] = bracketed regions. */
 void *hawk_ctx_stream(hawk_ctx *ctx);
 int hawk_ctx_set_profiling(hawk_ctx *ctx, int32_t enabled);
-int hawk_ctx_profile(hawk_ctx *ctx, double *ms /* [3] */, int64_t *n /* [3] */);
+int hawk_ctx_profile(hawk_ctx *ctx, double *ms /* [4] */, int64_t *n /* [4] */);
 
 /* ---- device layer (asynchronous on `stream`, a cudaStream_t) -------------- */
 /* K1: ASCII slot space -> planes. d_bad: one int64, must hold INT64_MAX on
