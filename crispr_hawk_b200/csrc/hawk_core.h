@@ -219,8 +219,21 @@ struct PamSelect {
   uint32_t skip[2];
 };
 
-HAWK_HD void match_chunk2(const Planes& cur, const Planes& nxt, const PamSelect& S, int P,
-                          uint32_t m[2]) {
+template <int P>
+HAWK_HD void match_fixed(const Planes& cur, const Planes& nxt, const PamSelect& S, uint32_t m[2]) {
+  m[0] = m[1] = 0xFFFFFFFFu;
+  HAWK_UNROLL
+  for (int k = 0; k < P; ++k) {
+    const bool s0 = !((S.skip[0] >> k) & 1u), s1 = !((S.skip[1] >> k) & 1u);
+    if (!(s0 || s1)) continue;
+    const uint32_t a = funnel_r(cur.a, nxt.a, (uint32_t)k), c = funnel_r(cur.c, nxt.c, (uint32_t)k),
+                   g = funnel_r(cur.g, nxt.g, (uint32_t)k), t = funnel_r(cur.t, nxt.t, (uint32_t)k);
+    if (s0) m[0] &= (a & S.sel[0][k][0]) | (c & S.sel[0][k][1]) | (g & S.sel[0][k][2]) | (t & S.sel[0][k][3]);
+    if (s1) m[1] &= (a & S.sel[1][k][0]) | (c & S.sel[1][k][1]) | (g & S.sel[1][k][2]) | (t & S.sel[1][k][3]);
+  }
+}
+
+HAWK_HD void match_loop(const Planes& cur, const Planes& nxt, const PamSelect& S, int P, uint32_t m[2]) {
   m[0] = m[1] = 0xFFFFFFFFu;
   for (int k = 0; k < P; ++k) {
     const bool s0 = !((S.skip[0] >> k) & 1u), s1 = !((S.skip[1] >> k) & 1u);
@@ -229,6 +242,18 @@ HAWK_HD void match_chunk2(const Planes& cur, const Planes& nxt, const PamSelect&
                    g = funnel_r(cur.g, nxt.g, (uint32_t)k), t = funnel_r(cur.t, nxt.t, (uint32_t)k);
     if (s0) m[0] &= (a & S.sel[0][k][0]) | (c & S.sel[0][k][1]) | (g & S.sel[0][k][2]) | (t & S.sel[0][k][3]);
     if (s1) m[1] &= (a & S.sel[1][k][0]) | (c & S.sel[1][k][1]) | (g & S.sel[1][k][2]) | (t & S.sel[1][k][3]);
+  }
+}
+
+// the common PAM lengths get a fully unrolled matcher (P is uniform over the launch)
+HAWK_HD void match_chunk2(const Planes& cur, const Planes& nxt, const PamSelect& S, int P, uint32_t m[2]) {
+  switch (P) {
+    case 2: match_fixed<2>(cur, nxt, S, m); break;
+    case 3: match_fixed<3>(cur, nxt, S, m); break;
+    case 4: match_fixed<4>(cur, nxt, S, m); break;
+    case 5: match_fixed<5>(cur, nxt, S, m); break;
+    case 6: match_fixed<6>(cur, nxt, S, m); break;
+    default: match_loop(cur, nxt, S, P, m); break;
   }
 }
 
@@ -400,6 +425,7 @@ struct ScanConst {
   int32_t raw;          // 1: pam_search semantics (no in-range / REF-core filter)
   int32_t small;        // G <= 32 and C <= 33: a guide core reaches at most one case word either side
   int32_t back, ahead;  // case words before / after a chunk that can hold a core's variant base
+  uint32_t prev_mask, next_mask;  // K.small: bits of the previous / next case word within reach
   uint8_t pat[2][HAWK_MAX_PAM];  // [0] forward PAM, [1] reverse complement
   PamSelect sel;                 // plane-select masks of pat
   StrandGeom geom[2];   // per strand (right' = right XOR strand)
@@ -416,6 +442,9 @@ HAWK_HD ScanConst make_scan_const(const hawk_params& p, int raw) {
   k.small = (k.G <= 32 && k.C <= 33) ? 1 : 0;
   k.back = (k.G + 31) >> 5;       // left core starts G bases before the PAM position
   k.ahead = (31 + k.C - 1) >> 5;  // right core ends C - 1 bases after it
+  // chunk c holds a candidate position iff a variant bit lies in [32c - G, 32c + 31 + C - 1]
+  k.prev_mask = k.G >= 32 ? 0xFFFFFFFFu : (k.G <= 0 ? 0u : ~0u << (32 - k.G));
+  k.next_mask = (k.C - 1) >= 32 ? 0xFFFFFFFFu : ((1u << (k.C - 1)) - 1u);
   for (int i = 0; i < HAWK_MAX_PAM; ++i) {
     k.pat[0][i] = p.pam_fwd[i];
     k.pat[1][i] = p.pam_rc[i];
@@ -469,6 +498,39 @@ HAWK_HD HapScan load_hap_scan(const BatchView& B, const ScanConst& K, int32_t h)
   H.c_in_lo = in_lo <= 0 ? 0 : (in_lo + 31) >> 5;
   H.c_in_hi = in_hi <= 0 ? 0 : in_hi >> 5;
   return H;
+}
+
+// K.small form of scan_chunk below with the three case words of chunks c - 1, c, c + 1
+// handed in (the kernel queues them with the candidate); use_v = false for REF / pam_search
+// mode, where the case words play no role.
+HAWK_HD void scan_chunk_small(const BatchView& B, const ScanConst& K, const HapScan& H, int32_t c, uint32_t w0,
+                              uint32_t w1, uint32_t w2, bool use_v, uint32_t out[2], uint32_t raw[2]) {
+  const int32_t p0 = c << 5;
+  out[0] = out[1] = raw[0] = raw[1] = 0;
+  uint32_t inscan = 0xFFFFFFFFu, cand[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+  if (c < H.c_in_lo || c >= H.c_in_hi) {  // boundary chunk of the scan / window intervals
+    inscan = interval_mask(H.a, H.b, p0);
+    if (!inscan) return;
+    cand[0] = interval_mask(H.lo[0], H.hi[0], p0);
+    cand[1] = interval_mask(H.lo[1], H.hi[1], p0);
+  }
+  if (use_v) {
+    dilate96(w0, w1, w2, K.C);
+    HAWK_UNROLL
+    for (int s = 0; s < 2; ++s) {
+      // core of position p0 + i starts at window bit 32 + c0 + i (c0 = 0 or -G, G <= 32)
+      const uint32_t off = (uint32_t)(32 + K.geom[s].c0);
+      cand[s] &= (off == 32u) ? w1 : funnel_r(w0, w1, off);
+    }
+    if (!(cand[0] | cand[1])) return;
+  }
+  const Planes cur = B.q[H.chunk0 + c], nxt = B.q[H.chunk0 + c + 1];
+  uint32_t m[2];
+  match_chunk2(cur, nxt, K.sel, K.P, m);
+  raw[0] = m[0] & inscan;
+  raw[1] = m[1] & inscan;
+  out[0] = m[0] & cand[0];
+  out[1] = m[1] & cand[1];
 }
 
 // The whole per-position work of pam_search + the fused filters for the 32

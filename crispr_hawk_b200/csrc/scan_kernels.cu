@@ -68,7 +68,9 @@ constexpr int SPAN = HAWK_SPAN_CHUNKS;
 constexpr int SPAN_ROUNDS = SPAN / 128;
 constexpr int HALO = 4;  // case words either side of a span (HAWK_SLOT_GAP / 32)
 constexpr int VBUF_WORDS = SPAN + 2 * HALO;
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;
+constexpr int QCAP = 160;  // candidate ring entries per warp (<= 31 carried + 128 per round)
+__device__ __forceinline__ uint32_t qwrap(uint32_t x) { return x >= QCAP ? x - QCAP : x; }  // x < 2 QCAP
 static_assert(SPAN == 256, "candidate indices are stored as uint8");
 static_assert(HALO * 32 == HAWK_SLOT_GAP, "halo must be covered by the layout's zero gap");
 static_assert((VBUF_WORDS * 4) % 16 == 0, "tiles must keep 16-byte alignment");
@@ -149,8 +151,8 @@ __global__ void span_table_kernel(const int64_t* __restrict__ span_off, const in
 
 __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_kernel(const __grid_constant__ ScanArgs A) {
   __shared__ __align__(16) uint32_t vbuf[SCAN_WARPS][STAGES][VBUF_WORDS];
+  __shared__ __align__(16) uint4 queue[SCAN_WARPS][QCAP];  // candidate ring: {w(c-1), w(c), w(c+1), c}
   __shared__ __align__(8) uint64_t full_bar[SCAN_WARPS][STAGES];
-  __shared__ uint8_t cand_list[SCAN_WARPS][SPAN];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int unit = blockIdx.x * SCAN_WARPS + warp;
   if (unit >= A.n_units) return;
@@ -163,18 +165,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_kernel(co
   __syncwarp();
 
   // this warp's segment of the staging buffers
-  uint64_t seg_off[2], seg_cap[2];
+  uint64_t* seg_dst[2];
+  uint32_t seg_cap[2];
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
+    uint64_t off, cap;
     if (A.seg_prev) {  // exact retry: segments sized by the previous launch's per-unit totals
-      seg_off[s] = A.seg_prev_off[s * A.n_units + unit];
-      seg_cap[s] = A.seg_prev[s * A.n_units + unit];
+      off = A.seg_prev_off[s * A.n_units + unit];
+      cap = A.seg_prev[s * A.n_units + unit];
     } else {
-      const uint64_t lo = (uint64_t)(A.unit_frac[unit] * (double)A.cap[s]);
+      off = (uint64_t)(A.unit_frac[unit] * (double)A.cap[s]);
       const uint64_t hi = unit + 1 == A.n_units ? (uint64_t)A.cap[s] : (uint64_t)(A.unit_frac[unit + 1] * (double)A.cap[s]);
-      seg_off[s] = lo;
-      seg_cap[s] = hi - lo;
+      cap = hi - off;
     }
+    seg_dst[s] = A.stage[s] + off;
+    seg_cap[s] = cap > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cap;
   }
 
   // tile producer state (lane 0): haplotype of the last issued span
@@ -199,49 +204,116 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_kernel(co
 
   uint32_t raw_acc[2] = {0, 0};
   uint32_t run[2] = {0, 0};  // records this warp has produced so far
-  const uint32_t lt_mask = (1u << lane) - 1u;
   int32_t cur_hap = -1;
   HapScan H;
+  H.is_ref = 0;
+  uint32_t q_head = 0, q_n = 0;  // ring state (warp-uniform)
+
+  // hit bits of one chunk per lane -> records in the warp's segment, chunk order = lane order
+  auto emit = [&](const uint32_t out[2], int32_t c) {
+    const uint32_t pk = (uint32_t)__popc(out[0]) | ((uint32_t)__popc(out[1]) << 16);
+    if (!__any_sync(0xFFFFFFFFu, pk != 0)) return;
+    uint32_t incl = pk;  // both strands' counts in one word (<= 1024 each)
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += y;
+    }
+    const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31), excl = incl - pk;
+    const uint64_t p0 = ((uint64_t)(uint32_t)cur_hap << 32) | ((uint64_t)(uint32_t)c << 5);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      uint32_t bits = out[s];
+      uint32_t p = run[s] + ((excl >> (16 * s)) & 0xFFFFu);
+      const uint32_t t = (tot >> (16 * s)) & 0xFFFFu;
+      if (run[s] + t <= seg_cap[s]) {  // warp-uniform: the whole batch fits
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          seg_dst[s][p++] = p0 + (uint32_t)b;
+        }
+      } else {
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          if (p < seg_cap[s]) seg_dst[s][p] = p0 + (uint32_t)b;
+          ++p;
+        }
+      }
+      run[s] += t;
+    }
+  };
+
+  // match + filters for up to 32 queued candidates (n <= 32 taken from the ring head)
+  auto drain = [&](uint32_t n, const uint32_t* vs, int32_t c_first) {
+    uint32_t out[2] = {0, 0}, raw[2] = {0, 0};
+    int32_t c = 0;
+    if ((uint32_t)lane < n) {
+      const uint4 e = queue[warp][qwrap(q_head + lane)];
+      c = (int32_t)e.w;
+      if (A.K.small) {
+        scan_chunk_small(A.B, A.K, H, c, e.x, e.y, e.z, true, out, raw);
+      } else {  // long guides: the candidate's span is still resident (queue is flushed per span)
+        auto vword = [&](int64_t w) -> uint32_t {
+          const int32_t j = (int32_t)w - c_first + HALO;
+          return (w < 0 || w >= H.nchunks || j < 0 || j >= VBUF_WORDS) ? 0u : vs[j];
+        };
+        scan_chunk(A.B, A.K, H, (int64_t)c, vword, out, raw);
+      }
+    }
+    q_head = qwrap(q_head + n);
+    q_n -= n;
+    emit(out, c);
+  };
+
   int it = 0;
   for (int64_t span = sp0; span < sp1; ++span, ++it) {
     const int st = it % STAGES;
     const int2 e = __ldg(&A.span_tab[span]);
+    const uint32_t* vs = vbuf[warp][st];
     if (e.x != cur_hap) {
+      if (q_n) drain(q_n, vs, 0);  // K.small only: long-guide queues are empty between spans
       cur_hap = e.x;
       H = load_hap_scan(A.B, A.K, e.x);
     }
     mbar_wait(&full_bar[warp][st], (it / STAGES) & 1);
     const int32_t c_first = e.y;
-    const uint32_t* vs = vbuf[warp][st];
     const int32_t c_lo = H.a >> 5, c_end = (H.b + 31) >> 5;
-    const bool dense = A.K.raw || H.is_ref;
 
-    // ---- phase A: candidate chunks of this span
-    int n_cand = 0;
+    if (A.K.raw || H.is_ref) {
+      // ---- dense: every chunk of the scan interval is matched, 32 chunks per pass
+      for (int32_t base = c_first; base < c_first + SPAN && base < c_end; base += 32) {
+        const int32_t c = base + lane;
+        uint32_t out[2] = {0, 0}, raw[2] = {0, 0};
+        if (c >= c_lo && c < c_end) scan_chunk_small(A.B, A.K, H, c, 0u, 0u, 0u, false, out, raw);
+        raw_acc[0] += __popc(raw[0]);
+        raw_acc[1] += __popc(raw[1]);
+        emit(out, c);
+      }
+    } else {
+      // ---- sparse: chunks with a variant base in reach of a guide core go to the ring
 #pragma unroll
-    for (int r = 0; r < SPAN_ROUNDS; ++r) {
-      const int32_t base = c_first + r * 128;
-      const int32_t c4 = base + 4 * lane;  // first of this lane's 4 chunks
-      uint32_t cm = 0;
-      if (base < c_end) {  // warp-uniform
-        if (dense) {
-          cm = 0xF;
+      for (int r = 0; r < SPAN_ROUNDS; ++r) {
+        const int32_t base = c_first + r * 128;
+        if (base >= c_end) break;  // warp-uniform
+        const int32_t c4 = base + 4 * lane;  // first of this lane's 4 chunks
+        const uint4* t4 = reinterpret_cast<const uint4*>(vs + (c4 - c_first));  // words c4 - HALO ..
+        const uint4 L = t4[0], M = t4[1], R = t4[2];
+        uint32_t cm;
+        if (A.K.small) {
+          const uint32_t pm = A.K.prev_mask, nm = A.K.next_mask;
+          cm = (((L.w & pm) | M.x | (M.y & nm)) ? 1u : 0u) | (((M.x & pm) | M.y | (M.z & nm)) ? 2u : 0u) |
+               (((M.y & pm) | M.z | (M.w & nm)) ? 4u : 0u) | (((M.z & pm) | M.w | (R.x & nm)) ? 8u : 0u);
         } else {
-          const uint4* t4 = reinterpret_cast<const uint4*>(vs + (c4 - c_first));  // words c4 - HALO ..
-          const uint4 L = t4[0], M = t4[1], R = t4[2];
-          if (A.K.back == 1 && A.K.ahead == 1) {
-            cm = ((L.w | M.x | M.y) ? 1u : 0u) | ((M.x | M.y | M.z) ? 2u : 0u) |
-                 ((M.y | M.z | M.w) ? 4u : 0u) | ((M.z | M.w | R.x) ? 8u : 0u);
-          } else {
-            const uint32_t w[12] = {L.x, L.y, L.z, L.w, M.x, M.y, M.z, M.w, R.x, R.y, R.z, R.w};
+          const uint32_t w[12] = {L.x, L.y, L.z, L.w, M.x, M.y, M.z, M.w, R.x, R.y, R.z, R.w};
+          cm = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              uint32_t any = 0;
+          for (int k = 0; k < 4; ++k) {
+            uint32_t any = 0;
 #pragma unroll
-              for (int d = -4; d <= 4; ++d)
-                if (d >= -A.K.back && d <= A.K.ahead) any |= w[4 + k + d];
-              cm |= any ? (1u << k) : 0u;
-            }
+            for (int d = -4; d <= 4; ++d)
+              if (d >= -A.K.back && d <= A.K.ahead) any |= w[4 + k + d];
+            cm |= any ? (1u << k) : 0u;
           }
         }
         if (base < c_lo || base + 128 > c_end) {  // warp-uniform: round straddles the scan interval
@@ -249,60 +321,28 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_kernel(co
           for (int k = 0; k < 4; ++k)
             if (c4 + k < c_lo || c4 + k >= c_end) cm &= ~(1u << k);
         }
-      }
-      if (__any_sync(0xFFFFFFFFu, cm != 0)) {
-        const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, cm & 1u), b1 = __ballot_sync(0xFFFFFFFFu, cm & 2u),
-                       b2 = __ballot_sync(0xFFFFFFFFu, cm & 4u), b3 = __ballot_sync(0xFFFFFFFFu, cm & 8u);
-        int idx = n_cand + __popc(b0 & lt_mask) + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) +
-                  __popc(b3 & lt_mask);
-        const int local = r * 128 + 4 * lane;
+        if (!__any_sync(0xFFFFFFFFu, cm != 0)) continue;
+        // append this lane's candidates behind the earlier lanes' (chunk order)
+        const uint32_t mine = __popc(cm);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+          if (lane >= d) incl += y;
+        }
+        uint32_t idx = qwrap(qwrap(q_head + q_n) + (incl - mine));
+        const uint32_t wv[6] = {L.w, M.x, M.y, M.z, M.w, R.x};
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (cm & (1u << k)) cand_list[warp][idx++] = (uint8_t)(local + k);
-        n_cand += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+          if (cm & (1u << k)) {
+            queue[warp][idx] = make_uint4(wv[k], wv[k + 1], wv[k + 2], (uint32_t)(c4 + k));
+            idx = qwrap(idx + 1);
+          }
+        q_n += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        __syncwarp();
+        while (q_n >= 32) drain(32, vs, c_first);
       }
-    }
-    __syncwarp();
-
-    // ---- phase B: PAM match + filters on the candidates, 32 at a time, records out
-    auto vword = [&](int64_t w) -> uint32_t {
-      const int32_t j = (int32_t)w - c_first + HALO;
-      return (w < 0 || w >= H.nchunks || j >= VBUF_WORDS) ? 0u : vs[j];
-    };
-    const uint64_t hkey = (uint64_t)(uint32_t)cur_hap << 32;
-    for (int i0 = 0; i0 < n_cand; i0 += 32) {
-      const int i = i0 + lane;
-      uint32_t out[2] = {0, 0}, raw[2] = {0, 0};
-      int32_t c = 0;
-      if (i < n_cand) {
-        c = c_first + cand_list[warp][i];
-        scan_chunk(A.B, A.K, H, (int64_t)c, vword, out, raw);
-      }
-      raw_acc[0] += __popc(raw[0]);
-      raw_acc[1] += __popc(raw[1]);
-      const uint32_t pk = (uint32_t)__popc(out[0]) | ((uint32_t)__popc(out[1]) << 16);
-      if (!__any_sync(0xFFFFFFFFu, pk != 0)) continue;
-      uint32_t incl = pk;  // both strands' counts in one word (<= 1024 each)
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= d) incl += y;
-      }
-      const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31), excl = incl - pk;
-      const uint64_t p0 = hkey | ((uint64_t)(uint32_t)c << 5);
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        uint32_t bits = out[s];
-        uint64_t p = (uint64_t)run[s] + ((excl >> (16 * s)) & 0xFFFFu);
-        uint64_t* dst = A.stage[s] + seg_off[s];
-        while (bits) {
-          const int b = __ffs(bits) - 1;
-          bits &= bits - 1;
-          if (p < seg_cap[s]) dst[p] = p0 + (uint32_t)b;
-          ++p;
-        }
-        run[s] += (tot >> (16 * s)) & 0xFFFFu;
-      }
+      if (!A.K.small && q_n) drain(q_n, vs, c_first);  // <= 31 left: the tile goes away with the span
     }
     __syncwarp();
     // refill this stage with the span STAGES ahead (generic reads above are ordered before the
@@ -312,6 +352,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_kernel(co
       issue(span + STAGES, st);
     }
   }
+  if (q_n) drain(q_n, nullptr, 0);
 
   if (lane == 0) {
 #pragma unroll
@@ -372,9 +413,10 @@ struct CompactArgs {
   int32_t n_units;
 };
 
-__global__ void __launch_bounds__(256) compact_kernel(const __grid_constant__ CompactArgs A) {
-  const int unit = blockIdx.x * 8 + (threadIdx.x >> 5), s = blockIdx.y, lane = threadIdx.x & 31;
-  if (unit >= A.n_units) return;
+__global__ void __launch_bounds__(128) compact_kernel(const __grid_constant__ CompactArgs A) {
+  // one CTA per (unit, strand): segments are a few thousand records, so 128 threads with
+  // 4 independent 8-byte copies in flight each cover one in a couple of passes
+  const int unit = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
   uint64_t src_off, src_cap;
   if (A.seg_prev) {
     src_off = A.seg_prev_off[s * A.n_units + unit];
@@ -387,10 +429,19 @@ __global__ void __launch_bounds__(256) compact_kernel(const __grid_constant__ Co
   uint64_t n = A.seg_count[s * A.n_units + unit];
   if (n > src_cap) n = src_cap;  // overflowed segment: the launch is retried anyway
   const uint64_t base = A.seg_base[s * A.n_units + unit], cap = (uint64_t)A.out_cap[s];
-  const uint64_t* src = A.stage[s] + src_off;
-  uint64_t* dst = A.hits[s] + base;
-  for (uint64_t k = lane; k < n; k += 32)
-    if (base + k < cap) dst[k] = src[k];
+  if (base >= cap) return;
+  if (base + n > cap) n = cap - base;
+  const uint64_t* __restrict__ src = A.stage[s] + src_off;
+  uint64_t* __restrict__ dst = A.hits[s] + base;
+  uint64_t k = tid;
+  for (; k + 3 * 128 < n; k += 4 * 128) {
+    const uint64_t a = src[k], b = src[k + 128], c = src[k + 256], d = src[k + 384];
+    dst[k] = a;
+    dst[k + 128] = b;
+    dst[k + 256] = c;
+    dst[k + 384] = d;
+  }
+  for (; k < n; k += 128) dst[k] = src[k];
 }
 
 }  // namespace hawk
@@ -580,7 +631,7 @@ extern "C" int hawk_scan_compact_dev(void* stream, const double* d_unit_frac, in
   C.out_cap[0] = out_cap_fwd;
   C.out_cap[1] = out_cap_rev;
   C.n_units = n_units;
-  compact_kernel<<<dim3((unsigned)((n_units + 7) / 8), 2), 256, 0, (cudaStream_t)stream>>>(C);
+  compact_kernel<<<dim3((unsigned)n_units, 2), 128, 0, (cudaStream_t)stream>>>(C);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "compact_kernel launch");
 }
