@@ -36,6 +36,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL banners off stdout: rank 0 prints exactly one JSON line
+
 import numpy as np  # noqa: E402
 
 METRIC = "haplotype_bp_scanned_per_s"
@@ -212,7 +214,7 @@ def workload_config(args, scanned_bp, n_hap, sample=False):
                     f"{int(k['bed_len'] * args.scale):,} bp region, phased, {n_hap} haplotypes per rank"
                     + (" (CPU sample)" if sample else ""),
         "haplotypes_per_rank": n_hap, "scanned_bp_per_rank_per_step": scanned_bp,
-        "l2": "inputs exceed L2 (no flush needed)" if scanned_bp > 400e6 else "L2 flushed between steps",
+        "l2": "n/a (CPU arm)" if sample else ("inputs exceed L2 (no flush needed)" if scanned_bp > 400e6 else "L2 flushed between steps"),
         "seed": k["seed"],
     }  # fmt: skip
 
@@ -269,9 +271,7 @@ def run_product_arm(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         n_guides, n_hits = one_step()
     barrier()
-    ctx.set_profiling(True)
-    ctx.profile()
-    sampler = ClockSampler(local_rank).start()
+    sampler = None if args.no_clocks else ClockSampler(local_rank).start()
     launches0 = lib.hawk_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -283,8 +283,14 @@ def run_product_arm(args, rank, world, local_rank):
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     dev_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled"]}
     launches = lib.hawk_launch_count() - launches0
+    # per-kernel times: a separate pass with the library's CUDA-event brackets switched on
+    ctx.set_profiling(True)
+    ctx.profile()
+    prof_steps = max(3, min(args.steps, 10))
+    for _ in range(prof_steps):
+        one_step()
     prof = ctx.profile()
     ctx.set_profiling(False)
     # CUDA events on the context's stream (the launching stream); the host layer synchronises
@@ -309,12 +315,13 @@ def run_product_arm(args, rank, world, local_rank):
     pack_bytes = wl.pack_algorithmic_bytes()
     scan_bytes = wl.scan_algorithmic_bytes(hits_total)
     kernels["pack_kernel"] = {"ms": pack_ms, "algorithmic_bytes": pack_bytes, "gbs": pack_bytes / pack_ms / 1e6 if pack_ms else None,
-                              "launches_per_step": prof["pack"][1] / args.steps}  # fmt: skip
+                              "launches_per_step": prof["pack"][1] / prof_steps}  # fmt: skip
     kernels["scan_kernel"] = {"ms": scan_ms, "algorithmic_bytes": scan_bytes, "gbs": scan_bytes / scan_ms / 1e6 if scan_ms else None,
-                              "launches_per_step": prof["scan"][1] / args.steps}  # fmt: skip
-    kernels["post_pipeline"] = {"ms": post_ms, "launches_per_step": prof["post"][1] / args.steps}
+                              "launches_per_step": prof["scan"][1] / prof_steps,
+                              "note": "bracket = span table + scan_kernel + segment prefix"}  # fmt: skip
+    kernels["table_pipeline"] = {"ms": post_ms, "launches_per_step": prof["post"][1] / prof_steps}
     kernels["compact_kernel"] = {"ms": prof["compact"][0] / max(prof["compact"][1], 1),
-                                 "launches_per_step": prof["compact"][1] / args.steps}
+                                 "launches_per_step": prof["compact"][1] / prof_steps}
     dom = "pack_kernel" if pack_ms >= scan_ms else "scan_kernel"
     ach = kernels[dom]["gbs"] or 0.0
     roofline = {
@@ -379,7 +386,7 @@ def run_product_arm(args, rank, world, local_rank):
             "guides_per_step": total_guides, "hits_per_step_rank0": hits_total,
             "device_ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "profile_steps": prof_steps,
         }  # fmt: skip
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -410,6 +417,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not run nvidia-smi beside the timed region")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

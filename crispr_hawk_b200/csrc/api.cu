@@ -669,58 +669,64 @@ static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const Bat
       CK(launch_blk_prefix(st, blk_cnt[s].as<uint32_t>(), n_blk[s], blk_base[s].as<uint64_t>(),
                            d_tot.as<uint64_t>() + s));
   }
-  uint64_t kept[2] = {0, 0};
-  CKCUDA(cudaMemcpyAsync(kept, d_tot.p, 16, cudaMemcpyDeviceToHost, st));
-  CKCUDA(cudaStreamSynchronize(st));
-  tr.tick("table: rows + prefix + sync");
-  const int64_t n = (int64_t)(kept[0] + kept[1]);
+  // no host round trip here: the table is allocated for the upper bound (every hit kept)
+  // and the surviving-row totals are read once, after the last kernel
+  const int64_t n_max = n_hits[0] + n_hits[1];
   const int W = K.C + 2 * HAWK_GUIDESEQPAD;
-  r->n_guides = n;
   r->text_stride = (W + 15) / 16 * 16;
-  CK(r->hap.alloc(c, (size_t)n * 4));
-  CK(r->strand.alloc(c, (size_t)n));
-  CK(r->pos.alloc(c, (size_t)n * 4));
-  CK(r->start.alloc(c, (size_t)n * 4));
-  CK(r->stop.alloc(c, (size_t)n * 4));
-  CK(r->bucket.alloc(c, (size_t)n * 8));
-  CK(r->text.alloc(c, (size_t)n * r->text_stride));
-  if (n == 0) return HAWK_OK;
-  CK(d_kb.alloc(c, (size_t)(b->n_hap + 1) * 16));
-  CK(launch_hap_offsets(st, recs[0], recs[1], n_hits[0], n_hits[1], keep[0].as<uint8_t>(), keep[1].as<uint8_t>(),
-                        blk_base[0].as<uint64_t>(), blk_base[1].as<uint64_t>(), kept[0], kept[1], b->n_hap,
-                        d_kb.as<uint64_t>()));
-  // first-seen bucket ids: direct-address table over (start, strand) when the coordinate
-  // range allows it, else the hash table of post_kernels.cu
-  const int64_t key_span = b->gmax >= b->gmin ? ((int64_t)b->gmax - b->gmin + 1) * 2 : 0;
-  const bool direct = key_span > 0 && key_span <= (1ll << 28) && n < 0xFFFFFFFFll;
-  DevBuf key_table;
-  if (direct) {
-    CK(key_table.alloc(c, (size_t)key_span * 4));
-    CKCUDA(cudaMemsetAsync(key_table.p, 0xFF, (size_t)key_span * 4, st));
-  }
-  for (int s = 0; s < 2; ++s)
-    CK(launch_gather_fast(st, B, K, recs[s], keep[s].as<uint8_t>(), blk_base[s].as<uint64_t>(),
-                          start[s].as<int32_t>(), stop[s].as<int32_t>(),
-                          d_kb.as<uint64_t>() + (size_t)(1 - s) * (b->n_hap + 1), n_hits[s], s, r->text_stride,
-                          r->hap.as<int32_t>(), r->strand.as<uint8_t>(), r->pos.as<int32_t>(),
-                          r->start.as<int32_t>(), r->stop.as<int32_t>(), r->text.as<uint8_t>(),
-                          direct ? key_table.as<uint32_t>() : nullptr, b->gmin));
-  if (direct) {
-    CK(launch_bucket_read(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n, key_table.as<uint32_t>(), b->gmin,
-                          r->bucket.as<int64_t>()));
+  CK(r->hap.alloc(c, (size_t)n_max * 4));
+  CK(r->strand.alloc(c, (size_t)n_max));
+  CK(r->pos.alloc(c, (size_t)n_max * 4));
+  CK(r->start.alloc(c, (size_t)n_max * 4));
+  CK(r->stop.alloc(c, (size_t)n_max * 4));
+  CK(r->bucket.alloc(c, (size_t)n_max * 8));
+  CK(r->text.alloc(c, (size_t)n_max * r->text_stride));
+  uint64_t kept[2] = {0, 0};
+  if (n_max > 0) {
+    CK(d_kb.alloc(c, (size_t)(b->n_hap + 1) * 16));
+    CK(launch_hap_offsets(st, recs[0], recs[1], n_hits[0], n_hits[1], keep[0].as<uint8_t>(), keep[1].as<uint8_t>(),
+                          blk_base[0].as<uint64_t>(), blk_base[1].as<uint64_t>(), d_tot.as<uint64_t>(), b->n_hap,
+                          d_kb.as<uint64_t>()));
+    // first-seen bucket ids: direct-address table over (start, strand) when the coordinate
+    // range allows it, else the hash table of post_kernels.cu
+    const int64_t key_span = b->gmax >= b->gmin ? ((int64_t)b->gmax - b->gmin + 1) * 2 : 0;
+    const bool direct = key_span > 0 && key_span <= (1ll << 28) && n_max < 0xFFFFFFFFll;
+    DevBuf key_table;
+    if (direct) {
+      CK(key_table.alloc(c, (size_t)key_span * 4));
+      CKCUDA(cudaMemsetAsync(key_table.p, 0xFF, (size_t)key_span * 4, st));
+    }
+    for (int s = 0; s < 2; ++s)
+      CK(launch_gather_fast(st, B, K, recs[s], keep[s].as<uint8_t>(), blk_base[s].as<uint64_t>(),
+                            start[s].as<int32_t>(), stop[s].as<int32_t>(),
+                            d_kb.as<uint64_t>() + (size_t)(1 - s) * (b->n_hap + 1), n_hits[s], s, r->text_stride,
+                            r->hap.as<int32_t>(), r->strand.as<uint8_t>(), r->pos.as<int32_t>(),
+                            r->start.as<int32_t>(), r->stop.as<int32_t>(), r->text.as<uint8_t>(),
+                            direct ? key_table.as<uint32_t>() : nullptr, b->gmin));
+    if (direct)
+      CK(launch_bucket_read(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n_max, d_tot.as<uint64_t>(),
+                            key_table.as<uint32_t>(), b->gmin, r->bucket.as<int64_t>()));
+    CKCUDA(cudaMemcpyAsync(kept, d_tot.p, 16, cudaMemcpyDeviceToHost, st));
+    c->close_mark();
+    CKCUDA(cudaStreamSynchronize(st));
+    tr.tick("table: pipeline + sync");
+    const int64_t n = (int64_t)(kept[0] + kept[1]);
+    r->n_guides = n;
+    if (!direct && n > 0) {
+      uint64_t tsize = 1024;
+      while (tsize < (uint64_t)n * 2) tsize <<= 1;
+      DevBuf keys, vals;
+      CK(keys.alloc(c, tsize * 8));
+      CK(vals.alloc(c, tsize * 8));
+      CKCUDA(cudaMemsetAsync(keys.p, 0xFF, tsize * 8, st));
+      CKCUDA(cudaMemsetAsync(vals.p, 0xFF, tsize * 8, st));
+      CK(launch_buckets(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n, keys.as<unsigned long long>(),
+                        vals.as<unsigned long long>(), tsize, r->bucket.as<int64_t>()));
+      CKCUDA(cudaStreamSynchronize(st));  // keys / vals are released on return
+    }
   } else {
-    uint64_t tsize = 1024;
-    while (tsize < (uint64_t)n * 2) tsize <<= 1;
-    DevBuf keys, vals;
-    CK(keys.alloc(c, tsize * 8));
-    CK(vals.alloc(c, tsize * 8));
-    CKCUDA(cudaMemsetAsync(keys.p, 0xFF, tsize * 8, st));
-    CKCUDA(cudaMemsetAsync(vals.p, 0xFF, tsize * 8, st));
-    CK(launch_buckets(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n, keys.as<unsigned long long>(),
-                      vals.as<unsigned long long>(), tsize, r->bucket.as<int64_t>()));
-    CKCUDA(cudaStreamSynchronize(st));  // keys / vals are released on return
+    c->close_mark();
   }
-  tr.tick("table: gather launched");
   return HAWK_OK;
 }
 
@@ -767,9 +773,6 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
     const int64_t n_hits[2] = {so.n[0], so.n[1]};
     if (!unphased) {
       if ((rc = search_fast(c, b, K, B, so, ref_h, r))) break;
-      c->close_mark();
-      if ((rc = hawk_check_cuda(cudaStreamSynchronize(st), "search sync"))) break;
-      tr.tick("table: final sync");
       for (int s = 0; s < 2; ++s) {
         r->n_hits[s] = n_hits[s];
         r->hits[s].move_from(so.hits[s]);

@@ -21,7 +21,7 @@
 
 namespace hawk {
 
-struct Planes {
+struct alignas(16) Planes {
   uint32_t a, c, g, t;
 };
 
@@ -375,14 +375,16 @@ HAWK_HD uint32_t lower_at(const uint32_t* v, int64_t chunk0, int64_t pos) {
 HAWK_HD bool cores_equal(const Planes* q, int64_t chunk0_a, int64_t pos_a, int64_t chunk0_b,
                          int64_t pos_b, int C) {
   for (int done = 0; done < C; done += 32) {
-    int n = C - done < 32 ? C - done : 32;
-    uint32_t keep = n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
-    uint32_t diff = 0;
-    for (int plane = 0; plane < 4; ++plane) {
-      auto wa = [&](int64_t w) { return (&q[chunk0_a + w].a)[plane]; };
-      auto wb = [&](int64_t w) { return (&q[chunk0_b + w].a)[plane]; };
-      diff |= bits32_at(wa, pos_a + done) ^ bits32_at(wb, pos_b + done);
-    }
+    const int n = C - done < 32 ? C - done : 32;
+    const uint32_t keep = n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
+    const int64_t ba = pos_a + done, bb = pos_b + done;
+    const Planes a0 = q[chunk0_a + (ba >> 5)], a1 = q[chunk0_a + (ba >> 5) + 1];
+    const Planes b0 = q[chunk0_b + (bb >> 5)], b1 = q[chunk0_b + (bb >> 5) + 1];
+    const uint32_t sa = (uint32_t)(ba & 31), sb = (uint32_t)(bb & 31);
+    const uint32_t diff = (funnel_r(a0.a, a1.a, sa) ^ funnel_r(b0.a, b1.a, sb)) |
+                          (funnel_r(a0.c, a1.c, sa) ^ funnel_r(b0.c, b1.c, sb)) |
+                          (funnel_r(a0.g, a1.g, sa) ^ funnel_r(b0.g, b1.g, sb)) |
+                          (funnel_r(a0.t, a1.t, sa) ^ funnel_r(b0.t, b1.t, sb));
     if (diff & keep) return false;
   }
   return true;
@@ -598,8 +600,17 @@ HAWK_HD RowCoords row_coords(const BatchView& B, const ScanConst& K, int32_t h, 
   const StrandGeom& g = K.geom[s];
   r.pivot = pos + g.c0;
   int64_t s0 = B.seg_off[h], s1 = B.seg_off[h + 1];
-  r.start = posmap_eval(B.seg_rel, B.seg_gen, B.seg_step, s0, s1, r.pivot);
-  r.stop = posmap_eval(B.seg_rel, B.seg_gen, B.seg_step, s0, s1, pos + g.stop_off);
+  // last segment with seg_rel <= pivot, then walk forward to the one holding the stop index
+  // (a guide spans G + P bases: almost always the same segment or the next)
+  int64_t lo = s0, hi = s1;
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (B.seg_rel[mid] <= r.pivot) lo = mid; else hi = mid;
+  }
+  r.start = B.seg_gen[lo] + (B.seg_step[lo] ? (r.pivot - B.seg_rel[lo]) : 0);
+  const int32_t j = pos + g.stop_off;
+  while (lo + 1 < s1 && B.seg_rel[lo + 1] <= j) ++lo;
+  r.stop = B.seg_gen[lo] + (B.seg_step[lo] ? (j - B.seg_rel[lo]) : 0);
   return r;
 }
 

@@ -49,15 +49,15 @@ int launch_rows_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, co
                      int32_t* stop, uint8_t* keep, uint32_t* blk_cnt);
 int launch_blk_prefix(cudaStream_t st, const uint32_t* cnt, int64_t n_blk, uint64_t* base, uint64_t* total);
 int launch_hap_offsets(cudaStream_t st, const uint64_t* r0, const uint64_t* r1, int64_t n0, int64_t n1,
-                       const uint8_t* k0, const uint8_t* k1, const uint64_t* b0, const uint64_t* b1, uint64_t t0,
-                       uint64_t t1, int32_t n_hap, uint64_t* kb);
+                       const uint8_t* k0, const uint8_t* k1, const uint64_t* b0, const uint64_t* b1,
+                       const uint64_t* totals, int32_t n_hap, uint64_t* kb);
 int launch_gather_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* recs,
                        const uint8_t* keep, const uint64_t* blk_base, const int32_t* start, const int32_t* stop,
                        const uint64_t* kb_other, int64_t n, int s, int32_t text_stride, int32_t* o_hap,
                        uint8_t* o_strand, int32_t* o_pos, int32_t* o_start, int32_t* o_stop, uint8_t* o_text,
                        uint32_t* key_table, int32_t key_min);
-int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n,
-                       const uint32_t* key_table, int32_t key_min, int64_t* bucket);
+int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n_max,
+                       const uint64_t* totals, const uint32_t* key_table, int32_t key_min, int64_t* bucket);
 
 int64_t scan_tiles(int64_t n);
 int exclusive_scan_u8(cudaStream_t st, const uint8_t* in, int64_t n, uint64_t* out, uint64_t* tile_sums);

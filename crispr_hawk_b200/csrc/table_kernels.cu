@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(1024) blk_prefix_kernel(const uint32_t* __rest
 __global__ void hap_offsets_kernel(const uint64_t* __restrict__ recs0, const uint64_t* __restrict__ recs1,
                                    int64_t n0, int64_t n1, const uint8_t* __restrict__ keep0,
                                    const uint8_t* __restrict__ keep1, const uint64_t* __restrict__ base0,
-                                   const uint64_t* __restrict__ base1, uint64_t total0, uint64_t total1,
+                                   const uint64_t* __restrict__ base1, const uint64_t* __restrict__ totals,
                                    int32_t n_hap, uint64_t* __restrict__ kb) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 2 * (int64_t)(n_hap + 1)) return;
@@ -141,7 +141,7 @@ __global__ void hap_offsets_kernel(const uint64_t* __restrict__ recs0, const uin
   }
   uint64_t r;
   if (lo >= n) {
-    r = s ? total1 : total0;
+    r = totals[s];
   } else {
     const int64_t b0 = lo / ROW_T * ROW_T;
     r = base[lo / ROW_T];
@@ -173,21 +173,35 @@ struct GatherFastArgs {
   int32_t key_min;      // smallest genomic coordinate of the batch
 };
 
-// 16 window characters starting at window offset j0 from the plane bits of [o, o + 32)
+// four plane bits (one per character) -> one bit per byte: bit j lands at 8j (the 16 partial
+// products of the multiply fall on distinct bit positions, so nothing carries)
+__device__ __forceinline__ uint32_t spread4(uint32_t x) { return (x * 0x00204081u) & 0x01010101u; }
+
+// 4 window characters from the plane bits at bit offset i: the nibbles are spread to bytes,
+// turned into a byte-permute selector and looked up in the 16-letter table "?ACMGRSVTWYHKDBN"
+// held in four registers; lower-case = bit 5 from the case plane
+__device__ __forceinline__ uint32_t chars4(uint32_t pa, uint32_t pc, uint32_t pg, uint32_t pt, uint32_t pv, int i) {
+  const uint32_t lo3 = spread4((pa >> i) & 0xFu) | (spread4((pc >> i) & 0xFu) << 1) | (spread4((pg >> i) & 0xFu) << 2);
+  const uint32_t hi = spread4((pt >> i) & 0xFu);  // base T: table entries 8..15
+  uint32_t sel = (lo3 | (lo3 >> 4)) & 0x00FF00FFu;
+  sel = (sel | (sel >> 8)) & 0xFFFFu;
+  const uint32_t x0 = __byte_perm(0x4D43413Fu /* ?ACM */, 0x56535247u /* GRSV */, sel);
+  const uint32_t x1 = __byte_perm(0x48595754u /* TWYH */, 0x4E42444Bu /* KDBN */, sel);
+  const uint32_t m = hi * 0xFFu;
+  return ((x0 & ~m) | (x1 & m)) | (spread4((pv >> i) & 0xFu) << 5);
+}
+
+// 16 window characters starting at window offset j0 (plane bits i0 .. i0 + 15); bytes at or
+// beyond W are zero
 __device__ __forceinline__ uint4 window_chars(uint32_t pa, uint32_t pc, uint32_t pg, uint32_t pt, uint32_t pv,
                                               int i0, int W, int j0) {
   uint32_t w[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    uint32_t word = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = i0 + 4 * q + j;
-      const uint32_t n = ((pa >> i) & 1u) | (((pc >> i) & 1u) << 1) | (((pg >> i) & 1u) << 2) | (((pt >> i) & 1u) << 3);
-      uint32_t ch = (uint32_t)(uint8_t)nibble_letter(n) | (((pv >> i) & 1u) << 5);
-      if (j0 + 4 * q + j >= W) ch = 0;
-      word |= ch << (8 * j);
-    }
+    uint32_t word = chars4(pa, pc, pg, pt, pv, i0 + 4 * q);
+    const int left = W - (j0 + 4 * q);  // characters of this word inside the window
+    if (left <= 0) word = 0;
+    else if (left < 4) word &= (1u << (8 * left)) - 1u;
     w[q] = word;
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
@@ -233,11 +247,11 @@ __global__ void __launch_bounds__(ROW_T) gather_fast_kernel(const __grid_constan
   }
 }
 
-__global__ void bucket_read_kernel(const int32_t* __restrict__ start, const uint8_t* __restrict__ strand, int64_t n,
-                                   const uint32_t* __restrict__ key_table, int32_t key_min,
-                                   int64_t* __restrict__ bucket) {
+__global__ void bucket_read_kernel(const int32_t* __restrict__ start, const uint8_t* __restrict__ strand,
+                                   const uint64_t* __restrict__ totals, const uint32_t* __restrict__ key_table,
+                                   int32_t key_min, int64_t* __restrict__ bucket) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= (int64_t)(totals[0] + totals[1])) return;
   bucket[i] = (int64_t)key_table[((uint32_t)(start[i] - key_min) << 1) | strand[i]];
 }
 
@@ -273,10 +287,10 @@ int launch_blk_prefix(cudaStream_t st, const uint32_t* cnt, int64_t n_blk, uint6
 }
 
 int launch_hap_offsets(cudaStream_t st, const uint64_t* r0, const uint64_t* r1, int64_t n0, int64_t n1,
-                       const uint8_t* k0, const uint8_t* k1, const uint64_t* b0, const uint64_t* b1, uint64_t t0,
-                       uint64_t t1, int32_t n_hap, uint64_t* kb) {
+                       const uint8_t* k0, const uint8_t* k1, const uint64_t* b0, const uint64_t* b1,
+                       const uint64_t* totals, int32_t n_hap, uint64_t* kb) {
   const int64_t n = 2 * (int64_t)(n_hap + 1);
-  hap_offsets_kernel<<<blocks_for(n, 128), 128, 0, st>>>(r0, r1, n0, n1, k0, k1, b0, b1, t0, t1, n_hap, kb);
+  hap_offsets_kernel<<<blocks_for(n, 128), 128, 0, st>>>(r0, r1, n0, n1, k0, k1, b0, b1, totals, n_hap, kb);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "hap_offsets_kernel launch");
 }
@@ -294,10 +308,10 @@ int launch_gather_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, 
   return hawk_check_cuda(cudaGetLastError(), "gather_fast_kernel launch");
 }
 
-int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n,
-                       const uint32_t* key_table, int32_t key_min, int64_t* bucket) {
-  if (n <= 0) return HAWK_OK;
-  bucket_read_kernel<<<blocks_for(n, 256), 256, 0, st>>>(start, strand, n, key_table, key_min, bucket);
+int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n_max,
+                       const uint64_t* totals, const uint32_t* key_table, int32_t key_min, int64_t* bucket) {
+  if (n_max <= 0) return HAWK_OK;
+  bucket_read_kernel<<<blocks_for(n_max, 256), 256, 0, st>>>(start, strand, totals, key_table, key_min, bucket);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "bucket_read_kernel launch");
 }
