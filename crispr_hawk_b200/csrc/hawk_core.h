@@ -86,17 +86,34 @@ HAWK_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
 #endif
 }
 
-// 8x8 bit-matrix transpose: byte k of the result holds bit k of the eight input bytes
-// (bit i of it comes from input byte i)
-HAWK_HD uint64_t transpose8x8(uint64_t x) {
-  uint64_t t;
-  t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;
-  x ^= t ^ (t << 7);
-  t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull;
-  x ^= t ^ (t << 14);
-  t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull;
-  x ^= t ^ (t << 28);
-  return x;
+// 8x8 bit-matrix transpose of the eight bytes held in (lo, hi): afterwards byte k holds bit k
+// of the eight input bytes (bit i of it comes from input byte i). Three delta swaps; the first
+// two stay inside each 32-bit half. t and its shifted copy never overlap, so "t ^ (t << s)"
+// is the multiply t * (1 + 2^s): that moves a third of the work from the ALU pipe (shifts,
+// LOP3) to the otherwise idle FMA pipe (IMAD) -- K1 is bound by the ALU pipe, not by HBM.
+// x >> S through the multiplier (high half of x * 2^(32-S)) on the GPU
+template <int S>
+HAWK_HD uint32_t shr_mul(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(x, 1u << (32 - S));
+#else
+  return x >> S;
+#endif
+}
+
+HAWK_HD void transpose8x8(uint32_t& lo, uint32_t& hi) {
+  uint32_t t;
+  t = (lo ^ shr_mul<7>(lo)) & 0x00AA00AAu;
+  lo ^= t * 129u;
+  t = (hi ^ shr_mul<7>(hi)) & 0x00AA00AAu;
+  hi ^= t * 129u;
+  t = (lo ^ shr_mul<14>(lo)) & 0x0000CCCCu;
+  lo ^= t * 16385u;
+  t = (hi ^ shr_mul<14>(hi)) & 0x0000CCCCu;
+  hi ^= t * 16385u;
+  t = (lo ^ (hi * 16u)) & 0xF0F0F0F0u;
+  lo ^= t;
+  hi ^= shr_mul<4>(t);
 }
 
 // truth table over the letter number (ch & 31): bit L set <=> the IUPAC code of letter L
@@ -132,9 +149,9 @@ HAWK_HD PackedChunk pack_chunk(const uint32_t* words) {
   uint32_t lo[4], hi[4];
   HAWK_UNROLL
   for (int g = 0; g < 4; ++g) {
-    uint64_t t = transpose8x8(((uint64_t)words[2 * g + 1] << 32) | words[2 * g]);
-    lo[g] = (uint32_t)t;          // bytes: bit planes 0..3 of characters 8g .. 8g+7
-    hi[g] = (uint32_t)(t >> 32);  // bit planes 4..7
+    lo[g] = words[2 * g];      // -> bytes: bit planes 0..3 of characters 8g .. 8g+7
+    hi[g] = words[2 * g + 1];  // -> bit planes 4..7
+    transpose8x8(lo[g], hi[g]);
   }
   uint32_t b[8];
   HAWK_UNROLL
