@@ -125,3 +125,43 @@ def test_full_size_config2_properties():
     got = {kcol: table[kcol][sel] for kcol in COLS + ("text",)}
     got["hap"] = np.searchsorted(subset, got["hap"]).astype(np.int32)
     assert_tables_equal(got, {kcol: want[kcol][oo] for kcol in COLS + ("text",)}, "config 2 subset")
+
+
+def _run_against_oracle(c, pam, G, right):
+    wl = Workload(c, pam, G, right)
+    res = wl.step_resident()
+    table = res.table()
+    res.close()
+    check_bucket_ids(table)
+    want = oracle_table(wl, np.arange(c.n_hap))
+    assert_tables_equal(final_order(table), want, f"{pam}/{G}")
+    return wl, table
+
+
+def test_dense_hits_force_the_exact_retry():
+    """PAM `N` hits every position on both strands: far more records than the staging
+    estimate, so K2 is re-run with the exact per-warp segment sizes (and a larger staging
+    area). The table must still be bit-exact."""
+    c = synth.make_cohort(bed_len=150_000, n_alt_hap=5, n_sites=1500, mean_alts_per_hap=300, seed=8,
+                          snv_frac=0.7, ins_frac=0.15, max_indel=6)  # fmt: skip
+    wl, table = _run_against_oracle(c, "N", 20, False)
+    assert len(table["hap"]) > 2 * 150_000 - 200  # every REF position, both strands
+    raw = _cabi.pam_search(wl.ctx, wl.batch, wl.params, wl.a, wl.b)
+    assert raw.n_hits[0] == raw.n_hits[1] == wl.scanned_bp
+    raw.close()
+
+
+@pytest.mark.parametrize("pam,G,right", [("NGG", 40, False), ("TTTV", 70, True), ("NNGRRT", 33, False)])
+def test_long_guides_take_the_generic_path(pam, G, right):
+    """G > 32 or G + P > 33 leaves the 96-bit case-window fast path of the scan kernel."""
+    c = synth.make_cohort(bed_len=60_000, n_alt_hap=9, n_sites=900, mean_alts_per_hap=150, seed=12,
+                          snv_frac=0.6, ins_frac=0.2, max_indel=8)  # fmt: skip
+    _, table = _run_against_oracle(c, pam, G, right)
+    assert len(table["hap"]) > 500
+
+
+def test_sacas9_and_short_guides():
+    c = synth.make_cohort(bed_len=80_000, n_alt_hap=12, n_sites=1200, mean_alts_per_hap=200, seed=13,
+                          snv_frac=0.7, ins_frac=0.15, max_indel=10)  # fmt: skip
+    for pam, G, right in (("NNGRRT", 21, False), ("TTN", 23, True), ("NGG", 1, False), ("G", 5, True)):
+        _run_against_oracle(c, pam, G, right)

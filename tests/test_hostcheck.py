@@ -49,3 +49,44 @@ def test_core_matches_golden(case):
     assert got_hits == case["pam_hits"]
     tab = hostcheck.search(case["pam"], region, haps, G, case["right"], case["variants_present"], case["phased"])
     assert table_to_tuples(tab, haps, G, P, case["right"]) == golden_guides(case)
+
+
+LONG = CASES[:4] + CASES[4:36:4] + CASES[36:55:5]
+
+
+@pytest.mark.parametrize("case", LONG, ids=[c["name"] for c in LONG])
+@pytest.mark.parametrize("guidelen", [33, 60])
+def test_core_long_guides_match_oracle(case, guidelen):
+    """Guides longer than 32 nt leave the kernels' 96-bit fast path (K.small == 0): the generic
+    sliding-window code must agree with the oracle too. (Hits near the region ends disappear
+    because the fixed 100-bp padding no longer covers guide + pad -- same in the reference.)"""
+    region, haps = fixture_objects(case)
+    P = len(case["pam"])
+    tab = hostcheck.search(case["pam"], region, haps, guidelen, case["right"], case["variants_present"], case["phased"])
+    want = O.search(case["pam"], region.start, region.stop, [O.OracleHap.from_object(h) for h in haps], guidelen,
+                    case["right"], case["variants_present"], case["phased"])  # fmt: skip
+    assert table_to_tuples(tab, haps, guidelen, P, case["right"]) == want
+
+
+def test_pack_every_byte_value():
+    """K1's boolean network against the table for all 256 byte values (NUL = unused slot)."""
+    valid = "ACGTNRYSWKMBDHV"
+    buf = np.zeros(256 + 128, np.uint8)
+    buf[128:384] = np.arange(256, dtype=np.uint8)
+    q = np.zeros((len(buf) // 32 + 8) * 4, np.uint32)
+    v = np.zeros(len(buf) // 32 + 8, np.uint32)
+    import ctypes as C
+
+    bad = hostcheck.lib().hawkcheck_pack(buf.ctypes.data_as(C.c_void_p), C.c_int64(len(buf)),
+                                         q.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p))  # fmt: skip
+    assert bad == 128 + 1  # first non-IUPAC, non-NUL byte
+    planes = q.reshape(-1, 4)
+    for b in range(256):
+        slot = 128 + b
+        nib = sum(((int(planes[slot // 32, k]) >> (slot % 32)) & 1) << k for k in range(4))
+        low = (int(v[slot // 32]) >> (slot % 32)) & 1
+        ch = chr(b)
+        if ch.upper() in valid and ch.isalpha() and b < 128:
+            assert nib == O.IUPAC_BITS[ch.upper()] and low == int(ch.islower()), b
+        else:
+            assert nib == 0 and low == 0, b
