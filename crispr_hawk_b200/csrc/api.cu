@@ -115,6 +115,24 @@ struct hawk_ctx {
     return p;
   }
   void give(void* p, size_t bytes) { free_blocks.push_back(Block{p, bytes}); }
+  // pinned host staging for the small per-search uploads (one H2D copy instead of six)
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  void* pinned_get(size_t n) {
+    if (n > pinned_bytes) {
+      if (pinned) cudaFreeHost(pinned);
+      pinned = nullptr;
+      pinned_bytes = 0;
+      const size_t want = (n * 2 + 4095) & ~(size_t)4095;
+      if (cudaHostAlloc(&pinned, want, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        pinned = nullptr;
+        return nullptr;
+      }
+      pinned_bytes = want;
+    }
+    return pinned;
+  }
   void trim() {
     for (auto& b : free_blocks) cudaFree(b.p);
     free_blocks.clear();
@@ -233,6 +251,7 @@ extern "C" int hawk_ctx_destroy(hawk_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->trim();
+  if (c->pinned) cudaFreeHost(c->pinned);
   cudaStreamDestroy(c->stream);
   delete c;
   return HAWK_OK;
@@ -513,19 +532,33 @@ struct ScanOut {
 // run K2 into the staging segments; if a warp's share of the staging capacity overflowed,
 // run it once more with the exact per-warp sizes the first launch counted; then concatenate
 // the segments into exactly-sized hit lists
+struct ScanInputs {  // per-search arrays on the device, carved out of one upload
+  DevBuf buf;
+  int32_t *a = nullptr, *b = nullptr;
+  uint8_t* is_ref = nullptr;
+  int64_t *span_off = nullptr, *unit_span = nullptr;
+  double* unit_frac = nullptr;
+};
+
 static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const int32_t* scan_start,
-                    const int32_t* scan_stop, const uint8_t* is_ref, int raw, DevBuf& d_a,
-                    DevBuf& d_b, DevBuf& d_isref, ScanOut& out) {
+                    const int32_t* scan_stop, const uint8_t* is_ref, int raw, ScanInputs& in, ScanOut& out) {
   cudaStream_t st = c->stream;
   Trace tr;
   const int32_t n_hap = b->n_hap;
-  std::vector<int64_t> span_off(n_hap + 1);
-  const int64_t n_spans = hawk_scan_plan(scan_start, scan_stop, is_ref, n_hap, raw, 0, span_off.data(), nullptr, nullptr);
+  // layout of the staging block (8-byte aligned pieces)
+  auto al8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
+  const int32_t max_units = hawk_scan_units(c->sm_count, INT64_MAX);
+  const size_t o_span = 0, o_unit = o_span + (size_t)(n_hap + 1) * 8, o_frac = o_unit + (size_t)(max_units + 1) * 8,
+               o_a = o_frac + (size_t)(max_units + 1) * 8, o_b = o_a + al8((size_t)n_hap * 4),
+               o_ref = o_b + al8((size_t)n_hap * 4), total_bytes = o_ref + al8((size_t)n_hap);
+  char* hp = (char*)c->pinned_get(total_bytes);
+  if (!hp) return hawk_fail(HAWK_ENOMEM, "pinned staging allocation failed");
+  int64_t* span_off = (int64_t*)(hp + o_span);
+  int64_t* unit_span = (int64_t*)(hp + o_unit);
+  double* unit_frac = (double*)(hp + o_frac);
+  const int64_t n_spans = hawk_scan_plan(scan_start, scan_stop, is_ref, n_hap, raw, 0, span_off, nullptr, nullptr);
   const int32_t n_units = hawk_scan_units(c->sm_count, n_spans);
-  std::vector<int64_t> unit_span((size_t)n_units + 1);
-  std::vector<double> unit_frac((size_t)n_units + 1);
-  if (n_units > 0)
-    hawk_scan_plan(scan_start, scan_stop, is_ref, n_hap, raw, n_units, span_off.data(), unit_span.data(), unit_frac.data());
+  if (n_units > 0) hawk_scan_plan(scan_start, scan_stop, is_ref, n_hap, raw, n_units, nullptr, unit_span, unit_frac);
   int64_t est = 4096;
   out.scanned_bp = 0;
   for (int32_t h = 0; h < n_hap; ++h) {
@@ -534,14 +567,22 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
     out.scanned_bp += e - a;
     est += (raw || is_ref[h]) ? (e - a) / 3 : (e - a) / 48;
   }
-  CK(upload(c, d_a, scan_start, (size_t)n_hap * 4));
-  CK(upload(c, d_b, scan_stop, (size_t)n_hap * 4));
-  CK(upload(c, d_isref, is_ref, (size_t)n_hap));
+  if (n_hap > 0) {
+    memcpy(hp + o_a, scan_start, (size_t)n_hap * 4);
+    memcpy(hp + o_b, scan_stop, (size_t)n_hap * 4);
+    memcpy(hp + o_ref, is_ref, (size_t)n_hap);
+  }
+  CK(in.buf.alloc(c, total_bytes));
+  CKCUDA(cudaMemcpyAsync(in.buf.p, hp, total_bytes, cudaMemcpyHostToDevice, st));
+  char* dp = (char*)in.buf.p;
+  in.span_off = (int64_t*)(dp + o_span);
+  in.unit_span = (int64_t*)(dp + o_unit);
+  in.unit_frac = (double*)(dp + o_frac);
+  in.a = (int32_t*)(dp + o_a);
+  in.b = (int32_t*)(dp + o_b);
+  in.is_ref = (uint8_t*)(dp + o_ref);
   if (n_spans == 0) return HAWK_OK;
-  DevBuf d_span_off, d_unit_span, d_unit_frac, d_counts, d_ws;
-  CK(upload(c, d_span_off, span_off.data(), (size_t)(n_hap + 1) * 8));
-  CK(upload(c, d_unit_span, unit_span.data(), ((size_t)n_units + 1) * 8));
-  CK(upload(c, d_unit_frac, unit_frac.data(), ((size_t)n_units + 1) * 8));
+  DevBuf d_counts, d_ws;
   CK(d_counts.alloc(c, 64));
   tr.tick("scan: plan + uploads");
   int64_t cap[2] = {est, est};
@@ -551,10 +592,9 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
     cudaEvent_t ev;
     c->mark(1, &ev);
     int src = hawk_scan_dev(st, b->q.p, b->v.as<uint32_t>(), b->d_slot_off.as<int64_t>(),
-                            b->d_len.as<int32_t>(), d_a.as<int32_t>(), d_b.as<int32_t>(),
-                            d_isref.as<uint8_t>(), d_span_off.as<int64_t>(), d_unit_span.as<int64_t>(),
-                            d_unit_frac.as<double>(), n_hap, n_spans, n_units, params, raw, exact,
-                            cap[0], cap[1], d_counts.as<uint64_t>(), d_ws.p);
+                            b->d_len.as<int32_t>(), in.a, in.b, in.is_ref, in.span_off, in.unit_span,
+                            in.unit_frac, n_hap, n_spans, n_units, params, raw, exact, cap[0], cap[1],
+                            d_counts.as<uint64_t>(), d_ws.p);
     c->close_mark();
     CK(src);
     tr.tick("scan: launch");
@@ -582,7 +622,7 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
   }
   for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(c, (size_t)(out.n[s] > 0 ? out.n[s] : 1) * 8));
   c->mark(3, nullptr);
-  int crc = hawk_scan_compact_dev(st, d_unit_frac.as<double>(), n_units, n_spans, exact, cap[0], cap[1], d_ws.p,
+  int crc = hawk_scan_compact_dev(st, in.unit_frac, n_units, n_spans, exact, cap[0], cap[1], d_ws.p,
                                   out.hits[0].as<uint64_t>(), out.hits[1].as<uint64_t>(), out.n[0], out.n[1]);
   c->close_mark();
   CK(crc);
@@ -615,9 +655,9 @@ extern "C" int hawk_pam_search(hawk_ctx* c, hawk_batch* b, const hawk_params* pa
   r->ctx = c;
   r->window = params->pam_len + params->guide_len + 2 * HAWK_GUIDESEQPAD;
   std::vector<uint8_t> isref(b->n_hap, 1);
-  DevBuf d_a, d_b, d_isref;
+  ScanInputs in;
   ScanOut so;
-  int rc = run_scan(c, b, params, scan_start, scan_stop, isref.data(), 1, d_a, d_b, d_isref, so);
+  int rc = run_scan(c, b, params, scan_start, scan_stop, isref.data(), 1, in, so);
   if (rc != HAWK_OK) {
     delete r;
     return rc;
@@ -759,17 +799,18 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
   r->window = W;
 
   int rc = HAWK_OK;
-  DevBuf d_a, d_b, d_isref, d_refrange, d_err;
+  ScanInputs in;
+  DevBuf d_refrange, d_err;
   DevBuf start[2], stop[2], keep[2], kept_excl[2], tile_sums, cnt[2], off[2], text_pre[2], row_hit[2];
   ScanOut so;
   do {
     Trace tr;
-    if ((rc = run_scan(c, b, params, scan_start, scan_stop, is_ref, 0, d_a, d_b, d_isref, so))) break;
+    if ((rc = run_scan(c, b, params, scan_start, scan_stop, is_ref, 0, in, so))) break;
     tr.tick("run_scan total");
     r->scanned_bp = so.scanned_bp;
     cudaEvent_t ev_post;
     c->mark(2, &ev_post);
-    const BatchView B = batch_view(b, d_a.as<int32_t>(), d_b.as<int32_t>(), d_isref.as<uint8_t>());
+    const BatchView B = batch_view(b, in.a, in.b, in.is_ref);
     const int64_t n_hits[2] = {so.n[0], so.n[1]};
     if (!unphased) {
       if ((rc = search_fast(c, b, K, B, so, ref_h, r))) break;
