@@ -81,13 +81,13 @@ SIGNATURES = {
     "hawk_result_info": (C.c_int, [_P, _I64P, _I64P, _I32P, _I32P, _I64P]),
     "hawk_result_fetch": (C.c_int, [_P, _I32P, _U8P, _I32P, _I32P, _I32P, _I64P, _U8P]),
     "hawk_result_fetch_hits": (C.c_int, [_P, C.c_int32, _U64P]),
-    "hawk_pack_dev": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
+    "hawk_pack_dev": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P]),
     "hawk_scan_units": (C.c_int32, [C.c_int32, C.c_int64]),
     "hawk_scan_plan": (C.c_int64, [_I32P, _I32P, _U8P, C.c_int32, C.c_int32, C.c_int32, _I64P, _I64P, C.POINTER(C.c_double)]),
     "hawk_scan_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int64, C.c_int64]),
     "hawk_scan_dev": (
         C.c_int,
-        [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_int32,
+        [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_int32,
          C.POINTER(HawkParams), C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, _P],
     ),  # fmt: skip
     "hawk_scan_compact_dev": (

@@ -204,7 +204,7 @@ struct hawk_batch {
   int64_t total_slots;
   std::vector<int64_t> slot_off;
   std::vector<int32_t> len;
-  DevBuf q, v, d_slot_off, d_len;
+  DevBuf q, v, nz, d_slot_off, d_len;
   DevBuf seg_off, seg_rel, seg_gen, seg_step;
   DevBuf va_off, va_idx, va_ent_off, va_ref;
   bool has_posmap = false, has_alleles = false;
@@ -308,11 +308,13 @@ static int batch_create_impl(hawk_ctx* c, const uint8_t* ascii, bool ascii_on_de
   int rc = HAWK_OK;
   DevBuf d_ascii, d_bad;
   const size_t n_chunks = (size_t)total / HAWK_CHUNK + HAWK_SLACK_CHUNKS;
+  // K1 writes every chunk of the slot space; only the readable slack behind it is zeroed
+  const size_t used = (size_t)total / HAWK_CHUNK;
   do {
-    // K1 writes every chunk of the slot space; only the readable slack behind it is zeroed
-    const size_t used = (size_t)total / HAWK_CHUNK;
     if ((rc = b->q.alloc(c, n_chunks * 16))) break;
     if ((rc = b->v.alloc(c, n_chunks * 4))) break;
+    const size_t nz_words = (used + 31) / 32 + HAWK_SLACK_CHUNKS;
+    if ((rc = b->nz.alloc(c, nz_words * 4, true))) break;
     if ((rc = hawk_check_cuda(cudaMemsetAsync(b->q.as<uint8_t>() + used * 16, 0, (n_chunks - used) * 16, st), "slack memset"))) break;
     if ((rc = hawk_check_cuda(cudaMemsetAsync(b->v.as<uint8_t>() + used * 4, 0, (n_chunks - used) * 4, st), "slack memset"))) break;
     if ((rc = upload(c, b->d_slot_off, b->slot_off.data(), (size_t)(n_hap + 1) * 8))) break;
@@ -330,7 +332,7 @@ static int batch_create_impl(hawk_ctx* c, const uint8_t* ascii, bool ascii_on_de
       if ((rc = upload(c, d_bad, &init, 8))) break;
       cudaEvent_t ev;
       c->mark(0, &ev);
-      rc = hawk_pack_dev(st, src, total, b->q.p, b->v.as<uint32_t>(), d_bad.as<int64_t>());
+      rc = hawk_pack_dev(st, src, total, b->q.p, b->v.as<uint32_t>(), b->nz.as<uint32_t>(), d_bad.as<int64_t>());
       c->close_mark();
       if (rc) break;
       int64_t bad = INT64_MAX;
@@ -377,7 +379,8 @@ extern "C" int hawk_batch_repack_dev(hawk_batch* b, const uint8_t* d_ascii, int6
   CK(upload(c, d_bad, &init, 8));
   cudaEvent_t ev;
   c->mark(0, &ev);
-  int rc = hawk_pack_dev(st, d_ascii, b->total_slots, b->q.p, b->v.as<uint32_t>(), d_bad.as<int64_t>());
+  int rc = hawk_pack_dev(st, d_ascii, b->total_slots, b->q.p, b->v.as<uint32_t>(), b->nz.as<uint32_t>(),
+                         d_bad.as<int64_t>());
   c->close_mark();
   CK(rc);
   int64_t bad = INT64_MAX;
@@ -506,6 +509,7 @@ static BatchView batch_view(const hawk_batch* b, const int32_t* d_a, const int32
   BatchView B{};
   B.q = b->q.as<Planes>();
   B.v = b->v.as<uint32_t>();
+  B.nz = b->nz.as<uint32_t>();
   B.slot_off = b->d_slot_off.as<int64_t>();
   B.len = b->d_len.as<int32_t>();
   B.scan_start = d_a;
@@ -591,7 +595,7 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
   for (int attempt = 0; attempt < 2; ++attempt) {
     cudaEvent_t ev;
     c->mark(1, &ev);
-    int src = hawk_scan_dev(st, b->q.p, b->v.as<uint32_t>(), b->d_slot_off.as<int64_t>(),
+    int src = hawk_scan_dev(st, b->q.p, b->v.as<uint32_t>(), b->nz.as<uint32_t>(), b->d_slot_off.as<int64_t>(),
                             b->d_len.as<int32_t>(), in.a, in.b, in.is_ref, in.span_off, in.unit_span,
                             in.unit_frac, n_hap, n_spans, n_units, params, raw, exact, cap[0], cap[1],
                             d_counts.as<uint64_t>(), d_ws.p);

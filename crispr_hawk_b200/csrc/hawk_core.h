@@ -419,6 +419,7 @@ namespace hawk {
 struct BatchView {
   const Planes* q;            // planes, one per chunk
   const uint32_t* v;          // case bits, one word per chunk
+  const uint32_t* nz;         // summary of v: bit c of the plane = chunk c holds a variant base
   const int64_t* slot_off;    // n_hap + 1
   const int32_t* len;         // n_hap
   const int32_t* scan_start;  // n_hap (search_guides.py:49-84)

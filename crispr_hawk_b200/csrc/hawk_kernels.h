@@ -5,9 +5,9 @@
 
 #include "../../include/hawkscan.h"
 
-// chunks per scan span (the unit one warp processes at a time): 256 chunks = 8,192 base
-// slots = 1 KB of case words
-#define HAWK_SPAN_CHUNKS 256
+// chunks per scan span (the unit one warp processes at a time): 1,024 chunks = 32,768 base
+// slots = one 32-bit slice of the nz summary per lane
+#define HAWK_SPAN_CHUNKS 1024
 
 int hawk_fail(int code, const char* fmt, ...);
 int hawk_check_cuda(cudaError_t err, const char* what);

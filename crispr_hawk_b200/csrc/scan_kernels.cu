@@ -29,51 +29,56 @@ namespace hawk {
 // One thread per chunk: 32 ASCII bytes -> {A,C,G,T} plane words + case word.
 __global__ void __launch_bounds__(256) pack_kernel(const uint4* __restrict__ ascii,
                                                    int64_t n_chunks, uint4* __restrict__ q,
-                                                   uint32_t* __restrict__ v,
+                                                   uint32_t* __restrict__ v, uint32_t* __restrict__ nz,
                                                    unsigned long long* __restrict__ bad) {
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += stride) {
-    uint4 w[2];
-    w[0] = __ldg(&ascii[2 * c]);
-    w[1] = __ldg(&ascii[2 * c + 1]);
-    const PackedChunk o = pack_chunk(reinterpret_cast<const uint32_t*>(w));
-    q[c] = make_uint4(o.a, o.c, o.g, o.t);
-    v[c] = o.v;
-    if (o.invalid) atomicMin(bad, (unsigned long long)(c * 32 + (__ffs(o.invalid) - 1)));
+  // a warp packs 32 consecutive chunks per pass (chunk index = multiple of 32 + lane), so one
+  // ballot gives the 32 "chunk holds a variant base" bits of a whole nz word
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t c0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); c0 < n_chunks; c0 += stride) {
+    const int64_t c = c0 + lane;
+    uint32_t vw = 0;
+    if (c < n_chunks) {
+      uint4 w[2];
+      w[0] = __ldg(&ascii[2 * c]);
+      w[1] = __ldg(&ascii[2 * c + 1]);
+      const PackedChunk o = pack_chunk(reinterpret_cast<const uint32_t*>(w));
+      q[c] = make_uint4(o.a, o.c, o.g, o.t);
+      v[c] = o.v;
+      vw = o.v;
+      if (o.invalid) atomicMin(bad, (unsigned long long)(c * 32 + (__ffs(o.invalid) - 1)));
+    }
+    const uint32_t word = __ballot_sync(0xFFFFFFFFu, vw != 0);
+    if (lane == 0) nz[c0 >> 5] = word;
   }
 }
 
 // ------------------------------------------------------------------ K2: scan
-// Warp-autonomous, persistent. A *span* is HAWK_SPAN_CHUNKS = 256 chunks (8,192 base
-// slots, 1 KB of case words) of one haplotype; spans are numbered in (haplotype, position)
-// order and every warp ("unit") owns a contiguous span range [unit_span[u], unit_span[u+1])
-// balanced on the host (hawk_scan_plan). No warp ever waits for another one:
-//   tiles     each warp keeps a three-stage ring of case-word tiles in shared memory (1 KB +
-//             a 4-word halo either side -- the slot layout keeps the halo zero), filled by
-//             bulk-async copies (TMA) it issues itself three spans ahead, completion through
-//             an mbarrier per stage;
-//   phase A   128-bit reads of the tile find the chunks with a variant base in reach of a
-//             guide core (search_guides.py:468-471; REF haplotypes / pam_search mode take every
-//             chunk); candidates are compacted across the warp;
-//   phase B   32 candidates at a time load the {A,C,G,T} planes and run the branch-free
-//             AND-mask PAM test on both strands + the fused filters; a warp prefix sum of the
-//             hit counts places the (hap << 32 | pos) records directly into the warp's private
-//             segment of a staging buffer.
+// Warp-autonomous, persistent. A *span* is HAWK_SPAN_CHUNKS = 1,024 chunks (32,768 base
+// slots) of one haplotype; spans are numbered in (haplotype, position) order and every warp
+// ("unit") owns a contiguous span range [unit_span[u], unit_span[u+1]) balanced on the host
+// (hawk_scan_plan). No warp ever waits for another one:
+//   phase A   (non-REF haplotypes) one 32-bit slice of the nz summary per lane = 32 chunks;
+//             a chunk is a candidate iff it or a neighbour holds a variant base (a guide core
+//             reaches at most one chunk either side when G <= 32; search_guides.py:468-471);
+//             the candidates of the span are appended in order to a per-warp queue in shared
+//             memory (warp prefix sum). Variant-free stretches cost 1 bit per 1,024 bp.
+//   phase B   whenever 32 candidates are queued, one lane each: the chunk's three case words,
+//             a log-doubling sliding OR over that 96-bit window -> per-position "core holds a
+//             variant" masks for both strands; two 128-bit plane loads; the branch-free
+//             AND-mask PAM test on both strands over shared funnel-shifted planes
+//             (match_fixed<P>); interval masks for the scan bounds and is_pamhit_in_range;
+//             a packed warp prefix sum of the hit counts places the (hap << 32 | pos) records
+//             straight into the warp's private segment of a staging buffer.
+//   dense     REF haplotypes / pam_search mode take every chunk, 32 per pass, no queue.
 // seg_prefix_kernel + compact_kernel then concatenate the segments (exclusive prefix over the
 // per-unit totals), which yields the stream sorted by (haplotype, position) without a sort.
 constexpr int SCAN_WARPS = 8;
 constexpr int SCAN_THREADS = SCAN_WARPS * 32;
 constexpr int SCAN_CTAS_PER_SM = 4;
 constexpr int SPAN = HAWK_SPAN_CHUNKS;
-constexpr int SPAN_ROUNDS = SPAN / 128;
-constexpr int HALO = 4;  // case words either side of a span (HAWK_SLOT_GAP / 32)
-constexpr int VBUF_WORDS = SPAN + 2 * HALO;
-constexpr int STAGES = 2;
-constexpr int QCAP = 160;  // candidate ring entries per warp (<= 31 carried + 128 per round)
-__device__ __forceinline__ uint32_t qwrap(uint32_t x) { return x >= QCAP ? x - QCAP : x; }  // x < 2 QCAP
-static_assert(SPAN == 256, "candidate indices are stored as uint8");
-static_assert(HALO * 32 == HAWK_SLOT_GAP, "halo must be covered by the layout's zero gap");
-static_assert((VBUF_WORDS * 4) % 16 == 0, "tiles must keep 16-byte alignment");
+constexpr int QCAP = SPAN + 32;  // <= 31 carried candidates + a whole span
+static_assert(SPAN == 1024, "one nz bit per chunk, 32 chunks per lane");
 
 __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t x) {
 #pragma unroll
@@ -84,37 +89,6 @@ __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
   return x;
-}
-
-// ---- mbarrier / bulk-copy wrappers (PTX ISA 8.x, sm_90+) ----
-__device__ __forceinline__ uint32_t smem_addr(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-      "@P1 bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(smem_addr(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_addr(dst_smem)),
-               "l"(src), "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
 }
 
 struct ScanArgs {
@@ -150,19 +124,11 @@ __global__ void span_table_kernel(const int64_t* __restrict__ span_off, const in
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_kernel(const __grid_constant__ ScanArgs A) {
-  __shared__ __align__(16) uint32_t vbuf[SCAN_WARPS][STAGES][VBUF_WORDS];
-  __shared__ __align__(16) uint4 queue[SCAN_WARPS][QCAP];  // candidate ring: {w(c-1), w(c), w(c+1), c}
-  __shared__ __align__(8) uint64_t full_bar[SCAN_WARPS][STAGES];
+  __shared__ uint32_t queue_all[SCAN_WARPS][QCAP];  // candidate chunks of the current haplotype
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int unit = blockIdx.x * SCAN_WARPS + warp;
   if (unit >= A.n_units) return;
   const int64_t sp0 = A.unit_span[unit], sp1 = A.unit_span[unit + 1];
-
-  if (lane == 0) {
-    for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[warp][s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
 
   // this warp's segment of the staging buffers
   uint64_t* seg_dst[2];
@@ -182,32 +148,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_kernel(co
     seg_cap[s] = cap > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cap;
   }
 
-  // tile producer state (lane 0): haplotype of the last issued span
-  int32_t iss_hap = -1, iss_nch4 = 0;
-  int64_t iss_chunk0 = 0;
-  auto issue = [&](int64_t span, int st) {
-    const int2 e = __ldg(&A.span_tab[span]);
-    if (e.x != iss_hap) {
-      iss_hap = e.x;
-      iss_chunk0 = A.B.slot_off[e.x] >> 5;
-      iss_nch4 = ((A.B.len[e.x] + 127) >> 7) << 2;
-    }
-    // case words [c_first - HALO, min(c_first + SPAN + HALO, padded end + HALO))
-    int32_t w_end = e.y + SPAN + HALO;
-    if (w_end > iss_nch4 + HALO) w_end = iss_nch4 + HALO;
-    const uint32_t bytes = (uint32_t)(w_end - (e.y - HALO)) * 4u;
-    mbar_arrive_expect_tx(&full_bar[warp][st], bytes);
-    bulk_g2s(&vbuf[warp][st][0], A.B.v + iss_chunk0 + (e.y - HALO), bytes, &full_bar[warp][st]);
-  };
-  if (lane == 0)
-    for (int k = 0; k < STAGES && sp0 + k < sp1; ++k) issue(sp0 + k, k);
-
   uint32_t raw_acc[2] = {0, 0};
   uint32_t run[2] = {0, 0};  // records this warp has produced so far
   int32_t cur_hap = -1;
   HapScan H;
   H.is_ref = 0;
-  uint32_t q_head = 0, q_n = 0;  // ring state (warp-uniform)
+  uint32_t* const queue = queue_all[warp];
+  uint32_t q_n = 0;  // queued candidates, at queue[0 .. q_n) (warp-uniform)
 
   // hit bits of one chunk per lane -> records in the warp's segment, chunk order = lane order
   auto emit = [&](const uint32_t out[2], int32_t c) {
@@ -244,39 +191,52 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_kernel(co
     }
   };
 
-  // match + filters for up to 32 queued candidates (n <= 32 taken from the ring head)
-  auto drain = [&](uint32_t n, const uint32_t* vs, int32_t c_first) {
+  // match + filters for the n <= 32 queued candidates at queue[off ..)
+  auto drain = [&](uint32_t off, uint32_t n) {
     uint32_t out[2] = {0, 0}, raw[2] = {0, 0};
     int32_t c = 0;
     if ((uint32_t)lane < n) {
-      const uint4 e = queue[warp][qwrap(q_head + lane)];
-      c = (int32_t)e.w;
+      c = (int32_t)queue[off + lane];
       if (A.K.small) {
-        scan_chunk_small(A.B, A.K, H, c, e.x, e.y, e.z, true, out, raw);
-      } else {  // long guides: the candidate's span is still resident (queue is flushed per span)
-        auto vword = [&](int64_t w) -> uint32_t {
-          const int32_t j = (int32_t)w - c_first + HALO;
-          return (w < 0 || w >= H.nchunks || j < 0 || j >= VBUF_WORDS) ? 0u : vs[j];
-        };
-        scan_chunk(A.B, A.K, H, (int64_t)c, vword, out, raw);
+        // the slot layout's zero gap makes c - 1 / c + 1 safe at the haplotype's ends
+        const uint32_t* vp = A.B.v + H.chunk0 + c;
+        const uint32_t w0 = __ldg(vp - 1) & A.K.prev_mask, w1 = __ldg(vp), w2 = __ldg(vp + 1) & A.K.next_mask;
+        if (w0 | w1 | w2) scan_chunk_small(A.B, A.K, H, c, w0, w1, w2, true, out, raw);
+      } else {
+        scan_chunk(A.B, A.K, H, (int64_t)c, out, raw);
       }
     }
-    q_head = qwrap(q_head + n);
-    q_n -= n;
     emit(out, c);
   };
+  // drain every full batch, keep the remainder (< 32, or nothing when `all`) at the front
+  auto drain_queue = [&](bool all) {
+    uint32_t off = 0;
+    while (q_n - off >= 32) {
+      drain(off, 32);
+      off += 32;
+    }
+    if (all && q_n > off) {
+      drain(off, q_n - off);
+      off = q_n;
+    }
+    if (off) {
+      const uint32_t rem = q_n - off;
+      uint32_t t = 0;
+      if ((uint32_t)lane < rem) t = queue[off + lane];
+      __syncwarp();
+      if ((uint32_t)lane < rem) queue[lane] = t;
+      __syncwarp();
+      q_n = rem;
+    }
+  };
 
-  int it = 0;
-  for (int64_t span = sp0; span < sp1; ++span, ++it) {
-    const int st = it % STAGES;
+  for (int64_t span = sp0; span < sp1; ++span) {
     const int2 e = __ldg(&A.span_tab[span]);
-    const uint32_t* vs = vbuf[warp][st];
     if (e.x != cur_hap) {
-      if (q_n) drain(q_n, vs, 0);  // K.small only: long-guide queues are empty between spans
+      if (q_n) drain_queue(true);
       cur_hap = e.x;
       H = load_hap_scan(A.B, A.K, e.x);
     }
-    mbar_wait(&full_bar[warp][st], (it / STAGES) & 1);
     const int32_t c_first = e.y;
     const int32_t c_lo = H.a >> 5, c_end = (H.b + 31) >> 5;
 
@@ -290,69 +250,50 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_kernel(co
         raw_acc[1] += __popc(raw[1]);
         emit(out, c);
       }
-    } else {
-      // ---- sparse: chunks with a variant base in reach of a guide core go to the ring
-#pragma unroll
-      for (int r = 0; r < SPAN_ROUNDS; ++r) {
-        const int32_t base = c_first + r * 128;
-        if (base >= c_end) break;  // warp-uniform
-        const int32_t c4 = base + 4 * lane;  // first of this lane's 4 chunks
-        const uint4* t4 = reinterpret_cast<const uint4*>(vs + (c4 - c_first));  // words c4 - HALO ..
-        const uint4 L = t4[0], M = t4[1], R = t4[2];
-        uint32_t cm;
-        if (A.K.small) {
-          const uint32_t pm = A.K.prev_mask, nm = A.K.next_mask;
-          cm = (((L.w & pm) | M.x | (M.y & nm)) ? 1u : 0u) | (((M.x & pm) | M.y | (M.z & nm)) ? 2u : 0u) |
-               (((M.y & pm) | M.z | (M.w & nm)) ? 4u : 0u) | (((M.z & pm) | M.w | (R.x & nm)) ? 8u : 0u);
-        } else {
-          const uint32_t w[12] = {L.x, L.y, L.z, L.w, M.x, M.y, M.z, M.w, R.x, R.y, R.z, R.w};
-          cm = 0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint32_t any = 0;
-#pragma unroll
-            for (int d = -4; d <= 4; ++d)
-              if (d >= -A.K.back && d <= A.K.ahead) any |= w[4 + k + d];
-            cm |= any ? (1u << k) : 0u;
-          }
-        }
-        if (base < c_lo || base + 128 > c_end) {  // warp-uniform: round straddles the scan interval
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (c4 + k < c_lo || c4 + k >= c_end) cm &= ~(1u << k);
-        }
-        if (!__any_sync(0xFFFFFFFFu, cm != 0)) continue;
-        // append this lane's candidates behind the earlier lanes' (chunk order)
-        const uint32_t mine = __popc(cm);
-        uint32_t incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-          if (lane >= d) incl += y;
-        }
-        uint32_t idx = qwrap(qwrap(q_head + q_n) + (incl - mine));
-        const uint32_t wv[6] = {L.w, M.x, M.y, M.z, M.w, R.x};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (cm & (1u << k)) {
-            queue[warp][idx] = make_uint4(wv[k], wv[k + 1], wv[k + 2], (uint32_t)(c4 + k));
-            idx = qwrap(idx + 1);
-          }
-        q_n += __shfl_sync(0xFFFFFFFFu, incl, 31);
-        __syncwarp();
-        while (q_n >= 32) drain(32, vs, c_first);
-      }
-      if (!A.K.small && q_n) drain(q_n, vs, c_first);  // <= 31 left: the tile goes away with the span
+      continue;
     }
+    // ---- sparse: this lane's 32 chunks [c32, c32 + 32) and one nz bit either side
+    const int32_t c32 = c_first + 32 * lane;
+    uint32_t cand = 0, any = 0;
+    if (c32 < c_end) {
+      const int64_t bit = H.chunk0 + c32 - 1;  // >= 3: the slot space starts with a zero gap
+      const uint32_t* wp = A.B.nz + (bit >> 5);
+      const uint32_t sh = (uint32_t)(bit & 31);
+      const uint32_t x0 = __ldg(wp), x1 = __ldg(wp + 1), x2 = __ldg(wp + 2);
+      const uint32_t lo = funnel_r(x0, x1, sh), hi = funnel_r(x1, x2, sh);  // bits bit .. bit + 63
+      const uint32_t mid = (lo >> 1) | (hi << 31);                          // chunks c32 .. c32 + 31
+      cand = mid | (mid << 1) | (lo & 1u) | (mid >> 1) | ((hi << 30) & 0x80000000u);
+      any = lo | hi;
+    }
+    if (!A.K.small) {
+      // long guides reach up to 4 chunks either side: take every chunk of a 32-chunk slice
+      // whose neighbourhood (this slice, the one before, the one after) holds a variant;
+      // the slices at the ends of the span are always taken
+      const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, any, 1), next = __shfl_down_sync(0xFFFFFFFFu, any, 1);
+      const bool edge = lane == 0 || lane == 31 || c32 + 32 >= c_end;
+      cand = (c32 < c_end && ((any | prev | next) != 0 || edge)) ? 0xFFFFFFFFu : 0u;
+    }
+    if (c32 < c_end) cand &= interval_mask(c_lo, c_end, c32);
+    if (!__any_sync(0xFFFFFFFFu, cand != 0)) continue;
+    // append this lane's candidates behind the earlier lanes' (chunk order)
+    const uint32_t mine = __popc(cand);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += y;
+    }
+    uint32_t* qp = queue + q_n + (incl - mine);
+    while (cand) {
+      const int b = __ffs(cand) - 1;
+      cand &= cand - 1;
+      *qp++ = (uint32_t)(c32 + b);
+    }
+    q_n += __shfl_sync(0xFFFFFFFFu, incl, 31);
     __syncwarp();
-    // refill this stage with the span STAGES ahead (generic reads above are ordered before the
-    // async-proxy write by the fence)
-    if (lane == 0 && span + STAGES < sp1) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(span + STAGES, st);
-    }
+    if (q_n >= 32) drain_queue(false);
   }
-  if (q_n) drain(q_n, nullptr, 0);
+  if (q_n) drain_queue(true);
 
   if (lane == 0) {
 #pragma unroll
@@ -450,7 +391,7 @@ __global__ void __launch_bounds__(128) compact_kernel(const __grid_constant__ Co
 using namespace hawk;
 
 extern "C" int hawk_pack_dev(void* stream, const uint8_t* d_ascii, int64_t total_slots, void* d_q,
-                             uint32_t* d_v, int64_t* d_bad) {
+                             uint32_t* d_v, uint32_t* d_nz, int64_t* d_bad) {
   if (total_slots < 0 || (total_slots % HAWK_CHUNK) != 0)
     return hawk_fail(HAWK_EINVAL, "hawk_pack_dev: total_slots must be a multiple of 32");
   if (((uintptr_t)d_ascii & 15) || ((uintptr_t)d_q & 15))
@@ -460,7 +401,7 @@ extern "C" int hawk_pack_dev(void* stream, const uint8_t* d_ascii, int64_t total
   int64_t blocks = (n_chunks + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride: 16 CTAs per SM
   pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      (const uint4*)d_ascii, n_chunks, (uint4*)d_q, d_v, (unsigned long long*)d_bad);
+      (const uint4*)d_ascii, n_chunks, (uint4*)d_q, d_v, d_nz, (unsigned long long*)d_bad);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "pack_kernel launch");
 }
@@ -553,7 +494,7 @@ extern "C" size_t hawk_scan_workspace_bytes(int64_t n_spans, int32_t n_units, in
   return scan_ws_layout(nullptr, n_spans, n_units, cap_fwd, cap_rev).bytes;
 }
 
-extern "C" int hawk_scan_dev(void* stream, const void* d_q, const uint32_t* d_v,
+extern "C" int hawk_scan_dev(void* stream, const void* d_q, const uint32_t* d_v, const uint32_t* d_nz,
                              const int64_t* d_slot_off, const int32_t* d_len,
                              const int32_t* d_scan_start, const int32_t* d_scan_stop,
                              const uint8_t* d_is_ref, const int64_t* d_span_off,
@@ -582,6 +523,7 @@ extern "C" int hawk_scan_dev(void* stream, const void* d_q, const uint32_t* d_v,
   A.B = BatchView{};
   A.B.q = (const Planes*)d_q;
   A.B.v = d_v;
+  A.B.nz = d_nz;
   A.B.slot_off = d_slot_off;
   A.B.len = d_len;
   A.B.scan_start = d_scan_start;
@@ -601,7 +543,6 @@ extern "C" int hawk_scan_dev(void* stream, const void* d_q, const uint32_t* d_v,
   A.cap[1] = cap_rev;
   A.n_units = n_units;
   A.counts = d_counts;
-  cudaFuncSetAttribute(scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   scan_kernel<<<(unsigned)((n_units + SCAN_WARPS - 1) / SCAN_WARPS), SCAN_THREADS, 0, st>>>(A);
   hawk_note_launch(1);
   // per-unit exclusive prefix + totals (counts[0..1])

@@ -26,6 +26,8 @@
  *        the nibble of slot 32*chunk + i (0.5 B per base).
  *   v  : one uint32 per chunk, bit i = base was lower-case (a variant base,
  *        haplotype.py:106-121) (0.125 B per base).
+ *   nz : one bit per chunk (chunk c -> bit c & 31 of word c >> 5): the chunk's v word is
+ *        non-zero. Lets the scan skip the case plane of variant-free stretches.
  */
 #ifndef HAWKSCAN_H
 #define HAWKSCAN_H
@@ -41,7 +43,7 @@ extern "C" {
 #define HAWK_SLOT_ALIGN 128 /* bases; haplotypes start on a 64-byte plane boundary */
 #define HAWK_SLOT_GAP 128   /* unused (zero) slots before the first and after every haplotype */
 #define HAWK_CHUNK 32       /* bases per chunk (one uint4 of planes, one uint32 of case bits) */
-#define HAWK_SLACK_CHUNKS 8 /* readable zero chunks after the last slot */
+#define HAWK_SLACK_CHUNKS 8 /* readable zero chunks after the last slot (nz: 8 zero words) */
 #define HAWK_MAX_PAM 16
 #define HAWK_GUIDESEQPAD 10 /* guide.py:21 */
 #define HAWK_MAX_WINDOW 148 /* G + P + 2*PAD upper bound supported on device (G + P <= 128) */
@@ -179,7 +181,8 @@ int hawk_ctx_profile(hawk_ctx *ctx, double *ms /* [4] */, int64_t *n /* [4] */);
 /* K1: ASCII slot space -> planes. d_bad: one int64, must hold INT64_MAX on
  * entry; receives the smallest slot index with a non-IUPAC byte. */
 int hawk_pack_dev(void *stream, const uint8_t *d_ascii, int64_t total_slots, void *d_q,
-                  uint32_t *d_v, int64_t *d_bad);
+                  uint32_t *d_v, uint32_t *d_nz /* total_slots / 1024 rounded up, words */,
+                  int64_t *d_bad);
 
 /* Scan plan (host side). A span is 256 chunks (8,192 base slots) of one haplotype; spans
  * are numbered in (haplotype, position) order and every warp of the persistent scan grid
@@ -208,7 +211,8 @@ size_t hawk_scan_workspace_bytes(int64_t n_spans, int32_t n_units, int64_t cap_f
  * set, call again with caps >= the totals and exact_retry = 1 (same workspace, or a larger
  * one whose head was copied over), which sizes every unit's segment from the first launch's
  * exact counts. raw_hits = 1 gives pam_search semantics (no window / REF-core filter). */
-int hawk_scan_dev(void *stream, const void *d_q, const uint32_t *d_v, const int64_t *d_slot_off,
+int hawk_scan_dev(void *stream, const void *d_q, const uint32_t *d_v, const uint32_t *d_nz,
+                  const int64_t *d_slot_off,
                   const int32_t *d_len, const int32_t *d_scan_start, const int32_t *d_scan_stop,
                   const uint8_t *d_is_ref, const int64_t *d_span_off, const int64_t *d_unit_span,
                   const double *d_unit_frac, int32_t n_hap, int64_t n_spans, int32_t n_units,
