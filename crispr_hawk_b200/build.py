@@ -63,6 +63,15 @@ def build_hostcheck(force: bool = False) -> str:
         return _build_hostcheck(force)
 
 
+def build_variant(out: str, defines) -> str:
+    """Tuning aid: the same sources with -D overrides into another .so (HAWKSCAN_LIB selects it)."""
+    srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+           "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr", "-o", out] + [f"-D{d}" for d in defines] + srcs
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    return out
+
+
 def _build_cuda(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
     deps = srcs + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]

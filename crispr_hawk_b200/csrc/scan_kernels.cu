@@ -1,20 +1,7 @@
-// scan_kernels.cu -- K1 (pack) and K2 (PAM scan + fused filters + ordered
-// compaction) for sm_100a. Integer/bitwise, HBM-bound: no tensor cores.
-//
-// K2 structure (one CTA per *span* of SPAN_CHUNKS chunks of one haplotype,
-// spans handed out by an atomic ticket so that a span's predecessors are always
-// resident or finished):
-//   phase 1  every thread evaluates chunks (32 positions each): REF haplotypes
-//            load the planes unconditionally, non-REF haplotypes first look at
-//            the case plane and touch the planes only where a variant base is in
-//            reach of a guide core (search_guides.py:468-471) -- the "scan only the
-//            windows overlapping variants" rule, driven by a 0.125 B/bp stream;
-//   phase 2  per-strand hit bitmaps live in shared memory (fixed size, cannot
-//            overflow); popcounts are block-scanned;
-//   phase 3  decoupled look-back over a per-span status word gives the span's
-//            global output offset, so the record stream comes out sorted by
-//            (haplotype, position) without a sort pass;
-//   phase 4  bitmaps are expanded to (hap << 32 | pos) records.
+// scan_kernels.cu -- K1 (pack), K2 (PAM scan + fused filters) and K3 (segment
+// concatenation) for sm_100a, plus their host-side plan and launchers. Integer / bitwise
+// work on HBM-resident bit planes: no tensor cores. See DESIGN.md section 3; each kernel is
+// described where it is defined.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -288,6 +275,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_kernel(co
       const int b = __ffs(cand) - 1;
       cand &= cand - 1;
       *qp++ = (uint32_t)(c32 + b);
+#ifdef HAWK_PREFETCH
+      // the candidate's case words and planes are read when its batch is drained: start both
+      // DRAM fetches now so they overlap instead of following one another
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(A.B.v + H.chunk0 + c32 + b));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(&A.B.q[H.chunk0 + c32 + b]));
+#endif
     }
     q_n += __shfl_sync(0xFFFFFFFFu, incl, 31);
     __syncwarp();

@@ -184,7 +184,7 @@ int hawk_pack_dev(void *stream, const uint8_t *d_ascii, int64_t total_slots, voi
                   uint32_t *d_v, uint32_t *d_nz /* total_slots / 1024 rounded up, words */,
                   int64_t *d_bad);
 
-/* Scan plan (host side). A span is 256 chunks (8,192 base slots) of one haplotype; spans
+/* Scan plan (host side). A span is 1,024 chunks (32,768 base slots) of one haplotype; spans
  * are numbered in (haplotype, position) order and every warp of the persistent scan grid
  * (a "unit") owns a contiguous span range. hawk_scan_units gives the number of units the
  * kernel wants for a device with sm_count SMs. hawk_scan_plan fills span_off (n_hap + 1)
