@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle import refshim  # noqa: E402
-from tests.synth_cases import config1_cases, kat_cases, make_case, random_cases  # noqa: E402
+from tests.synth_cases import config1_cases, config4_cases, kat_cases, make_case, random_cases  # noqa: E402
 
 
 def hap_to_json(h):
@@ -117,6 +117,10 @@ def edge_cases():
 
 if __name__ == "__main__":
     os.environ.setdefault("PYTHONHASHSEED", "0")
+    if "--only-config4" in sys.argv:
+        dump("config4", config4_cases())
+        sys.exit(0)
+    dump("config4", config4_cases())
     dump("kat", kat_cases())
     dump("config1", config1_cases())
     dump("random", random_cases(5))

@@ -70,7 +70,7 @@ def load_golden(name: str) -> List[dict]:
 
 def all_golden_cases() -> List[dict]:
     out = []
-    for name in ("kat", "random", "edge", "config1"):
+    for name in ("kat", "random", "edge", "config1", "config4"):
         out.extend(load_golden(name))
     return out
 

@@ -183,3 +183,21 @@ def config1_cases() -> List[SmallCase]:
         make_case(1, phased=True, name="C1_phased", **kw),
         make_case(1, phased=False, name="C1_unphased", **kw),
     ]
+
+
+GNOMAD_POPS = ["afr", "amr", "asj", "eas", "fin", "mid", "nfe", "sas", "ami", "remaining"]
+
+
+def config4_cases() -> List[SmallCase]:
+    """BASELINE config 4 in miniature: SaCas9 NNGRRT / 21 nt over gnomAD-density variants
+    (one site per ~8 bp, 88 % SNV / 12 % indel, 5 % multi-allelic), unphased, the converter's
+    10 population pseudo-samples (converter.py:19-37). Slices this small are all the
+    reference can resolve in reasonable time."""
+    out = []
+    for k, (seed, bed_len) in enumerate([(4, 1200), (41, 1600), (42, 800)]):
+        c = make_case(seed, bed_len=bed_len, n_sites=bed_len // 8, n_samples=10, phased=False, pam="NNGRRT",
+                      guidelen=21, right=False, indel_frac=0.12, multiallelic_frac=0.05, max_indel=5,
+                      name=f"C4_gnomad_{k}")  # fmt: skip
+        c.samples[:] = GNOMAD_POPS
+        out.append(c)
+    return out
