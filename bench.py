@@ -326,7 +326,8 @@ def run_product_arm(args, rank, world, local_rank):
     ach = kernels[dom]["gbs"] or 0.0
     roofline = {
         "kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
+        "traffic": TRAFFIC.get(dom) if args.workload == "c2" and args.scale == 1.0 and not args.haplotypes else None,
+        "peak_source": peak_src,
         "scan_kernel_frac": (kernels["scan_kernel"]["gbs"] or 0.0) / peak,
         "pack_kernel_frac": (kernels["pack_kernel"]["gbs"] or 0.0) / peak,
     }  # fmt: skip
