@@ -82,17 +82,19 @@ SIGNATURES = {
     "hawk_result_fetch": (C.c_int, [_P, _I32P, _U8P, _I32P, _I32P, _I32P, _I64P, _U8P]),
     "hawk_result_fetch_hits": (C.c_int, [_P, C.c_int32, _U64P]),
     "hawk_pack_dev": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P]),
-    "hawk_scan_units": (C.c_int32, [C.c_int32, C.c_int64]),
-    "hawk_scan_plan": (C.c_int64, [_I32P, _I32P, _U8P, C.c_int32, C.c_int32, C.c_int32, _I64P, _I64P, C.POINTER(C.c_double)]),
-    "hawk_scan_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int64, C.c_int64]),
-    "hawk_scan_dev": (
-        C.c_int,
-        [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_int32,
-         C.POINTER(HawkParams), C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, _P],
-    ),  # fmt: skip
-    "hawk_scan_compact_dev": (
-        C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, C.c_int64, C.c_int64],
+    "hawk_scan_plan": (C.c_int64, [_I32P, _I32P, C.c_int32, _I64P]),
+    "hawk_scan_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
+    "hawk_scan_match_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "hawk_scan_totals": (C.c_void_p, [_P]),
+    "hawk_scan_count_dev": (
+        C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.POINTER(HawkParams), C.c_int32, _P],
     ),
+    "hawk_scan_match_dev": (
+        C.c_int,
+        [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.POINTER(HawkParams), C.c_int32,
+         C.c_int64, _P, _P, _P, _P],
+    ),  # fmt: skip
+    "hawk_scan_expand_dev": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
 }
 
 _lib = None
@@ -192,9 +194,9 @@ class Context:
 
     def profile(self):
         """{'pack'|'scan'|'post': (total ms, launches)} since the last call."""
-        ms, n = (C.c_double * 4)(), (C.c_int64 * 4)()
+        ms, n = (C.c_double * 5)(), (C.c_int64 * 5)()
         check(self.lib.hawk_ctx_profile(self.handle, ms, n))
-        return {k: (ms[i], n[i]) for i, k in enumerate(("pack", "scan", "post", "compact"))}
+        return {k: (ms[i], n[i]) for i, k in enumerate(("pack", "cand", "post", "expand", "match"))}
 
     def close(self):
         if self.handle:

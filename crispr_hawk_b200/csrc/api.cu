@@ -225,6 +225,19 @@ struct hawk_result {
   DevBuf hap, strand, pos, start, stop, bucket, text;
 };
 
+// profiling hooks for the device layer: the context the calling thread is running a search on
+static thread_local hawk_ctx* g_prof_ctx = nullptr;
+void hawk_prof_begin(cudaStream_t st, int kind) {
+  if (g_prof_ctx && g_prof_ctx->stream == st) g_prof_ctx->mark(kind, nullptr);
+}
+void hawk_prof_end(cudaStream_t st) {
+  if (g_prof_ctx && g_prof_ctx->stream == st) g_prof_ctx->close_mark();
+}
+struct ProfScope {
+  explicit ProfScope(hawk_ctx* c) { g_prof_ctx = c->profiling ? c : nullptr; }
+  ~ProfScope() { g_prof_ctx = nullptr; }
+};
+
 // ------------------------------------------------------------------ context
 extern "C" int hawk_ctx_create(int device, hawk_ctx** out) {
   if (!out) return hawk_fail(HAWK_EINVAL, "hawk_ctx_create: null output");
@@ -405,10 +418,10 @@ extern "C" int hawk_ctx_profile(hawk_ctx* c, double* ms, int64_t* n) {
   if (!c || !ms || !n) return hawk_fail(HAWK_EINVAL, "hawk_ctx_profile: bad arguments");
   CKCUDA(cudaSetDevice(c->device));
   CKCUDA(cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < 4; ++i) { ms[i] = 0; n[i] = 0; }
+  for (int i = 0; i < 5; ++i) { ms[i] = 0; n[i] = 0; }
   for (auto& s : c->spans) {
     float t = 0;
-    if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess && s.kind >= 0 && s.kind < 4) {
+    if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess && s.kind >= 0 && s.kind < 5) {
       ms[s.kind] += t;
       n[s.kind] += 1;
     }
@@ -533,15 +546,13 @@ struct ScanOut {
   int64_t scanned_bp = 0;
 };
 
-// run K2 into the staging segments; if a warp's share of the staging capacity overflowed,
-// run it once more with the exact per-warp sizes the first launch counted; then concatenate
-// the segments into exactly-sized hit lists
+// K2: candidates -> match -> records; two host round trips read the totals that size the
+// next stage (candidates, then hits), everything else is stream-ordered
 struct ScanInputs {  // per-search arrays on the device, carved out of one upload
   DevBuf buf;
   int32_t *a = nullptr, *b = nullptr;
   uint8_t* is_ref = nullptr;
-  int64_t *span_off = nullptr, *unit_span = nullptr;
-  double* unit_frac = nullptr;
+  int64_t* sblock_off = nullptr;
 };
 
 static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const int32_t* scan_start,
@@ -549,27 +560,16 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
   cudaStream_t st = c->stream;
   Trace tr;
   const int32_t n_hap = b->n_hap;
-  // layout of the staging block (8-byte aligned pieces)
   auto al8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
-  const int32_t max_units = hawk_scan_units(c->sm_count, INT64_MAX);
-  const size_t o_span = 0, o_unit = o_span + (size_t)(n_hap + 1) * 8, o_frac = o_unit + (size_t)(max_units + 1) * 8,
-               o_a = o_frac + (size_t)(max_units + 1) * 8, o_b = o_a + al8((size_t)n_hap * 4),
+  const size_t o_sb = 0, o_a = o_sb + (size_t)(n_hap + 1) * 8, o_b = o_a + al8((size_t)n_hap * 4),
                o_ref = o_b + al8((size_t)n_hap * 4), total_bytes = o_ref + al8((size_t)n_hap);
   char* hp = (char*)c->pinned_get(total_bytes);
   if (!hp) return hawk_fail(HAWK_ENOMEM, "pinned staging allocation failed");
-  int64_t* span_off = (int64_t*)(hp + o_span);
-  int64_t* unit_span = (int64_t*)(hp + o_unit);
-  double* unit_frac = (double*)(hp + o_frac);
-  const int64_t n_spans = hawk_scan_plan(scan_start, scan_stop, is_ref, n_hap, raw, 0, span_off, nullptr, nullptr);
-  const int32_t n_units = hawk_scan_units(c->sm_count, n_spans);
-  if (n_units > 0) hawk_scan_plan(scan_start, scan_stop, is_ref, n_hap, raw, n_units, nullptr, unit_span, unit_frac);
-  int64_t est = 4096;
+  const int64_t n_sblocks = hawk_scan_plan(scan_start, scan_stop, n_hap, (int64_t*)(hp + o_sb));
   out.scanned_bp = 0;
   for (int32_t h = 0; h < n_hap; ++h) {
     int64_t a = scan_start[h] < 0 ? 0 : scan_start[h], e = scan_stop[h];
-    if (e <= a) continue;
-    out.scanned_bp += e - a;
-    est += (raw || is_ref[h]) ? (e - a) / 3 : (e - a) / 48;
+    if (e > a) out.scanned_bp += e - a;
   }
   if (n_hap > 0) {
     memcpy(hp + o_a, scan_start, (size_t)n_hap * 4);
@@ -579,58 +579,43 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
   CK(in.buf.alloc(c, total_bytes));
   CKCUDA(cudaMemcpyAsync(in.buf.p, hp, total_bytes, cudaMemcpyHostToDevice, st));
   char* dp = (char*)in.buf.p;
-  in.span_off = (int64_t*)(dp + o_span);
-  in.unit_span = (int64_t*)(dp + o_unit);
-  in.unit_frac = (double*)(dp + o_frac);
+  in.sblock_off = (int64_t*)(dp + o_sb);
   in.a = (int32_t*)(dp + o_a);
   in.b = (int32_t*)(dp + o_b);
   in.is_ref = (uint8_t*)(dp + o_ref);
-  if (n_spans == 0) return HAWK_OK;
-  DevBuf d_counts, d_ws;
-  CK(d_counts.alloc(c, 64));
-  tr.tick("scan: plan + uploads");
-  int64_t cap[2] = {est, est};
-  CK(d_ws.alloc(c, hawk_scan_workspace_bytes(n_spans, n_units, cap[0], cap[1])));
-  int exact = 0;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    cudaEvent_t ev;
-    c->mark(1, &ev);
-    int src = hawk_scan_dev(st, b->q.p, b->v.as<uint32_t>(), b->nz.as<uint32_t>(), b->d_slot_off.as<int64_t>(),
-                            b->d_len.as<int32_t>(), in.a, in.b, in.is_ref, in.span_off, in.unit_span,
-                            in.unit_frac, n_hap, n_spans, n_units, params, raw, exact, cap[0], cap[1],
-                            d_counts.as<uint64_t>(), d_ws.p);
-    c->close_mark();
-    CK(src);
-    tr.tick("scan: launch");
-    uint64_t counts[8];
-    CKCUDA(cudaMemcpyAsync(counts, d_counts.p, 64, cudaMemcpyDeviceToHost, st));
-    CKCUDA(cudaStreamSynchronize(st));
-    out.n[0] = (int64_t)counts[0];
-    out.n[1] = (int64_t)counts[1];
-    tr.tick("scan: sync");
-    if (!counts[4] && out.n[0] <= cap[0] && out.n[1] <= cap[1]) break;
-    if (attempt == 1) return hawk_fail(HAWK_ECAPACITY, "scan output did not fit after the exact retry");
-    exact = 1;
-    if (out.n[0] > cap[0] || out.n[1] > cap[1]) {
-      // grow the staging area; the per-unit counts of the first launch move with it
-      const int64_t ncap[2] = {out.n[0] > cap[0] ? out.n[0] : cap[0], out.n[1] > cap[1] ? out.n[1] : cap[1]};
-      DevBuf bigger;
-      CK(bigger.alloc(c, hawk_scan_workspace_bytes(n_spans, n_units, ncap[0], ncap[1])));
-      // everything in front of the staging buffers has the same layout for any capacity
-      const size_t head = hawk_scan_workspace_bytes(n_spans, n_units, 0, 0);
-      CKCUDA(cudaMemcpyAsync(bigger.p, d_ws.p, head, cudaMemcpyDeviceToDevice, st));
-      d_ws.move_from(bigger);
-      cap[0] = ncap[0];
-      cap[1] = ncap[1];
-    }
-  }
+  for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(c, 16));
+  if (n_sblocks == 0) return HAWK_OK;
+  DevBuf d_ws, d_mws, d_cand, d_masks;
+  CK(d_ws.alloc(c, hawk_scan_workspace_bytes(n_hap, n_sblocks)));
+  tr.tick("scan: plan + upload");
+  ProfScope prof_scope(c);
+  int rc = hawk_scan_count_dev(st, b->q.p, b->v.as<uint32_t>(), b->nz.as<uint32_t>(), b->d_slot_off.as<int64_t>(),
+                               b->d_len.as<int32_t>(), in.a, in.b, in.is_ref, in.sblock_off, n_hap, n_sblocks, params,
+                               raw, d_ws.p);
+  CK(rc);
+  uint64_t totals[8];
+  CKCUDA(cudaMemcpyAsync(totals, hawk_scan_totals(d_ws.p), 64, cudaMemcpyDeviceToHost, st));
+  CKCUDA(cudaStreamSynchronize(st));
+  const int64_t n_cand = (int64_t)totals[0];
+  tr.tick("scan: candidates");
+  if (n_cand == 0) return HAWK_OK;
+  CK(d_mws.alloc(c, hawk_scan_match_workspace_bytes(n_cand)));
+  CK(d_cand.alloc(c, (size_t)n_cand * 8));
+  CK(d_masks.alloc(c, (size_t)n_cand * 8));
+  rc = hawk_scan_match_dev(st, b->q.p, b->v.as<uint32_t>(), b->nz.as<uint32_t>(), b->d_slot_off.as<int64_t>(),
+                           b->d_len.as<int32_t>(), in.a, in.b, in.is_ref, in.sblock_off, n_hap, n_sblocks, params, raw,
+                           n_cand, d_cand.as<uint64_t>(), d_masks.as<uint64_t>(), d_ws.p, d_mws.p);
+  CK(rc);
+  CKCUDA(cudaMemcpyAsync(totals, hawk_scan_totals(d_ws.p), 64, cudaMemcpyDeviceToHost, st));
+  CKCUDA(cudaStreamSynchronize(st));
+  out.n[0] = (int64_t)totals[1];
+  out.n[1] = (int64_t)totals[2];
+  tr.tick("scan: match");
   for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(c, (size_t)(out.n[s] > 0 ? out.n[s] : 1) * 8));
-  c->mark(3, nullptr);
-  int crc = hawk_scan_compact_dev(st, in.unit_frac, n_units, n_spans, exact, cap[0], cap[1], d_ws.p,
-                                  out.hits[0].as<uint64_t>(), out.hits[1].as<uint64_t>(), out.n[0], out.n[1]);
-  c->close_mark();
-  CK(crc);
-  tr.tick("scan: compact launched");
+  rc = hawk_scan_expand_dev(st, n_cand, d_cand.as<uint64_t>(), d_masks.as<uint64_t>(), d_mws.p,
+                            out.hits[0].as<uint64_t>(), out.hits[1].as<uint64_t>());
+  CK(rc);
+  tr.tick("scan: expand launched");
   return HAWK_OK;
 }
 

@@ -5,12 +5,14 @@
 
 #include "../../include/hawkscan.h"
 
-// chunks per scan span (the unit one warp processes at a time): 1,024 chunks = 32,768 base
-// slots = one 32-bit slice of the nz summary per lane
-#define HAWK_SPAN_CHUNKS 1024
 
 int hawk_fail(int code, const char* fmt, ...);
 int hawk_check_cuda(cudaError_t err, const char* what);
 
 // every kernel launch of the library is counted (bench.py reports it as gpu_launches)
 void hawk_note_launch(int n);
+
+// optional CUDA-event brackets around single kernels of the device layer (active while the
+// host layer runs with hawk_ctx_set_profiling on; no-ops otherwise)
+void hawk_prof_begin(cudaStream_t st, int kind);
+void hawk_prof_end(cudaStream_t st);

@@ -62,6 +62,9 @@ int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* str
 int64_t scan_tiles(int64_t n);
 int exclusive_scan_u8(cudaStream_t st, const uint8_t* in, int64_t n, uint64_t* out, uint64_t* tile_sums);
 int exclusive_scan_u64(cudaStream_t st, const uint64_t* in, int64_t n, uint64_t* out, uint64_t* tile_sums);
+// also stores the grand total at *total_out (device pointer, may be null)
+int exclusive_scan_u32(cudaStream_t st, const uint32_t* in, int64_t n, uint64_t* out, uint64_t* tile_sums,
+                       uint64_t* total_out);
 int launch_ref_range(cudaStream_t st, const uint64_t* r0, int64_t n0, const uint64_t* r1, int64_t n1,
                      int32_t ref_h, int64_t* out);
 int launch_rows(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* recs,

@@ -190,7 +190,7 @@ __global__ void tile_sum_kernel(const T* __restrict__ in, int64_t n, uint64_t* _
 }
 
 // single CTA: in-place exclusive scan of the tile sums; total -> sums[n_tiles]
-__global__ void tile_scan_kernel(uint64_t* sums, int64_t n_tiles) {
+__global__ void tile_scan_kernel(uint64_t* sums, int64_t n_tiles, uint64_t* total_out) {
   __shared__ uint64_t sh[1024];
   __shared__ uint64_t carry;
   if (threadIdx.x == 0) carry = 0;
@@ -212,7 +212,10 @@ __global__ void tile_scan_kernel(uint64_t* sums, int64_t n_tiles) {
     if (threadIdx.x == 1023) carry = c + incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) sums[n_tiles] = carry;
+  if (threadIdx.x == 0) {
+    sums[n_tiles] = carry;
+    if (total_out) *total_out = carry;
+  }
 }
 
 template <class T>
@@ -245,12 +248,12 @@ __global__ void tile_apply_kernel(const T* __restrict__ in, int64_t n,
 
 template <class T>
 static int exclusive_scan_impl(cudaStream_t st, const T* in, int64_t n, uint64_t* out,
-                               uint64_t* tile_sums /* n_tiles + 1 */) {
+                               uint64_t* tile_sums /* n_tiles + 1 */, uint64_t* total_out = nullptr) {
   int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   if (n_tiles < 1) n_tiles = 1;
   tile_sum_kernel<T><<<(unsigned)n_tiles, SCAN_T, 0, st>>>(in, n, tile_sums);
   hawk_note_launch(1);
-  tile_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, n_tiles);
+  tile_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, n_tiles, total_out);
   hawk_note_launch(1);
   tile_apply_kernel<T><<<(unsigned)n_tiles, SCAN_T, 0, st>>>(in, n, tile_sums, out);
   hawk_note_launch(1);
@@ -266,6 +269,10 @@ int exclusive_scan_u8(cudaStream_t st, const uint8_t* in, int64_t n, uint64_t* o
 }
 int exclusive_scan_u64(cudaStream_t st, const uint64_t* in, int64_t n, uint64_t* out, uint64_t* tile_sums) {
   return exclusive_scan_impl<uint64_t>(st, in, n, out, tile_sums);
+}
+int exclusive_scan_u32(cudaStream_t st, const uint32_t* in, int64_t n, uint64_t* out, uint64_t* tile_sums,
+                       uint64_t* total_out) {
+  return exclusive_scan_impl<uint32_t>(st, in, n, out, tile_sums, total_out);
 }
 
 // ---------------------------------------------------------------- final gather

@@ -171,11 +171,11 @@ int hawk_batch_repack_dev(hawk_batch *batch, const uint8_t *d_ascii, int64_t *ba
 /* The context's cudaStream_t (so callers can time with events on the stream the kernels
  * run on) and optional per-kernel timing: with profiling on, every K1 / K2 launch of the
  * host layer is bracketed by CUDA events; hawk_ctx_profile returns and resets the sums.
- * ms[0] = K1 pack, ms[1] = K2 scan (span table + scan + segment prefix), ms[2] = guide-table
- * pipeline, ms[3] = K3 segment compaction; n[i] = bracketed regions. */
+ * ms[0] = K1 pack_kernel, ms[1] = K2 candidate kernels + prefix sums, ms[2] = guide-table
+ * pipeline, ms[3] = K2 expand_kernel, ms[4] = K2 match_kernel; n[i] = bracketed regions. */
 void *hawk_ctx_stream(hawk_ctx *ctx);
 int hawk_ctx_set_profiling(hawk_ctx *ctx, int32_t enabled);
-int hawk_ctx_profile(hawk_ctx *ctx, double *ms /* [4] */, int64_t *n /* [4] */);
+int hawk_ctx_profile(hawk_ctx *ctx, double *ms /* [5] */, int64_t *n /* [5] */);
 
 /* ---- device layer (asynchronous on `stream`, a cudaStream_t) -------------- */
 /* K1: ASCII slot space -> planes. d_bad: one int64, must hold INT64_MAX on
@@ -184,47 +184,39 @@ int hawk_pack_dev(void *stream, const uint8_t *d_ascii, int64_t total_slots, voi
                   uint32_t *d_v, uint32_t *d_nz /* total_slots / 1024 rounded up, words */,
                   int64_t *d_bad);
 
-/* Scan plan (host side). A span is 1,024 chunks (32,768 base slots) of one haplotype; spans
- * are numbered in (haplotype, position) order and every warp of the persistent scan grid
- * (a "unit") owns a contiguous span range. hawk_scan_units gives the number of units the
- * kernel wants for a device with sm_count SMs. hawk_scan_plan fills span_off (n_hap + 1)
- * and, when unit_span is non-NULL, the balanced assignment of span ranges to n_units
- * (unit_span, n_units + 1) with each unit's cumulative share of the staging capacity
- * (unit_frac, n_units + 1, 0..1). is_ref may be NULL; raw_hits as in hawk_scan_dev.
- * Returns the number of spans. */
-int32_t hawk_scan_units(int32_t sm_count, int64_t n_spans);
-int64_t hawk_scan_plan(const int32_t *scan_start, const int32_t *scan_stop, const uint8_t *is_ref,
-                       int32_t n_hap, int32_t raw_hits, int32_t n_units, int64_t *span_off,
-                       int64_t *unit_span, double *unit_frac);
-/* bytes of device workspace for hawk_scan_dev / hawk_scan_compact_dev (no initialisation
- * required). cap_* = staging capacity in records; everything in front of the staging
- * buffers has the same layout for any capacity. */
-size_t hawk_scan_workspace_bytes(int64_t n_spans, int32_t n_units, int64_t cap_fwd, int64_t cap_rev);
-
-/* K2: PAM match on both strands + in-range / REF-core filters
- * (search_guides.py:32-131, :395-420, :468-471). All d_* are device pointers;
- * per-haplotype arrays have n_hap entries; d_span_off / d_unit_span / d_unit_frac are the
- * uploaded outputs of hawk_scan_plan. Every unit writes its (hap << 32 | pos) records,
- * ascending, into its own segment of the staging buffers inside the workspace.
- * d_counts (uint64[8]): [0..1] totals per strand, [2..3] raw PAM-hit totals, [4] != 0 when
- * a unit's share of the staging capacity overflowed. If a total exceeds its cap or [4] is
- * set, call again with caps >= the totals and exact_retry = 1 (same workspace, or a larger
- * one whose head was copied over), which sizes every unit's segment from the first launch's
- * exact counts. raw_hits = 1 gives pam_search semantics (no window / REF-core filter). */
-int hawk_scan_dev(void *stream, const void *d_q, const uint32_t *d_v, const uint32_t *d_nz,
-                  const int64_t *d_slot_off,
-                  const int32_t *d_len, const int32_t *d_scan_start, const int32_t *d_scan_stop,
-                  const uint8_t *d_is_ref, const int64_t *d_span_off, const int64_t *d_unit_span,
-                  const double *d_unit_frac, int32_t n_hap, int64_t n_spans, int32_t n_units,
-                  const hawk_params *params, int32_t raw_hits, int32_t exact_retry, int64_t cap_fwd,
-                  int64_t cap_rev, uint64_t *d_counts, void *d_workspace);
-/* K3: concatenate the staging segments into dense hit lists sorted by (haplotype,
- * position): d_hits[s] receives min(total[s], out_cap[s]) records. Same n_units / n_spans /
- * caps / exact_retry / workspace as the hawk_scan_dev call it follows. */
-int hawk_scan_compact_dev(void *stream, const double *d_unit_frac, int32_t n_units, int64_t n_spans,
-                          int32_t exact_retry, int64_t cap_fwd, int64_t cap_rev, void *d_workspace,
-                          uint64_t *d_hits_fwd, uint64_t *d_hits_rev, int64_t out_cap_fwd,
-                          int64_t out_cap_rev);
+/* K2, the PAM scan (search_guides.py:32-131 + the filters of :395-420, :468-471), as three
+ * stream-ordered stages; the caller synchronises after stages 1 and 2 to read the totals
+ * that size the next stage. Haplotypes are cut into slices of 32 chunks (1,024 base slots);
+ * hawk_scan_plan (host) fills sblock_off (n_hap + 1): first thread block (256 slices) of
+ * every haplotype, and returns the number of blocks. All d_* are device pointers;
+ * per-haplotype arrays have n_hap entries; d_sblock_off is the uploaded plan.
+ *   stage 1  hawk_scan_count_dev: candidate chunks (non-REF haplotypes: chunks with a variant
+ *            base in reach of a guide core, found in the nz summary plane; REF haplotypes
+ *            and raw_hits = 1 (pam_search semantics): every chunk). totals[0] = candidates.
+ *   stage 2  hawk_scan_match_dev: ordered candidate list (d_cand, n_cand x 8 bytes) + PAM match
+ *            on both strands + filters -> hit masks (d_masks, n_cand x 8 bytes).
+ *            totals[1..2] = hits per strand, totals[3..4] = raw PAM hits (raw_hits = 1).
+ *   stage 3  hawk_scan_expand_dev: (hap << 32 | pos) records, ascending, totals[1] / totals[2]
+ *            of them in d_hits_fwd / d_hits_rev.
+ * hawk_scan_totals(workspace) is the device address of uint64 totals[8]. */
+int64_t hawk_scan_plan(const int32_t *scan_start, const int32_t *scan_stop, int32_t n_hap,
+                       int64_t *sblock_off);
+size_t hawk_scan_workspace_bytes(int32_t n_hap, int64_t n_sblocks);
+size_t hawk_scan_match_workspace_bytes(int64_t n_cand);
+const uint64_t *hawk_scan_totals(const void *d_workspace);
+int hawk_scan_count_dev(void *stream, const void *d_q, const uint32_t *d_v, const uint32_t *d_nz,
+                        const int64_t *d_slot_off, const int32_t *d_len, const int32_t *d_scan_start,
+                        const int32_t *d_scan_stop, const uint8_t *d_is_ref, const int64_t *d_sblock_off,
+                        int32_t n_hap, int64_t n_sblocks, const hawk_params *params, int32_t raw_hits,
+                        void *d_workspace);
+int hawk_scan_match_dev(void *stream, const void *d_q, const uint32_t *d_v, const uint32_t *d_nz,
+                        const int64_t *d_slot_off, const int32_t *d_len, const int32_t *d_scan_start,
+                        const int32_t *d_scan_stop, const uint8_t *d_is_ref, const int64_t *d_sblock_off,
+                        int32_t n_hap, int64_t n_sblocks, const hawk_params *params, int32_t raw_hits,
+                        int64_t n_cand, uint64_t *d_cand, uint64_t *d_masks, void *d_workspace,
+                        void *d_match_workspace);
+int hawk_scan_expand_dev(void *stream, int64_t n_cand, const uint64_t *d_cand, const uint64_t *d_masks,
+                         void *d_match_workspace, uint64_t *d_hits_fwd, uint64_t *d_hits_rev);
 
 /* N1 (next row): materialise haplotype texts on the device from the reference text and
  * per-haplotype sorted, non-overlapping edit lists (haplotype.py:106-121,185-252
