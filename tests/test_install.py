@@ -1,0 +1,106 @@
+"""The drop-in seam: install() rebinds the three names crisprhawk/crisprhawk.py resolves at
+call time (crisprhawk.py:18 encode, :29 search, :64 encode_haplotypes) and uninstall() puts
+the originals back. Needs libhawkscan.so (it is loaded up front so a missing library fails
+here, not in the middle of a run) but no GPU."""
+
+import types
+
+import pytest
+
+import crispr_hawk_b200 as hawk
+from crispr_hawk_b200 import _cabi, encoder, search_guides
+
+
+def _fake_driver():
+    m = types.ModuleType("crisprhawk.crisprhawk")
+    m.encode = lambda *a: "ref-encode"
+    m.search = lambda *a: "ref-search"
+    m.encode_haplotypes = lambda *a: "ref-encode-haplotypes"
+    return m
+
+
+def test_install_rebinds_and_uninstall_restores():
+    drv = _fake_driver()
+    orig = (drv.encode, drv.search, drv.encode_haplotypes)
+    assert hawk.install(drv) is drv
+    assert drv.encode is encoder.encode
+    assert drv.search is search_guides.search
+    assert drv.encode_haplotypes is encoder.encode_haplotypes
+    hawk.install(drv)  # idempotent
+    hawk.uninstall(drv)
+    assert (drv.encode, drv.search, drv.encode_haplotypes) == orig
+
+
+def test_install_fails_loudly_without_the_library(monkeypatch, tmp_path):
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "libhawkscan.so"))
+    with pytest.raises(_cabi.HawkLibraryError):
+        hawk.install(_fake_driver())
+
+
+def test_signatures_match_the_reference():
+    import inspect
+
+    assert list(inspect.signature(hawk.encode).parameters) == ["sequence", "verbosity", "debug"]
+    assert list(inspect.signature(hawk.search).parameters) == [
+        "pam", "region", "haplotypes", "haplotypes_bits", "guidelen", "right", "variants_present", "phased",
+        "verbosity", "debug",
+    ]  # fmt: skip  (search_guides.py:510-521)
+    assert list(inspect.signature(hawk.encode_haplotypes).parameters) == ["haplotypes", "args"]  # crisprhawk.py:64
+
+
+@pytest.mark.ref
+def test_signatures_equal_live_reference():
+    import inspect
+
+    from oracle import refshim
+
+    ref = refshim.load()
+    assert list(inspect.signature(ref.search_guides.search).parameters) == list(inspect.signature(hawk.search).parameters)
+    assert list(inspect.signature(ref.encoder.encode).parameters) == list(inspect.signature(hawk.encode).parameters)
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function include/hawkscan.h declares is exported by libhawkscan.so and bound by
+    the ctypes layer (no compute calls: works without a GPU)."""
+    import ctypes
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "hawkscan.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(hawk_[a-z0-9_]+)\s*\(", text))
+    declared -= {"hawk_ctx", "hawk_batch", "hawk_result", "hawk_params"}
+    assert len(declared) >= 30
+    lib = _cabi.load_library()
+    raw = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in hawkscan.h but not exported"
+        assert name in _cabi.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.hawk_abi_version() == 1
+    assert lib.hawk_strerror(_cabi.HAWK_EIUPAC).decode() == "non-IUPAC character"
+    # host-only helpers work without a device
+    import numpy as np
+
+    lens = np.array([5, 300, 0], np.int32)
+    off = np.zeros(4, np.int64)
+    total = ctypes.c_int64()
+    assert lib.hawk_layout(_cabi.ptr(lens, ctypes.c_int32), 3, _cabi.ptr(off, ctypes.c_int64), ctypes.byref(total)) == 0
+    from crispr_hawk_b200 import marshal
+
+    want, wtotal = marshal.layout(lens)
+    assert off.tolist() == want.tolist() and total.value == wtotal
+
+
+def test_no_cpu_fallback_without_a_device():
+    """On a box without a GPU the product path must fail loudly, never compute on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(_cabi.HawkLibraryError) as ei:
+        _cabi.Context(0)
+    assert "no CPU path" in str(ei.value) or "CUDA" in str(ei.value)
+    with pytest.raises(_cabi.HawkLibraryError):
+        hawk.encode("ACGT", 0, True)
