@@ -65,11 +65,17 @@ SIGNATURES = {
     "hawk_batch_create": (C.c_int, [_P, _U8P, _I64P, _I32P, C.c_int32, C.POINTER(_P), _I64P]),
     "hawk_batch_create_dev": (C.c_int, [_P, _P, _I64P, _I32P, C.c_int32, C.POINTER(_P), _I64P]),
     "hawk_batch_repack_dev": (C.c_int, [_P, _P, _I64P]),
+    "hawk_batch_create_from_edits": (
+        C.c_int,
+        [_P, _U8P, C.c_int64, C.c_int32, C.c_int32, _I64P, _I32P, _I32P, _I32P, _I64P, _U8P, C.c_int64,
+         C.POINTER(_P), _I64P],
+    ),  # fmt: skip
+    "hawk_batch_layout": (C.c_int, [_P, _I64P, _I32P]),
     "hawk_ctx_stream": (C.c_void_p, [_P]),
     "hawk_ctx_set_profiling": (C.c_int, [_P, C.c_int32]),
     "hawk_ctx_profile": (C.c_int, [_P, C.POINTER(C.c_double), _I64P]),
     "hawk_materialize_dev": (
-        C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P],
+        C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P],
     ),
     "hawk_batch_destroy": (C.c_int, [_P]),
     "hawk_batch_export_nibbles": (C.c_int, [_P, C.c_int32, _U8P, _U8P]),
@@ -235,6 +241,44 @@ class Batch:
         self.handle = h
         self.has_posmap = False
         self.has_alleles = False
+
+    @classmethod
+    def from_edits(cls, ctx: "Context", ref_ascii: np.ndarray, region_start: int, edit_off, edit_pos, edit_reflen,
+                   edit_altlen, edit_altoff, alt_pool) -> "Batch":  # fmt: skip
+        """hawk_batch_create_from_edits: haplotypes materialised on the device from edit lists."""
+        self = cls.__new__(cls)
+        self.ctx, self.lib = ctx, ctx.lib
+        ref = np.ascontiguousarray(ref_ascii, dtype=np.uint8)
+        eo = np.ascontiguousarray(edit_off, dtype=np.int64)
+        ep = np.ascontiguousarray(edit_pos, dtype=np.int32)
+        rl = np.ascontiguousarray(edit_reflen, dtype=np.int32)
+        al = np.ascontiguousarray(edit_altlen, dtype=np.int32)
+        ao = np.ascontiguousarray(edit_altoff, dtype=np.int64)
+        pool = np.ascontiguousarray(alt_pool, dtype=np.uint8)
+        self.n_hap = len(eo) - 1
+        h, bad = _P(), C.c_int64(-1)
+        rc = self.lib.hawk_batch_create_from_edits(
+            ctx.handle, ptr(ref, C.c_uint8), len(ref), int(region_start), self.n_hap, ptr(eo, C.c_int64),
+            ptr(ep, C.c_int32), ptr(rl, C.c_int32), ptr(al, C.c_int32), ptr(ao, C.c_int64), ptr(pool, C.c_uint8),
+            len(pool), C.byref(h), C.byref(bad),
+        )  # fmt: skip
+        self.bad_slot = bad.value
+        if rc != HAWK_OK:
+            err = HawkLibraryError(self.lib.hawk_last_error().decode(), rc)
+            err.bad_slot = bad.value
+            raise err
+        self.handle = h
+        self.slot_off = np.zeros(self.n_hap + 1, np.int64)
+        self.lens = np.zeros(self.n_hap, np.int32)
+        check(self.lib.hawk_batch_layout(h, ptr(self.slot_off, C.c_int64), ptr(self.lens, C.c_int32)))
+        self.has_posmap, self.has_alleles = True, False
+        return self
+
+    def export_text(self, hap: int) -> str:
+        """Haplotype text rebuilt from the planes and the case plane."""
+        nib, low = self.export_nibbles(hap, want_lower=True)
+        lut = np.frombuffer(b"?ACMGRSVTWYHKDBN", np.uint8)
+        return (lut[nib] | (low << 5).astype(np.uint8)).tobytes().decode("ascii")
 
     def repack(self, device_ptr: int) -> None:
         """Re-run K1 from device-resident texts of the same layout (hawk_batch_repack_dev)."""

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <new>
 #include <vector>
@@ -377,6 +378,106 @@ extern "C" int hawk_batch_create_dev(hawk_ctx* c, const uint8_t* d_ascii, const 
                                      int64_t* bad_slot) {
   if ((uintptr_t)d_ascii & 15) return hawk_fail(HAWK_EINVAL, "hawk_batch_create_dev: d_ascii must be 16-byte aligned");
   return batch_create_impl(c, d_ascii, true, slot_off, len, n_hap, out, bad_slot);
+}
+
+// ---- N1: haplotypes as edit lists against the reference text --------------------------------
+extern "C" int hawk_batch_create_from_edits(hawk_ctx* c, const uint8_t* ref_ascii, int64_t ref_len,
+                                            int32_t region_start, int32_t n_hap, const int64_t* edit_off,
+                                            const int32_t* edit_pos, const int32_t* edit_reflen,
+                                            const int32_t* edit_altlen, const int64_t* edit_altoff,
+                                            const uint8_t* alt_pool, int64_t alt_pool_len, hawk_batch** out,
+                                            int64_t* bad_slot) {
+  if (!c || !out || !ref_ascii || ref_len <= 0 || n_hap < 0 || (n_hap > 0 && !edit_off))
+    return hawk_fail(HAWK_EINVAL, "hawk_batch_create_from_edits: bad arguments");
+  if (ref_len > INT32_MAX - 4096) return hawk_fail(HAWK_EINVAL, "hawk_batch_create_from_edits: reference too long");
+  CKCUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  Trace tr;
+  const int64_t n_edits = n_hap ? edit_off[n_hap] : 0;
+  const size_t ne = (size_t)(n_edits > 0 ? n_edits : 1), nh = (size_t)(n_hap > 0 ? n_hap : 1);
+  DevBuf d_ref, d_eoff, d_pos, d_rl, d_al, d_ao, d_op, d_pool, d_so, d_len, d_segcnt, d_bad, d_ascii;
+  // the reference text with readable slack behind it (block copies read whole aligned words)
+  CK(d_ref.alloc(c, (size_t)ref_len + 32));
+  CKCUDA(cudaMemsetAsync(d_ref.as<uint8_t>() + ref_len, 0, 32, st));
+  CKCUDA(cudaMemcpyAsync(d_ref.p, ref_ascii, (size_t)ref_len, cudaMemcpyHostToDevice, st));
+  const int64_t zero64 = 0;
+  const int32_t zero32 = 0;
+  const uint8_t zero8 = 0;
+  CK(upload(c, d_eoff, n_hap ? (const void*)edit_off : (const void*)&zero64, (size_t)(n_hap + 1) * 8));
+  CK(upload(c, d_pos, n_edits ? (const void*)edit_pos : (const void*)&zero32, ne * 4));
+  CK(upload(c, d_rl, n_edits ? (const void*)edit_reflen : (const void*)&zero32, ne * 4));
+  CK(upload(c, d_al, n_edits ? (const void*)edit_altlen : (const void*)&zero32, ne * 4));
+  CK(upload(c, d_ao, n_edits ? (const void*)edit_altoff : (const void*)&zero64, ne * 8));
+  CK(upload(c, d_pool, alt_pool_len > 0 ? alt_pool : &zero8, (size_t)(alt_pool_len > 0 ? alt_pool_len : 1)));
+  CK(d_op.alloc(c, ne * 4));
+  CK(d_len.alloc(c, nh * 4));
+  CK(d_segcnt.alloc(c, nh * 4));
+  const int32_t int_max = INT32_MAX;
+  CK(upload(c, d_bad, &int_max, 4));
+  // pass 0 on the device: validation, output positions, lengths, segment counts
+  CK(launch_derive(st, n_hap, d_eoff.as<int64_t>(), d_pos.as<int32_t>(), d_rl.as<int32_t>(), d_al.as<int32_t>(),
+                   d_ao.as<int64_t>(), ref_len, alt_pool_len, region_start, d_op.as<int32_t>(), d_len.as<int32_t>(),
+                   d_segcnt.as<int32_t>(), d_bad.as<int32_t>(), nullptr, nullptr, nullptr, nullptr, 0));
+  std::vector<int32_t> len(n_hap), seg_count(n_hap);
+  int32_t bad_hap = INT32_MAX;
+  if (n_hap) {
+    CKCUDA(cudaMemcpyAsync(len.data(), d_len.p, (size_t)n_hap * 4, cudaMemcpyDeviceToHost, st));
+    CKCUDA(cudaMemcpyAsync(seg_count.data(), d_segcnt.p, (size_t)n_hap * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CKCUDA(cudaMemcpyAsync(&bad_hap, d_bad.p, 4, cudaMemcpyDeviceToHost, st));
+  CKCUDA(cudaStreamSynchronize(st));
+  tr.tick("edits: upload + derive");
+  if (bad_hap != INT32_MAX)
+    return hawk_fail(HAWK_EINVAL,
+                     "hawk_batch_create_from_edits: the edits of haplotype %d are not sorted, non-overlapping "
+                     "SNVs / anchored insertions / anchored deletions inside the reference", bad_hap);
+  std::vector<int64_t> slot_off(n_hap + 1), seg_off(n_hap + 1);
+  int64_t total = 0;
+  CK(hawk_layout(len.data(), n_hap, slot_off.data(), &total));
+  seg_off[0] = 0;
+  for (int32_t h = 0; h < n_hap; ++h) seg_off[h + 1] = seg_off[h] + seg_count[h];
+  CK(upload(c, d_so, slot_off.data(), (size_t)(n_hap + 1) * 8));
+  CK(d_ascii.alloc(c, (size_t)total));
+  CK(hawk_materialize_dev(st, d_ref.as<uint8_t>(), ref_len, d_eoff.as<int64_t>(), d_pos.as<int32_t>(),
+                          d_rl.as<int32_t>(), d_al.as<int32_t>(), d_ao.as<int64_t>(), d_op.as<int32_t>(),
+                          d_pool.as<uint8_t>(), d_so.as<int64_t>(), d_len.as<int32_t>(), n_hap, total, n_edits,
+                          n_hap ? *std::max_element(len.begin(), len.end()) : 0, d_ascii.as<uint8_t>()));
+  hawk_batch* b = nullptr;
+  CK(batch_create_impl(c, d_ascii.as<uint8_t>(), true, slot_off.data(), len.data(), n_hap, &b, bad_slot));
+  tr.tick("edits: materialise + pack");
+  // pass 1: the run-length coordinate maps, straight into the batch
+  const size_t n_seg = (size_t)seg_off[n_hap];
+  int rc = upload(c, b->seg_off, seg_off.data(), (size_t)(n_hap + 1) * 8);
+  if (!rc) rc = b->seg_rel.alloc(c, (n_seg ? n_seg : 1) * 4);
+  if (!rc) rc = b->seg_gen.alloc(c, (n_seg ? n_seg : 1) * 4);
+  if (!rc) rc = b->seg_step.alloc(c, n_seg ? n_seg : 1);
+  if (!rc)
+    rc = launch_derive(st, n_hap, d_eoff.as<int64_t>(), d_pos.as<int32_t>(), d_rl.as<int32_t>(), d_al.as<int32_t>(),
+                       d_ao.as<int64_t>(), ref_len, alt_pool_len, region_start, nullptr, nullptr, nullptr, nullptr,
+                       b->seg_off.as<int64_t>(), b->seg_rel.as<int32_t>(), b->seg_gen.as<int32_t>(),
+                       b->seg_step.as<uint8_t>(), 1);
+  if (!rc) rc = hawk_check_cuda(cudaStreamSynchronize(st), "segments sync");
+  if (rc != HAWK_OK) {
+    hawk_batch_destroy(b);
+    return rc;
+  }
+  b->h_seg_off = seg_off;
+  b->first_gen.assign(n_hap, region_start);
+  b->linear.resize(n_hap);
+  for (int32_t h = 0; h < n_hap; ++h) b->linear[h] = seg_count[h] == 1 ? 1 : 0;
+  b->gmin = region_start;
+  b->gmax = (int32_t)(region_start + ref_len - 1);  // edits never create coordinates outside the reference
+  b->has_posmap = true;
+  tr.tick("edits: segments");
+  *out = b;
+  return HAWK_OK;
+}
+
+extern "C" int hawk_batch_layout(hawk_batch* b, int64_t* slot_off, int32_t* len) {
+  if (!b) return hawk_fail(HAWK_EINVAL, "hawk_batch_layout: null batch");
+  if (slot_off) memcpy(slot_off, b->slot_off.data(), (size_t)(b->n_hap + 1) * 8);
+  if (len && b->n_hap) memcpy(len, b->len.data(), (size_t)b->n_hap * 4);
+  return HAWK_OK;
 }
 
 extern "C" int hawk_batch_repack_dev(hawk_batch* b, const uint8_t* d_ascii, int64_t* bad_slot) {

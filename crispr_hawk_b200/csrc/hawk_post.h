@@ -59,6 +59,12 @@ int launch_gather_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, 
 int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n_max,
                        const uint64_t* totals, const uint32_t* key_table, int32_t key_min, int64_t* bucket);
 
+// synth_kernels.cu: edit lists -> lengths, output positions, posmap segments (two passes)
+int launch_derive(cudaStream_t st, int32_t n_hap, const int64_t* edit_off, const int32_t* pos, const int32_t* reflen,
+                  const int32_t* altlen, const int64_t* altoff, int64_t ref_len, int64_t alt_pool_len,
+                  int32_t region_start, int32_t* outpos, int32_t* len, int32_t* seg_count, int32_t* bad,
+                  const int64_t* seg_off, int32_t* seg_rel, int32_t* seg_gen, uint8_t* seg_step, int pass);
+
 int64_t scan_tiles(int64_t n);
 int exclusive_scan_u8(cudaStream_t st, const uint8_t* in, int64_t n, uint64_t* out, uint64_t* tile_sums);
 int exclusive_scan_u64(cudaStream_t st, const uint64_t* in, int64_t n, uint64_t* out, uint64_t* tile_sums);

@@ -68,7 +68,11 @@ class PackedRegion:
     def __iter__(self):
         return (self[i] for i in range(len(self)))
 
+    owners = None  # ids of the haplotype objects the batch was built for (device-materialised)
+
     def matches(self, haplotypes) -> bool:
+        if self.owners is not None:
+            return [id(h) for h in haplotypes] == self.owners
         return len(haplotypes) == len(self._texts) and all(
             marshal.hap_text(h) is t or marshal.hap_text(h) == t for h, t in zip(haplotypes, self._texts)
         )

@@ -1,0 +1,184 @@
+"""N1 (next row of the scope table): phased haplotypes materialised on the device.
+
+The reference assembles every haplotype on the host, one variant at a time, rewriting a
+Python list of characters and two dicts of `len(haplotype)` entries per indel
+(haplotype.py:106-159, 185-252) -- the real wall of a run at BASELINE scale.
+Here the host keeps what it is good at (which variants each haplotype copy carries, sample
+strings, variant ids, allele frequencies: all metadata) and hands the device only the
+*edit lists*; `hawk_batch_create_from_edits` materialises the texts in HBM, packs them and
+attaches run-length coordinate maps. Nothing of haplotype length ever crosses PCIe or lives
+in a Python object unless somebody asks for it.
+
+`EditHaplotype` is duck-typed like the reference's `Haplotype` (haplotype.py:23-77) as far
+as `search()` and its callers read it; `.sequence`, `.posmap` and `.posmap_rev` are lazy.
+Edits must be sorted, non-overlapping SNVs / anchored insertions / anchored deletions: what
+`add_variants_phased` produces for a phased VCF whose records do not overlap on a haplotype
+(SURVEY.md Appendix B)."""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _cabi, marshal
+from .encoder import PackedRegion
+
+PADDING = marshal.PADDING
+
+
+@dataclass
+class Edit:
+    pos: int  # genomic coordinate of the anchor base (VCF POS)
+    ref: str  # REF allele
+    alt: str  # ALT allele
+
+
+class SegmentMap:
+    """`posmap` of one haplotype as run-length segments: int -> genomic coordinate."""
+
+    def __init__(self, rel: np.ndarray, gen: np.ndarray, step: np.ndarray, length: int):
+        self.rel, self.gen, self.step, self.length = rel, gen, step, int(length)
+
+    def __len__(self) -> int:
+        return self.length
+
+    def __getitem__(self, i: int) -> int:
+        if i < 0 or i >= self.length:
+            raise KeyError(i)
+        k = int(np.searchsorted(self.rel, i, side="right")) - 1
+        return int(self.gen[k] + (i - self.rel[k] if self.step[k] else 0))
+
+    def values(self) -> np.ndarray:
+        return marshal.eval_segments(self.rel, self.gen, self.step, np.arange(self.length))
+
+    def last_index_of(self, g: int) -> Optional[int]:
+        """posmap_rev[g] (haplotype.py:104,159: the LAST index carrying coordinate g), or None
+        when the coordinate was deleted."""
+        seg_len = np.diff(np.append(self.rel, self.length))
+        hit1 = self.step.astype(bool) & (self.gen <= g) & (g < self.gen + seg_len)
+        hit0 = (~self.step.astype(bool)) & (self.gen == g)
+        best = -1
+        if hit1.any():
+            k = np.flatnonzero(hit1)
+            best = int((self.rel[k] + (g - self.gen[k])).max())
+        if hit0.any():
+            k = np.flatnonzero(hit0)
+            best = max(best, int((self.rel[k] + seg_len[k] - 1).max()))
+        return best if best >= 0 else None
+
+
+class _LazySeq:
+    def __init__(self, hap):
+        self._hap = hap
+
+    @property
+    def sequence(self) -> str:
+        return self._hap.text()
+
+    def __len__(self) -> int:
+        return len(self._hap)
+
+
+class EditHaplotype:
+    def __init__(self, batch: "_cabi.Batch", index: int, length: int, posmap: SegmentMap, start: int, stop: int,
+                 samples: str, variants: str, afs: Dict[str, float], hapid: str):  # fmt: skip
+        self._batch, self._index, self._len = batch, index, int(length)
+        self.posmap = posmap
+        self.start, self.stop = start, stop
+        self.samples, self.variants, self.afs, self.id = samples, variants, afs, hapid
+        self.variant_alleles: dict = {}
+        self.sequence = _LazySeq(self)
+        self._text: Optional[str] = None
+        self._rev: Optional[dict] = None
+
+    def __len__(self) -> int:
+        return self._len
+
+    def text(self) -> str:
+        if self._text is None:
+            self._text = self._batch.export_text(self._index)
+        return self._text
+
+    def __getitem__(self, idx):
+        return list(self.text()[idx]) if isinstance(idx, slice) else self.text()[idx]
+
+    @property
+    def posmap_rev(self) -> dict:
+        if self._rev is None:  # full dict only on request (the scan itself never needs it)
+            self._rev = {int(g): i for i, g in enumerate(self.posmap.values())}
+        return self._rev
+
+    def scan_bounds(self, region_start: int, region_stop: int, pamlen: int):
+        """compute_scan_start_stop (search_guides.py:49-84) from the segments."""
+        stop_g = min(region_stop - PADDING, self.stop)
+        i_stop = self.posmap.last_index_of(stop_g)
+        if i_stop is None and stop_g == region_stop - PADDING:
+            top = int(self.posmap.values().max())
+            g = stop_g
+            while i_stop is None and g <= top:
+                g += 1
+                i_stop = self.posmap.last_index_of(g)
+        if i_stop is None:
+            raise KeyError(stop_g)
+        i_start = self.posmap.last_index_of(max(region_start + PADDING, self.start))
+        if i_start is None:
+            raise KeyError(max(region_start + PADDING, self.start))
+        return i_start, i_stop - pamlen + 1
+
+
+def build_phased(ref_text: str, region_start: int, hap_edits: Sequence[Sequence[Edit]],
+                 samples: Optional[Sequence[str]] = None, variants: Optional[Sequence[str]] = None,
+                 afs: Optional[Sequence[Dict[str, float]]] = None, ids: Optional[Sequence[str]] = None,
+                 contig: str = "chr1", ctx: Optional["_cabi.Context"] = None):  # fmt: skip
+    """Materialise haplotypes `REF + edits` on the device. `ref_text` is the padded region's
+    reference (upper-case), `region_start` the genomic coordinate of its first base;
+    `hap_edits[h]` the edits of haplotype h sorted by position (an empty list = the REF
+    haplotype). Returns (haplotypes, PackedRegion) ready for `search()`."""
+    ctx = ctx or _cabi.Context.default()
+    n = len(hap_edits)
+    ref = np.frombuffer(ref_text.encode("ascii"), np.uint8)
+    edit_off = np.zeros(n + 1, np.int64)
+    pos, rl, al, pool = [], [], [], []
+    for h, edits in enumerate(hap_edits):
+        for e in edits:
+            if ref_text[e.pos - region_start : e.pos - region_start + len(e.ref)].upper() != e.ref.upper():
+                raise ValueError(f"Mismatching reference alleles in VCF and reference sequence at {e.pos}")  # haplotype.py:206-210
+            pos.append(e.pos - region_start)
+            rl.append(len(e.ref))
+            al.append(len(e.alt))
+            pool.append(e.alt.upper())
+        edit_off[h + 1] = len(pos)
+    al_arr = np.asarray(al, np.int32)
+    ao_arr = np.concatenate(([0], np.cumsum(al_arr)[:-1])).astype(np.int64) if len(al) else np.zeros(0, np.int64)
+    pool_arr = np.frombuffer("".join(pool).encode("ascii"), np.uint8) if pool else np.zeros(0, np.uint8)
+    batch = _cabi.Batch.from_edits(ctx, ref, region_start, edit_off, np.asarray(pos, np.int32), np.asarray(rl, np.int32),
+                                   al_arr, ao_arr, pool_arr)  # fmt: skip
+    region_stop = region_start + len(ref_text) - 1
+    haps: List[EditHaplotype] = []
+    for h, edits in enumerate(hap_edits):
+        rel, gen, step = [0], [region_start], [1]
+        shift = 0
+        for e in edits:
+            op = e.pos - region_start + shift
+            if len(e.alt) > 1:
+                rel += [op + 1, op + len(e.alt)]
+                gen += [e.pos, e.pos + 1]
+                step += [0, 1]
+            elif len(e.ref) > 1:
+                rel.append(op + 1)
+                gen.append(e.pos + len(e.ref))
+                step.append(1)
+            shift += len(e.alt) - len(e.ref)
+        pm = SegmentMap(np.asarray(rel, np.int64), np.asarray(gen, np.int64), np.asarray(step, np.uint8), int(batch.lens[h]))
+        is_ref = len(edits) == 0
+        haps.append(EditHaplotype(
+            batch, h, int(batch.lens[h]), pm, region_start, region_stop,
+            (samples[h] if samples else ("REF" if is_ref else f"hap{h}")),
+            (variants[h] if variants else ("NA" if is_ref else ",".join(f"{contig}-{e.pos}-{e.ref}/{e.alt}" for e in edits))),
+            (afs[h] if afs else {}), (ids[h] if ids else f"hap{h}"),
+        ))  # fmt: skip
+    packed = PackedRegion(batch, [None] * n)
+    packed.owners = [id(h) for h in haps]
+    return haps, packed

@@ -95,6 +95,8 @@ def eval_segments(rel, gen, step, idx):
 def scan_bounds(hap, region_start: int, region_stop: int, pamlen: int) -> Tuple[int, int]:
     """Mirror of compute_scan_start_stop (search_guides.py:49-84): haplotype-relative
     [start, stop) of the PAM scan, from the haplotype's own position maps."""
+    if hasattr(hap, "scan_bounds"):  # device-materialised haplotypes answer from their segments
+        return hap.scan_bounds(region_start, region_stop, pamlen)
     rev = hap.posmap_rev
     stop_g = min(region_stop - PADDING, hap.stop)
     if stop_g == region_stop - PADDING and stop_g not in rev:

@@ -291,7 +291,7 @@ def materialize_device(c: Cohort, ctx=None, device=None):
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     sites = c.hap_sites
-    g_ref = t(c.ref)
+    g_ref = t(np.concatenate((c.ref, np.zeros(32, np.uint8))))  # block copies read whole aligned words
     g_off = t(c.hap_off)
     g_pos = t(c.site_pos[sites])
     g_rl = t(c.site_reflen[sites])
@@ -307,7 +307,7 @@ def materialize_device(c: Cohort, ctx=None, device=None):
     _cabi.check(
         lib.hawk_materialize_dev(
             C.c_void_p(stream), p(g_ref), len(c.ref), p(g_off), p(g_pos), p(g_rl), p(g_al), p(g_ao),
-            p(g_op), p(g_pool), p(g_slot), p(g_len), c.n_hap, d.total_slots, p(out),
+            p(g_op), p(g_pool), p(g_slot), p(g_len), c.n_hap, d.total_slots, len(sites), int(d.lens.max()), p(out),
         ),  # fmt: skip
         "hawk_materialize_dev",
     )

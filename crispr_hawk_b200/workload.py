@@ -97,6 +97,36 @@ class Workload:
         batch.close()
         return table, h2d, d2h
 
+    def step_edits(self):
+        """N1 path: only the reference text and the per-haplotype edit lists start on the host;
+        texts are materialised on the device (hawk_batch_create_from_edits), then K1, K2 and the
+        table pipeline as usual; the guide table ends in pinned host memory."""
+        torch = self.torch
+        c = self.cohort
+        if not hasattr(self, "_edits"):
+            sites = c.hap_sites
+            pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+            self._edits = dict(ref=pin(c.ref), off=pin(c.hap_off), pos=pin(c.site_pos[sites]), rl=pin(c.site_reflen[sites]),
+                               al=pin(c.site_altlen[sites]), ao=pin(c.site_altoff[sites]),
+                               pool=pin(c.alt_pool if len(c.alt_pool) else np.zeros(1, np.uint8)))  # fmt: skip
+            self._edits_out = None
+        e = self._edits
+        batch = _cabi.Batch.from_edits(self.ctx, e["ref"], c.region_start, e["off"], e["pos"], e["rl"], e["al"], e["ao"], e["pool"])
+        res = _cabi.search(self.ctx, batch, self.params, self.a, self.b, self.d.is_ref)
+        n, w = res.n_guides, res.text_stride
+        if self._edits_out is None or len(self._edits_out["hap"]) < n:
+            cap = int(n * 1.05) + 1024
+            mk = lambda dt, k=1: torch.empty(cap * k, dtype=dt, pin_memory=True).numpy()  # noqa: E731
+            self._edits_out = {"hap": mk(torch.int32), "strand": mk(torch.uint8), "pos": mk(torch.int32),
+                               "start": mk(torch.int32), "stop": mk(torch.int32), "bucket": mk(torch.int64),
+                               "text": mk(torch.uint8, w)}  # fmt: skip
+        table = res.table(self._edits_out)
+        h2d = sum(v.nbytes for v in e.values()) + self.a.nbytes * 2 + self.d.is_ref.nbytes
+        d2h = n * (4 + 1 + 4 + 4 + 4 + 8 + w)
+        res.close()
+        batch.close()
+        return table, h2d, d2h
+
     def host_arrays_for_oracle(self, hap_indices):
         """(ascii slots, slot_off, lens, a, b, is_ref, segments) of a subset of haplotypes,
         copied to the host, in the form oracle/c_oracle.search takes."""

@@ -164,6 +164,25 @@ int hawk_result_fetch_hits(hawk_result *result, int32_t strand, uint64_t *hits /
 int hawk_batch_create_dev(hawk_ctx *ctx, const uint8_t *d_ascii, const int64_t *slot_off,
                           const int32_t *len, int32_t n_hap, hawk_batch **batch, int64_t *bad_slot);
 
+/* N1 (next row): haplotypes given as edit lists against the reference text of
+ * the padded region instead of as texts -- what Haplotype._update_sequence / _update_posmap
+ * (haplotype.py:106-159, 185-252) do per variant on the host. Haplotype h applies edits
+ * [edit_off[h], edit_off[h+1]), sorted by edit_pos (0-based index into ref_ascii of the anchor
+ * base) and non-overlapping; each is an SNV (reflen = altlen = 1), an anchored insertion
+ * (reflen 1, ALT = anchor + inserted bases) or an anchored deletion (altlen 1, REF = anchor +
+ * deleted bases); ALT text = alt_pool[edit_altoff .. + edit_altlen). The texts are
+ * materialised on the device (ALT characters lower-case, as the reference writes them), packed
+ * by K1, and the run-length coordinate maps are attached (posmap(0) = region_start), so the
+ * batch is ready for hawk_search. Only the edits cross PCIe. hawk_batch_layout returns the
+ * resulting lengths / slot offsets (n_hap + 1 and n_hap entries). */
+int hawk_batch_create_from_edits(hawk_ctx *ctx, const uint8_t *ref_ascii, int64_t ref_len,
+                                 int32_t region_start, int32_t n_hap, const int64_t *edit_off,
+                                 const int32_t *edit_pos, const int32_t *edit_reflen,
+                                 const int32_t *edit_altlen, const int64_t *edit_altoff,
+                                 const uint8_t *alt_pool, int64_t alt_pool_len, hawk_batch **batch,
+                                 int64_t *bad_slot);
+int hawk_batch_layout(hawk_batch *batch, int64_t *slot_off, int32_t *len);
+
 /* Re-run K1 into an existing batch from device-resident texts of the same layout (the
  * coordinate maps / allele tables attached to the batch are kept). */
 int hawk_batch_repack_dev(hawk_batch *batch, const uint8_t *d_ascii, int64_t *bad_slot);
@@ -222,13 +241,15 @@ int hawk_scan_expand_dev(void *stream, int64_t n_cand, const uint64_t *d_cand, c
  * per-haplotype sorted, non-overlapping edit lists (haplotype.py:106-121,185-252
  * conventions: ALT allele characters lower-case; SNV 1 base, insertion anchor + inserted
  * bases, deletion the 1-base anchor). edit_outpos[e] = haplotype index where edit e's ALT
- * text starts. Output: the ASCII slot space consumed by hawk_pack_dev. */
+ * text starts. Output: the ASCII slot space consumed by hawk_pack_dev. d_ref must be readable
+ * for 8 bytes past ref_len (block copies read whole aligned words). */
 int hawk_materialize_dev(void *stream, const uint8_t *d_ref, int64_t ref_len,
                          const int64_t *d_edit_off, const int32_t *d_edit_pos,
                          const int32_t *d_edit_reflen, const int32_t *d_edit_altlen,
                          const int64_t *d_edit_altoff, const int32_t *d_edit_outpos,
                          const uint8_t *d_alt_pool, const int64_t *d_slot_off,
                          const int32_t *d_len, int32_t n_hap, int64_t total_slots,
+                         int64_t n_edits, int32_t max_len /* longest haplotype */,
                          uint8_t *d_ascii_out);
 
 #ifdef __cplusplus
