@@ -76,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )  # fmt: skip
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -87,12 +87,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples taken inside [t_begin, t_end] (the timed region); when the
+        region was too short to catch one, of all samples since start() (warm-up + timed: the
+        same kernels back to back) -- `window` says which."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -100,7 +103,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if t_begin is not None and t_begin <= t <= t_end]
+        window = "timed region" if inside else "warm-up + timed region"
+        for r in inside or [r for _, r in self.rows]:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -116,6 +121,7 @@ class ClockSampler:
             "sm_mhz": statistics.median(sm) if sm else None,
             "sm_max_mhz": max(mx) if mx else None,
             "samples": len(sm),
+            "window": window,
             "reasons": sorted(reasons),
         }
 
@@ -268,22 +274,24 @@ def run_product_arm(args, rank, world, local_rank):
         return n, h
 
     torch.cuda.set_stream(stream)  # NCCL / flush work is ordered with the library's stream
+    sampler = None if args.no_clocks else ClockSampler(local_rank).start()
     for _ in range(max(args.warmup, 3)):
         n_guides, n_hits = one_step()
     barrier()
-    sampler = None if args.no_clocks else ClockSampler(local_rank).start()
     launches0 = lib.hawk_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
+    w0 = time.time()
     ev0.record(stream)
     for _ in range(args.steps):
         n_guides, n_hits = one_step()
     ev1.record(stream)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
+    w1 = time.time()
     dev_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if sampler else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled"]}
+    clocks = sampler.stop(w0, w1) if sampler else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled"]}
     launches = lib.hawk_launch_count() - launches0
     # per-kernel times: a separate pass with the library's CUDA-event brackets switched on
     ctx.set_profiling(True)
@@ -435,7 +443,7 @@ if os.path.exists(_traffic):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
