@@ -97,10 +97,10 @@ SIGNATURES = {
     ),
     "hawk_scan_match_dev": (
         C.c_int,
-        [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.POINTER(HawkParams), C.c_int32,
-         C.c_int64, _P, _P, _P, _P],
+        [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.POINTER(HawkParams), C.c_int32,
+         C.c_int64, _P, _P, _P],
     ),  # fmt: skip
-    "hawk_scan_expand_dev": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
+    "hawk_scan_expand_dev": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -686,7 +686,7 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
   in.is_ref = (uint8_t*)(dp + o_ref);
   for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(c, 16));
   if (n_sblocks == 0) return HAWK_OK;
-  DevBuf d_ws, d_mws, d_cand, d_masks;
+  DevBuf d_ws, d_mws, d_masks;
   CK(d_ws.alloc(c, hawk_scan_workspace_bytes(n_hap, n_sblocks)));
   tr.tick("scan: plan + upload");
   ProfScope prof_scope(c);
@@ -700,12 +700,11 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
   const int64_t n_cand = (int64_t)totals[0];
   tr.tick("scan: candidates");
   if (n_cand == 0) return HAWK_OK;
-  CK(d_mws.alloc(c, hawk_scan_match_workspace_bytes(n_cand)));
-  CK(d_cand.alloc(c, (size_t)n_cand * 8));
+  CK(d_mws.alloc(c, hawk_scan_match_workspace_bytes(n_sblocks)));
   CK(d_masks.alloc(c, (size_t)n_cand * 8));
   rc = hawk_scan_match_dev(st, b->q.p, b->v.as<uint32_t>(), b->nz.as<uint32_t>(), b->d_slot_off.as<int64_t>(),
-                           b->d_len.as<int32_t>(), in.a, in.b, in.is_ref, in.sblock_off, n_hap, n_sblocks, params, raw,
-                           n_cand, d_cand.as<uint64_t>(), d_masks.as<uint64_t>(), d_ws.p, d_mws.p);
+                           b->d_len.as<int32_t>(), in.a, in.b, in.is_ref, n_hap, n_sblocks, params, raw, n_cand,
+                           d_masks.as<uint64_t>(), d_ws.p, d_mws.p);
   CK(rc);
   CKCUDA(cudaMemcpyAsync(totals, hawk_scan_totals(d_ws.p), 64, cudaMemcpyDeviceToHost, st));
   CKCUDA(cudaStreamSynchronize(st));
@@ -713,7 +712,7 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
   out.n[1] = (int64_t)totals[2];
   tr.tick("scan: match");
   for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(c, (size_t)(out.n[s] > 0 ? out.n[s] : 1) * 8));
-  rc = hawk_scan_expand_dev(st, n_cand, d_cand.as<uint64_t>(), d_masks.as<uint64_t>(), d_mws.p,
+  rc = hawk_scan_expand_dev(st, n_hap, n_sblocks, n_cand, d_masks.as<uint64_t>(), d_ws.p, d_mws.p,
                             out.hits[0].as<uint64_t>(), out.hits[1].as<uint64_t>());
   CK(rc);
   tr.tick("scan: expand launched");

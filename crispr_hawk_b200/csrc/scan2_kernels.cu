@@ -11,13 +11,15 @@
 //                core reaches at most one chunk either side when G <= 32) -- this is the
 //                "scan non-reference haplotypes only in windows overlapping their variants"
 //                rule, at 1 bit per 32 bp. REF haplotypes / pam_search mode: every chunk.
-//   cand_write   the slice masks -> ordered candidate list (hap << 32 | chunk)
-//   match        one thread per candidate: the chunk's three case words (masked to the guide's
+//   match        one CTA per block of 256 slices: its candidates are compacted in shared memory
+//                (chunk order) and matched 256 at a time, so every lane is busy although only a
+//                few per cent of the chunks are candidates. Per candidate: the chunk's three
+//                case words (masked to the guide's
 //                reach), log-doubling sliding OR over that 96-bit window -> per-position "core
 //                holds a variant" masks for both strands; two 128-bit plane loads; branch-free
 //                AND-mask PAM test on both strands over shared funnel-shifted planes; interval
 //                masks for the scan bounds and is_pamhit_in_range -> two 32-bit hit masks
-//   expand       hit masks -> records at their exact offsets
+//   expand       one CTA per slice block again: hit masks -> records at their exact offsets
 // The per-block counts of cand_count / match are prefix-summed by the tile scan of
 // post_kernels.cu; the host reads two totals (candidates, hits) to size the next stage.
 #include <cuda_runtime.h>
@@ -129,15 +131,11 @@ __global__ void __launch_bounds__(S2_T) cand_count_kernel(BatchView B, ScanConst
   }
 }
 
-__global__ void __launch_bounds__(S2_T) cand_write_kernel(const HapScan* __restrict__ hs, const int2* __restrict__ blk_tab,
-                                                          const uint32_t* __restrict__ slice_mask,
-                                                          const uint64_t* __restrict__ blk_base,
-                                                          uint64_t* __restrict__ cand_out) {
-  __shared__ uint32_t wsum[S2_T / 32];
-  const int2 e = __ldg(&blk_tab[blockIdx.x]);
-  uint32_t cand = slice_mask[(int64_t)blockIdx.x * S2_T + threadIdx.x];
-  const uint32_t mine = __popc(cand);
+// Candidates of one slice block (256 slices = 8,192 chunks), in chunk order, as 16-bit chunk
+// offsets from the block's first chunk in shared memory. Returns their number.
+__device__ __forceinline__ uint32_t compact_block_candidates(uint32_t cand, uint16_t* list, uint32_t* wsum) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t mine = __popc(cand);
   uint32_t incl = mine;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -146,34 +144,49 @@ __global__ void __launch_bounds__(S2_T) cand_write_kernel(const HapScan* __restr
   }
   if (lane == 31) wsum[warp] = incl;
   __syncthreads();
-  if (!mine) return;
-  uint32_t wbase = 0;
-  for (int k = 0; k < warp; ++k) wbase += wsum[k];
-  uint64_t p = blk_base[blockIdx.x] + wbase + (incl - mine);
-  const uint64_t c32 = (uint64_t)(uint32_t)((hs[e.x].a >> 5) + 32 * (e.y + (int32_t)threadIdx.x));
-  const uint64_t key = ((uint64_t)(uint32_t)e.x << 32) | c32;
+  uint32_t wbase = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < S2_T / 32; ++k) {
+    const uint32_t t = wsum[k];
+    if (k < warp) wbase += t;
+    total += t;
+  }
+  uint32_t p = wbase + (incl - mine);
+  const uint32_t off = 32u * threadIdx.x;
   while (cand) {
     const int b = __ffs(cand) - 1;
     cand &= cand - 1;
-    cand_out[p++] = key + (uint32_t)b;
+    list[p++] = (uint16_t)(off + b);
   }
+  __syncthreads();
+  return total;
 }
 
 // ---------------------------------------------------------------- match
-__global__ void __launch_bounds__(S2_T) match_kernel(BatchView B, ScanConst K, const HapScan* __restrict__ hs,
-                                                     const uint64_t* __restrict__ cand, int64_t n_cand,
-                                                     uint2* __restrict__ masks, uint32_t* __restrict__ blk_hits0,
-                                                     uint32_t* __restrict__ blk_hits1,
+// One CTA per slice block: its candidates are compacted in shared memory, then matched 256 at
+// a time (every lane busy). Hit masks go to masks[cand_base[block] + k]; per-block hit counts.
+__global__ void __launch_bounds__(S2_T, 6) match_kernel(BatchView B, ScanConst K, const HapScan* __restrict__ hs,
+                                                        const int2* __restrict__ blk_tab,
+                                                     const uint32_t* __restrict__ slice_mask,
+                                                     const uint64_t* __restrict__ cand_base, uint2* __restrict__ masks,
+                                                     uint32_t* __restrict__ blk_hits0, uint32_t* __restrict__ blk_hits1,
                                                      unsigned long long* __restrict__ raw_tot) {
+  __shared__ uint16_t list[S2_T * 32];
+  __shared__ uint32_t wsum[S2_T / 32];
   __shared__ uint32_t red[3][S2_T / 32];
-  const int64_t i = (int64_t)blockIdx.x * S2_T + threadIdx.x;
-  uint32_t out[2] = {0, 0}, raw[2] = {0, 0};
-  if (i < n_cand) {
-    const uint64_t e = cand[i];
-    const int32_t h = (int32_t)(e >> 32), c = (int32_t)(e & 0xFFFFFFFFu);
-    const HapScan H = hs[h];
+  __shared__ HapScan sH;  // block-uniform: kept out of the registers
+  const int2 e = __ldg(&blk_tab[blockIdx.x]);
+  if (threadIdx.x == 0) sH = hs[e.x];
+  const uint32_t total = compact_block_candidates(slice_mask[(int64_t)blockIdx.x * S2_T + threadIdx.x], list, wsum);
+  const HapScan& H = sH;  // published by the barriers inside the compaction
+  const int32_t c_block = (H.a >> 5) + 32 * e.y;  // first chunk of the block's first slice
+  uint2* const out_masks = masks + cand_base[blockIdx.x];
+  const bool use_v = !(K.raw || H.is_ref);
+  uint32_t n0 = 0, n1 = 0, nr = 0;
+  for (uint32_t k = threadIdx.x; k < total; k += S2_T) {
+    const int32_t c = c_block + list[k];
+    uint32_t out[2] = {0, 0}, raw[2] = {0, 0};
     if (K.small) {
-      const bool use_v = !(K.raw || H.is_ref);
       uint32_t w0 = 0, w1 = 0, w2 = 0;
       bool go = true;
       if (use_v) {
@@ -188,80 +201,106 @@ __global__ void __launch_bounds__(S2_T) match_kernel(BatchView B, ScanConst K, c
     } else {
       scan_chunk(B, K, H, (int64_t)c, out, raw);
     }
-    masks[i] = make_uint2(out[0], out[1]);
+    out_masks[k] = make_uint2(out[0], out[1]);
+    n0 += __popc(out[0]);
+    n1 += __popc(out[1]);
+    nr += (uint32_t)__popc(raw[0]) | ((uint32_t)__popc(raw[1]) << 16);
   }
-  uint32_t n0 = __popc(out[0]), n1 = __popc(out[1]), nr = (uint32_t)__popc(raw[0]) | ((uint32_t)__popc(raw[1]) << 16);
+  // raw counts: <= 32 per chunk and strand, <= 32 rounds of a dense block: fits 16 bits per lane
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     n0 += __shfl_xor_sync(0xFFFFFFFFu, n0, o);
     n1 += __shfl_xor_sync(0xFFFFFFFFu, n1, o);
-    nr += __shfl_xor_sync(0xFFFFFFFFu, nr, o);
+  }
+  uint32_t r0 = nr & 0xFFFFu, r1 = nr >> 16;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    r0 += __shfl_xor_sync(0xFFFFFFFFu, r0, o);
+    r1 += __shfl_xor_sync(0xFFFFFFFFu, r1, o);
   }
   if ((threadIdx.x & 31) == 0) {
     red[0][threadIdx.x >> 5] = n0;
     red[1][threadIdx.x >> 5] = n1;
-    red[2][threadIdx.x >> 5] = nr;
+    red[2][threadIdx.x >> 5] = r0;
+    wsum[threadIdx.x >> 5] = r1;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t t0 = 0, t1 = 0, r0 = 0, r1 = 0;
+    uint32_t t0 = 0, t1 = 0, s0 = 0, s1 = 0;
     for (int k = 0; k < S2_T / 32; ++k) {
       t0 += red[0][k];
       t1 += red[1][k];
-      r0 += red[2][k] & 0xFFFFu;
-      r1 += red[2][k] >> 16;
+      s0 += red[2][k];
+      s1 += wsum[k];
     }
     blk_hits0[blockIdx.x] = t0;
     blk_hits1[blockIdx.x] = t1;
-    if (K.raw && (r0 | r1)) {
-      atomicAdd(&raw_tot[0], (unsigned long long)r0);
-      atomicAdd(&raw_tot[1], (unsigned long long)r1);
+    if (K.raw && (s0 | s1)) {
+      atomicAdd(&raw_tot[0], (unsigned long long)s0);
+      atomicAdd(&raw_tot[1], (unsigned long long)s1);
     }
   }
 }
 
 // ---------------------------------------------------------------- expand
-__global__ void __launch_bounds__(S2_T) expand_kernel(const uint64_t* __restrict__ cand, const uint2* __restrict__ masks,
-                                                      int64_t n_cand, const uint64_t* __restrict__ base0,
+// One CTA per slice block again: same compaction, then the block's hit masks become records at
+// hit_base[block] + running offset, 256 candidates per pass (warp scan + carry across passes).
+__global__ void __launch_bounds__(S2_T) expand_kernel(const HapScan* __restrict__ hs, const int2* __restrict__ blk_tab,
+                                                      const uint32_t* __restrict__ slice_mask,
+                                                      const uint64_t* __restrict__ cand_base,
+                                                      const uint2* __restrict__ masks, const uint64_t* __restrict__ base0,
                                                       const uint64_t* __restrict__ base1, uint64_t* __restrict__ hits0,
                                                       uint64_t* __restrict__ hits1) {
+  __shared__ uint16_t list[S2_T * 32];
   __shared__ uint32_t wsum[S2_T / 32];
-  const int64_t i = (int64_t)blockIdx.x * S2_T + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint2 m = make_uint2(0u, 0u);
-  uint64_t p0 = 0;
-  if (i < n_cand) {
-    m = masks[i];
-    const uint64_t e = cand[i];
-    p0 = (e & 0xFFFFFFFF00000000ull) | ((e & 0xFFFFFFFFull) << 5);
-  }
-  const uint32_t pk = (uint32_t)__popc(m.x) | ((uint32_t)__popc(m.y) << 16);  // <= 32 each
-  uint32_t incl = pk;
+  const int2 e = __ldg(&blk_tab[blockIdx.x]);
+  const int32_t c_block = (hs[e.x].a >> 5) + 32 * e.y;
+  const uint32_t total = compact_block_candidates(slice_mask[(int64_t)blockIdx.x * S2_T + threadIdx.x], list, wsum);
+  const uint2* const in_masks = masks + cand_base[blockIdx.x];
+  const uint64_t hkey = (uint64_t)(uint32_t)e.x << 32;
+  uint64_t run0 = base0[blockIdx.x], run1 = base1[blockIdx.x];  // uniform over the CTA
+  for (uint32_t k0 = 0; k0 < total; k0 += S2_T) {
+    const uint32_t k = k0 + threadIdx.x;
+    uint2 m = make_uint2(0u, 0u);
+    uint64_t p0 = 0;
+    if (k < total) {
+      m = in_masks[k];
+      p0 = hkey | ((uint64_t)(uint32_t)(c_block + list[k]) << 5);
+    }
+    const uint32_t pk = (uint32_t)__popc(m.x) | ((uint32_t)__popc(m.y) << 16);  // <= 32 each
+    uint32_t incl = pk;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-    if (lane >= d) incl += y;
-  }
-  if (lane == 31) wsum[warp] = incl;
-  __syncthreads();
-  uint32_t wb0 = 0, wb1 = 0;
-  for (int k = 0; k < warp; ++k) {
-    wb0 += wsum[k] & 0xFFFFu;
-    wb1 += wsum[k] >> 16;
-  }
-  const uint32_t excl = incl - pk;
-  uint64_t a = base0[blockIdx.x] + wb0 + (excl & 0xFFFFu), b = base1[blockIdx.x] + wb1 + (excl >> 16);
-  uint32_t bits = m.x;
-  while (bits) {
-    const int k = __ffs(bits) - 1;
-    bits &= bits - 1;
-    hits0[a++] = p0 + (uint32_t)k;
-  }
-  bits = m.y;
-  while (bits) {
-    const int k = __ffs(bits) - 1;
-    bits &= bits - 1;
-    hits1[b++] = p0 + (uint32_t)k;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += y;
+    }
+    __syncthreads();  // wsum is reused from the previous pass
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t wb = 0, tot = 0;
+#pragma unroll
+    for (int j = 0; j < S2_T / 32; ++j) {
+      const uint32_t t = wsum[j];
+      if (j < warp) wb += t;
+      tot += t;
+    }
+    const uint32_t excl = incl - pk;
+    uint64_t a = run0 + (wb & 0xFFFFu) + (excl & 0xFFFFu), b = run1 + (wb >> 16) + (excl >> 16);
+    uint32_t bits = m.x;
+    while (bits) {
+      const int j = __ffs(bits) - 1;
+      bits &= bits - 1;
+      hits0[a++] = p0 + (uint32_t)j;
+    }
+    bits = m.y;
+    while (bits) {
+      const int j = __ffs(bits) - 1;
+      bits &= bits - 1;
+      hits1[b++] = p0 + (uint32_t)j;
+    }
+    run0 += tot & 0xFFFFu;
+    run1 += tot >> 16;
   }
 }
 
@@ -353,8 +392,8 @@ struct MatchWs {
   size_t bytes;
 };
 
-static MatchWs match_ws_layout(void* base, int64_t n_cand) {
-  const int64_t nb = (n_cand + S2_T - 1) / S2_T + 1;
+static MatchWs match_ws_layout(void* base, int64_t n_sblocks) {
+  const int64_t nb = n_sblocks + 1;
   MatchWs w;
   char* p = (char*)base;
   size_t off = 0;
@@ -375,7 +414,7 @@ static MatchWs match_ws_layout(void* base, int64_t n_cand) {
 extern "C" size_t hawk_scan_workspace_bytes(int32_t n_hap, int64_t n_sblocks) {
   return ws_layout(nullptr, n_hap, n_sblocks).bytes;
 }
-extern "C" size_t hawk_scan_match_workspace_bytes(int64_t n_cand) { return match_ws_layout(nullptr, n_cand).bytes; }
+extern "C" size_t hawk_scan_match_workspace_bytes(int64_t n_sblocks) { return match_ws_layout(nullptr, n_sblocks).bytes; }
 
 // stage 1: candidate chunks. d_totals-style results land in the workspace head: after a stream
 // sync the caller reads uint64 totals[0] = number of candidates (hawk_scan_totals).
@@ -404,48 +443,45 @@ extern "C" int hawk_scan_count_dev(void* stream, const void* d_q, const uint32_t
   return hawk_check_cuda(cudaGetLastError(), "scan stage 1 launch");
 }
 
-// stage 2: ordered candidate list + PAM match. totals[1..2] = hits per strand, [3..4] raw hits.
+// stage 2: PAM match of the candidates (d_masks: n_cand x 8 bytes). totals[1..2] = hits per
+// strand, [3..4] raw hits.
 extern "C" int hawk_scan_match_dev(void* stream, const void* d_q, const uint32_t* d_v, const uint32_t* d_nz,
                                    const int64_t* d_slot_off, const int32_t* d_len, const int32_t* d_scan_start,
-                                   const int32_t* d_scan_stop, const uint8_t* d_is_ref, const int64_t* d_sblock_off,
-                                   int32_t n_hap, int64_t n_sblocks, const hawk_params* params, int32_t raw_hits,
-                                   int64_t n_cand, uint64_t* d_cand, uint64_t* d_masks, void* d_workspace,
-                                   void* d_match_workspace) {
+                                   const int32_t* d_scan_stop, const uint8_t* d_is_ref, int32_t n_hap,
+                                   int64_t n_sblocks, const hawk_params* params, int32_t raw_hits, int64_t n_cand,
+                                   uint64_t* d_masks, void* d_workspace, void* d_match_workspace) {
   CK_RET(check_params(params));
-  if (n_cand <= 0 || n_hap <= 0) return HAWK_OK;
+  if (n_cand <= 0 || n_hap <= 0 || n_sblocks <= 0) return HAWK_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const Scan2Ws W = ws_layout(d_workspace, n_hap, n_sblocks);
-  const MatchWs M = match_ws_layout(d_match_workspace, n_cand);
+  const MatchWs M = match_ws_layout(d_match_workspace, n_sblocks);
   const BatchView B = view_of(d_q, d_v, d_nz, d_slot_off, d_len, d_scan_start, d_scan_stop, d_is_ref, n_hap);
   const ScanConst K = make_scan_const(*params, raw_hits);
-  hawk_prof_begin(st, 1);
-  cand_write_kernel<<<(unsigned)n_sblocks, S2_T, 0, st>>>(W.hs, W.blk_tab, W.slice_mask, W.cand_base, d_cand);
-  hawk_note_launch(1);
-  hawk_prof_end(st);
-  const int64_t nb = (n_cand + S2_T - 1) / S2_T;
   hawk_prof_begin(st, 4);
-  match_kernel<<<(unsigned)nb, S2_T, 0, st>>>(B, K, W.hs, d_cand, n_cand, (uint2*)d_masks, M.hit_cnt[0], M.hit_cnt[1],
-                                             (unsigned long long*)(W.totals + 3));
+  match_kernel<<<(unsigned)n_sblocks, S2_T, 0, st>>>(B, K, W.hs, W.blk_tab, W.slice_mask, W.cand_base, (uint2*)d_masks,
+                                                    M.hit_cnt[0], M.hit_cnt[1], (unsigned long long*)(W.totals + 3));
   hawk_note_launch(1);
   hawk_prof_end(st);
   hawk_prof_begin(st, 1);
-  CK_RET(exclusive_scan_u32(st, M.hit_cnt[0], nb, M.hit_base[0], M.tile_sums, W.totals + 1));
-  CK_RET(exclusive_scan_u32(st, M.hit_cnt[1], nb, M.hit_base[1], M.tile_sums, W.totals + 2));
+  CK_RET(exclusive_scan_u32(st, M.hit_cnt[0], n_sblocks, M.hit_base[0], M.tile_sums, W.totals + 1));
+  CK_RET(exclusive_scan_u32(st, M.hit_cnt[1], n_sblocks, M.hit_base[1], M.tile_sums, W.totals + 2));
   hawk_prof_end(st);
   return hawk_check_cuda(cudaGetLastError(), "scan stage 2 launch");
 }
 
 // stage 3: records. d_hits_* must hold totals[1] / totals[2] records.
-extern "C" int hawk_scan_expand_dev(void* stream, int64_t n_cand, const uint64_t* d_cand, const uint64_t* d_masks,
-                                    void* d_match_workspace, uint64_t* d_hits_fwd, uint64_t* d_hits_rev) {
-  if (n_cand <= 0) return HAWK_OK;
-  const MatchWs M = match_ws_layout(d_match_workspace, n_cand);
-  const int64_t nb = (n_cand + S2_T - 1) / S2_T;
-  hawk_prof_begin((cudaStream_t)stream, 3);
-  expand_kernel<<<(unsigned)nb, S2_T, 0, (cudaStream_t)stream>>>(d_cand, (const uint2*)d_masks, n_cand, M.hit_base[0],
-                                                                 M.hit_base[1], d_hits_fwd, d_hits_rev);
+extern "C" int hawk_scan_expand_dev(void* stream, int32_t n_hap, int64_t n_sblocks, int64_t n_cand,
+                                    const uint64_t* d_masks, void* d_workspace, void* d_match_workspace,
+                                    uint64_t* d_hits_fwd, uint64_t* d_hits_rev) {
+  if (n_cand <= 0 || n_sblocks <= 0) return HAWK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const Scan2Ws W = ws_layout(d_workspace, n_hap, n_sblocks);
+  const MatchWs M = match_ws_layout(d_match_workspace, n_sblocks);
+  hawk_prof_begin(st, 3);
+  expand_kernel<<<(unsigned)n_sblocks, S2_T, 0, st>>>(W.hs, W.blk_tab, W.slice_mask, W.cand_base, (const uint2*)d_masks,
+                                                     M.hit_base[0], M.hit_base[1], d_hits_fwd, d_hits_rev);
   hawk_note_launch(1);
-  hawk_prof_end((cudaStream_t)stream);
+  hawk_prof_end(st);
   return hawk_check_cuda(cudaGetLastError(), "expand_kernel launch");
 }
 

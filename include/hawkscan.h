@@ -212,16 +212,17 @@ int hawk_pack_dev(void *stream, const uint8_t *d_ascii, int64_t total_slots, voi
  *   stage 1  hawk_scan_count_dev: candidate chunks (non-REF haplotypes: chunks with a variant
  *            base in reach of a guide core, found in the nz summary plane; REF haplotypes
  *            and raw_hits = 1 (pam_search semantics): every chunk). totals[0] = candidates.
- *   stage 2  hawk_scan_match_dev: ordered candidate list (d_cand, n_cand x 8 bytes) + PAM match
- *            on both strands + filters -> hit masks (d_masks, n_cand x 8 bytes).
+ *   stage 2  hawk_scan_match_dev: PAM match on both strands + filters for the candidates ->
+ *            hit masks (d_masks, n_cand x 8 bytes, in candidate = (haplotype, chunk) order).
  *            totals[1..2] = hits per strand, totals[3..4] = raw PAM hits (raw_hits = 1).
  *   stage 3  hawk_scan_expand_dev: (hap << 32 | pos) records, ascending, totals[1] / totals[2]
  *            of them in d_hits_fwd / d_hits_rev.
- * hawk_scan_totals(workspace) is the device address of uint64 totals[8]. */
+ * hawk_scan_totals(workspace) is the device address of uint64 totals[8]. The two workspaces
+ * need no initialisation and must stay untouched between the stages. */
 int64_t hawk_scan_plan(const int32_t *scan_start, const int32_t *scan_stop, int32_t n_hap,
                        int64_t *sblock_off);
 size_t hawk_scan_workspace_bytes(int32_t n_hap, int64_t n_sblocks);
-size_t hawk_scan_match_workspace_bytes(int64_t n_cand);
+size_t hawk_scan_match_workspace_bytes(int64_t n_sblocks);
 const uint64_t *hawk_scan_totals(const void *d_workspace);
 int hawk_scan_count_dev(void *stream, const void *d_q, const uint32_t *d_v, const uint32_t *d_nz,
                         const int64_t *d_slot_off, const int32_t *d_len, const int32_t *d_scan_start,
@@ -230,12 +231,12 @@ int hawk_scan_count_dev(void *stream, const void *d_q, const uint32_t *d_v, cons
                         void *d_workspace);
 int hawk_scan_match_dev(void *stream, const void *d_q, const uint32_t *d_v, const uint32_t *d_nz,
                         const int64_t *d_slot_off, const int32_t *d_len, const int32_t *d_scan_start,
-                        const int32_t *d_scan_stop, const uint8_t *d_is_ref, const int64_t *d_sblock_off,
-                        int32_t n_hap, int64_t n_sblocks, const hawk_params *params, int32_t raw_hits,
-                        int64_t n_cand, uint64_t *d_cand, uint64_t *d_masks, void *d_workspace,
-                        void *d_match_workspace);
-int hawk_scan_expand_dev(void *stream, int64_t n_cand, const uint64_t *d_cand, const uint64_t *d_masks,
-                         void *d_match_workspace, uint64_t *d_hits_fwd, uint64_t *d_hits_rev);
+                        const int32_t *d_scan_stop, const uint8_t *d_is_ref, int32_t n_hap,
+                        int64_t n_sblocks, const hawk_params *params, int32_t raw_hits, int64_t n_cand,
+                        uint64_t *d_masks, void *d_workspace, void *d_match_workspace);
+int hawk_scan_expand_dev(void *stream, int32_t n_hap, int64_t n_sblocks, int64_t n_cand,
+                         const uint64_t *d_masks, void *d_workspace, void *d_match_workspace,
+                         uint64_t *d_hits_fwd, uint64_t *d_hits_rev);
 
 /* N1 (next row): materialise haplotype texts on the device from the reference text and
  * per-haplotype sorted, non-overlapping edit lists (haplotype.py:106-121,185-252
