@@ -13,6 +13,7 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HAWKSCAN_LIB", os.path.join(PKG_DIR, "libhawkscan.so"))
 
+ABI_VERSION = 2
 HAWK_MAX_PAM = 16
 HAWK_F_UNPHASED = 1
 
@@ -45,6 +46,22 @@ class HawkParams(C.Structure):
     ]
 
 
+class HawkTableOut(C.Structure):
+    """hawk_table_out: caller-owned host columns of the streamed search."""
+
+    _fields_ = [
+        ("hap", C.POINTER(C.c_int32)),
+        ("strand", C.POINTER(C.c_uint8)),
+        ("pos", C.POINTER(C.c_int32)),
+        ("start", C.POINTER(C.c_int32)),
+        ("stop", C.POINTER(C.c_int32)),
+        ("bucket", C.POINTER(C.c_int64)),
+        ("text", C.POINTER(C.c_uint8)),
+        ("capacity", C.c_int64),
+        ("text_stride", C.c_int32),
+    ]
+
+
 _P = C.c_void_p
 _I32P = C.POINTER(C.c_int32)
 _I64P = C.POINTER(C.c_int64)
@@ -61,6 +78,7 @@ SIGNATURES = {
     "hawk_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "hawk_ctx_destroy": (C.c_int, [_P]),
     "hawk_ctx_info": (C.c_int, [_P, _I32P, _I64P, _I64P]),
+    "hawk_ctx_traffic": (C.c_int, [_P, _I64P, _I64P]),
     "hawk_layout": (C.c_int, [_I32P, C.c_int32, _I64P, _I64P]),
     "hawk_batch_create": (C.c_int, [_P, _U8P, _I64P, _I32P, C.c_int32, C.POINTER(_P), _I64P]),
     "hawk_batch_create_dev": (C.c_int, [_P, _P, _I64P, _I32P, C.c_int32, C.POINTER(_P), _I64P]),
@@ -101,6 +119,17 @@ SIGNATURES = {
          C.c_int64, _P, _P, _P],
     ),  # fmt: skip
     "hawk_scan_expand_dev": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
+    "hawk_table_text_stride": (C.c_int32, [C.c_int32, C.c_int32]),
+    "hawk_search_stream": (
+        C.c_int,
+        [_P, _U8P, _I64P, _I32P, C.c_int32, _I64P, _I32P, _I32P, _U8P, C.POINTER(HawkParams), _I32P, _I32P, _U8P,
+         C.c_int32, C.POINTER(HawkTableOut), _I64P, _I64P, _I64P, _I64P],
+    ),  # fmt: skip
+    "hawk_search_stream_edits": (
+        C.c_int,
+        [_P, _U8P, C.c_int64, C.c_int32, C.c_int32, _I64P, _I32P, _I32P, _I32P, _I64P, _U8P, C.c_int64,
+         C.POINTER(HawkParams), _I32P, _I32P, _U8P, C.c_int32, C.POINTER(HawkTableOut), _I64P, _I64P, _I64P],
+    ),  # fmt: skip
 }
 
 _lib = None
@@ -130,7 +159,7 @@ def load_library(path: Optional[str] = None):
                 raise HawkLibraryError(f"{p} does not export {name}") from e
             fn.restype = res
             fn.argtypes = args
-        if lib.hawk_abi_version() != 1:
+        if lib.hawk_abi_version() != ABI_VERSION:
             raise HawkLibraryError(f"{p}: unexpected ABI version {lib.hawk_abi_version()}")
         if path is None:
             _lib = lib
@@ -189,6 +218,12 @@ class Context:
         sm, tot, free = C.c_int32(), C.c_int64(), C.c_int64()
         check(self.lib.hawk_ctx_info(self.handle, C.byref(sm), C.byref(tot), C.byref(free)))
         return {"sm_count": sm.value, "total_mem": tot.value, "free_mem": free.value}
+
+    def traffic(self):
+        """(host-to-device, device-to-host) bytes moved by the host layer so far."""
+        a, b = C.c_int64(), C.c_int64()
+        check(self.lib.hawk_ctx_traffic(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     @property
     def stream(self) -> int:
@@ -399,3 +434,131 @@ def pam_search(ctx: Context, batch: Batch, params: HawkParams, scan_start, scan_
         "hawk_pam_search",
     )  # fmt: skip
     return Result(ctx.lib, h)
+
+
+# --------------------------------------------------------------------------- streamed search
+TABLE_COLUMNS = (("hap", np.int32), ("strand", np.uint8), ("pos", np.int32), ("start", np.int32),
+                 ("stop", np.int32), ("bucket", np.int64))  # fmt: skip
+
+
+def text_stride(params: HawkParams) -> int:
+    return int(load_library().hawk_table_text_stride(params.pam_len, params.guide_len))
+
+
+def alloc_table(capacity: int, stride: int, pinned: bool = False):
+    """Host columns for `capacity` guide rows (pinned through torch when asked: the streamed
+    search overlaps its copies only with page-locked memory)."""
+    if pinned:
+        import torch
+
+        mk = lambda dt, k=1: torch.empty(max(capacity * k, 1), dtype=dt, pin_memory=True).numpy()  # noqa: E731
+        tdt = {np.int32: torch.int32, np.uint8: torch.uint8, np.int64: torch.int64}
+        out = {name: mk(tdt[dt]) for name, dt in TABLE_COLUMNS}
+        out["text"] = mk(torch.uint8, stride)
+    else:
+        out = {name: np.empty(max(capacity, 1), dt) for name, dt in TABLE_COLUMNS}
+        out["text"] = np.empty(max(capacity * stride, 1), np.uint8)
+    return out
+
+
+def _table_out(buffers, stride: int) -> HawkTableOut:
+    t = HawkTableOut()
+    cap = min(len(buffers[name]) for name, _ in TABLE_COLUMNS)
+    cap = min(cap, len(buffers["text"].reshape(-1)) // stride)
+    t.hap, t.strand, t.pos = ptr(buffers["hap"], C.c_int32), ptr(buffers["strand"], C.c_uint8), ptr(buffers["pos"], C.c_int32)
+    t.start, t.stop = ptr(buffers["start"], C.c_int32), ptr(buffers["stop"], C.c_int32)
+    t.bucket, t.text = ptr(buffers["bucket"], C.c_int64), ptr(buffers["text"].reshape(-1), C.c_uint8)
+    t.capacity, t.text_stride = cap, stride
+    return t
+
+
+def _table_views(buffers, n: int, stride: int, window: int):
+    out = {name: buffers[name][:n] for name, _ in TABLE_COLUMNS}
+    out["text"] = buffers["text"].reshape(-1)[: n * stride].reshape(n, stride)[:, :window]
+    return out
+
+
+class StreamResult:
+    """Guide table of a streamed search, in host memory."""
+
+    def __init__(self, table, n_guides, n_hits, scanned_bp, window, stride, buffers):
+        self.table_, self.n_guides, self.n_hits, self.scanned_bp = table, n_guides, n_hits, scanned_bp
+        self.window, self.text_stride, self.buffers = window, stride, buffers
+
+    def table(self):
+        return self.table_
+
+
+def _run_stream(call, params: HawkParams, buffers, pinned: bool, what: str) -> StreamResult:
+    """Run `call(table_out_ptr, n, hits, bp)`; on HAWK_ECAPACITY grow the buffers and repeat."""
+    stride = text_stride(params)
+    window = params.pam_len + params.guide_len + 20
+    if buffers is None:
+        # count first: one pass without output sizes the table exactly
+        n, hits, bp = C.c_int64(), (C.c_int64 * 2)(), C.c_int64()
+        check(call(None, n, hits, bp), what)
+        buffers = alloc_table(n.value, stride, pinned)
+    for _ in range(2):
+        t = _table_out(buffers, stride)
+        n, hits, bp = C.c_int64(), (C.c_int64 * 2)(), C.c_int64()
+        rc = call(C.byref(t), n, hits, bp)
+        if rc == HAWK_ECAPACITY and n.value > t.capacity:
+            buffers = alloc_table(int(n.value * 1.05) + 1024, stride, pinned)
+            continue
+        check(rc, what)
+        return StreamResult(_table_views(buffers, n.value, stride, window), n.value, (hits[0], hits[1]), bp.value,
+                            window, stride, buffers)  # fmt: skip
+    raise HawkLibraryError(f"{what}: output capacity still too small after growing", HAWK_ECAPACITY)
+
+
+def search_stream(ctx: Context, ascii_slots: np.ndarray, slot_off, lens, seg, params: HawkParams, scan_start,
+                  scan_stop, is_ref, n_groups: int = 0, buffers=None, pinned: bool = False) -> StreamResult:  # fmt: skip
+    """hawk_search_stream: host texts in, host guide table out, PCIe copies overlapped.
+    `buffers` (see alloc_table) are reused when large enough."""
+    asc = np.ascontiguousarray(ascii_slots, dtype=np.uint8)
+    so = np.ascontiguousarray(slot_off, dtype=np.int64)
+    ln = np.ascontiguousarray(lens, dtype=np.int32)
+    a = np.ascontiguousarray(scan_start, dtype=np.int32)
+    b = np.ascontiguousarray(scan_stop, dtype=np.int32)
+    r = np.ascontiguousarray(is_ref, dtype=np.uint8)
+    bad = C.c_int64(-1)
+
+    def call(t, n, hits, bp):
+        return ctx.lib.hawk_search_stream(
+            ctx.handle, ptr(asc, C.c_uint8), ptr(so, C.c_int64), ptr(ln, C.c_int32), len(ln),
+            ptr(seg.seg_off, C.c_int64), ptr(seg.seg_rel, C.c_int32), ptr(seg.seg_gen, C.c_int32),
+            ptr(seg.seg_step, C.c_uint8), C.byref(params), ptr(a, C.c_int32), ptr(b, C.c_int32), ptr(r, C.c_uint8),
+            int(n_groups), t, C.byref(n), hits, C.byref(bp), C.byref(bad),
+        )  # fmt: skip
+
+    try:
+        return _run_stream(call, params, buffers, pinned, "hawk_search_stream")
+    except HawkLibraryError as e:
+        e.bad_slot = bad.value
+        raise
+
+
+def search_stream_edits(ctx: Context, ref_ascii, region_start: int, edit_off, edit_pos, edit_reflen, edit_altlen,
+                        edit_altoff, alt_pool, params: HawkParams, scan_start, scan_stop, is_ref,
+                        n_groups: int = 0, buffers=None, pinned: bool = False) -> StreamResult:  # fmt: skip
+    """hawk_search_stream_edits: reference text + edit lists in, host guide table out."""
+    ref = np.ascontiguousarray(ref_ascii, dtype=np.uint8)
+    eo = np.ascontiguousarray(edit_off, dtype=np.int64)
+    ep = np.ascontiguousarray(edit_pos, dtype=np.int32)
+    rl = np.ascontiguousarray(edit_reflen, dtype=np.int32)
+    al = np.ascontiguousarray(edit_altlen, dtype=np.int32)
+    ao = np.ascontiguousarray(edit_altoff, dtype=np.int64)
+    pool = np.ascontiguousarray(alt_pool, dtype=np.uint8)
+    a = np.ascontiguousarray(scan_start, dtype=np.int32)
+    b = np.ascontiguousarray(scan_stop, dtype=np.int32)
+    r = np.ascontiguousarray(is_ref, dtype=np.uint8)
+
+    def call(t, n, hits, bp):
+        return ctx.lib.hawk_search_stream_edits(
+            ctx.handle, ptr(ref, C.c_uint8), len(ref), int(region_start), len(eo) - 1, ptr(eo, C.c_int64),
+            ptr(ep, C.c_int32), ptr(rl, C.c_int32), ptr(al, C.c_int32), ptr(ao, C.c_int64), ptr(pool, C.c_uint8),
+            len(pool), C.byref(params), ptr(a, C.c_int32), ptr(b, C.c_int32), ptr(r, C.c_uint8), int(n_groups), t,
+            C.byref(n), hits, C.byref(bp),
+        )  # fmt: skip
+
+    return _run_stream(call, params, buffers, pinned, "hawk_search_stream_edits")

@@ -16,6 +16,7 @@
 #include "hawk_core.h"
 #include "hawk_kernels.h"
 #include "hawk_post.h"
+#include "hawk_host.h"
 
 using namespace hawk;
 
@@ -35,13 +36,6 @@ int hawk_check_cuda(cudaError_t err, const char* what) {
   return hawk_fail(err == cudaErrorMemoryAllocation ? HAWK_ENOMEM : HAWK_ECUDA, "%s: %s (%s)", what,
                    cudaGetErrorString(err), cudaGetErrorName(err));
 }
-
-#define CK(expr)                                   \
-  do {                                             \
-    int _rc = (expr);                              \
-    if (_rc != HAWK_OK) return _rc;                \
-  } while (0)
-#define CKCUDA(expr) CK(hawk_check_cuda((expr), #expr))
 
 #include <atomic>
 static std::atomic<long long> g_launches{0};
@@ -64,167 +58,86 @@ extern "C" const char* hawk_strerror(int code) {
   }
 }
 
-// HAWK_TRACE=1: host-side wall-clock trace of the search pipeline on stderr (debugging aid)
-struct Trace {
-  bool on;
-  std::chrono::steady_clock::time_point t0;
-  Trace() : on(getenv("HAWK_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
-  void tick(const char* what) {
-    if (!on) return;
-    auto t1 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[hawk] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-    t0 = t1;
+// ------------------------------------------------------------------ small transfers
+namespace hawk {
+// 16-byte words when both pointers and the size allow it, bytes otherwise
+__global__ void small_copy_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t n, int wide) {
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  if (wide) {
+    for (size_t i = i0; i < n / 16; i += step) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+  } else {
+    for (size_t i = i0; i < n; i += step) dst[i] = src[i];
   }
-};
+}
+}  // namespace hawk
 
-// ------------------------------------------------------------------ objects
-struct hawk_ctx {
-  int device;
-  cudaStream_t stream;
-  int sm_count;
-  // Device-memory cache: every buffer of the library lives on this one stream, so a freed
-  // block can be handed to the next request without synchronising (stream order protects
-  // it). Avoids the per-search cost of the driver allocator for multi-GB temporaries.
-  struct Block { void* p; size_t bytes; };
-  std::vector<Block> free_blocks;
-  void* take(size_t n, size_t* got) {
-    size_t best = (size_t)-1;
-    for (size_t i = 0; i < free_blocks.size(); ++i)
-      if (free_blocks[i].bytes >= n && free_blocks[i].bytes <= 2 * n + (4u << 20) &&
-          (best == (size_t)-1 || free_blocks[i].bytes < free_blocks[best].bytes))
-        best = i;
-    if (best != (size_t)-1) {
-      Block b = free_blocks[best];
-      free_blocks.erase(free_blocks.begin() + best);
-      *got = b.bytes;
-      return b.p;
-    }
-    size_t want = n < (1u << 20) ? ((n + 511) & ~(size_t)511) : ((n + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1));
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) {  // give the cached blocks back to the driver and try once more
-      cudaGetLastError();
-      cudaStreamSynchronize(stream);
-      trim();
-      e = cudaMalloc(&p, want);
-      if (e != cudaSuccess) {
+static const size_t SMALL_MAX = 8u << 20;  // larger transfers use the copy engines
+
+static int launch_small_copy(cudaStream_t st, void* dst, const void* src, size_t n) {
+  const int wide = (((uintptr_t)dst | (uintptr_t)src | n) & 15) == 0;
+  const size_t items = wide ? n / 16 : n;
+  size_t blocks = (items + 255) / 256;
+  if (blocks > 592) blocks = 592;
+  if (blocks < 1) blocks = 1;
+  small_copy_kernel<<<(unsigned)blocks, 256, 0, st>>>((uint8_t*)dst, (const uint8_t*)src, n, wide);
+  hawk_note_launch(1);
+  return hawk_check_cuda(cudaGetLastError(), "small_copy_kernel launch");
+}
+
+static int arena_take(hawk_ctx* c, size_t n, uint8_t** out) {
+  const size_t need = (n + 15) & ~(size_t)15;
+  if (c->arena_used + need > c->arena_bytes) {
+    // everything staged so far has been consumed once the stream is idle
+    CKCUDA(cudaStreamSynchronize(c->stream));
+    c->arena_used = 0;
+    if (need > c->arena_bytes) {
+      if (c->arena) cudaFreeHost(c->arena);
+      c->arena = nullptr;
+      c->arena_bytes = 0;
+      size_t want = 4u << 20;
+      while (want < 2 * need) want <<= 1;
+      void* p = nullptr;
+      if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
         cudaGetLastError();
-        return nullptr;
+        return hawk_fail(HAWK_ENOMEM, "pinned staging allocation failed (%zu bytes)", want);
       }
+      c->arena = (uint8_t*)p;
+      c->arena_bytes = want;
     }
-    *got = want;
-    return p;
   }
-  void give(void* p, size_t bytes) { free_blocks.push_back(Block{p, bytes}); }
-  // pinned host staging for the small per-search uploads (one H2D copy instead of six)
-  void* pinned = nullptr;
-  size_t pinned_bytes = 0;
-  void* pinned_get(size_t n) {
-    if (n > pinned_bytes) {
-      if (pinned) cudaFreeHost(pinned);
-      pinned = nullptr;
-      pinned_bytes = 0;
-      const size_t want = (n * 2 + 4095) & ~(size_t)4095;
-      if (cudaHostAlloc(&pinned, want, cudaHostAllocDefault) != cudaSuccess) {
-        cudaGetLastError();
-        pinned = nullptr;
-        return nullptr;
-      }
-      pinned_bytes = want;
-    }
-    return pinned;
-  }
-  void trim() {
-    for (auto& b : free_blocks) cudaFree(b.p);
-    free_blocks.clear();
-  }
-  // optional per-kernel timing (hawk_ctx_set_profiling)
-  bool profiling = false;
-  struct Span { cudaEvent_t a, b; int kind; };
-  std::vector<Span> spans;
-  void mark(int kind, cudaEvent_t* a) {
-    if (!profiling) return;
-    Span s; s.kind = kind;
-    cudaEventCreate(&s.a); cudaEventCreate(&s.b);
-    cudaEventRecord(s.a, stream);
-    spans.push_back(s);
-    if (a) *a = s.a;
-  }
-  void close_mark() {
-    if (!profiling || spans.empty()) return;
-    cudaEventRecord(spans.back().b, stream);
-  }
-};
-
-// device buffer owned through the context's block cache
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  hawk_ctx* ctx = nullptr;
-  DevBuf() {}
-  DevBuf(const DevBuf&) = delete;
-  DevBuf& operator=(const DevBuf&) = delete;
-  ~DevBuf() { release(); }
-  int alloc(hawk_ctx* c, size_t n, bool zero = false) {
-    release();
-    ctx = c;
-    p = c->take(n ? n : 16, &bytes);
-    if (!p) {
-      bytes = 0;
-      return hawk_fail(HAWK_ENOMEM, "out of device memory (%zu bytes requested)", n);
-    }
-    if (zero) return hawk_check_cuda(cudaMemsetAsync(p, 0, n ? n : 16, c->stream), "cudaMemsetAsync");
-    return HAWK_OK;
-  }
-  void release() {
-    if (p) ctx->give(p, bytes);
-    p = nullptr;
-    bytes = 0;
-  }
-  void move_from(DevBuf& o) {
-    release();
-    p = o.p;
-    bytes = o.bytes;
-    ctx = o.ctx;
-    o.p = nullptr;
-    o.bytes = 0;
-  }
-  template <class T>
-  T* as() const { return (T*)p; }
-};
-
-static int upload(hawk_ctx* c, DevBuf& b, const void* src, size_t bytes) {
-  CK(b.alloc(c, bytes));
-  if (bytes) CKCUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  *out = c->arena + c->arena_used;
+  c->arena_used += need;
   return HAWK_OK;
 }
 
-struct hawk_batch {
-  hawk_ctx* ctx;
-  int32_t n_hap;
-  int64_t total_slots;
-  std::vector<int64_t> slot_off;
-  std::vector<int32_t> len;
-  DevBuf q, v, nz, d_slot_off, d_len;
-  DevBuf seg_off, seg_rel, seg_gen, seg_step;
-  DevBuf va_off, va_idx, va_ent_off, va_ref;
-  bool has_posmap = false, has_alleles = false;
-  // host-side facts about the coordinate maps (hawk_batch_set_posmap)
-  std::vector<int64_t> h_seg_off;
-  std::vector<int32_t> first_gen;   // posmap(0) per haplotype
-  std::vector<uint8_t> linear;      // one step-1 segment
-  int32_t gmin = 0, gmax = -1;      // genomic coordinate range over all haplotypes
-};
+int hawk_ctx::small_h2d(void* dst_dev, const void* src_host, size_t n) {
+  if (n == 0) return HAWK_OK;
+  h2d_bytes += (int64_t)n;
+  if (n > SMALL_MAX) return hawk_check_cuda(cudaMemcpyAsync(dst_dev, src_host, n, cudaMemcpyHostToDevice, stream), "H2D copy");
+  uint8_t* stage = nullptr;
+  CK(arena_take(this, n, &stage));
+  memcpy(stage, src_host, n);
+  return launch_small_copy(stream, dst_dev, stage, n);
+}
 
-struct hawk_result {
-  hawk_ctx* ctx;
-  int64_t n_guides = 0;
-  int64_t n_hits[2] = {0, 0};
-  int32_t window = 0, text_stride = 0;
-  int64_t scanned_bp = 0;
-  DevBuf hits[2];
-  DevBuf hap, strand, pos, start, stop, bucket, text;
-};
+int hawk_ctx::small_d2h_sync(void* dst_host, const void* src_dev, size_t n) {
+  d2h_bytes += (int64_t)n;
+  if (n > SMALL_MAX) {
+    CKCUDA(cudaMemcpyAsync(dst_host, src_dev, n, cudaMemcpyDeviceToHost, stream));
+    CKCUDA(cudaStreamSynchronize(stream));
+    arena_used = 0;
+    return HAWK_OK;
+  }
+  uint8_t* stage = nullptr;
+  if (n) {
+    CK(arena_take(this, n, &stage));
+    CK(launch_small_copy(stream, stage, src_dev, n));
+  }
+  CKCUDA(cudaStreamSynchronize(stream));
+  if (n) memcpy(dst_host, stage, n);
+  arena_used = 0;
+  return HAWK_OK;
+}
 
 // profiling hooks for the device layer: the context the calling thread is running a search on
 static thread_local hawk_ctx* g_prof_ctx = nullptr;
@@ -266,8 +179,18 @@ extern "C" int hawk_ctx_destroy(hawk_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->trim();
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->arena) cudaFreeHost(c->arena);
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   cudaStreamDestroy(c->stream);
   delete c;
+  return HAWK_OK;
+}
+
+extern "C" int hawk_ctx_traffic(hawk_ctx* c, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  if (!c) return hawk_fail(HAWK_EINVAL, "hawk_ctx_traffic: null context");
+  if (h2d_bytes) *h2d_bytes = c->h2d_bytes;
+  if (d2h_bytes) *d2h_bytes = c->d2h_bytes;
   return HAWK_OK;
 }
 
@@ -298,7 +221,7 @@ extern "C" int hawk_layout(const int32_t* len, int32_t n_hap, int64_t* slot_off,
 }
 
 // ------------------------------------------------------------------ batch
-static int batch_create_impl(hawk_ctx* c, const uint8_t* ascii, bool ascii_on_device,
+int batch_create_impl(hawk_ctx* c, const uint8_t* ascii, bool ascii_on_device,
                              const int64_t* slot_off, const int32_t* len, int32_t n_hap,
                              hawk_batch** out, int64_t* bad_slot) {
   if (!c || !out || n_hap < 0 || (n_hap > 0 && (!ascii || !slot_off || !len)))
@@ -350,8 +273,7 @@ static int batch_create_impl(hawk_ctx* c, const uint8_t* ascii, bool ascii_on_de
       c->close_mark();
       if (rc) break;
       int64_t bad = INT64_MAX;
-      if ((rc = hawk_check_cuda(cudaMemcpyAsync(&bad, d_bad.p, 8, cudaMemcpyDeviceToHost, st), "bad D2H"))) break;
-      if ((rc = hawk_check_cuda(cudaStreamSynchronize(st), "pack sync"))) break;
+      if ((rc = c->small_d2h_sync(&bad, d_bad.p, 8))) break;
       if (bad != INT64_MAX) {
         if (bad_slot) *bad_slot = bad;
         rc = hawk_fail(HAWK_EIUPAC, "non-IUPAC character at slot %lld", (long long)bad);
@@ -399,7 +321,7 @@ extern "C" int hawk_batch_create_from_edits(hawk_ctx* c, const uint8_t* ref_asci
   // the reference text with readable slack behind it (block copies read whole aligned words)
   CK(d_ref.alloc(c, (size_t)ref_len + 32));
   CKCUDA(cudaMemsetAsync(d_ref.as<uint8_t>() + ref_len, 0, 32, st));
-  CKCUDA(cudaMemcpyAsync(d_ref.p, ref_ascii, (size_t)ref_len, cudaMemcpyHostToDevice, st));
+  CK(c->small_h2d(d_ref.p, ref_ascii, (size_t)ref_len));
   const int64_t zero64 = 0;
   const int32_t zero32 = 0;
   const uint8_t zero8 = 0;
@@ -421,11 +343,10 @@ extern "C" int hawk_batch_create_from_edits(hawk_ctx* c, const uint8_t* ref_asci
   std::vector<int32_t> len(n_hap), seg_count(n_hap);
   int32_t bad_hap = INT32_MAX;
   if (n_hap) {
-    CKCUDA(cudaMemcpyAsync(len.data(), d_len.p, (size_t)n_hap * 4, cudaMemcpyDeviceToHost, st));
-    CKCUDA(cudaMemcpyAsync(seg_count.data(), d_segcnt.p, (size_t)n_hap * 4, cudaMemcpyDeviceToHost, st));
+    CK(c->small_d2h_sync(len.data(), d_len.p, (size_t)n_hap * 4));
+    CK(c->small_d2h_sync(seg_count.data(), d_segcnt.p, (size_t)n_hap * 4));
   }
-  CKCUDA(cudaMemcpyAsync(&bad_hap, d_bad.p, 4, cudaMemcpyDeviceToHost, st));
-  CKCUDA(cudaStreamSynchronize(st));
+  CK(c->small_d2h_sync(&bad_hap, d_bad.p, 4));
   tr.tick("edits: upload + derive");
   if (bad_hap != INT32_MAX)
     return hawk_fail(HAWK_EINVAL,
@@ -498,8 +419,7 @@ extern "C" int hawk_batch_repack_dev(hawk_batch* b, const uint8_t* d_ascii, int6
   c->close_mark();
   CK(rc);
   int64_t bad = INT64_MAX;
-  CKCUDA(cudaMemcpyAsync(&bad, d_bad.p, 8, cudaMemcpyDeviceToHost, st));
-  CKCUDA(cudaStreamSynchronize(st));
+  CK(c->small_d2h_sync(&bad, d_bad.p, 8));
   if (bad != INT64_MAX) {
     if (bad_slot) *bad_slot = bad;
     return hawk_fail(HAWK_EIUPAC, "non-IUPAC character at slot %lld", (long long)bad);
@@ -678,7 +598,7 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
     memcpy(hp + o_ref, is_ref, (size_t)n_hap);
   }
   CK(in.buf.alloc(c, total_bytes));
-  CKCUDA(cudaMemcpyAsync(in.buf.p, hp, total_bytes, cudaMemcpyHostToDevice, st));
+  CK(c->small_h2d(in.buf.p, hp, total_bytes));
   char* dp = (char*)in.buf.p;
   in.sblock_off = (int64_t*)(dp + o_sb);
   in.a = (int32_t*)(dp + o_a);
@@ -695,8 +615,7 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
                                raw, d_ws.p);
   CK(rc);
   uint64_t totals[8];
-  CKCUDA(cudaMemcpyAsync(totals, hawk_scan_totals(d_ws.p), 64, cudaMemcpyDeviceToHost, st));
-  CKCUDA(cudaStreamSynchronize(st));
+  CK(c->small_d2h_sync(totals, hawk_scan_totals(d_ws.p), 64));
   const int64_t n_cand = (int64_t)totals[0];
   tr.tick("scan: candidates");
   if (n_cand == 0) return HAWK_OK;
@@ -706,8 +625,7 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
                            b->d_len.as<int32_t>(), in.a, in.b, in.is_ref, n_hap, n_sblocks, params, raw, n_cand,
                            d_masks.as<uint64_t>(), d_ws.p, d_mws.p);
   CK(rc);
-  CKCUDA(cudaMemcpyAsync(totals, hawk_scan_totals(d_ws.p), 64, cudaMemcpyDeviceToHost, st));
-  CKCUDA(cudaStreamSynchronize(st));
+  CK(c->small_d2h_sync(totals, hawk_scan_totals(d_ws.p), 64));
   out.n[0] = (int64_t)totals[1];
   out.n[1] = (int64_t)totals[2];
   tr.tick("scan: match");
@@ -762,7 +680,7 @@ extern "C" int hawk_pam_search(hawk_ctx* c, hawk_batch* b, const hawk_params* pa
 
 // phased / variant-free pipeline downstream of the scan (table_kernels.cu)
 static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const BatchView& B, ScanOut& so,
-                       int32_t ref_h, hawk_result* r) {
+                       int32_t ref_h, const StreamLink* link, hawk_result* r) {
   cudaStream_t st = c->stream;
   Trace tr;
   const int64_t n_hits[2] = {so.n[0], so.n[1]};
@@ -792,8 +710,8 @@ static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const Bat
     CK(blk_cnt[s].alloc(c, (size_t)(n_blk[s] + 1) * 4));
     CK(blk_base[s].alloc(c, (size_t)(n_blk[s] + 1) * 8));
     CK(launch_rows_fast(st, B, K, recs[s], n_hits[s], s, ref, d_refbm[s].as<uint32_t>(), d_refrange.as<int64_t>(),
-                        start[s].as<int32_t>(), stop[s].as<int32_t>(), keep[s].as<uint8_t>(),
-                        blk_cnt[s].as<uint32_t>()));
+                        link ? link->drop_ref : 0, start[s].as<int32_t>(), stop[s].as<int32_t>(),
+                        keep[s].as<uint8_t>(), blk_cnt[s].as<uint32_t>()));
     if (n_hits[s] > 0)
       CK(launch_blk_prefix(st, blk_cnt[s].as<uint32_t>(), n_blk[s], blk_base[s].as<uint64_t>(),
                            d_tot.as<uint64_t>() + s));
@@ -819,11 +737,21 @@ static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const Bat
     // first-seen bucket ids: direct-address table over (start, strand) when the coordinate
     // range allows it, else the hash table of post_kernels.cu
     const int64_t key_span = b->gmax >= b->gmin ? ((int64_t)b->gmax - b->gmin + 1) * 2 : 0;
-    const bool direct = key_span > 0 && key_span <= (1ll << 28) && n_max < 0xFFFFFFFFll;
-    DevBuf key_table;
-    if (direct) {
-      CK(key_table.alloc(c, (size_t)key_span * 4));
-      CKCUDA(cudaMemsetAsync(key_table.p, 0xFF, (size_t)key_span * 4, st));
+    const bool direct = link || (key_span > 0 && key_span <= HAWK_DIRECT_KEY_SPAN && n_max < 0xFFFFFFFFll);
+    DevBuf key_table_own;
+    uint32_t* key_table = nullptr;
+    int32_t key_min = b->gmin;
+    RowMap rm{0, -1, 0, 0};
+    if (link) {  // one group of a streamed search: the key table and the row numbering are global
+      if (link->row_base + n_max >= 0xFFFFFFFFll)
+        return hawk_fail(HAWK_ECAPACITY, "streamed search: more than 2^32 guide rows");
+      key_table = link->key_table;
+      key_min = link->key_min;
+      rm = RowMap{link->row_base, link->ref_local, link->ref_global, link->hap_add};
+    } else if (direct) {
+      CK(key_table_own.alloc(c, (size_t)key_span * 4));
+      CKCUDA(cudaMemsetAsync(key_table_own.p, 0xFF, (size_t)key_span * 4, st));
+      key_table = key_table_own.as<uint32_t>();
     }
     for (int s = 0; s < 2; ++s)
       CK(launch_gather_fast(st, B, K, recs[s], keep[s].as<uint8_t>(), blk_base[s].as<uint64_t>(),
@@ -831,13 +759,18 @@ static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const Bat
                             d_kb.as<uint64_t>() + (size_t)(1 - s) * (b->n_hap + 1), n_hits[s], s, r->text_stride,
                             r->hap.as<int32_t>(), r->strand.as<uint8_t>(), r->pos.as<int32_t>(),
                             r->start.as<int32_t>(), r->stop.as<int32_t>(), r->text.as<uint8_t>(),
-                            direct ? key_table.as<uint32_t>() : nullptr, b->gmin));
+                            direct ? key_table : nullptr, key_min, rm));
     if (direct)
       CK(launch_bucket_read(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n_max, d_tot.as<uint64_t>(),
-                            key_table.as<uint32_t>(), b->gmin, r->bucket.as<int64_t>()));
-    CKCUDA(cudaMemcpyAsync(kept, d_tot.p, 16, cudaMemcpyDeviceToHost, st));
+                            key_table, key_min, r->bucket.as<int64_t>()));
     c->close_mark();
-    CKCUDA(cudaStreamSynchronize(st));
+    if (link) {
+      int64_t rr[4];
+      CK(c->small_d2h_sync(rr, d_refrange.p, 32));
+      r->ref_hits[0] = rr[1] - rr[0];
+      r->ref_hits[1] = rr[3] - rr[2];
+    }
+    CK(c->small_d2h_sync(kept, d_tot.p, 16));
     tr.tick("table: pipeline + sync");
     const int64_t n = (int64_t)(kept[0] + kept[1]);
     r->n_guides = n;
@@ -862,10 +795,16 @@ static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const Bat
 extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params,
                            const int32_t* scan_start, const int32_t* scan_stop,
                            const uint8_t* is_ref, hawk_result** out) {
+  return hawk_search_impl(c, b, params, scan_start, scan_stop, is_ref, nullptr, out);
+}
+
+int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const int32_t* scan_start,
+                     const int32_t* scan_stop, const uint8_t* is_ref, const StreamLink* link, hawk_result** out) {
   CK(check_scan_args(c, b, params, scan_start, scan_stop, out));
   if (b->n_hap > 0 && !is_ref) return hawk_fail(HAWK_EINVAL, "hawk_search: is_ref missing");
   if (!b->has_posmap) return hawk_fail(HAWK_EINVAL, "hawk_search: call hawk_batch_set_posmap first");
   const bool unphased = (params->flags & HAWK_F_UNPHASED) != 0;
+  if (unphased && link) return hawk_fail(HAWK_EINVAL, "hawk_search: the streamed search is phased / variant-free only");
   if (unphased && !b->has_alleles)
     return hawk_fail(HAWK_EINVAL, "hawk_search: unphased search needs hawk_batch_set_alleles");
   CKCUDA(cudaSetDevice(c->device));
@@ -902,7 +841,7 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
     const BatchView B = batch_view(b, in.a, in.b, in.is_ref);
     const int64_t n_hits[2] = {so.n[0], so.n[1]};
     if (!unphased) {
-      if ((rc = search_fast(c, b, K, B, so, ref_h, r))) break;
+      if ((rc = search_fast(c, b, K, B, so, ref_h, link, r))) break;
       for (int s = 0; s < 2; ++s) {
         r->n_hits[s] = n_hits[s];
         r->hits[s].move_from(so.hits[s]);
@@ -940,15 +879,11 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
         if ((rc = exclusive_scan_u64(st, cnt[s].as<uint64_t>(), n_hits[s], off[s].as<uint64_t>(),
                                      tile_sums.as<uint64_t>())))
           break;
-        rc = hawk_check_cuda(cudaMemcpyAsync(&totals[s], tile_sums.as<uint64_t>() + scan_tiles(n_hits[s]), 8,
-                                             cudaMemcpyDeviceToHost, st), "expansion total D2H");
-        if (rc) break;
-        rc = hawk_check_cuda(cudaStreamSynchronize(st), "expansion count sync");
+        rc = c->small_d2h_sync(&totals[s], tile_sums.as<uint64_t>() + scan_tiles(n_hits[s]), 8);
       }
       if (rc) break;
       int err = 0;
-      if ((rc = hawk_check_cuda(cudaMemcpyAsync(&err, d_err.p, 4, cudaMemcpyDeviceToHost, st), "err D2H"))) break;
-      if ((rc = hawk_check_cuda(cudaStreamSynchronize(st), "err sync"))) break;
+      if ((rc = c->small_d2h_sync(&err, d_err.p, 4))) break;
       if (err == HAWK_EALLELES) {
         rc = hawk_fail(HAWK_EALLELES, "ambiguity code inside a guide window has no variant_alleles entry");
         break;
@@ -986,10 +921,7 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
       if ((rc = exclusive_scan_u8(st, keep[s].as<uint8_t>(), n_rows[s], kept_excl[s].as<uint64_t>(),
                                   tile_sums.as<uint64_t>())))
         break;
-      if ((rc = hawk_check_cuda(cudaMemcpyAsync(&kept_total[s], tile_sums.as<uint64_t>() + scan_tiles(n_rows[s]),
-                                                8, cudaMemcpyDeviceToHost, st), "kept total D2H")))
-        break;
-      rc = hawk_check_cuda(cudaStreamSynchronize(st), "kept sync");
+      rc = c->small_d2h_sync(&kept_total[s], tile_sums.as<uint64_t>() + scan_tiles(n_rows[s]), 8);
     }
     if (rc) break;
     const int64_t n = (int64_t)(kept_total[0] + kept_total[1]);
@@ -1085,6 +1017,8 @@ extern "C" int hawk_result_fetch(hawk_result* r, int32_t* hap, uint8_t* strand, 
   cudaStream_t st = r->ctx->stream;
   size_t n = (size_t)r->n_guides;
   if (n == 0) return HAWK_OK;
+  r->ctx->d2h_bytes += (int64_t)(n * ((hap ? 4 : 0) + (strand ? 1 : 0) + (pos ? 4 : 0) + (start ? 4 : 0) + (stop ? 4 : 0) +
+                                     (bucket ? 8 : 0) + (text ? (size_t)r->text_stride : 0)));
   if (hap) CKCUDA(cudaMemcpyAsync(hap, r->hap.p, n * 4, cudaMemcpyDeviceToHost, st));
   if (strand) CKCUDA(cudaMemcpyAsync(strand, r->strand.p, n, cudaMemcpyDeviceToHost, st));
   if (pos) CKCUDA(cudaMemcpyAsync(pos, r->pos.p, n * 4, cudaMemcpyDeviceToHost, st));
@@ -1102,6 +1036,7 @@ extern "C" int hawk_result_fetch_hits(hawk_result* r, int32_t strand, uint64_t* 
   size_t n = (size_t)r->n_hits[strand];
   if (n == 0) return HAWK_OK;
   if (!hits) return hawk_fail(HAWK_EINVAL, "hawk_result_fetch_hits: null output");
+  r->ctx->d2h_bytes += (int64_t)(n * 8);
   CKCUDA(cudaMemcpyAsync(hits, r->hits[strand].p, n * 8, cudaMemcpyDeviceToHost, r->ctx->stream));
   CKCUDA(cudaStreamSynchronize(r->ctx->stream));
   return HAWK_OK;

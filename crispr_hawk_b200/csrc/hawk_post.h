@@ -40,13 +40,21 @@ struct RefInfo {
   int32_t len;
 };
 
+// row numbering of one group of a streamed search (all zero / -1 otherwise)
+struct RowMap {
+  int64_t row_base;    // added to the row index before it enters the shared first-seen table
+  int32_t ref_local;   // haplotype index that maps to ref_global, -1: none
+  int32_t ref_global;
+  int32_t hap_add;     // other haplotypes: index + hap_add
+};
+
 // table_kernels.cu (phased / variant-free pipeline)
 int64_t row_blocks(int64_t n);
 int launch_ref_bitmap(cudaStream_t st, const uint64_t* r0, const uint64_t* r1, const int64_t* ref_range,
                       uint32_t* bm0, uint32_t* bm1);
 int launch_rows_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* recs, int64_t n,
-                     int s, const RefInfo& ref, const uint32_t* ref_bm, const int64_t* ref_range, int32_t* start,
-                     int32_t* stop, uint8_t* keep, uint32_t* blk_cnt);
+                     int s, const RefInfo& ref, const uint32_t* ref_bm, const int64_t* ref_range, int32_t drop_ref,
+                     int32_t* start, int32_t* stop, uint8_t* keep, uint32_t* blk_cnt);
 int launch_blk_prefix(cudaStream_t st, const uint32_t* cnt, int64_t n_blk, uint64_t* base, uint64_t* total);
 int launch_hap_offsets(cudaStream_t st, const uint64_t* r0, const uint64_t* r1, int64_t n0, int64_t n1,
                        const uint8_t* k0, const uint8_t* k1, const uint64_t* b0, const uint64_t* b1,
@@ -55,7 +63,7 @@ int launch_gather_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, 
                        const uint8_t* keep, const uint64_t* blk_base, const int32_t* start, const int32_t* stop,
                        const uint64_t* kb_other, int64_t n, int s, int32_t text_stride, int32_t* o_hap,
                        uint8_t* o_strand, int32_t* o_pos, int32_t* o_start, int32_t* o_stop, uint8_t* o_text,
-                       uint32_t* key_table, int32_t key_min);
+                       uint32_t* key_table, int32_t key_min, const RowMap& rm);
 int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n_max,
                        const uint64_t* totals, const uint32_t* key_table, int32_t key_min, int64_t* bucket);
 

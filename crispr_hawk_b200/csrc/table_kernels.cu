@@ -50,6 +50,7 @@ struct RowsArgs {
   int32_t ref_g0, ref_len;
   const uint32_t* ref_bm;     // REF guide bitmap of this strand (ref_linear)
   const int64_t* ref_range;   // REF record range per strand (general REF posmap)
+  int32_t drop_ref;           // streamed search, later groups: REF rows serve as partners only
   int32_t* start;
   int32_t* stop;
   uint8_t* keep;
@@ -66,7 +67,9 @@ __global__ void __launch_bounds__(ROW_T) rows_fast_kernel(const __grid_constant_
     A.start[i] = rc.start;
     A.stop[i] = rc.stop;
     k = 1;
-    if (A.ref_h >= 0 && !A.B.is_ref[h]) {
+    if (A.drop_ref && A.B.is_ref[h]) {
+      k = 0;
+    } else if (A.ref_h >= 0 && !A.B.is_ref[h]) {
       // remove_redundant_guides (:356-369): a non-REF guide whose upper-cased core equals the
       // REF guide's at the same (start, strand) is dropped
       int32_t rpivot = -1;
@@ -171,6 +174,7 @@ struct GatherFastArgs {
   uint8_t* o_text;
   uint32_t* key_table;  // direct-address first-seen table, or null
   int32_t key_min;      // smallest genomic coordinate of the batch
+  RowMap rm;            // streamed search: global row numbering / haplotype indices
 };
 
 // four plane bits (one per character) -> one bit per byte: bit j lands at 8j (the 16 partial
@@ -223,12 +227,12 @@ __global__ void __launch_bounds__(ROW_T) gather_fast_kernel(const __grid_constan
   // rows of the other stream emitted before this one: haplotype < h (strand 0) or <= h (strand 1)
   const uint64_t f = A.blk_base[blockIdx.x] + rank + A.kb_other[h + (A.s == 1 ? 1 : 0)];
   const int32_t st = A.start[i];
-  A.o_hap[f] = h;
+  A.o_hap[f] = h == A.rm.ref_local ? A.rm.ref_global : h + A.rm.hap_add;
   A.o_strand[f] = (uint8_t)A.s;
   A.o_pos[f] = pos;
   A.o_start[f] = st;
   A.o_stop[f] = A.stop[i];
-  if (A.key_table) atomicMin(&A.key_table[((uint32_t)(st - A.key_min) << 1) | (uint32_t)A.s], (uint32_t)f);
+  if (A.key_table) atomicMin(&A.key_table[((uint32_t)(st - A.key_min) << 1) | (uint32_t)A.s], (uint32_t)(f + A.rm.row_base));
   // extract_guide_sequence (:134-160): padded window text from planes + case bits
   const int W = A.K.C + 2 * HAWK_GUIDESEQPAD;
   const int64_t chunk0 = A.B.slot_off[h] >> 5;
@@ -271,10 +275,10 @@ int launch_ref_bitmap(cudaStream_t st, const uint64_t* r0, const uint64_t* r1, c
 }
 
 int launch_rows_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* recs, int64_t n,
-                     int s, const RefInfo& ref, const uint32_t* ref_bm, const int64_t* ref_range, int32_t* start,
-                     int32_t* stop, uint8_t* keep, uint32_t* blk_cnt) {
+                     int s, const RefInfo& ref, const uint32_t* ref_bm, const int64_t* ref_range, int32_t drop_ref,
+                     int32_t* start, int32_t* stop, uint8_t* keep, uint32_t* blk_cnt) {
   if (n <= 0) return HAWK_OK;
-  RowsArgs A{B, K, recs, n, s, ref.h, ref.linear, ref.g0, ref.len, ref_bm, ref_range, start, stop, keep, blk_cnt};
+  RowsArgs A{B, K, recs, n, s, ref.h, ref.linear, ref.g0, ref.len, ref_bm, ref_range, drop_ref, start, stop, keep, blk_cnt};
   rows_fast_kernel<<<blocks_for(n, ROW_T), ROW_T, 0, st>>>(A);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "rows_fast_kernel launch");
@@ -299,10 +303,10 @@ int launch_gather_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, 
                        const uint8_t* keep, const uint64_t* blk_base, const int32_t* start, const int32_t* stop,
                        const uint64_t* kb_other, int64_t n, int s, int32_t text_stride, int32_t* o_hap,
                        uint8_t* o_strand, int32_t* o_pos, int32_t* o_start, int32_t* o_stop, uint8_t* o_text,
-                       uint32_t* key_table, int32_t key_min) {
+                       uint32_t* key_table, int32_t key_min, const RowMap& rm) {
   if (n <= 0) return HAWK_OK;
   GatherFastArgs A{B, K, recs, keep, blk_base, start, stop, kb_other, n, s, text_stride,
-                   o_hap, o_strand, o_pos, o_start, o_stop, o_text, key_table, key_min};
+                   o_hap, o_strand, o_pos, o_start, o_stop, o_text, key_table, key_min, rm};
   gather_fast_kernel<<<blocks_for(n, ROW_T), ROW_T, 0, st>>>(A);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "gather_fast_kernel launch");

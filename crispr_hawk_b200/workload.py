@@ -75,32 +75,40 @@ class Workload:
             self._host = {"ascii": ascii_host, "out": None}
         return self._host
 
-    def step_host(self):
-        """Host ASCII in, host guide table out: H2D copy, K1, K2, post, D2H, all inside."""
+    def step_host(self, n_groups: int = 0):
+        """Host ASCII in, host guide table out through ONE call (hawk_search_stream): the H2D
+        copies of the texts, K1, K2, the table pipeline and the D2H copies of the rows all
+        inside, group by group, PCIe traffic of both directions overlapped. Returns
+        (table, h2d bytes, d2h bytes) -- the byte counts are the library's own counters."""
+        hb = self.host_buffers()
+        t0 = self.ctx.traffic()
+        res = _cabi.search_stream(self.ctx, hb["ascii"].numpy(), self.d.slot_off, self.d.lens, self.d.seg, self.params,
+                                  self.a, self.b, self.d.is_ref, n_groups=n_groups, buffers=hb["out"], pinned=True)  # fmt: skip
+        hb["out"] = res.buffers
+        t1 = self.ctx.traffic()
+        self.last_stream = res
+        return res.table(), t1[0] - t0[0], t1[1] - t0[1]
+
+    def step_host_twocall(self):
+        """The same as two calls, the way the reference's driver is written (encode_haplotypes,
+        then search): the whole batch goes up, is searched, and the table comes down, nothing
+        overlapped."""
         torch = self.torch
         hb = self.host_buffers()
+        t0 = self.ctx.traffic()
         batch = _cabi.Batch(self.ctx, hb["ascii"].numpy(), self.d.slot_off, self.d.lens)
         batch.set_posmap(self.d.seg)
         res = _cabi.search(self.ctx, batch, self.params, self.a, self.b, self.d.is_ref)
         n, w = res.n_guides, res.text_stride
-        if hb["out"] is None or len(hb["out"]["hap"]) < n:
-            cap = int(n * 1.05) + 1024
-            mk = lambda dt, k=1: torch.empty(cap * k, dtype=dt, pin_memory=True).numpy()  # noqa: E731
-            hb["out"] = {"hap": mk(torch.int32), "strand": mk(torch.uint8), "pos": mk(torch.int32),
-                         "start": mk(torch.int32), "stop": mk(torch.int32), "bucket": mk(torch.int64),
-                         "text": mk(torch.uint8, w)}  # fmt: skip
-        table = res.table(hb["out"])
-        h2d = self.d.total_slots + self.d.seg.seg_rel.nbytes * 2 + self.d.seg.seg_step.nbytes + \
-            self.d.seg.seg_off.nbytes + self.a.nbytes * 2 + self.d.is_ref.nbytes + self.d.slot_off.nbytes + self.d.lens.nbytes
-        d2h = n * (4 + 1 + 4 + 4 + 4 + 8 + w)
+        if hb.get("out2") is None or len(hb["out2"]["hap"]) < n:
+            hb["out2"] = _cabi.alloc_table(int(n * 1.05) + 1024, w, pinned=True)
+        table = res.table(hb["out2"])
         res.close()
         batch.close()
-        return table, h2d, d2h
+        t1 = self.ctx.traffic()
+        return table, t1[0] - t0[0], t1[1] - t0[1]
 
-    def step_edits(self):
-        """N1 path: only the reference text and the per-haplotype edit lists start on the host;
-        texts are materialised on the device (hawk_batch_create_from_edits), then K1, K2 and the
-        table pipeline as usual; the guide table ends in pinned host memory."""
+    def _edit_buffers(self):
         torch = self.torch
         c = self.cohort
         if not hasattr(self, "_edits"):
@@ -110,22 +118,38 @@ class Workload:
                                al=pin(c.site_altlen[sites]), ao=pin(c.site_altoff[sites]),
                                pool=pin(c.alt_pool if len(c.alt_pool) else np.zeros(1, np.uint8)))  # fmt: skip
             self._edits_out = None
-        e = self._edits
+        return self._edits
+
+    def step_edits(self, n_groups: int = 0):
+        """N1 path through ONE call (hawk_search_stream_edits): only the reference text and the
+        per-haplotype edit lists start on the host; texts are materialised on the device group
+        by group, then K1, K2 and the table pipeline as usual, while the previous group's guide
+        rows leave for pinned host memory."""
+        c = self.cohort
+        e = self._edit_buffers()
+        t0 = self.ctx.traffic()
+        res = _cabi.search_stream_edits(self.ctx, e["ref"], c.region_start, e["off"], e["pos"], e["rl"], e["al"], e["ao"],
+                                        e["pool"], self.params, self.a, self.b, self.d.is_ref, n_groups=n_groups,
+                                        buffers=self._edits_out, pinned=True)  # fmt: skip
+        self._edits_out = res.buffers
+        t1 = self.ctx.traffic()
+        return res.table(), t1[0] - t0[0], t1[1] - t0[1]
+
+    def step_edits_twocall(self):
+        """hawk_batch_create_from_edits + hawk_search + fetch, nothing overlapped."""
+        c = self.cohort
+        e = self._edit_buffers()
+        t0 = self.ctx.traffic()
         batch = _cabi.Batch.from_edits(self.ctx, e["ref"], c.region_start, e["off"], e["pos"], e["rl"], e["al"], e["ao"], e["pool"])
         res = _cabi.search(self.ctx, batch, self.params, self.a, self.b, self.d.is_ref)
         n, w = res.n_guides, res.text_stride
-        if self._edits_out is None or len(self._edits_out["hap"]) < n:
-            cap = int(n * 1.05) + 1024
-            mk = lambda dt, k=1: torch.empty(cap * k, dtype=dt, pin_memory=True).numpy()  # noqa: E731
-            self._edits_out = {"hap": mk(torch.int32), "strand": mk(torch.uint8), "pos": mk(torch.int32),
-                               "start": mk(torch.int32), "stop": mk(torch.int32), "bucket": mk(torch.int64),
-                               "text": mk(torch.uint8, w)}  # fmt: skip
-        table = res.table(self._edits_out)
-        h2d = sum(v.nbytes for v in e.values()) + self.a.nbytes * 2 + self.d.is_ref.nbytes
-        d2h = n * (4 + 1 + 4 + 4 + 4 + 8 + w)
+        if getattr(self, "_edits_out2", None) is None or len(self._edits_out2["hap"]) < n:
+            self._edits_out2 = _cabi.alloc_table(int(n * 1.05) + 1024, w, pinned=True)
+        table = res.table(self._edits_out2)
         res.close()
         batch.close()
-        return table, h2d, d2h
+        t1 = self.ctx.traffic()
+        return table, t1[0] - t0[0], t1[1] - t0[1]
 
     def host_arrays_for_oracle(self, hap_indices):
         """(ascii slots, slot_off, lens, a, b, is_ref, segments) of a subset of haplotypes,

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define HAWK_ABI_VERSION 1
+#define HAWK_ABI_VERSION 2
 #define HAWK_SLOT_ALIGN 128 /* bases; haplotypes start on a 64-byte plane boundary */
 #define HAWK_SLOT_GAP 128   /* unused (zero) slots before the first and after every haplotype */
 #define HAWK_CHUNK 32       /* bases per chunk (one uint4 of planes, one uint32 of case bits) */
@@ -88,6 +88,9 @@ int hawk_ctx_create(int device, hawk_ctx **ctx);
 int hawk_ctx_destroy(hawk_ctx *ctx);
 /* SM count etc. for callers sizing grids/benchmarks */
 int hawk_ctx_info(hawk_ctx *ctx, int32_t *sm_count, int64_t *total_mem, int64_t *free_mem);
+/* bytes the host layer has moved across PCIe through this context so far, per direction
+ * (bench.py's e2e h2d_bytes_per_step / d2h_bytes_per_step are differences of these) */
+int hawk_ctx_traffic(hawk_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes);
 
 /* ---- layout helper -------------------------------------------------------
  * slot_off[0..n_hap]: slot_off[0] = HAWK_SLOT_GAP, slot_off[h+1] = slot_off[h] +
@@ -182,6 +185,52 @@ int hawk_batch_create_from_edits(hawk_ctx *ctx, const uint8_t *ref_ascii, int64_
                                  const uint8_t *alt_pool, int64_t alt_pool_len, hawk_batch **batch,
                                  int64_t *bad_slot);
 int hawk_batch_layout(hawk_batch *batch, int64_t *slot_off, int32_t *len);
+
+/* ---- streamed search: host buffers in, host table out, PCIe overlapped --------------------
+ * One call for encode_haplotypes + search (crisprhawk.py:64-115) when the haplotype texts and
+ * the guide table both live in HOST memory: the haplotypes other than REF are cut into groups;
+ * while group g is packed and searched (as REF + the group's block, so that
+ * remove_redundant_guides has its REF partners), the texts of group g + 1 are on their way to
+ * the device and the guide rows of group g - 1 on their way back. The table is the same as
+ * hawk_batch_create + hawk_batch_set_posmap + hawk_search + hawk_result_fetch give: rows in the
+ * reference's emission order, REF rows once, bucket = smallest row index of the row's
+ * (start, strand) key over the whole table. Phased / variant-free searches only
+ * (HAWK_F_UNPHASED is refused); REF, if present, should be haplotype 0 (any other position is
+ * served by a single group). `ascii`, and the columns of `out`, should be pinned host memory
+ * (cudaHostAlloc / cudaHostRegister / torch pin_memory): pageable memory works but the copies
+ * then do not overlap. n_groups = 0 lets the library choose (about 192 MB of text per group).
+ * Rows beyond out->capacity are counted but not copied and the call returns HAWK_ECAPACITY with
+ * the needed row count in *n_guides; out = NULL counts only. Columns of `out` may be NULL. */
+typedef struct hawk_table_out {
+  int32_t *hap;
+  uint8_t *strand;
+  int32_t *pos;
+  int32_t *start;
+  int32_t *stop;
+  int64_t *bucket;
+  uint8_t *text;       /* capacity * text_stride bytes */
+  int64_t capacity;    /* rows every non-NULL column can hold */
+  int32_t text_stride; /* must equal hawk_table_text_stride(pam_len, guide_len) */
+} hawk_table_out;
+/* bytes per row of the text column: G + P + 20 rounded up to 16 */
+int32_t hawk_table_text_stride(int32_t pam_len, int32_t guide_len);
+int hawk_search_stream(hawk_ctx *ctx, const uint8_t *ascii, const int64_t *slot_off, const int32_t *len,
+                       int32_t n_hap, const int64_t *seg_off, const int32_t *seg_rel,
+                       const int32_t *seg_gen, const uint8_t *seg_step, const hawk_params *params,
+                       const int32_t *scan_start, const int32_t *scan_stop, const uint8_t *is_ref,
+                       int32_t n_groups, const hawk_table_out *out, int64_t *n_guides,
+                       int64_t *n_hits /* [2] */, int64_t *scanned_bp, int64_t *bad_slot);
+/* The same from edit lists (see hawk_batch_create_from_edits): only the reference text and the
+ * edits cross PCIe, group by group; the guide rows of one group leave while the next group's
+ * texts are materialised, packed and searched. */
+int hawk_search_stream_edits(hawk_ctx *ctx, const uint8_t *ref_ascii, int64_t ref_len,
+                             int32_t region_start, int32_t n_hap, const int64_t *edit_off,
+                             const int32_t *edit_pos, const int32_t *edit_reflen,
+                             const int32_t *edit_altlen, const int64_t *edit_altoff,
+                             const uint8_t *alt_pool, int64_t alt_pool_len, const hawk_params *params,
+                             const int32_t *scan_start, const int32_t *scan_stop, const uint8_t *is_ref,
+                             int32_t n_groups, const hawk_table_out *out, int64_t *n_guides,
+                             int64_t *n_hits /* [2] */, int64_t *scanned_bp);
 
 /* Re-run K1 into an existing batch from device-resident texts of the same layout (the
  * coordinate maps / allele tables attached to the batch are kept). */

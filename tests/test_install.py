@@ -78,7 +78,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(raw, name), f"{name} declared in hawkscan.h but not exported"
         assert name in _cabi.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.hawk_abi_version() == 1
+    assert lib.hawk_abi_version() == _cabi.ABI_VERSION
     assert lib.hawk_strerror(_cabi.HAWK_EIUPAC).decode() == "non-IUPAC character"
     # host-only helpers work without a device
     import numpy as np
