@@ -370,23 +370,34 @@ def run_product_arm(args, rank, world, local_rank):
         e_ms = float(te.item())
         e2e = {"value": total_bp / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e_ms, "steps": e2e_steps, "rows_per_step": int(len(table["hap"])),
+               "call": "hawk_search_stream: one C-ABI call, haplotype groups pipelined, H2D / compute / D2H overlapped",
                "input": "haplotype texts (pinned ASCII slot space), the reference's own input to this path"}  # fmt: skip
+
+        def timed(fn, reps):
+            fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                out = fn()
+            torch.cuda.synchronize(local_rank)
+            ms = 1e3 * (time.perf_counter() - t0) / reps
+            tt = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item()), out
+
+        # the same as two calls with nothing overlapped (encode_haplotypes, then search + fetch)
+        two_ms, (_, h2d_b, d2h_b) = timed(wl.step_host_twocall, max(1, e2e_steps - 1))
+        e2e["two_calls_no_overlap"] = {"value": total_bp / (two_ms / 1e3), "unit": UNIT, "ms_per_step": two_ms,
+                                       "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b)}  # fmt: skip
         # N1 (next row): the same search when the host holds the reference text and per-haplotype
         # edit lists (what its VCF reader produced) and the texts are materialised on the device
-        wl.step_edits()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            table2, h2d2, d2h2 = wl.step_edits()
-        torch.cuda.synchronize(local_rank)
-        n1_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
-        tn = torch.tensor([n1_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-        if dist is not None:
-            dist.all_reduce(tn, op=dist.ReduceOp.MAX)
-        n1_ms = float(tn.item())
+        n1_ms, (table2, h2d2, d2h2) = timed(wl.step_edits, e2e_steps)
         e2e["from_edit_lists"] = {"value": total_bp / (n1_ms / 1e3), "unit": UNIT, "ms_per_step": n1_ms,
                                   "h2d_bytes_per_step": int(h2d2), "d2h_bytes_per_step": int(d2h2),
-                                  "rows_per_step": int(len(table2["hap"]))}  # fmt: skip
+                                  "rows_per_step": int(len(table2["hap"])), "call": "hawk_search_stream_edits"}  # fmt: skip
+        n1b_ms, _ = timed(wl.step_edits_twocall, max(1, e2e_steps - 1))
+        e2e["from_edit_lists"]["two_calls_no_overlap_ms"] = n1b_ms
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None

@@ -113,7 +113,16 @@ static int arena_take(hawk_ctx* c, size_t n, uint8_t** out) {
 int hawk_ctx::small_h2d(void* dst_dev, const void* src_host, size_t n) {
   if (n == 0) return HAWK_OK;
   h2d_bytes += (int64_t)n;
-  if (n > SMALL_MAX) return hawk_check_cuda(cudaMemcpyAsync(dst_dev, src_host, n, cudaMemcpyHostToDevice, stream), "H2D copy");
+  // the copy engine is the better mover for anything sizeable unless a streamed search keeps it
+  // busy with its bulk input copies (a transfer would queue behind them, whatever its stream)
+  if (n > SMALL_MAX || (!bulk_h2d && n >= (64u << 10)))
+    return hawk_check_cuda(cudaMemcpyAsync(dst_dev, src_host, n, cudaMemcpyHostToDevice, stream), "H2D copy");
+  // page-locked source (the caller pinned it): the SMs read it in place
+  cudaPointerAttributes attr;
+  if (n >= 4096 && cudaPointerGetAttributes(&attr, src_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+      attr.devicePointer != nullptr)
+    return launch_small_copy(stream, dst_dev, attr.devicePointer, n);
+  cudaGetLastError();
   uint8_t* stage = nullptr;
   CK(arena_take(this, n, &stage));
   memcpy(stage, src_host, n);

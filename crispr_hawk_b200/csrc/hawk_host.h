@@ -105,6 +105,7 @@ struct hawk_ctx {
   int small_d2h_sync(void* dst_host, const void* src_dev, size_t n);   // returns after a stream sync
   // bulk-copy streams of the streamed search (created on first use)
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  bool bulk_h2d = false;  // a streamed search owns the H2D copy engine: uploads go through the SMs
   // bytes the host layer moved across PCIe since the context was created (hawk_ctx_traffic)
   int64_t h2d_bytes = 0, d2h_bytes = 0;
   // optional per-kernel timing (hawk_ctx_set_profiling)

@@ -338,7 +338,9 @@ extern "C" int hawk_search_stream(hawk_ctx* c, const uint8_t* ascii, const int64
     return HAWK_OK;
   };
 
+  c->bulk_h2d = true;
   int rc = run_groups(c, P, params, scan_start, scan_stop, is_ref, gmin, gmax, prefetch, make_batch, out, T);
+  c->bulk_h2d = false;
   store_totals(T, n_guides, n_hits, scanned_bp);
   return rc;
 }
@@ -366,7 +368,10 @@ extern "C" int hawk_search_stream_edits(hawk_ctx* c, const uint8_t* ref_ascii, i
   std::vector<int64_t> pseudo(n_hap + 1);
   for (int32_t h = 0; h <= n_hap; ++h) pseudo[h] = (int64_t)h * ref_len;
   Plan P;
-  CK(make_plan(pseudo.data(), n_hap, is_ref, n_groups, 384ll << 20, P));
+  // fewer, larger groups than the text path: nothing bulky goes up, so a group only has to be
+  // small enough for its rows to leave while the next one is computed (measured: about 8 groups
+  // for 5 G haplotype-bp; more groups pay more stream synchronisations than they hide)
+  CK(make_plan(pseudo.data(), n_hap, is_ref, n_groups, 640ll << 20, P));
   if (P.ref_first && edit_off[1] != edit_off[0])
     return hawk_fail(HAWK_EINVAL, "hawk_search_stream_edits: the REF haplotype must have no edits");
 
