@@ -36,7 +36,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL banners off stdout: rank 0 prints exactly one JSON line
+# Rank 0 prints exactly ONE line on stdout, the JSON result. Libraries that write to the
+# process's stdout behind Python's back (NCCL prints its version banner there) are kept out of
+# it: file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a
+# duplicate of the original stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 import numpy as np  # noqa: E402
 
@@ -207,7 +217,7 @@ def run_reference_arm(args, rank, world):
         "note": "CPU arm: oracle/scan_oracle.c (C restatement of encoder.py + search_guides.py, OpenMP over haplotypes). "
                 "The reference itself is single-threaded pure Python and cannot travel to this box.",
     }  # fmt: skip
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -434,7 +444,7 @@ def run_product_arm(args, rank, world, local_rank):
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "profile_steps": prof_steps,
         }  # fmt: skip
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
