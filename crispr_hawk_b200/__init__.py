@@ -9,6 +9,7 @@ Public mirror of the reference interface for this path:
 (hand-written CUDA for sm_100a) through the C-ABI in include/hawkscan.h.
 """
 
+from .annotation import annotate_table  # noqa: F401
 from .encoder import encode, encode_haplotypes, encode_region  # noqa: F401
 from .guide import Guide, guide_class  # noqa: F401
 from .haplotypes import Edit, EditHaplotype, build_phased  # noqa: F401

@@ -25,6 +25,7 @@ HAWK_EIUPAC = -4
 HAWK_ECAPACITY = -5
 HAWK_EALLELES = -6
 HAWK_EDUPREF = -7
+HAWK_EASSERT = -8
 
 
 class HawkLibraryError(RuntimeError):
@@ -119,6 +120,9 @@ SIGNATURES = {
          C.c_int64, _P, _P, _P],
     ),  # fmt: skip
     "hawk_scan_expand_dev": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
+    "hawk_batch_set_variants": (C.c_int, [_P, _I64P, _I32P, _I32P, _I32P, _I64P, _U8P, C.c_int64]),
+    "hawk_result_annotate": (C.c_int, [_P, _P, _U8P, _I32P, _I32P, _I64P, _I64P]),
+    "hawk_result_fetch_variants": (C.c_int, [_P, _I32P]),
     "hawk_table_text_stride": (C.c_int32, [C.c_int32, C.c_int32]),
     "hawk_search_stream": (
         C.c_int,
@@ -276,6 +280,7 @@ class Batch:
         self.handle = h
         self.has_posmap = False
         self.has_alleles = False
+        self.has_variants = False
 
     @classmethod
     def from_edits(cls, ctx: "Context", ref_ascii: np.ndarray, region_start: int, edit_off, edit_pos, edit_reflen,
@@ -307,6 +312,7 @@ class Batch:
         self.lens = np.zeros(self.n_hap, np.int32)
         check(self.lib.hawk_batch_layout(h, ptr(self.slot_off, C.c_int64), ptr(self.lens, C.c_int32)))
         self.has_posmap, self.has_alleles = True, False
+        self.has_variants = True  # the edit lists stay on the device as the variant table (N2)
         return self
 
     def export_text(self, hap: int) -> str:
@@ -347,6 +353,18 @@ class Batch:
             "hawk_batch_set_alleles",
         )
         self.has_alleles = True
+
+    def set_variants(self, vt):
+        """N2: the haplotypes' variant tables (marshal.VariantTable) for Result.annotate."""
+        check(
+            self.lib.hawk_batch_set_variants(
+                self.handle, ptr(vt.var_off, C.c_int64), ptr(vt.var_pos, C.c_int32), ptr(vt.var_reflen, C.c_int32),
+                ptr(vt.var_altlen, C.c_int32), ptr(vt.var_altoff, C.c_int64), ptr(vt.alt_pool, C.c_uint8),
+                len(vt.alt_pool),
+            ),  # fmt: skip
+            "hawk_batch_set_variants",
+        )
+        self.has_variants = True
 
     def close(self):
         if getattr(self, "handle", None):
@@ -393,6 +411,25 @@ class Result:
         )
         out["text"] = out["text"][:, :w]  # rows are padded to text_stride bytes on the device
         return out
+
+    def annotate(self, batch: "Batch", want_variants: bool = True):
+        """hawk_result_annotate (N2): reverse-complemented text of the strand-1 rows, GC counts
+        of the guides, and per-row CSR lists of the haplotype-local variant indices that
+        polish_guide_variants keeps. Row order = table order."""
+        n, ts, w = self.n_guides, self.text_stride, self.window
+        rc = np.zeros((n, ts), np.uint8)
+        num, den = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        off = np.zeros(n + 1, np.int64) if want_variants else None
+        total = C.c_int64(0)
+        check(
+            self.lib.hawk_result_annotate(self.handle, batch.handle, ptr(rc, C.c_uint8), ptr(num, C.c_int32),
+                                          ptr(den, C.c_int32), ptr(off, C.c_int64), C.byref(total)),
+            "hawk_result_annotate",
+        )  # fmt: skip
+        idx = np.zeros(total.value, np.int32)
+        if total.value:
+            check(self.lib.hawk_result_fetch_variants(self.handle, ptr(idx, C.c_int32)), "hawk_result_fetch_variants")
+        return {"rc_text": rc[:, :w], "gc_num": num, "gc_den": den, "gv_off": off, "gv_idx": idx}
 
     def hits(self, strand: int) -> np.ndarray:
         out = np.empty(self.n_hits[strand], np.uint64)

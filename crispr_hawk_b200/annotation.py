@@ -1,0 +1,71 @@
+"""N2 (next row of the scope table): the post-search pure functions of the reference's
+annotation.py -- `_annotate_variants` / `polish_guide_variants` (:246-315),
+`annotate_variants_afs` (:334-365), `reverse_guides` (:27-51), `gc_content` (:513-541) --
+for the guide table of a phased / variant-free search.
+
+The per-base work (which variants are visible in which guide, reverse complements, GC counts)
+runs on the device over the resident table (`hawk_result_annotate`); what is left here is
+string assembly: joining the sorted variant ids, looking up and formatting their allele
+frequencies, `str()` of the GC fraction. The reference does all of it per `Guide` in Python
+and re-parses the haplotype's whole variant list for every guide."""
+
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import marshal
+from .errors import error_class, exception_handler
+
+
+def format_af(af: float) -> str:
+    """annotation.py:316-331 (_format_af)."""
+    s = f"{af:.10f}".rstrip("0").rstrip(".")
+    decimal_digits = len(s.split(".")) if "." in s else 0
+    return f"{af:.6e}" if decimal_digits > 3 else str(round(af, 6))
+
+
+def annotate_table(table: Dict[str, np.ndarray], res, batch, haplotypes, right: bool,
+                   vt: Optional[marshal.VariantTable] = None, debug: bool = True) -> Dict[str, list]:  # fmt: skip
+    """Columns of annotation.annotate_guides' first four steps for every row of `table`
+    (the dict `search_table` returned, rows in emission order): `variants`, `afs_str`,
+    `sequence` (after reverse_guides), `right` (after it) and `gc` -- the values the
+    reference leaves in Guide.variants / .afs_str / .sequence / .right / .gc."""
+    from . import _cabi
+
+    if not getattr(batch, "has_variants", False):
+        vt = vt or marshal.variant_table(haplotypes)
+        batch.set_variants(vt)
+    elif vt is None:
+        vt = marshal.variant_table(haplotypes)
+    try:
+        ann = res.annotate(batch)
+    except _cabi.HawkLibraryError as e:
+        if e.code == _cabi.HAWK_EASSERT:
+            raise AssertionError(str(e)) from e  # annotation.py:191
+        raise
+    n = len(table["hap"])
+    off, idx = ann["gv_off"], ann["gv_idx"]
+    hap, strand = table["hap"], table["strand"]
+    variants: List[str] = []
+    afs_str: List[str] = []
+    for i in range(n):
+        h = haplotypes[int(hap[i])]
+        if h.variants == "NA":  # _is_reference_guide, annotation.py:104-126
+            variants.append("NA")
+            afs_str.append("NA")
+            continue
+        ids = sorted(vt.ids[int(hap[i])][j] for j in idx[off[i] : off[i + 1]])
+        v = ",".join(ids)
+        variants.append(v)
+        vals = [format_af(h.afs[x]) if str(h.afs[x]) != "nan" else "NA" for x in v.split(",")]
+        afs_str.append("NA" if not vals or (len(set(vals)) == 1 and vals[0] == "NA") else ",".join(vals))  # guide.py:311-328
+    seq = [bytes(r).decode("ascii") for r in ann["rc_text"]]
+    num, den = ann["gc_num"], ann["gc_den"]
+    if n and int(den.min()) == 0:
+        # gc_fraction returns the int 0 and Guide.gc refuses it (guide.py:598-618, annotation.py:531-538)
+        exception_handler(error_class("CrisprHawkGcContentError"), "GC content calculation failed", 65, debug, None)
+    gc = [str(int(a) / int(b)) for a, b in zip(num, den)]
+    rp = [((not right) if s == 1 else bool(right)) != (s == 1) for s in strand.tolist()]
+    return {"variants": variants, "afs_str": afs_str, "sequence": seq, "right": rp, "gc": gc}

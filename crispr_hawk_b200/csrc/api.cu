@@ -54,6 +54,7 @@ extern "C" const char* hawk_strerror(int code) {
     case HAWK_ECAPACITY: return "capacity exceeded";
     case HAWK_EALLELES: return "ambiguity code without variant alleles";
     case HAWK_EDUPREF: return "duplicate REF guide";
+    case HAWK_EASSERT: return "the reference asserts on this input";
     default: return "unknown error";
   }
 }
@@ -391,6 +392,15 @@ extern "C" int hawk_batch_create_from_edits(hawk_ctx* c, const uint8_t* ref_asci
     hawk_batch_destroy(b);
     return rc;
   }
+  // N2: anchored edits are the reference's normalised variants (variant.py:456-486) already
+  b->var_off.move_from(d_eoff);
+  b->var_pos.move_from(d_pos);
+  b->var_rl.move_from(d_rl);
+  b->var_al.move_from(d_al);
+  b->var_ao.move_from(d_ao);
+  b->var_pool.move_from(d_pool);
+  b->var_pos_base = region_start;
+  b->has_variants = true;
   b->h_seg_off = seg_off;
   b->first_gen.assign(n_hap, region_start);
   b->linear.resize(n_hap);
@@ -851,6 +861,8 @@ int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, cons
     const int64_t n_hits[2] = {so.n[0], so.n[1]};
     if (!unphased) {
       if ((rc = search_fast(c, b, K, B, so, ref_h, link, r))) break;
+      r->params = *params;
+      r->is_table = true;
       for (int s = 0; s < 2; ++s) {
         r->n_hits[s] = n_hits[s];
         r->hits[s].move_from(so.hits[s]);

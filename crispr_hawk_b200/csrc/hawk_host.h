@@ -179,6 +179,10 @@ struct hawk_batch {
   DevBuf seg_off, seg_rel, seg_gen, seg_step;
   DevBuf va_off, va_idx, va_ent_off, va_ref;
   bool has_posmap = false, has_alleles = false;
+  // N2: the haplotypes' variant tables (hawk_batch_set_variants, or kept from the edit lists)
+  DevBuf var_off, var_pos, var_rl, var_al, var_ao, var_pool;
+  int32_t var_pos_base = 0;
+  bool has_variants = false;
   // host-side facts about the coordinate maps (hawk_batch_set_posmap)
   std::vector<int64_t> h_seg_off;
   std::vector<int32_t> first_gen;   // posmap(0) per haplotype
@@ -195,6 +199,10 @@ struct hawk_result {
   int64_t ref_hits[2] = {0, 0};  // REF records per strand (filled for the groups of a streamed search)
   DevBuf hits[2];
   DevBuf hap, strand, pos, start, stop, bucket, text;
+  hawk_params params;     // of the search that produced the table
+  bool is_table = false;  // a phased / variant-free hawk_search result (hawk_result_annotate)
+  DevBuf gv_idx;          // N2: variant indices of the last hawk_result_annotate
+  int64_t gv_total = 0;
 };
 
 

@@ -30,6 +30,14 @@ class CrisprHawkGuideError(CrisprHawkError):
     pass
 
 
+class CrisprHawkGcContentError(CrisprHawkError):
+    pass
+
+
+class CrisprHawkAnnotationError(CrisprHawkError):
+    pass
+
+
 def _reference_module(name: str):
     try:
         import importlib

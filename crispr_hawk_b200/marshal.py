@@ -166,3 +166,52 @@ def segment_table(haps) -> SegmentTable:
 
 def pam_nibbles(seq: str) -> List[int]:
     return [_NIBBLE[c] for c in seq.upper()]
+
+
+# --------------------------------------------------------------------------- N2: variant tables
+def normalise_variant(ref: str, alt: str, pos: int):
+    """variant.py:456-486 (adjust_multiallelic): the form annotation._parse_variant compares in."""
+    if len(ref) == len(alt):
+        return ref[0], alt[0], pos
+    if len(ref) > len(alt):
+        return ref[len(alt) - 1 :], alt[-1], pos + len(alt) - 1
+    return ref[-1], alt[len(ref) - 1 :], pos + len(ref) - 1
+
+
+class VariantTable:
+    """Per-haplotype variant lists for hawk_batch_set_variants, plus the ids in table order."""
+
+    def __init__(self, var_off, var_pos, var_reflen, var_altlen, var_altoff, alt_pool, ids):
+        self.var_off, self.var_pos, self.var_reflen = var_off, var_pos, var_reflen
+        self.var_altlen, self.var_altoff, self.alt_pool, self.ids = var_altlen, var_altoff, alt_pool, ids
+
+
+def variant_table(haps) -> VariantTable:
+    """Parse every haplotype's `variants` string ('NA' or 'chrom-pos-ref/alt,...',
+    variant.py:436-453) into the normalised, position-sorted table the device walks."""
+    off, pos, rl, al, ao, pool, ids = [0], [], [], [], [], [], []
+    n_pool = 0
+    for h in haps:
+        rows = []
+        if h.variants and h.variants != "NA":
+            # annotation.py:96 splits into a set: duplicates collapse
+            for vid in dict.fromkeys(h.variants.split(",")):
+                parts = vid.split("-")
+                ref, alt = parts[2].split("/")
+                r2, a2, p2 = normalise_variant(ref, alt, int(parts[1]))
+                rows.append((p2, vid, len(r2), a2))
+        rows.sort(key=lambda t: t[0])
+        ids.append([t[1] for t in rows])
+        for p2, _, r_len, a2 in rows:
+            pos.append(p2)
+            rl.append(r_len)
+            al.append(len(a2))
+            ao.append(n_pool)
+            pool.append(a2)
+            n_pool += len(a2)
+        off.append(len(pos))
+    return VariantTable(
+        np.asarray(off, np.int64), np.asarray(pos, np.int32), np.asarray(rl, np.int32), np.asarray(al, np.int32),
+        np.asarray(ao, np.int64), np.frombuffer("".join(pool).encode("ascii"), np.uint8).copy() if pool else np.zeros(0, np.uint8),
+        ids,
+    )  # fmt: skip

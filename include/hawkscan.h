@@ -56,7 +56,8 @@ enum {
   HAWK_EIUPAC = -4,   /* non-IUPAC character (encoder.py:38-44) */
   HAWK_ECAPACITY = -5,/* caller-provided output capacity too small (dev layer) */
   HAWK_EALLELES = -6, /* ambiguity code without variant_alleles entry (KeyError, search_guides.py:207-213) */
-  HAWK_EDUPREF = -7   /* two REF guides at one (start, strand) (search_guides.py:328-334) */
+  HAWK_EDUPREF = -7,  /* two REF guides at one (start, strand) (search_guides.py:328-334) */
+  HAWK_EASSERT = -8   /* input on which the reference itself fails an assert (annotation.py:191) */
 };
 
 /* mode flags of hawk_params.flags */
@@ -231,6 +232,34 @@ int hawk_search_stream_edits(hawk_ctx *ctx, const uint8_t *ref_ascii, int64_t re
                              const int32_t *scan_start, const int32_t *scan_stop, const uint8_t *is_ref,
                              int32_t n_groups, const hawk_table_out *out, int64_t *n_guides,
                              int64_t *n_hits /* [2] */, int64_t *scanned_bp);
+
+/* ---- N2 (next row): post-search pure functions on the guide table -----------
+ * What annotation.annotate_guides does to every Guide right after search() (annotation.py:
+ * 563-572), for the rows of a phased / variant-free hawk_search result, in row order:
+ *   _annotate_variants / polish_guide_variants (:246-315): the variants of the row's haplotype
+ *       that are visible in the guide, as a CSR list (gv_off, n_guides + 1 entries; the indices
+ *       count inside the haplotype's own variant list and come back through
+ *       hawk_result_fetch_variants, *gv_total of them). The host joins the sorted variant ids
+ *       and looks the allele frequencies up (annotate_variants_afs, :334-365: string work).
+ *   reverse_guides (:27-51): rc_text = the window text, reverse-complemented (IUPAC-aware,
+ *       case kept, utils.py:46-79) for rows of strand 1; text_stride bytes per row.
+ *   gc_content (:513-541): gc_num / gc_den = G+C+S and A+C+G+T+S+W counts of the guide without
+ *       its PAM (Bio.SeqUtils.gc_fraction, ambiguous="remove"); gc = gc_num / gc_den.
+ * The variant table: haplotype h carries variants [var_off[h], var_off[h+1]) sorted by
+ * position, each in the reference's normalised form (variant.py:456-486, adjust_multiallelic):
+ * var_pos = genomic coordinate, allele lengths, ALT text (upper-case, as in the variant id) =
+ * alt_pool[var_altoff .. + var_altlen). Batches made by hawk_batch_create_from_edits keep their
+ * edit lists as this table (anchored edits are normalised already). At most one variant per
+ * position and haplotype is what a phased VCF yields; with more the reference's own answer
+ * depends on Python's set order (variants at one position are taken in table order here).
+ * Any output pointer may be NULL (gv_off = NULL skips the variant pass). Returns HAWK_EASSERT on
+ * the input the reference's _find_insertion_stop asserts on. */
+int hawk_batch_set_variants(hawk_batch *batch, const int64_t *var_off, const int32_t *var_pos,
+                            const int32_t *var_reflen, const int32_t *var_altlen,
+                            const int64_t *var_altoff, const uint8_t *alt_pool, int64_t alt_pool_len);
+int hawk_result_annotate(hawk_result *result, hawk_batch *batch, uint8_t *rc_text, int32_t *gc_num,
+                         int32_t *gc_den, int64_t *gv_off, int64_t *gv_total);
+int hawk_result_fetch_variants(hawk_result *result, int32_t *gv_idx /* gv_total */);
 
 /* Re-run K1 into an existing batch from device-resident texts of the same layout (the
  * coordinate maps / allele tables attached to the batch are kept). */
