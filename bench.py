@@ -409,6 +409,24 @@ def run_product_arm(args, rank, world, local_rank):
         n1b_ms, _ = timed(wl.step_edits_twocall, max(1, e2e_steps - 1))
         e2e["from_edit_lists"]["two_calls_no_overlap_ms"] = n1b_ms
 
+    # ---- next rows of the scope table on the same workload (rank 0, N = 1 only) ----
+    next_rows = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        from oracle import annot_oracle
+
+        m = wl.annotate_measure(oracle=annot_oracle)
+        ms = m["variants_ms"] + m["text_gc_ms"]
+        next_rows = {"N2_annotate": {
+            "what": "hawk_result_annotate over the step's whole guide table: polish_guide_variants (CSR lists of the "
+                    "haplotype's variants visible in each guide), reverse complement of strand-1 rows, GC counts; "
+                    "outputs copied to pinned host memory inside the timed calls",
+            "rows": m["rows"], "variant_refs": m["variant_refs"], "variants_ms": m["variants_ms"],
+            "text_gc_ms": m["text_gc_ms"], "rows_per_s": m["rows"] / (ms / 1e3) if ms else None,
+            "cpu_port_rows_per_s": m.get("oracle_rows_per_s"), "cpu_port_rows_checked": m.get("oracle_rows_checked"),
+            "cpu_port": "oracle/annot_oracle.py (pure Python, like the reference) on a random sample of non-REF rows, "
+                        "each also compared with the device result",
+        }}  # fmt: skip
+
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -441,7 +459,7 @@ def run_product_arm(args, rank, world, local_rank):
             "config": workload_config(args, wl.scanned_bp, cohort.n_hap),
             "guides_per_step": total_guides, "hits_per_step_rank0": hits_total,
             "device_ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "next_rows": next_rows,
             "gpu_launches": int(launches), "clocks": clocks, "profile_steps": prof_steps,
         }  # fmt: skip
         emit(line)

@@ -412,14 +412,21 @@ class Result:
         out["text"] = out["text"][:, :w]  # rows are padded to text_stride bytes on the device
         return out
 
-    def annotate(self, batch: "Batch", want_variants: bool = True):
+    def annotate(self, batch: "Batch", want_variants: bool = True, want_text: bool = True, buffers=None):
         """hawk_result_annotate (N2): reverse-complemented text of the strand-1 rows, GC counts
         of the guides, and per-row CSR lists of the haplotype-local variant indices that
-        polish_guide_variants keeps. Row order = table order."""
+        polish_guide_variants keeps. Row order = table order. `buffers`: optional dict of
+        preallocated (e.g. pinned) arrays `rc_text` (n * text_stride), `gc_num`, `gc_den` (n),
+        `gv_off` (n + 1)."""
         n, ts, w = self.n_guides, self.text_stride, self.window
-        rc = np.zeros((n, ts), np.uint8)
-        num, den = np.zeros(n, np.int32), np.zeros(n, np.int32)
-        off = np.zeros(n + 1, np.int64) if want_variants else None
+        b = buffers or {}
+        rc = num = den = off = None
+        if want_text:
+            rc = b["rc_text"][: n * ts] if "rc_text" in b else np.zeros(n * ts, np.uint8)
+            num = b["gc_num"][:n] if "gc_num" in b else np.zeros(n, np.int32)
+            den = b["gc_den"][:n] if "gc_den" in b else np.zeros(n, np.int32)
+        if want_variants:
+            off = b["gv_off"][: n + 1] if "gv_off" in b else np.zeros(n + 1, np.int64)
         total = C.c_int64(0)
         check(
             self.lib.hawk_result_annotate(self.handle, batch.handle, ptr(rc, C.c_uint8), ptr(num, C.c_int32),
@@ -429,7 +436,8 @@ class Result:
         idx = np.zeros(total.value, np.int32)
         if total.value:
             check(self.lib.hawk_result_fetch_variants(self.handle, ptr(idx, C.c_int32)), "hawk_result_fetch_variants")
-        return {"rc_text": rc[:, :w], "gc_num": num, "gc_den": den, "gv_off": off, "gv_idx": idx}
+        return {"rc_text": rc.reshape(n, ts)[:, :w] if want_text else None, "gc_num": num, "gc_den": den,
+                "gv_off": off, "gv_idx": idx}  # fmt: skip
 
     def hits(self, strand: int) -> np.ndarray:
         out = np.empty(self.n_hits[strand], np.uint64)

@@ -151,6 +151,74 @@ class Workload:
         t1 = self.ctx.traffic()
         return table, t1[0] - t0[0], t1[1] - t0[1]
 
+    # ---- N2: post-search pure functions on the resident table ----
+    def annotate_measure(self, reps: int = 3, n_sample: int = 192, oracle=None):
+        """hawk_result_annotate over the whole guide table of this workload (batch built from
+        the edit lists, which stay on the device as the variant table). Returns timings and,
+        when `oracle` (oracle.annot_oracle, tests / bench only) is given, checks a random
+        sample of non-REF rows against it and times it."""
+        import time
+
+        torch = self.torch
+        c = self.cohort
+        e = self._edit_buffers()
+        batch = _cabi.Batch.from_edits(self.ctx, e["ref"], c.region_start, e["off"], e["pos"], e["rl"], e["al"], e["ao"], e["pool"])
+        res = _cabi.search(self.ctx, batch, self.params, self.a, self.b, self.d.is_ref)
+        n, ts = res.n_guides, res.text_stride
+        pin = lambda m, dt: torch.empty(max(m, 1), dtype=dt, pin_memory=True).numpy()  # noqa: E731
+        bufs = {"rc_text": pin(n * ts, torch.uint8), "gc_num": pin(n, torch.int32), "gc_den": pin(n, torch.int32),
+                "gv_off": pin(n + 1, torch.int64)}  # fmt: skip
+        ann = res.annotate(batch, buffers=bufs)
+        out = {"rows": int(n), "variant_refs": int(len(ann["gv_idx"]))}
+        for key, kw in (("variants_ms", dict(want_text=False)), ("text_gc_ms", dict(want_variants=False))):
+            torch.cuda.synchronize(self.device)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                res.annotate(batch, buffers=bufs, **kw)
+            out[key] = 1e3 * (time.perf_counter() - t0) / reps
+        if oracle is not None and n:
+            if getattr(self, "_edits_out2", None) is None or len(self._edits_out2["hap"]) < n:
+                self._edits_out2 = _cabi.alloc_table(int(n * 1.05) + 1024, ts, pinned=True)
+            table = res.table(self._edits_out2)
+            rng = np.random.default_rng(7)
+            alt_rows = np.flatnonzero(table["hap"] != 0)
+            rows = rng.choice(alt_rows, size=min(n_sample, len(alt_rows)), replace=False) if len(alt_rows) else []
+            G, P = self.guidelen, len(self.fwd)
+            seg = self.d.seg
+            pool = c.alt_pool.tobytes().decode("ascii")
+            reft = c.ref.tobytes().decode("ascii")
+            ids_cache = {}
+            cpu_s = 0.0
+            for r in rows:
+                h, s_ = int(table["hap"][r]), int(table["strand"][r])
+                if h not in ids_cache:
+                    sites = c.hap_sites[c.hap_off[h] : c.hap_off[h + 1]]
+                    ids_cache[h] = [
+                        f"chr1-{c.region_start + int(c.site_pos[k])}-{reft[int(c.site_pos[k]) : int(c.site_pos[k]) + int(c.site_reflen[k])]}/"
+                        f"{pool[int(c.site_altoff[k]) : int(c.site_altoff[k]) + int(c.site_altlen[k])]}" for k in sites
+                    ]  # fmt: skip
+                ids = ids_cache[h]
+                rp = (not self.right) if s_ == 1 else bool(self.right)
+                pivot = int(table["pos"][r]) - (0 if rp else G)
+                s0, s1 = int(seg.seg_off[h]), int(seg.seg_off[h + 1])
+                pm = marshal.eval_segments(seg.seg_rel[s0:s1], seg.seg_gen[s0:s1], seg.seg_step[s0:s1],
+                                           np.arange(pivot, pivot + G + P)).tolist()  # fmt: skip
+                text = table["text"][r].tobytes().decode("ascii")
+                t0 = time.perf_counter()
+                v, _, seq2, _, gc = oracle.annotate_guide(text, G, P, s_, rp, int(table["stop"][r]), pm, ",".join(ids),
+                                                          {x: 0.5 for x in ids})  # fmt: skip
+                cpu_s += time.perf_counter() - t0
+                got_v = ",".join(sorted(ids[j] for j in ann["gv_idx"][ann["gv_off"][r] : ann["gv_off"][r + 1]]))
+                got_seq = ann["rc_text"][r].tobytes().decode("ascii")
+                got_gc = str(int(ann["gc_num"][r]) / int(ann["gc_den"][r]))
+                if (got_v, got_seq, got_gc) != (v, seq2, gc):
+                    raise AssertionError(f"N2 mismatch at row {int(r)}: {(got_v, got_seq, got_gc)} != {(v, seq2, gc)}")
+            out["oracle_rows_checked"] = int(len(rows))
+            out["oracle_rows_per_s"] = (len(rows) / cpu_s) if cpu_s > 0 else None
+        res.close()
+        batch.close()
+        return out
+
     def host_arrays_for_oracle(self, hap_indices):
         """(ascii slots, slot_off, lens, a, b, is_ref, segments) of a subset of haplotypes,
         copied to the host, in the form oracle/c_oracle.search takes."""
