@@ -728,13 +728,20 @@ static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const Bat
     CK(keep[s].alloc(c, (size_t)n_hits[s]));
     CK(blk_cnt[s].alloc(c, (size_t)(n_blk[s] + 1) * 4));
     CK(blk_base[s].alloc(c, (size_t)(n_blk[s] + 1) * 8));
-    CK(launch_rows_fast(st, B, K, recs[s], n_hits[s], s, ref, d_refbm[s].as<uint32_t>(), d_refrange.as<int64_t>(),
-                        link ? link->drop_ref : 0, start[s].as<int32_t>(), stop[s].as<int32_t>(),
-                        keep[s].as<uint8_t>(), blk_cnt[s].as<uint32_t>()));
+  }
+  {
+    const uint32_t* bm[2] = {d_refbm[0].as<uint32_t>(), d_refbm[1].as<uint32_t>()};
+    int32_t* st_[2] = {start[0].as<int32_t>(), start[1].as<int32_t>()};
+    int32_t* sp_[2] = {stop[0].as<int32_t>(), stop[1].as<int32_t>()};
+    uint8_t* kp_[2] = {keep[0].as<uint8_t>(), keep[1].as<uint8_t>()};
+    uint32_t* bc_[2] = {blk_cnt[0].as<uint32_t>(), blk_cnt[1].as<uint32_t>()};
+    CK(launch_rows_fast(st, B, K, recs, n_hits, ref, bm, d_refrange.as<int64_t>(), link ? link->drop_ref : 0, st_, sp_,
+                        kp_, bc_));
+  }
+  for (int s = 0; s < 2; ++s)
     if (n_hits[s] > 0)
       CK(launch_blk_prefix(st, blk_cnt[s].as<uint32_t>(), n_blk[s], blk_base[s].as<uint64_t>(),
                            d_tot.as<uint64_t>() + s));
-  }
   // no host round trip here: the table is allocated for the upper bound (every hit kept)
   // and the surviving-row totals are read once, after the last kernel
   const int64_t n_max = n_hits[0] + n_hits[1];
@@ -772,13 +779,16 @@ static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const Bat
       CKCUDA(cudaMemsetAsync(key_table_own.p, 0xFF, (size_t)key_span * 4, st));
       key_table = key_table_own.as<uint32_t>();
     }
-    for (int s = 0; s < 2; ++s)
-      CK(launch_gather_fast(st, B, K, recs[s], keep[s].as<uint8_t>(), blk_base[s].as<uint64_t>(),
-                            start[s].as<int32_t>(), stop[s].as<int32_t>(),
-                            d_kb.as<uint64_t>() + (size_t)(1 - s) * (b->n_hap + 1), n_hits[s], s, r->text_stride,
-                            r->hap.as<int32_t>(), r->strand.as<uint8_t>(), r->pos.as<int32_t>(),
-                            r->start.as<int32_t>(), r->stop.as<int32_t>(), r->text.as<uint8_t>(),
-                            direct ? key_table : nullptr, key_min, rm));
+    {
+      const uint8_t* kp_[2] = {keep[0].as<uint8_t>(), keep[1].as<uint8_t>()};
+      const uint64_t* bb_[2] = {blk_base[0].as<uint64_t>(), blk_base[1].as<uint64_t>()};
+      const int32_t* st_[2] = {start[0].as<int32_t>(), start[1].as<int32_t>()};
+      const int32_t* sp_[2] = {stop[0].as<int32_t>(), stop[1].as<int32_t>()};
+      const uint64_t* kb_[2] = {d_kb.as<uint64_t>() + (size_t)(b->n_hap + 1), d_kb.as<uint64_t>()};
+      CK(launch_gather_fast(st, B, K, recs, kp_, bb_, st_, sp_, kb_, n_hits, r->text_stride, r->hap.as<int32_t>(),
+                            r->strand.as<uint8_t>(), r->pos.as<int32_t>(), r->start.as<int32_t>(), r->stop.as<int32_t>(),
+                            r->text.as<uint8_t>(), direct ? key_table : nullptr, key_min, rm));
+    }
     if (direct)
       CK(launch_bucket_read(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n_max, d_tot.as<uint64_t>(),
                             key_table, key_min, r->bucket.as<int64_t>()));

@@ -73,18 +73,19 @@ int launch_annot_text(cudaStream_t st, const ScanConst& K, const uint8_t* strand
 int64_t row_blocks(int64_t n);
 int launch_ref_bitmap(cudaStream_t st, const uint64_t* r0, const uint64_t* r1, const int64_t* ref_range,
                       uint32_t* bm0, uint32_t* bm1);
-int launch_rows_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* recs, int64_t n,
-                     int s, const RefInfo& ref, const uint32_t* ref_bm, const int64_t* ref_range, int32_t drop_ref,
-                     int32_t* start, int32_t* stop, uint8_t* keep, uint32_t* blk_cnt);
+int launch_rows_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* const recs[2],
+                     const int64_t n[2], const RefInfo& ref, const uint32_t* const ref_bm[2], const int64_t* ref_range,
+                     int32_t drop_ref, int32_t* const start[2], int32_t* const stop[2], uint8_t* const keep[2],
+                     uint32_t* const blk_cnt[2]);
 int launch_blk_prefix(cudaStream_t st, const uint32_t* cnt, int64_t n_blk, uint64_t* base, uint64_t* total);
 int launch_hap_offsets(cudaStream_t st, const uint64_t* r0, const uint64_t* r1, int64_t n0, int64_t n1,
                        const uint8_t* k0, const uint8_t* k1, const uint64_t* b0, const uint64_t* b1,
                        const uint64_t* totals, int32_t n_hap, uint64_t* kb);
-int launch_gather_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* recs,
-                       const uint8_t* keep, const uint64_t* blk_base, const int32_t* start, const int32_t* stop,
-                       const uint64_t* kb_other, int64_t n, int s, int32_t text_stride, int32_t* o_hap,
-                       uint8_t* o_strand, int32_t* o_pos, int32_t* o_start, int32_t* o_stop, uint8_t* o_text,
-                       uint32_t* key_table, int32_t key_min, const RowMap& rm);
+int launch_gather_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* const recs[2],
+                       const uint8_t* const keep[2], const uint64_t* const blk_base[2], const int32_t* const start[2],
+                       const int32_t* const stop[2], const uint64_t* const kb_other[2], const int64_t n[2],
+                       int32_t text_stride, int32_t* o_hap, uint8_t* o_strand, int32_t* o_pos, int32_t* o_start,
+                       int32_t* o_stop, uint8_t* o_text, uint32_t* key_table, int32_t key_min, const RowMap& rm);
 int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n_max,
                        const uint64_t* totals, const uint32_t* key_table, int32_t key_min, int64_t* bucket);
 

@@ -10,7 +10,23 @@
 namespace hawk {
 
 // ------------------------------------------------------------------ K1: pack
+// 32 ASCII bytes of one chunk: one 256-bit load (sm_100 has LDG.256; a warp instruction then
+// covers 1 KB of consecutive text) when the text is 32-byte aligned, else two 128-bit loads.
+template <bool WIDE>
+__device__ __forceinline__ void load_chunk_text(const uint4* __restrict__ ascii, int64_t c, uint32_t* w) {
+  if (WIDE) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(ascii + 2 * c));
+  } else {
+    const uint4 a = __ldg(&ascii[2 * c]), b = __ldg(&ascii[2 * c + 1]);
+    w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w;
+    w[4] = b.x, w[5] = b.y, w[6] = b.z, w[7] = b.w;
+  }
+}
+
 // One thread per chunk: 32 ASCII bytes -> {A,C,G,T} plane words + case word.
+template <bool WIDE>
 __global__ void __launch_bounds__(256) pack_kernel(const uint4* __restrict__ ascii,
                                                    int64_t n_chunks, uint4* __restrict__ q,
                                                    uint32_t* __restrict__ v, uint32_t* __restrict__ nz,
@@ -23,10 +39,9 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint4* __restrict__ asc
     const int64_t c = c0 + lane;
     uint32_t vw = 0;
     if (c < n_chunks) {
-      uint4 w[2];
-      w[0] = __ldg(&ascii[2 * c]);
-      w[1] = __ldg(&ascii[2 * c + 1]);
-      const PackedChunk o = pack_chunk(reinterpret_cast<const uint32_t*>(w));
+      uint32_t w[8];
+      load_chunk_text<WIDE>(ascii, c, w);
+      const PackedChunk o = pack_chunk(w);
       q[c] = make_uint4(o.a, o.c, o.g, o.t);
       v[c] = o.v;
       vw = o.v;
@@ -52,8 +67,12 @@ extern "C" int hawk_pack_dev(void* stream, const uint8_t* d_ascii, int64_t total
   if (n_chunks == 0) return HAWK_OK;
   int64_t blocks = (n_chunks + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride: 16 CTAs per SM
-  pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      (const uint4*)d_ascii, n_chunks, (uint4*)d_q, d_v, d_nz, (unsigned long long*)d_bad);
+  if (((uintptr_t)d_ascii & 31) == 0)
+    pack_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)d_ascii, n_chunks, (uint4*)d_q, d_v, d_nz, (unsigned long long*)d_bad);
+  else
+    pack_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)d_ascii, n_chunks, (uint4*)d_q, d_v, d_nz, (unsigned long long*)d_bad);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "pack_kernel launch");
 }

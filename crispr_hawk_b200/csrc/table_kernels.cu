@@ -39,33 +39,44 @@ __global__ void ref_bitmap_kernel(const uint64_t* __restrict__ recs0, const uint
 }
 
 // ---------------------------------------------------------------- rows
-struct RowsArgs {
-  BatchView B;
-  ScanConst K;
+// Both strands in one launch, blocks interleaved (even = strand 0, odd = strand 1): the two hit
+// streams are sorted by (haplotype, position) and about equally dense, so block k of either
+// stream works on the same stretch of the same haplotype and the second reader of a plane
+// sector finds it in L2 instead of DRAM.
+struct RowsStrand {
   const uint64_t* recs;
   int64_t n;
-  int32_t s;
-  int32_t ref_h;         // -1: no REF haplotype
-  int32_t ref_linear;    // REF posmap is one step-1 segment: posmap(i) = ref_g0 + i
-  int32_t ref_g0, ref_len;
   const uint32_t* ref_bm;     // REF guide bitmap of this strand (ref_linear)
-  const int64_t* ref_range;   // REF record range per strand (general REF posmap)
-  int32_t drop_ref;           // streamed search, later groups: REF rows serve as partners only
   int32_t* start;
   int32_t* stop;
   uint8_t* keep;
   uint32_t* blk_cnt;
 };
 
+struct RowsArgs {
+  BatchView B;
+  ScanConst K;
+  RowsStrand S[2];
+  int32_t ref_h;         // -1: no REF haplotype
+  int32_t ref_linear;    // REF posmap is one step-1 segment: posmap(i) = ref_g0 + i
+  int32_t ref_g0, ref_len;
+  const int64_t* ref_range;   // REF record range per strand (general REF posmap)
+  int32_t drop_ref;           // streamed search, later groups: REF rows serve as partners only
+};
+
 __global__ void __launch_bounds__(ROW_T) rows_fast_kernel(const __grid_constant__ RowsArgs A) {
-  const int64_t i = (int64_t)blockIdx.x * ROW_T + threadIdx.x;
+  const int s = blockIdx.x & 1;
+  const int64_t blk = blockIdx.x >> 1;
+  const RowsStrand S = A.S[s];
+  if (blk * ROW_T >= S.n) return;  // the shorter stream has fewer blocks (uniform over the CTA)
+  const int64_t i = blk * ROW_T + threadIdx.x;
   int k = 0;
-  if (i < A.n) {
-    const uint64_t rec = A.recs[i];
+  if (i < S.n) {
+    const uint64_t rec = S.recs[i];
     const int32_t h = (int32_t)(rec >> 32), pos = (int32_t)(rec & 0xFFFFFFFFu);
-    const RowCoords rc = row_coords(A.B, A.K, h, pos, A.s);
-    A.start[i] = rc.start;
-    A.stop[i] = rc.stop;
+    const RowCoords rc = row_coords(A.B, A.K, h, pos, s);
+    S.start[i] = rc.start;
+    S.stop[i] = rc.stop;
     k = 1;
     if (A.drop_ref && A.B.is_ref[h]) {
       k = 0;
@@ -74,13 +85,13 @@ __global__ void __launch_bounds__(ROW_T) rows_fast_kernel(const __grid_constant_
       // REF guide's at the same (start, strand) is dropped
       int32_t rpivot = -1;
       if (A.ref_linear) {
-        const int32_t rp = rc.start - A.ref_g0, rpos = rp - A.K.geom[A.s].c0;
-        if (rp >= 0 && rpos >= 0 && rpos < A.ref_len && ((A.ref_bm[rpos >> 5] >> (rpos & 31)) & 1u)) rpivot = rp;
+        const int32_t rp = rc.start - A.ref_g0, rpos = rp - A.K.geom[s].c0;
+        if (rp >= 0 && rpos >= 0 && rpos < A.ref_len && ((S.ref_bm[rpos >> 5] >> (rpos & 31)) & 1u)) rpivot = rp;
       } else {
-        const int64_t lo = A.ref_range[2 * A.s], hi = A.ref_range[2 * A.s + 1];
-        const int64_t j = find_ref_partner(A.B, A.K, A.recs, lo, hi, A.ref_h, A.s, rc.start);
+        const int64_t lo = A.ref_range[2 * s], hi = A.ref_range[2 * s + 1];
+        const int64_t j = find_ref_partner(A.B, A.K, S.recs, lo, hi, A.ref_h, s, rc.start);
         if (j < hi) {
-          const int32_t rp = (int32_t)(A.recs[j] & 0xFFFFFFFFu) + A.K.geom[A.s].c0;
+          const int32_t rp = (int32_t)(S.recs[j] & 0xFFFFFFFFu) + A.K.geom[s].c0;
           if (posmap_eval(A.B.seg_rel, A.B.seg_gen, A.B.seg_step, A.B.seg_off[A.ref_h], A.B.seg_off[A.ref_h + 1], rp) ==
               rc.start)
             rpivot = rp;
@@ -90,10 +101,10 @@ __global__ void __launch_bounds__(ROW_T) rows_fast_kernel(const __grid_constant_
           cores_equal(A.B.q, A.B.slot_off[h] >> 5, rc.pivot, A.B.slot_off[A.ref_h] >> 5, rpivot, A.K.C))
         k = 0;
     }
-    A.keep[i] = (uint8_t)k;
+    S.keep[i] = (uint8_t)k;
   }
   const int cnt = __syncthreads_count(k);
-  if (threadIdx.x == 0) A.blk_cnt[blockIdx.x] = (uint32_t)cnt;
+  if (threadIdx.x == 0) S.blk_cnt[blk] = (uint32_t)cnt;
 }
 
 // ---------------------------------------------------------------- block prefix (single CTA)
@@ -154,9 +165,7 @@ __global__ void hap_offsets_kernel(const uint64_t* __restrict__ recs0, const uin
 }
 
 // ---------------------------------------------------------------- gather
-struct GatherFastArgs {
-  BatchView B;
-  ScanConst K;
+struct GatherStrand {
   const uint64_t* recs;
   const uint8_t* keep;
   const uint64_t* blk_base;
@@ -164,7 +173,12 @@ struct GatherFastArgs {
   const int32_t* stop;
   const uint64_t* kb_other;  // kb of the other stream, n_hap + 1 entries
   int64_t n;
-  int32_t s;
+};
+
+struct GatherFastArgs {  // both strands in one launch, blocks interleaved (see RowsArgs)
+  BatchView B;
+  ScanConst K;
+  GatherStrand S[2];
   int32_t text_stride;  // bytes per text row, multiple of 16
   int32_t* o_hap;
   uint8_t* o_strand;
@@ -213,30 +227,34 @@ __device__ __forceinline__ uint4 window_chars(uint32_t pa, uint32_t pc, uint32_t
 
 __global__ void __launch_bounds__(ROW_T) gather_fast_kernel(const __grid_constant__ GatherFastArgs A) {
   __shared__ uint32_t warp_cnt[ROW_T / 32];
-  const int64_t i = (int64_t)blockIdx.x * ROW_T + threadIdx.x;
+  const int s = blockIdx.x & 1;
+  const int64_t blk = blockIdx.x >> 1;
+  const GatherStrand S = A.S[s];
+  if (blk * ROW_T >= S.n) return;
+  const int64_t i = blk * ROW_T + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool k = i < A.n && A.keep[i];
+  const bool k = i < S.n && S.keep[i];
   const uint32_t bal = __ballot_sync(0xFFFFFFFFu, k);
   if (lane == 0) warp_cnt[warp] = __popc(bal);
   __syncthreads();
   if (!k) return;
   uint32_t rank = __popc(bal & ((1u << lane) - 1u));
   for (int w = 0; w < warp; ++w) rank += warp_cnt[w];
-  const uint64_t rec = A.recs[i];
+  const uint64_t rec = S.recs[i];
   const int32_t h = (int32_t)(rec >> 32), pos = (int32_t)(rec & 0xFFFFFFFFu);
   // rows of the other stream emitted before this one: haplotype < h (strand 0) or <= h (strand 1)
-  const uint64_t f = A.blk_base[blockIdx.x] + rank + A.kb_other[h + (A.s == 1 ? 1 : 0)];
-  const int32_t st = A.start[i];
+  const uint64_t f = S.blk_base[blk] + rank + S.kb_other[h + (s == 1 ? 1 : 0)];
+  const int32_t st = S.start[i];
   A.o_hap[f] = h == A.rm.ref_local ? A.rm.ref_global : h + A.rm.hap_add;
-  A.o_strand[f] = (uint8_t)A.s;
+  A.o_strand[f] = (uint8_t)s;
   A.o_pos[f] = pos;
   A.o_start[f] = st;
-  A.o_stop[f] = A.stop[i];
-  if (A.key_table) atomicMin(&A.key_table[((uint32_t)(st - A.key_min) << 1) | (uint32_t)A.s], (uint32_t)(f + A.rm.row_base));
+  A.o_stop[f] = S.stop[i];
+  if (A.key_table) atomicMin(&A.key_table[((uint32_t)(st - A.key_min) << 1) | (uint32_t)s], (uint32_t)(f + A.rm.row_base));
   // extract_guide_sequence (:134-160): padded window text from planes + case bits
   const int W = A.K.C + 2 * HAWK_GUIDESEQPAD;
   const int64_t chunk0 = A.B.slot_off[h] >> 5;
-  const int32_t w0 = pos + A.K.geom[A.s].w0;
+  const int32_t w0 = pos + A.K.geom[s].w0;
   uint4* dst = reinterpret_cast<uint4*>(A.o_text + f * (uint64_t)A.text_stride);
   for (int j0 = 0; j0 < A.text_stride; j0 += 32) {
     const int32_t o = w0 + j0;
@@ -274,12 +292,23 @@ int launch_ref_bitmap(cudaStream_t st, const uint64_t* r0, const uint64_t* r1, c
   return hawk_check_cuda(cudaGetLastError(), "ref_bitmap_kernel launch");
 }
 
-int launch_rows_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* recs, int64_t n,
-                     int s, const RefInfo& ref, const uint32_t* ref_bm, const int64_t* ref_range, int32_t drop_ref,
-                     int32_t* start, int32_t* stop, uint8_t* keep, uint32_t* blk_cnt) {
-  if (n <= 0) return HAWK_OK;
-  RowsArgs A{B, K, recs, n, s, ref.h, ref.linear, ref.g0, ref.len, ref_bm, ref_range, drop_ref, start, stop, keep, blk_cnt};
-  rows_fast_kernel<<<blocks_for(n, ROW_T), ROW_T, 0, st>>>(A);
+int launch_rows_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* const recs[2],
+                     const int64_t n[2], const RefInfo& ref, const uint32_t* const ref_bm[2], const int64_t* ref_range,
+                     int32_t drop_ref, int32_t* const start[2], int32_t* const stop[2], uint8_t* const keep[2],
+                     uint32_t* const blk_cnt[2]) {
+  const int64_t nb = row_blocks(n[0] > n[1] ? n[0] : n[1]);
+  if (nb <= 0) return HAWK_OK;
+  RowsArgs A{};
+  A.B = B;
+  A.K = K;
+  for (int s = 0; s < 2; ++s) A.S[s] = RowsStrand{recs[s], n[s], ref_bm[s], start[s], stop[s], keep[s], blk_cnt[s]};
+  A.ref_h = ref.h;
+  A.ref_linear = ref.linear;
+  A.ref_g0 = ref.g0;
+  A.ref_len = ref.len;
+  A.ref_range = ref_range;
+  A.drop_ref = drop_ref;
+  rows_fast_kernel<<<(unsigned)(2 * nb), ROW_T, 0, st>>>(A);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "rows_fast_kernel launch");
 }
@@ -299,15 +328,28 @@ int launch_hap_offsets(cudaStream_t st, const uint64_t* r0, const uint64_t* r1, 
   return hawk_check_cuda(cudaGetLastError(), "hap_offsets_kernel launch");
 }
 
-int launch_gather_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* recs,
-                       const uint8_t* keep, const uint64_t* blk_base, const int32_t* start, const int32_t* stop,
-                       const uint64_t* kb_other, int64_t n, int s, int32_t text_stride, int32_t* o_hap,
-                       uint8_t* o_strand, int32_t* o_pos, int32_t* o_start, int32_t* o_stop, uint8_t* o_text,
-                       uint32_t* key_table, int32_t key_min, const RowMap& rm) {
-  if (n <= 0) return HAWK_OK;
-  GatherFastArgs A{B, K, recs, keep, blk_base, start, stop, kb_other, n, s, text_stride,
-                   o_hap, o_strand, o_pos, o_start, o_stop, o_text, key_table, key_min, rm};
-  gather_fast_kernel<<<blocks_for(n, ROW_T), ROW_T, 0, st>>>(A);
+int launch_gather_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* const recs[2],
+                       const uint8_t* const keep[2], const uint64_t* const blk_base[2], const int32_t* const start[2],
+                       const int32_t* const stop[2], const uint64_t* const kb_other[2], const int64_t n[2],
+                       int32_t text_stride, int32_t* o_hap, uint8_t* o_strand, int32_t* o_pos, int32_t* o_start,
+                       int32_t* o_stop, uint8_t* o_text, uint32_t* key_table, int32_t key_min, const RowMap& rm) {
+  const int64_t nb = row_blocks(n[0] > n[1] ? n[0] : n[1]);
+  if (nb <= 0) return HAWK_OK;
+  GatherFastArgs A{};
+  A.B = B;
+  A.K = K;
+  for (int s = 0; s < 2; ++s) A.S[s] = GatherStrand{recs[s], keep[s], blk_base[s], start[s], stop[s], kb_other[s], n[s]};
+  A.text_stride = text_stride;
+  A.o_hap = o_hap;
+  A.o_strand = o_strand;
+  A.o_pos = o_pos;
+  A.o_start = o_start;
+  A.o_stop = o_stop;
+  A.o_text = o_text;
+  A.key_table = key_table;
+  A.key_min = key_min;
+  A.rm = rm;
+  gather_fast_kernel<<<(unsigned)(2 * nb), ROW_T, 0, st>>>(A);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "gather_fast_kernel launch");
 }
