@@ -25,6 +25,11 @@ __device__ __forceinline__ void load_chunk_text(const uint4* __restrict__ ascii,
   }
 }
 
+#ifndef HAWK_PACK_RUN
+#define HAWK_PACK_RUN 32
+#endif
+constexpr int64_t PACK_RUN = HAWK_PACK_RUN;  // tiles of 256 chunks per CTA
+
 // One thread per chunk: 32 ASCII bytes -> {A,C,G,T} plane words + case word.
 template <bool WIDE>
 __global__ void __launch_bounds__(256) pack_kernel(const uint4* __restrict__ ascii,
@@ -34,8 +39,13 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint4* __restrict__ asc
   // a warp packs 32 consecutive chunks per pass (chunk index = multiple of 32 + lane), so one
   // ballot gives the 32 "chunk holds a variant base" bits of a whole nz word
   const int lane = threadIdx.x & 31;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t c0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); c0 < n_chunks; c0 += stride) {
+  // every CTA packs one contiguous run of PACK_RUN tiles of 256 chunks (256 KB of text), and
+  // consecutive CTAs take consecutive runs: at any moment the CTAs in flight work inside one
+  // moving window of ~150 MB instead of striding over the whole slot space (a grid-stride loop
+  // over 5 GB ran 10 % slower: 1.42 -> 1.27 ms)
+  const int64_t c_lo = (int64_t)blockIdx.x * (PACK_RUN * 256);
+  const int64_t c_end = c_lo + PACK_RUN * 256 < n_chunks ? c_lo + PACK_RUN * 256 : n_chunks;
+  for (int64_t c0 = c_lo + (threadIdx.x & ~31); c0 < c_end; c0 += 256) {
     const int64_t c = c0 + lane;
     uint32_t vw = 0;
     if (c < n_chunks) {
@@ -65,8 +75,7 @@ extern "C" int hawk_pack_dev(void* stream, const uint8_t* d_ascii, int64_t total
     return hawk_fail(HAWK_EINVAL, "hawk_pack_dev: buffers must be 16-byte aligned");
   int64_t n_chunks = total_slots / HAWK_CHUNK;
   if (n_chunks == 0) return HAWK_OK;
-  int64_t blocks = (n_chunks + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride: 16 CTAs per SM
+  const int64_t blocks = (n_chunks + PACK_RUN * 256 - 1) / (PACK_RUN * 256);
   if (((uintptr_t)d_ascii & 31) == 0)
     pack_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)d_ascii, n_chunks, (uint4*)d_q, d_v, d_nz, (unsigned long long*)d_bad);
