@@ -738,10 +738,11 @@ static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const Bat
     CK(launch_rows_fast(st, B, K, recs, n_hits, ref, bm, d_refrange.as<int64_t>(), link ? link->drop_ref : 0, st_, sp_,
                         kp_, bc_));
   }
-  for (int s = 0; s < 2; ++s)
-    if (n_hits[s] > 0)
-      CK(launch_blk_prefix(st, blk_cnt[s].as<uint32_t>(), n_blk[s], blk_base[s].as<uint64_t>(),
-                           d_tot.as<uint64_t>() + s));
+  {
+    const uint32_t* bc_[2] = {blk_cnt[0].as<uint32_t>(), blk_cnt[1].as<uint32_t>()};
+    uint64_t* bb_[2] = {blk_base[0].as<uint64_t>(), blk_base[1].as<uint64_t>()};
+    CK(launch_blk_prefix(st, bc_, n_blk, bb_, d_tot.as<uint64_t>()));
+  }
   // no host round trip here: the table is allocated for the upper bound (every hit kept)
   // and the surviving-row totals are read once, after the last kernel
   const int64_t n_max = n_hits[0] + n_hits[1];

@@ -77,7 +77,8 @@ int launch_rows_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, co
                      const int64_t n[2], const RefInfo& ref, const uint32_t* const ref_bm[2], const int64_t* ref_range,
                      int32_t drop_ref, int32_t* const start[2], int32_t* const stop[2], uint8_t* const keep[2],
                      uint32_t* const blk_cnt[2]);
-int launch_blk_prefix(cudaStream_t st, const uint32_t* cnt, int64_t n_blk, uint64_t* base, uint64_t* total);
+int launch_blk_prefix(cudaStream_t st, const uint32_t* const cnt[2], const int64_t n_blk[2], uint64_t* const base[2],
+                      uint64_t* totals);
 int launch_hap_offsets(cudaStream_t st, const uint64_t* r0, const uint64_t* r1, int64_t n0, int64_t n1,
                        const uint8_t* k0, const uint8_t* k1, const uint64_t* b0, const uint64_t* b1,
                        const uint64_t* totals, int32_t n_hap, uint64_t* kb);

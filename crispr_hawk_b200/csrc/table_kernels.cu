@@ -107,10 +107,15 @@ __global__ void __launch_bounds__(ROW_T) rows_fast_kernel(const __grid_constant_
   if (threadIdx.x == 0) S.blk_cnt[blk] = (uint32_t)cnt;
 }
 
-// ---------------------------------------------------------------- block prefix (single CTA)
-__global__ void __launch_bounds__(1024) blk_prefix_kernel(const uint32_t* __restrict__ in, int64_t n,
-                                                          uint64_t* __restrict__ out, uint64_t* total) {
+// ---------------------------------------------------------------- block prefix (one CTA per strand)
+__global__ void __launch_bounds__(1024) blk_prefix_kernel(const uint32_t* __restrict__ in0, const uint32_t* __restrict__ in1,
+                                                          int64_t n0, int64_t n1, uint64_t* __restrict__ out0,
+                                                          uint64_t* __restrict__ out1, uint64_t* totals) {
   __shared__ uint64_t part[1024];
+  const int s = blockIdx.x;
+  const uint32_t* in = s ? in1 : in0;
+  uint64_t* out = s ? out1 : out0;
+  const int64_t n = s ? n1 : n0;
   const int tid = threadIdx.x;
   const int64_t per = (n + 1023) / 1024;
   const int64_t lo = (int64_t)tid * per, hi = lo + per < n ? lo + per : n;
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(1024) blk_prefix_kernel(const uint32_t* __rest
     out[j] = run;
     run += in[j];
   }
-  if (tid == 1023) *total = part[1023];
+  if (tid == 1023) totals[s] = part[1023];
 }
 
 // ---------------------------------------------------------------- per-haplotype offsets
@@ -313,8 +318,9 @@ int launch_rows_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, co
   return hawk_check_cuda(cudaGetLastError(), "rows_fast_kernel launch");
 }
 
-int launch_blk_prefix(cudaStream_t st, const uint32_t* cnt, int64_t n_blk, uint64_t* base, uint64_t* total) {
-  blk_prefix_kernel<<<1, 1024, 0, st>>>(cnt, n_blk, base, total);
+int launch_blk_prefix(cudaStream_t st, const uint32_t* const cnt[2], const int64_t n_blk[2], uint64_t* const base[2],
+                      uint64_t* totals) {
+  blk_prefix_kernel<<<2, 1024, 0, st>>>(cnt[0], cnt[1], n_blk[0], n_blk[1], base[0], base[1], totals);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "blk_prefix_kernel launch");
 }
