@@ -44,7 +44,14 @@ def lib():
 
 
 def max_threads() -> int:
-    return int(lib().oracle_max_threads())
+    """Host threads the CPU arm may use: the cores this process is allowed to run on.
+    (torchrun exports OMP_NUM_THREADS=1 to every rank, so OpenMP's own default is not it.)"""
+    import os
+
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or int(lib().oracle_max_threads()))
 
 
 def _p(a):
