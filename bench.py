@@ -339,7 +339,7 @@ def run_product_arm(args, rank, world, local_rank):
                               "dram_traffic": traffic("pack_kernel"), "launches_per_step": 1}  # fmt: skip
     kernels["scan_k2_total"] = {
         "ms": scan_ms, "algorithmic_bytes": scan_bytes, "gbs": gbs(scan_bytes, scan_ms),
-        "note": "all K2 kernels (hapscan, block table, cand_count, cand_write, match_kernel, expand_kernel, prefix sums); "
+        "note": "all K2 kernels (hapscan, block table, cand_count, match_kernel, expand_kernel, prefix sums); "
                 "algorithmic bytes by the SURVEY 8(d) formula, which still charges the whole 0.125 B/bp case plane "
                 "although the nz summary lets K2 skip it",
     }  # fmt: skip
