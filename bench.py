@@ -409,6 +409,36 @@ def run_product_arm(args, rank, world, local_rank):
         n1b_ms, _ = timed(wl.step_edits_twocall, max(1, e2e_steps - 1))
         e2e["from_edit_lists"]["two_calls_no_overlap_ms"] = n1b_ms
 
+    # ---- final merge (N > 1): per-rank tables gathered to rank 0 over NCCL, rows resident in HBM ----
+    final_merge = None
+    if world > 1 and not args.no_e2e:
+        from crispr_hawk_b200 import shard
+
+        wl.prepare_resident()
+        res = wl.step_resident()
+        dev = f"cuda:{local_rank}"
+        key_min, key_span = cohort.region_start, cohort.region_stop - cohort.region_start + 1
+        m_ms = []
+        for _ in range(3):  # first pass warms NCCL's point-to-point channels
+            barrier()
+            t0 = time.perf_counter()
+            merged = shard.merge_tables_device(res, ctx, rank * n_alt, rank, world, dev, key_min, key_span)
+            barrier()
+            m_ms.append(1e3 * (time.perf_counter() - t0))
+        if rank == 0:
+            rows = int(merged["hap"].shape[0])
+            recv = (rows - res.n_guides) * (17 + res.text_stride)
+            final_merge = {"ms": min(m_ms[1:]), "rows": rows, "received_bytes": int(recv),
+                           "gbs": recv / (min(m_ms[1:]) / 1e3) / 1e9,
+                           "what": "ranks > 0 send their guide rows (REF rows dropped) to rank 0 with NCCL send/recv over "
+                                   "NVLink, tables resident in device memory on both ends; rank 0 recomputes the first-seen "
+                                   "bucket ids on the device (hawk_first_seen_dev). Outside the timed step: nothing "
+                                   "downstream consumes the merged table at this rate"}  # fmt: skip
+        del merged
+        res.close()
+        wl.batch.close()
+        wl.batch = None
+
     # ---- next rows of the scope table on the same workload (rank 0, N = 1 only) ----
     next_rows = None
     if rank == 0 and world == 1 and not args.no_e2e:
@@ -459,7 +489,7 @@ def run_product_arm(args, rank, world, local_rank):
             "config": workload_config(args, wl.scanned_bp, cohort.n_hap),
             "guides_per_step": total_guides, "hits_per_step_rank0": hits_total,
             "device_ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "next_rows": next_rows,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "final_merge": final_merge, "next_rows": next_rows,
             "gpu_launches": int(launches), "clocks": clocks, "profile_steps": prof_steps,
         }  # fmt: skip
         emit(line)

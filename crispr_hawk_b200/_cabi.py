@@ -106,6 +106,8 @@ SIGNATURES = {
     "hawk_result_info": (C.c_int, [_P, _I64P, _I64P, _I32P, _I32P, _I64P]),
     "hawk_result_fetch": (C.c_int, [_P, _I32P, _U8P, _I32P, _I32P, _I32P, _I64P, _U8P]),
     "hawk_result_fetch_hits": (C.c_int, [_P, C.c_int32, _U64P]),
+    "hawk_result_device_columns": (C.c_int, [_P, C.POINTER(_P)]),
+    "hawk_first_seen_dev": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P]),
     "hawk_pack_dev": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P]),
     "hawk_scan_plan": (C.c_int64, [_I32P, _I32P, C.c_int32, _I64P]),
     "hawk_scan_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
@@ -438,6 +440,12 @@ class Result:
             check(self.lib.hawk_result_fetch_variants(self.handle, ptr(idx, C.c_int32)), "hawk_result_fetch_variants")
         return {"rc_text": rc.reshape(n, ts)[:, :w] if want_text else None, "gc_num": num, "gc_den": den,
                 "gv_off": off, "gv_idx": idx}  # fmt: skip
+
+    def device_columns(self):
+        """Borrowed device addresses {column: int} of the table (hawk_result_device_columns)."""
+        cols = (_P * 7)()
+        check(self.lib.hawk_result_device_columns(self.handle, cols), "hawk_result_device_columns")
+        return {k: int(cols[i] or 0) for i, k in enumerate(("hap", "strand", "pos", "start", "stop", "bucket", "text"))}
 
     def hits(self, strand: int) -> np.ndarray:
         out = np.empty(self.n_hits[strand], np.uint64)

@@ -1062,6 +1062,18 @@ extern "C" int hawk_result_fetch(hawk_result* r, int32_t* hap, uint8_t* strand, 
   return HAWK_OK;
 }
 
+extern "C" int hawk_result_device_columns(hawk_result* r, void** cols) {
+  if (!r || !cols) return hawk_fail(HAWK_EINVAL, "hawk_result_device_columns: bad arguments");
+  cols[0] = r->hap.p;
+  cols[1] = r->strand.p;
+  cols[2] = r->pos.p;
+  cols[3] = r->start.p;
+  cols[4] = r->stop.p;
+  cols[5] = r->bucket.p;
+  cols[6] = r->text.p;
+  return HAWK_OK;
+}
+
 extern "C" int hawk_result_fetch_hits(hawk_result* r, int32_t strand, uint64_t* hits) {
   if (!r || strand < 0 || strand > 1) return hawk_fail(HAWK_EINVAL, "hawk_result_fetch_hits: bad arguments");
   CKCUDA(cudaSetDevice(r->ctx->device));

@@ -282,6 +282,22 @@ __global__ void bucket_read_kernel(const int32_t* __restrict__ start, const uint
   bucket[i] = (int64_t)key_table[((uint32_t)(start[i] - key_min) << 1) | strand[i]];
 }
 
+// first-seen table of a finished table (final merge of per-rank tables): key -> smallest row
+__global__ void first_seen_mark_kernel(const int32_t* __restrict__ start, const uint8_t* __restrict__ strand, int64_t n,
+                                       int32_t key_min, uint32_t* __restrict__ key_table) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  atomicMin(&key_table[((uint32_t)(start[i] - key_min) << 1) | strand[i]], (uint32_t)i);
+}
+
+__global__ void first_seen_read_kernel(const int32_t* __restrict__ start, const uint8_t* __restrict__ strand, int64_t n,
+                                       int32_t key_min, const uint32_t* __restrict__ key_table,
+                                       int64_t* __restrict__ bucket) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bucket[i] = (int64_t)key_table[((uint32_t)(start[i] - key_min) << 1) | strand[i]];
+}
+
 // ---------------------------------------------------------------- launch wrappers
 static inline unsigned blocks_for(int64_t n, int t) {
   int64_t b = (n + t - 1) / t;
@@ -369,3 +385,20 @@ int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* str
 }
 
 }  // namespace hawk
+
+// device layer: bucket ids of a table that already sits in device memory
+extern "C" int hawk_first_seen_dev(void* stream, const int32_t* d_start, const uint8_t* d_strand, int64_t n,
+                                   int32_t key_min, int64_t key_span, uint32_t* d_key_table, int64_t* d_bucket) {
+  if (n < 0 || key_span < 0 || n >= 0xFFFFFFFFll) return hawk_fail(HAWK_EINVAL, "hawk_first_seen_dev: bad sizes");
+  if (n == 0) return HAWK_OK;
+  if (!d_start || !d_strand || !d_key_table || !d_bucket || key_span == 0)
+    return hawk_fail(HAWK_EINVAL, "hawk_first_seen_dev: null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(d_key_table, 0xFF, (size_t)key_span * 2 * 4, st);
+  if (e != cudaSuccess) return hawk_check_cuda(e, "key table memset");
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  hawk::first_seen_mark_kernel<<<blocks, 256, 0, st>>>(d_start, d_strand, n, key_min, d_key_table);
+  hawk::first_seen_read_kernel<<<blocks, 256, 0, st>>>(d_start, d_strand, n, key_min, d_key_table, d_bucket);
+  hawk_note_launch(2);
+  return hawk_check_cuda(cudaGetLastError(), "first_seen kernels launch");
+}

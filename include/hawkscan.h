@@ -160,6 +160,11 @@ int hawk_result_info(hawk_result *result, int64_t *n_guides, int64_t *n_hits, in
  * row of which the first `window` are the text. Any pointer may be NULL. */
 int hawk_result_fetch(hawk_result *result, int32_t *hap, uint8_t *strand, int32_t *pos,
                       int32_t *start, int32_t *stop, int64_t *bucket, uint8_t *text);
+/* Borrowed DEVICE addresses of the table's columns (hap, strand, pos, start, stop, bucket,
+ * text; n_guides rows each, text_stride bytes per text row), valid until the result is
+ * destroyed and ordered on the context's stream: lets a multi-GPU caller gather the per-rank
+ * tables over NCCL without a detour through host memory (crispr_hawk_b200/shard.py). */
+int hawk_result_device_columns(hawk_result *result, void **cols /* [7] */);
 /* hit list of one strand: packed (hap << 32 | pos), ascending */
 int hawk_result_fetch_hits(hawk_result *result, int32_t strand, uint64_t *hits /* n_hits[strand] */);
 
@@ -315,6 +320,14 @@ int hawk_scan_match_dev(void *stream, const void *d_q, const uint32_t *d_v, cons
 int hawk_scan_expand_dev(void *stream, int32_t n_hap, int64_t n_sblocks, int64_t n_cand,
                          const uint64_t *d_masks, void *d_workspace, void *d_match_workspace,
                          uint64_t *d_hits_fwd, uint64_t *d_hits_rev);
+
+/* First-seen bucket ids of a guide table in device memory (group_guides_position,
+ * search_guides.py:306-337): d_bucket[i] = smallest row index sharing row i's (start, strand)
+ * key. The final step of the multi-GPU merge, after the per-rank tables were concatenated in
+ * rank order. Keys are direct addresses: key_span = largest start - key_min + 1;
+ * d_key_table holds 2 * key_span uint32 (any content); n < 2^32. */
+int hawk_first_seen_dev(void *stream, const int32_t *d_start, const uint8_t *d_strand, int64_t n,
+                        int32_t key_min, int64_t key_span, uint32_t *d_key_table, int64_t *d_bucket);
 
 /* N1 (next row): materialise haplotype texts on the device from the reference text and
  * per-haplotype sorted, non-overlapping edit lists (haplotype.py:106-121,185-252

@@ -130,3 +130,23 @@ def test_streamed_workload_equals_resident(name, scale, n_alt):
         assert np.array_equal(got[col], want[col])
     got, _, _ = wl.step_edits_twocall()
     assert np.array_equal(got["bucket"], want["bucket"]) and np.array_equal(got["text"], want["text"])
+
+
+def test_device_resident_merge_single_rank():
+    """shard.merge_tables_device with one rank: zero-copy views of the library's columns and
+    hawk_first_seen_dev give the table's own bucket ids back."""
+    import torch
+
+    from crispr_hawk_b200 import shard
+
+    k = synth.CONFIGS["c2"]
+    c = synth.config_cohort("c2", 0.05, n_alt_hap=12)
+    wl = Workload(c, k["pam"], k["guidelen"], k["right"])
+    res = wl.step_resident()
+    want = res.table()
+    dev = f"cuda:{torch.cuda.current_device()}"
+    m = shard.merge_tables_device(res, wl.ctx, 0, 0, 1, dev, c.region_start, c.region_stop - c.region_start + 1)
+    for col in COLS:
+        assert np.array_equal(m[col].cpu().numpy(), want[col]), col
+    assert np.array_equal(m["text"].cpu().numpy()[:, : want["text"].shape[1]], want["text"])
+    res.close()
