@@ -18,7 +18,8 @@ NGG / 20 nt, 1 Mb region, 2,504 phased samples -> 5,008 haplotypes + REF).
 
 `--impl reference` times only that CPU arm (all host threads). Under torchrun every rank
 scans its own block of haplotypes of the same region (weak scaling, no data-path
-collective; one NCCL all-reduce of the per-rank guide counts and checksums per step).
+collective; one NCCL all-reduce of the whole job's guide / hit counts at the end of the timed
+region).
 """
 
 from __future__ import annotations
@@ -242,6 +243,14 @@ def run_product_arm(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    if world > 1:
+        try:  # run (and first-touch the pinned staging buffers) on the CPUs next to this rank's GPU
+            import pynvml
+
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception:
+            pass
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -268,20 +277,26 @@ def run_product_arm(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize(local_rank)
 
-    tally = torch.zeros(2, dtype=torch.int64, device=f"cuda:{local_rank}")
+    tally_host = [0, 0]
 
     def one_step():
+        # the path shards with no exchange step: ranks never wait for each other inside a step
         res = wl.step_resident()
         n = res.n_guides
         h = res.n_hits
         res.close()
-        if dist is not None:  # the only exchange of the timed path: per-rank counts
-            tally[0] = n
-            tally[1] = h[0] + h[1]
-            dist.all_reduce(tally)
+        tally_host[0] += n
+        tally_host[1] += h[0] + h[1]
         if flush is not None:
             flush.fill_(1)
         return n, h
+
+    def exchange_counts():
+        # the one collective of the timed region: whole-job guide / hit counts, once, at its end
+        t = torch.tensor(tally_host, dtype=torch.int64, device=f"cuda:{local_rank}")
+        if dist is not None:
+            dist.all_reduce(t)
+        return t
 
     torch.cuda.set_stream(stream)  # NCCL / flush work is ordered with the library's stream
     sampler = None if args.no_clocks else ClockSampler(local_rank).start()
@@ -294,8 +309,10 @@ def run_product_arm(args, rank, world, local_rank):
     t0 = time.perf_counter()
     w0 = time.time()
     ev0.record(stream)
+    tally_host[0] = tally_host[1] = 0
     for _ in range(args.steps):
         n_guides, n_hits = one_step()
+    job_counts = exchange_counts()
     ev1.record(stream)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -488,6 +505,7 @@ def run_product_arm(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args, wl.scanned_bp, cohort.n_hap),
             "guides_per_step": total_guides, "hits_per_step_rank0": hits_total,
+            "job_guides_in_timed_region": int(job_counts[0].item()),
             "device_ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "final_merge": final_merge, "next_rows": next_rows,
             "gpu_launches": int(launches), "clocks": clocks, "profile_steps": prof_steps,

@@ -69,3 +69,83 @@ def annotate_table(table: Dict[str, np.ndarray], res, batch, haplotypes, right: 
     gc = [str(int(a) / int(b)) for a, b in zip(num, den)]
     rp = [((not right) if s == 1 else bool(right)) != (s == 1) for s in strand.tolist()]
     return {"variants": variants, "afs_str": afs_str, "sequence": seq, "right": rp, "gc": gc}
+
+
+# --------------------------------------------------------------------------- drop-in seam (N2)
+# Mirrors of the four per-guide loops annotation.annotate_guides runs right after search()
+# (annotation.py:563-572), same names, signatures and return values. On a list that came from
+# crispr_hawk_b200.search (a GuideList with its device-resident table) the first call computes
+# every column on the device and the four functions only assign them to the Guide objects; any
+# other list goes to the reference's own function (install() keeps it), untouched.
+_reference = {}
+
+
+def _columns(guides, debug: bool):
+    link = getattr(guides, "hawk", None)
+    if link is None:
+        return None
+    if "cols" not in link:
+        if link.get("res") is None or not getattr(link["res"], "handle", None):
+            return None
+        link["cols"] = annotate_table(link["table"], link["res"], link["batch"], link["haplotypes"], link["right"], debug=debug)
+        link["res"].close()  # the table has served its purpose: release the device memory
+        link["res"] = None
+    return link["cols"], link["order"]
+
+
+def _fallback(name, *args):
+    fn = _reference.get(name)
+    if fn is None:
+        raise RuntimeError(f"crispr_hawk_b200.annotation.{name}: not a crispr_hawk_b200 guide list and no reference "
+                           "implementation installed (there is no CPU path here)")  # fmt: skip
+    return fn(*args)
+
+
+def _annotate_variants(guides, verbosity: int, debug: bool):
+    """annotation.py:284-315."""
+    got = _columns(guides, debug)
+    if got is None:
+        return _fallback("_annotate_variants", guides, verbosity, debug)
+    cols, order = got
+    for g, i in zip(guides, order.tolist()):
+        g.variants = cols["variants"][i]
+    return guides
+
+
+def annotate_variants_afs(guides, verbosity: int):
+    """annotation.py:334-365."""
+    got = _columns(guides, True)
+    if got is None:
+        return _fallback("annotate_variants_afs", guides, verbosity)
+    cols, order = got
+    for g, i in zip(guides, order.tolist()):
+        g.afs_str = cols["afs_str"][i].split(",")  # the setter joins again (guide.py:311-328)
+    return guides
+
+
+def reverse_guides(guides, verbosity: int):
+    """annotation.py:27-51: the reverse-complemented text comes from the device."""
+    got = _columns(guides, True)
+    if got is None:
+        return _fallback("reverse_guides", guides, verbosity)
+    cols, order = got
+    for g, i in zip(guides, order.tolist()):
+        if g.strand == 1:
+            g._sequence = cols["sequence"][i]
+            g._right = cols["right"][i]
+            (getattr(g, "_compute_pamguide_sequences", None) or g._split)()  # guide.py:255
+    return guides
+
+
+def gc_content(guides, verbosity: int, debug: bool):
+    """annotation.py:513-541."""
+    got = _columns(guides, debug)
+    if got is None:
+        return _fallback("gc_content", guides, verbosity, debug)
+    cols, order = got
+    for g, i in zip(guides, order.tolist()):
+        g.gc = float(cols["gc"][i])  # the setter stores str(value) (guide.py:598-618)
+    return guides
+
+
+SEAM = ("_annotate_variants", "annotate_variants_afs", "reverse_guides", "gc_content")

@@ -85,6 +85,26 @@ class Guide:
         self._variants = value
 
     @property
+    def afs_str(self) -> str:  # guide.py:307-328
+        return self._afs_
+
+    @afs_str.setter
+    def afs_str(self, value) -> None:
+        self._afs_ = "NA" if not value or (len(set(value)) == 1 and value[0] == "NA") else ",".join(value)
+
+    @property
+    def gc(self) -> str:  # guide.py:594-618
+        return self._gc
+
+    @gc.setter
+    def gc(self, value: float) -> None:
+        if not isinstance(value, float):
+            from .errors import CrisprHawkGuideError
+
+            raise CrisprHawkGuideError(f"\n\nOut-of-frame score must be a float, got {type(value).__name__} instead")
+        self._gc = str(value)
+
+    @property
     def posmap(self) -> Dict[int, int]:
         return self._posmap
 

@@ -12,23 +12,52 @@ from . import encoder, search_guides
 _saved = {}
 
 
-def install(module: Optional[object] = None):
-    """Rebind in `crisprhawk.crisprhawk` (or the given module object). Returns it."""
+def install(module: Optional[object] = None, annotation_module: Optional[object] = None, annotation: bool = True):
+    """Rebind in `crisprhawk.crisprhawk` (or the given module object). Returns it.
+
+    With `annotation` (N2) the four per-guide loops `annotation.annotate_guides` runs right
+    after `search()` -- `_annotate_variants`, `annotate_variants_afs`, `reverse_guides`,
+    `gc_content` (annotation.py:563-572) -- are rebound in `crisprhawk.annotation` (or the
+    given module object) too; they act on lists returned by this package's `search` and hand
+    every other list to the reference's own functions."""
     from . import _cabi
+    from . import annotation as ann
 
     _cabi.load_library()  # fail loudly now, not in the middle of a run
     drv = module or importlib.import_module("crisprhawk.crisprhawk")
-    if drv in _saved:
-        return drv
-    _saved[drv] = {n: getattr(drv, n, None) for n in ("encode", "search", "encode_haplotypes")}
-    drv.encode = encoder.encode
-    drv.encode_haplotypes = encoder.encode_haplotypes
-    drv.search = search_guides.search
+    if drv not in _saved:
+        _saved[drv] = {n: getattr(drv, n, None) for n in ("encode", "search", "encode_haplotypes")}
+        drv.encode = encoder.encode
+        drv.encode_haplotypes = encoder.encode_haplotypes
+        drv.search = search_guides.search
+    if annotation:
+        amod = annotation_module
+        if amod is None and module is None:
+            amod = importlib.import_module("crisprhawk.annotation")
+        if amod is not None and amod not in _saved:
+            _saved[amod] = {n: getattr(amod, n, None) for n in ann.SEAM}
+            for n in ann.SEAM:
+                if _saved[amod][n] is not None:
+                    ann._reference[n] = _saved[amod][n]
+                setattr(amod, n, getattr(ann, n))
     return drv
 
 
-def uninstall(module: Optional[object] = None) -> None:
+def uninstall(module: Optional[object] = None, annotation_module: Optional[object] = None) -> None:
+    from . import annotation as ann
+
     drv = module or importlib.import_module("crisprhawk.crisprhawk")
     for name, fn in _saved.pop(drv, {}).items():
         if fn is not None:
             setattr(drv, name, fn)
+    amod = annotation_module
+    if amod is None and module is None:
+        try:
+            amod = importlib.import_module("crisprhawk.annotation")
+        except Exception:
+            amod = None
+    if amod is not None:
+        for name, fn in _saved.pop(amod, {}).items():
+            if fn is not None:
+                setattr(amod, name, fn)
+            ann._reference.pop(name, None)

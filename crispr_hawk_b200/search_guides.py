@@ -24,6 +24,18 @@ from .pam import pam_patterns
 GUIDESEQPAD = marshal.GUIDESEQPAD
 
 
+class GuideList(list):
+    """`search()`'s return value for phased / variant-free searches: a plain list of Guide
+    objects (buckets in first-seen order) that also carries the device-resident guide table it
+    was built from (`hawk`: table columns, `_cabi.Result`, batch, haplotypes, table order), for
+    the N2 mirrors in crispr_hawk_b200.annotation. Any list operation that builds a new list
+    drops the link, which is the safe direction."""
+
+    def __init__(self, guides, hawk):
+        super().__init__(guides)
+        self.hawk = hawk
+
+
 def _packed_for(haplotypes, haplotypes_bits, verbosity: int, debug: bool) -> PackedRegion:
     if isinstance(haplotypes_bits, PackedRegion) and haplotypes_bits.matches(haplotypes):
         return haplotypes_bits
@@ -100,7 +112,6 @@ def search(pam, region, haplotypes, haplotypes_bits, guidelen: int, right: bool,
     start_t = time()
     table, res = search_table(pam, region, haplotypes, haplotypes_bits, guidelen, right,
                               variants_present, phased, verbosity, debug)  # fmt: skip
-    res.close()
     Guide = guide_class()
     pamlen = len(pam_patterns(pam)[0])
     span = guidelen + pamlen
@@ -123,4 +134,11 @@ def search(pam, region, haplotypes, haplotypes_bits, guidelen: int, right: bool,
                   h.samples, h.variants, h.afs, gpm, debug, rp, h.id)
         )  # fmt: skip
     print_verbosity(f"Guides retrieved in {time() - start_t:.2f}s", verbosity, 3)
+    if not (variants_present and not phased):
+        # N2 seam: the device-resident table travels with the list, so the mirrors of
+        # annotation.py's per-guide loops (crispr_hawk_b200.annotation) can run on it
+        packed = _packed_for(haplotypes, haplotypes_bits, verbosity, debug)
+        return GuideList(guides, dict(table=table, res=res, batch=packed.batch, haplotypes=haplotypes,
+                                      right=bool(right), order=order))  # fmt: skip
+    res.close()
     return guides

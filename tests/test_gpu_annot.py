@@ -103,3 +103,26 @@ def test_variant_table_normalisation():
     assert vt.var_off.tolist() == [0, 0, 3]
     assert vt.var_pos.tolist() == [11, 15, 21] and vt.var_reflen.tolist() == [3, 1, 1] and vt.var_altlen.tolist() == [1, 1, 3]
     assert vt.alt_pool.tobytes() == b"CGCGG" and vt.ids[1] == ["chr1-10-ACGT/AC", "chr1-15-A/G", "chr1-20-AC/ACGG"]
+
+
+@pytest.mark.parametrize("case", CASES[:12], ids=[c["name"] for c in CASES[:12]])
+def test_annotation_seam_on_guide_objects(case):
+    """The drop-in form: search() returns a GuideList, the four mirrors of annotation.py's loops
+    leave in the Guide objects what the reference leaves in its own."""
+    from crispr_hawk_b200 import annotation as ann
+
+    region, haps = fixture_objects(case)
+    if not haps:
+        pytest.skip("no haplotypes")
+    pam = hawk.PAM(case["pam"], case["right"], True)
+    pam.encode(0)
+    guides = hawk.search(pam, region, haps, None, case["guidelen"], case["right"], case["variants_present"],
+                         case["phased"], 0, True)  # fmt: skip
+    guides = ann._annotate_variants(guides, 0, True)
+    guides = ann.annotate_variants_afs(guides, 0)
+    guides = ann.reverse_guides(guides, 0)
+    guides = ann.gc_content(guides, 0, True)
+    want = ANNOT[case["name"]]
+    assert len(guides) == len(want)
+    for g, w in zip(guides, want):
+        assert [g.variants, g.afs_str, g.sequence, bool(g.right), g.gc] == w

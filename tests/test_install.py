@@ -104,3 +104,40 @@ def test_no_cpu_fallback_without_a_device():
     assert "no CPU path" in str(ei.value) or "CUDA" in str(ei.value)
     with pytest.raises(_cabi.HawkLibraryError):
         hawk.encode("ACGT", 0, True)
+
+
+def test_install_rebinds_the_annotation_seam_and_falls_through_for_foreign_lists():
+    """N2: the four per-guide loops of annotation.annotate_guides (annotation.py:563-572) are
+    rebound; a list that did not come from crispr_hawk_b200.search goes to the originals."""
+    from crispr_hawk_b200 import annotation as ann
+
+    drv = _fake_driver()
+    amod = types.ModuleType("crisprhawk.annotation")
+    calls = []
+    for name in ann.SEAM:
+        setattr(amod, name, (lambda n: (lambda guides, *a: calls.append(n) or guides))(name))
+    orig = {n: getattr(amod, n) for n in ann.SEAM}
+    hawk.install(drv, annotation_module=amod)
+    for n in ann.SEAM:
+        assert getattr(amod, n) is getattr(ann, n)
+    plain = ["g1", "g2"]
+    assert amod._annotate_variants(plain, 0, True) is plain
+    assert amod.annotate_variants_afs(plain, 0) is plain
+    assert amod.reverse_guides(plain, 0) is plain
+    assert amod.gc_content(plain, 0, True) is plain
+    assert calls == list(ann.SEAM)
+    hawk.uninstall(drv, annotation_module=amod)
+    assert {n: getattr(amod, n) for n in ann.SEAM} == orig
+    with pytest.raises(RuntimeError):  # no reference installed and not our list: no CPU path here
+        ann.gc_content(plain, 0, True)
+
+
+def test_annotation_seam_signatures():
+    import inspect
+
+    from crispr_hawk_b200 import annotation as ann
+
+    assert list(inspect.signature(ann._annotate_variants).parameters) == ["guides", "verbosity", "debug"]
+    assert list(inspect.signature(ann.annotate_variants_afs).parameters) == ["guides", "verbosity"]
+    assert list(inspect.signature(ann.reverse_guides).parameters) == ["guides", "verbosity"]
+    assert list(inspect.signature(ann.gc_content).parameters) == ["guides", "verbosity", "debug"]
