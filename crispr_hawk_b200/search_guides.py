@@ -101,6 +101,7 @@ def search_table(pam, region, haplotypes, haplotypes_bits, guidelen: int, right:
                 65, debug, e,
             )  # fmt: skip
         raise
+    res.batch_ref = batch  # the batch the table was computed from (kept alive with the result)
     return res.table(), res
 
 
@@ -137,8 +138,7 @@ def search(pam, region, haplotypes, haplotypes_bits, guidelen: int, right: bool,
     if not (variants_present and not phased):
         # N2 seam: the device-resident table travels with the list, so the mirrors of
         # annotation.py's per-guide loops (crispr_hawk_b200.annotation) can run on it
-        packed = _packed_for(haplotypes, haplotypes_bits, verbosity, debug)
-        return GuideList(guides, dict(table=table, res=res, batch=packed.batch, haplotypes=haplotypes,
+        return GuideList(guides, dict(table=table, res=res, batch=res.batch_ref, haplotypes=haplotypes,
                                       right=bool(right), order=order))  # fmt: skip
     res.close()
     return guides
