@@ -28,8 +28,15 @@ def _case(seed):
     mean = float(rng.uniform(0, max(1.0, n_sites * 0.6)))
     snv = float(rng.uniform(0.2, 1.0))
     ins = float(rng.uniform(0, 1.0 - snv))
-    c = synth.make_cohort(bed_len, n_alt, n_sites, mean, seed=2000 + seed, snv_frac=snv, ins_frac=ins,
-                          max_indel=int(rng.integers(1, 12)))  # fmt: skip
+    max_indel = int(rng.integers(1, 12))
+    for bump in range(50):
+        c = synth.make_cohort(bed_len, n_alt, n_sites, mean, seed=2000 + seed + 1000 * bump, snv_frac=snv, ins_frac=ins,
+                              max_indel=max_indel)  # fmt: skip
+        # a non-reference haplotype without a single variant would be a second REF (the library
+        # refuses those like the reference does): draw again
+        if np.all(np.diff(c.hap_off)[1:] > 0):
+            break
+        n_alt = max(0, n_alt - 1)
     pam, G, right = PAMS[int(rng.integers(0, len(PAMS)))]
     return c, pam, G, right, rng
 
