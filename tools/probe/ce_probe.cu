@@ -1,3 +1,4 @@
+// build: nvcc -O2 -gencode arch=compute_100a,code=sm_100a -o tools/probe/ce_probe tools/probe/ce_probe.cu
 // ce_probe.cu -- does a small copy on stream B wait behind a large same-direction copy on
 // stream A? (decides how the streamed search moves its small per-group metadata)
 #include <cuda_runtime.h>
