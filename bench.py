@@ -197,7 +197,7 @@ def run_reference_arm(args, rank, world):
 
     threads = c_oracle.max_threads()
     # size the sample so one step is a few seconds of CPU work on all threads
-    n_alt = max(threads * 2, 16)
+    n_alt = max(threads * 2, 16) - 1  # REF + n_alt = a multiple of the thread count: no idle tail in the OpenMP loop
     s = cpu_sample(args.workload, n_alt, args.scale)
     times = []
     for i in range(args.warmup + args.steps):
@@ -480,7 +480,7 @@ def run_product_arm(args, rank, world, local_rank):
         from oracle import c_oracle
 
         threads = c_oracle.max_threads()
-        n_cpu = max(threads * 2, 16)
+        n_cpu = max(threads * 2, 16) - 1  # REF + n_cpu = a multiple of the thread count
         s = cpu_sample(args.workload, n_cpu, args.scale)
         cpu_step(s, threads)
         reps, acc = 0, 0.0
