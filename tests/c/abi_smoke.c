@@ -70,8 +70,38 @@ int main(int argc, char **argv) {
   /* 14 guides, 3 on '+', first at 989 */
   int ok = n == 14 && hits[0] == 3 && hits[1] == 11 && start[0] == 989 && bp == 77 &&
            memcmp(text, "TTAGGTATGTCTTAGTGACTCTAAATACCAAGGCAGTCCTCGA", 43) == 0;
+  /* N2 from plain C: reverse complements, GC counts; no variants on a REF-only batch */
+  uint8_t *rc_text = (uint8_t *)malloc((size_t)n * (size_t)stride);
+  int32_t *gc_num = (int32_t *)malloc((size_t)n * 4), *gc_den = (int32_t *)malloc((size_t)n * 4);
+  int64_t *gv_off = (int64_t *)malloc((size_t)(n + 1) * 8), gv_total = -1;
+  int64_t var_off[2] = {0, 0};
+  CHECK(hawk_batch_set_variants(batch, var_off, NULL, NULL, NULL, NULL, NULL, 0));
+  CHECK(hawk_result_annotate(res, batch, rc_text, gc_num, gc_den, gv_off, &gv_total));
+  int ok2 = gv_total == 0 && gv_off[n] == 0 && memcmp(rc_text, text, 43) == 0 /* strand 0: unchanged */ &&
+            gc_den[0] == 20 && gc_num[0] == 7 /* CTTAGTGACTCTAAATACCA */;
+  /* the streamed call gives the same table in caller-owned host columns */
+  hawk_table_out out;
+  memset(&out, 0, sizeof out);
+  out.start = (int32_t *)malloc((size_t)n * 4);
+  out.strand = (uint8_t *)malloc((size_t)n);
+  out.text = (uint8_t *)malloc((size_t)n * (size_t)stride);
+  out.capacity = n;
+  out.text_stride = hawk_table_text_stride(prm.pam_len, prm.guide_len);
+  int64_t n2 = 0, hits2[2] = {0, 0}, bp2 = 0;
+  CHECK(hawk_search_stream(ctx, ascii, slot_off, len, 1, seg_off, seg_rel, seg_gen, seg_step, &prm, a, b, is_ref, 0, &out,
+                           &n2, hits2, &bp2, &bad));
+  int ok3 = n2 == n && hits2[0] == hits[0] && hits2[1] == hits[1] && bp2 == bp && out.text_stride == stride &&
+            memcmp(out.start, start, (size_t)n * 4) == 0 && memcmp(out.strand, strand, (size_t)n) == 0 &&
+            memcmp(out.text, text, (size_t)n * (size_t)stride) == 0;
+  out.capacity = 3; /* too small: the needed row count comes back with HAWK_ECAPACITY */
+  int rc_small = hawk_search_stream(ctx, ascii, slot_off, len, 1, seg_off, seg_rel, seg_gen, seg_step, &prm, a, b, is_ref, 0,
+                                    &out, &n2, hits2, &bp2, &bad);
+  int ok4 = rc_small == HAWK_ECAPACITY && n2 == n;
+  int64_t h2d = 0, d2h = 0;
+  CHECK(hawk_ctx_traffic(ctx, &h2d, &d2h));
+  printf("annotate %d stream %d capacity %d traffic %d\n", ok2, ok3, ok4, h2d > 0 && d2h > 0);
   hawk_result_destroy(res);
   hawk_batch_destroy(batch);
   hawk_ctx_destroy(ctx);
-  return ok ? 0 : 5;
+  return ok && ok2 && ok3 && ok4 ? 0 : 5;
 }

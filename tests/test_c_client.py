@@ -37,3 +37,4 @@ def test_c_client_search(tmp_path):
     out = subprocess.run([_build(tmp_path), "gpu"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "guides 14 hits 3/11 window 43 scanned 77" in out.stdout
+    assert "annotate 1 stream 1 capacity 1 traffic 1" in out.stdout
