@@ -12,6 +12,7 @@ Public mirror of the reference interface for this path:
 from .annotation import annotate_table  # noqa: F401
 from .encoder import encode, encode_haplotypes, encode_region  # noqa: F401
 from .guide import Guide, guide_class  # noqa: F401
+from .guide_table import GuideTable  # noqa: F401
 from .haplotypes import Edit, EditHaplotype, build_phased  # noqa: F401
 from .install import install, uninstall  # noqa: F401
 from .pam import PAM  # noqa: F401

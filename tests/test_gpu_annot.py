@@ -126,3 +126,29 @@ def test_annotation_seam_on_guide_objects(case):
     assert len(guides) == len(want)
     for g, w in zip(guides, want):
         assert [g.variants, g.afs_str, g.sequence, bool(g.right), g.gc] == w
+
+
+@pytest.mark.parametrize("case", CASES[:10], ids=[c["name"] for c in CASES[:10]])
+def test_guide_table_wire_format(case):
+    """N3: the SoA table as the wire format -- lazy Guide views equal the reference's annotated
+    guides, and the batched scorer input equals scoring.py:49-84 applied to them."""
+    region, haps = fixture_objects(case)
+    if not haps:
+        pytest.skip("no haplotypes")
+    pam = hawk.PAM(case["pam"], case["right"], True)
+    pam.encode(0)
+    packed = hawk.encode_region(haps, 0, True)
+    table, res = hawk.search_table(pam, region, haps, packed, case["guidelen"], case["right"],
+                                   case["variants_present"], case["phased"], 0, True)  # fmt: skip
+    cols = hawk.annotate_table(table, res, packed.batch, haps, case["right"])
+    res.close()
+    gt = hawk.GuideTable(table, haps, pam, case["guidelen"], case["right"], annotation=cols, debug=True)
+    want = ANNOT[case["name"]]
+    assert len(gt) == len(want)
+    got = [[g.variants, g.afs_str, g.sequence, bool(g.right), g.gc] for g in gt]
+    assert got == want
+    assert gt[len(gt) - 1] is gt[-1]  # views are cached: mutations by downstream code persist
+    assert gt.scorer_sequences() == [w[2][6:-7].upper() for w in want]
+    assert gt.scorer_sequences(sgdesigner=True) == [w[2][10:-7].upper() for w in want]
+    plain = hawk.GuideTable(table, haps, pam, case["guidelen"], case["right"])
+    assert [g.sequence for g in plain] == [bytes(r).decode() for r in plain.sequences()]
