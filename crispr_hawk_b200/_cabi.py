@@ -419,7 +419,7 @@ class Result:
         of the guides, and per-row CSR lists of the haplotype-local variant indices that
         polish_guide_variants keeps. Row order = table order. `buffers`: optional dict of
         preallocated (e.g. pinned) arrays `rc_text` (n * text_stride), `gc_num`, `gc_den` (n),
-        `gv_off` (n + 1)."""
+        `gv_off` (n + 1), `gv_idx` (used when large enough for the variant references)."""
         n, ts, w = self.n_guides, self.text_stride, self.window
         b = buffers or {}
         rc = num = den = off = None
@@ -435,7 +435,10 @@ class Result:
                                           ptr(den, C.c_int32), ptr(off, C.c_int64), C.byref(total)),
             "hawk_result_annotate",
         )  # fmt: skip
-        idx = np.zeros(total.value, np.int32)
+        if "gv_idx" in b and len(b["gv_idx"]) >= total.value:
+            idx = b["gv_idx"][: total.value]
+        else:
+            idx = np.zeros(total.value, np.int32)
         if total.value:
             check(self.lib.hawk_result_fetch_variants(self.handle, ptr(idx, C.c_int32)), "hawk_result_fetch_variants")
         return {"rc_text": rc.reshape(n, ts)[:, :w] if want_text else None, "gc_num": num, "gc_den": den,

@@ -151,29 +151,39 @@ __device__ __forceinline__ uint8_t rc_char(uint8_t c) {
   return (uint8_t)(o | (c & 0x20));
 }
 
+// one thread per 16-byte word of the output text (coalesced 128-bit stores; the source bytes of
+// a row are shared by its words through L1); the row's first word also counts G/C
 __global__ void __launch_bounds__(256) annot_text_kernel(const __grid_constant__ AnnotTextArgs A) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int wpr = A.text_stride >> 4;  // words per row
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = t / wpr;
   if (r >= A.n) return;
+  const int w = (int)(t - r * wpr);
   const int s = A.strand[r];
   const int W = A.K.C + 2 * HAWK_GUIDESEQPAD;
   const uint8_t* src = A.text + (size_t)r * A.text_stride;
-  uint8_t* dst = A.rc_text + (size_t)r * A.text_stride;
-  // guide part of the forward core: right' = right XOR strand (search_guides.py:538)
-  const bool rp = (A.K.right != 0) != (s == 1);
-  const int g0 = HAWK_GUIDESEQPAD + (rp ? A.K.P : 0);
-  int num = 0, den = 0;
-  for (int i = 0; i < A.K.G; ++i) {
-    const uint8_t u = to_upper(src[g0 + i]);
-    const int gc = (u == 'G') | (u == 'C') | (u == 'S');
-    num += gc;
-    den += gc | (u == 'A') | (u == 'T') | (u == 'W');
-  }
-  A.gc_num[r] = num;
-  A.gc_den[r] = den;
-  for (int i = 0; i < A.text_stride; ++i) {
+  uint32_t word[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int b = 0; b < 16; ++b) {
+    const int i = 16 * w + b;
     uint8_t c = 0;
     if (i < W) c = s ? rc_char(src[W - 1 - i]) : src[i];
-    dst[i] = c;
+    word[b >> 2] |= (uint32_t)c << (8 * (b & 3));
+  }
+  reinterpret_cast<uint4*>(A.rc_text + (size_t)r * A.text_stride)[w] = make_uint4(word[0], word[1], word[2], word[3]);
+  if (w == 0) {
+    // guide part of the forward core: right' = right XOR strand (search_guides.py:538)
+    const bool rp = (A.K.right != 0) != (s == 1);
+    const int g0 = HAWK_GUIDESEQPAD + (rp ? A.K.P : 0);
+    int num = 0, den = 0;
+    for (int i = 0; i < A.K.G; ++i) {
+      const uint8_t u = to_upper(src[g0 + i]);
+      const int gc = (u == 'G') | (u == 'C') | (u == 'S');
+      num += gc;
+      den += gc | (u == 'A') | (u == 'T') | (u == 'W');
+    }
+    A.gc_num[r] = num;
+    A.gc_den[r] = den;
   }
 }
 
@@ -194,7 +204,8 @@ int launch_annot_text(cudaStream_t st, const ScanConst& K, const uint8_t* strand
                       int32_t text_stride, int64_t n, uint8_t* rc_text, int32_t* gc_num, int32_t* gc_den) {
   if (n <= 0) return HAWK_OK;
   AnnotTextArgs A{K, strand, text, text_stride, n, rc_text, gc_num, gc_den};
-  annot_text_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A);
+  const int64_t words = n * (text_stride >> 4);
+  annot_text_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(A);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "annot_text_kernel launch");
 }

@@ -167,7 +167,7 @@ class Workload:
         n, ts = res.n_guides, res.text_stride
         pin = lambda m, dt: torch.empty(max(m, 1), dtype=dt, pin_memory=True).numpy()  # noqa: E731
         bufs = {"rc_text": pin(n * ts, torch.uint8), "gc_num": pin(n, torch.int32), "gc_den": pin(n, torch.int32),
-                "gv_off": pin(n + 1, torch.int64)}  # fmt: skip
+                "gv_off": pin(n + 1, torch.int64), "gv_idx": pin(2 * n + 16, torch.int32)}  # fmt: skip
         ann = res.annotate(batch, buffers=bufs)
         out = {"rows": int(n), "variant_refs": int(len(ann["gv_idx"]))}
         for key, kw in (("variants_ms", dict(want_text=False)), ("text_gc_ms", dict(want_variants=False))):
