@@ -545,8 +545,7 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     import __graft_entry__ as entry
 
-    if rank == 0 or not os.path.exists(os.path.join(ROOT, "crispr_hawk_b200", "libhawkscan.so")):
-        entry.build()
+    entry.build()  # every rank: serialised by a file lock, a no-op when the libraries are up to date
     if args.impl == "reference":
         return run_reference_arm(args, rank, world)
     return run_product_arm(args, rank, world, local_rank)
