@@ -126,6 +126,7 @@ SIGNATURES = {
     "hawk_result_annotate": (C.c_int, [_P, _P, _U8P, _I32P, _I32P, _I64P, _I64P]),
     "hawk_result_fetch_variants": (C.c_int, [_P, _I32P]),
     "hawk_table_text_stride": (C.c_int32, [C.c_int32, C.c_int32]),
+    "hawk_stream_plan": (C.c_int32, [_I64P, C.c_int32, _U8P, C.c_int32, _I32P, _I32P, C.c_int32]),
     "hawk_search_stream": (
         C.c_int,
         [_P, _U8P, _I64P, _I32P, C.c_int32, _I64P, _I32P, _I32P, _U8P, C.POINTER(HawkParams), _I32P, _I32P, _U8P,
@@ -618,3 +619,15 @@ def search_stream_edits(ctx: Context, ref_ascii, region_start: int, edit_off, ed
         )  # fmt: skip
 
     return _run_stream(call, params, buffers, pinned, "hawk_search_stream_edits")
+
+
+def stream_plan(slot_off, is_ref, n_groups: int = 0):
+    """hawk_stream_plan: [(lo, hi), ...] haplotype groups of the streamed search (host only)."""
+    so = np.ascontiguousarray(slot_off, dtype=np.int64)
+    r = np.ascontiguousarray(is_ref, dtype=np.uint8)
+    lo, hi = np.zeros(256, np.int32), np.zeros(256, np.int32)
+    n = load_library().hawk_stream_plan(ptr(so, C.c_int64), len(r), ptr(r, C.c_uint8), int(n_groups), ptr(lo, C.c_int32),
+                                        ptr(hi, C.c_int32), 256)  # fmt: skip
+    if n < 0:
+        check(n, "hawk_stream_plan")
+    return [(int(lo[g]), int(hi[g])) for g in range(n)]

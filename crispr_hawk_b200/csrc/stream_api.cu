@@ -244,6 +244,24 @@ void store_totals(const Totals& T, int64_t* n_guides, int64_t* n_hits, int64_t* 
 
 }  // namespace
 
+// host-only: the group plan of the streamed search (for callers sizing their buffers, and for
+// the CPU tests): groups [lo[g], hi[g]) of haplotype indices; returns their number, or a
+// negative error code
+extern "C" int32_t hawk_stream_plan(const int64_t* slot_off, int32_t n_hap, const uint8_t* is_ref, int32_t n_groups,
+                                    int32_t* lo, int32_t* hi, int32_t capacity) {
+  if (n_hap < 0 || (n_hap > 0 && (!slot_off || !is_ref))) return hawk_fail(HAWK_EINVAL, "hawk_stream_plan: bad arguments");
+  if (n_hap == 0) return 0;
+  Plan P;
+  const int rc = make_plan(slot_off, n_hap, is_ref, n_groups, 192ll << 20, P);
+  if (rc != HAWK_OK) return rc;
+  if ((int64_t)P.groups.size() > capacity) return hawk_fail(HAWK_ECAPACITY, "hawk_stream_plan: %zu groups", P.groups.size());
+  for (size_t g = 0; g < P.groups.size(); ++g) {
+    if (lo) lo[g] = P.groups[g].lo;
+    if (hi) hi[g] = P.groups[g].hi;
+  }
+  return (int32_t)P.groups.size();
+}
+
 extern "C" int hawk_search_stream(hawk_ctx* c, const uint8_t* ascii, const int64_t* slot_off, const int32_t* len,
                                   int32_t n_hap, const int64_t* seg_off, const int32_t* seg_rel,
                                   const int32_t* seg_gen, const uint8_t* seg_step, const hawk_params* params,

@@ -220,6 +220,11 @@ typedef struct hawk_table_out {
 } hawk_table_out;
 /* bytes per row of the text column: G + P + 20 rounded up to 16 */
 int32_t hawk_table_text_stride(int32_t pam_len, int32_t guide_len);
+/* The haplotype groups hawk_search_stream would use (host only, no device needed): group g
+ * covers haplotypes [lo[g], hi[g]); REF, when it is haplotype 0, is added to every group and is
+ * not listed. Returns the number of groups (<= capacity, at most 256) or a negative HAWK_E*. */
+int32_t hawk_stream_plan(const int64_t *slot_off, int32_t n_hap, const uint8_t *is_ref, int32_t n_groups,
+                         int32_t *lo, int32_t *hi, int32_t capacity);
 int hawk_search_stream(hawk_ctx *ctx, const uint8_t *ascii, const int64_t *slot_off, const int32_t *len,
                        int32_t n_hap, const int64_t *seg_off, const int32_t *seg_rel,
                        const int32_t *seg_gen, const uint8_t *seg_step, const hawk_params *params,
