@@ -24,6 +24,30 @@ from .pam import pam_patterns
 GUIDESEQPAD = marshal.GUIDESEQPAD
 
 
+class _LiveTables:
+    """Device-resident tables kept alive behind GuideLists (crisprhawk.py searches every region
+    before it annotates any). Bounded: beyond `cap_bytes` of table memory the oldest links are
+    released -- their lists then go to the reference's own annotation functions."""
+
+    def __init__(self, cap_bytes: int = 16 << 30):
+        self.cap_bytes, self.total, self.links = cap_bytes, 0, []
+
+    def add(self, link: dict, nbytes: int) -> None:
+        self.links = [(lk, nb) for lk, nb in self.links if lk.get("res") is not None]
+        self.total = sum(nb for _, nb in self.links)
+        self.links.append((link, nbytes))
+        self.total += nbytes
+        while self.total > self.cap_bytes and len(self.links) > 1:
+            old, nb = self.links.pop(0)
+            if old.get("res") is not None:
+                old["res"].close()
+                old["res"] = None
+            self.total -= nb
+
+
+LIVE_TABLES = _LiveTables()
+
+
 class GuideList(list):
     """`search()`'s return value for phased / variant-free searches: a plain list of Guide
     objects (buckets in first-seen order) that also carries the device-resident guide table it
@@ -138,7 +162,8 @@ def search(pam, region, haplotypes, haplotypes_bits, guidelen: int, right: bool,
     if not (variants_present and not phased):
         # N2 seam: the device-resident table travels with the list, so the mirrors of
         # annotation.py's per-guide loops (crispr_hawk_b200.annotation) can run on it
-        return GuideList(guides, dict(table=table, res=res, batch=res.batch_ref, haplotypes=haplotypes,
-                                      right=bool(right), order=order))  # fmt: skip
+        link = dict(table=table, res=res, batch=res.batch_ref, haplotypes=haplotypes, right=bool(right), order=order)
+        LIVE_TABLES.add(link, int(res.n_guides) * (25 + int(res.text_stride)))
+        return GuideList(guides, link)
     res.close()
     return guides

@@ -141,3 +141,30 @@ def test_annotation_seam_signatures():
     assert list(inspect.signature(ann.annotate_variants_afs).parameters) == ["guides", "verbosity"]
     assert list(inspect.signature(ann.reverse_guides).parameters) == ["guides", "verbosity"]
     assert list(inspect.signature(ann.gc_content).parameters) == ["guides", "verbosity", "debug"]
+
+
+def test_live_device_tables_are_bounded():
+    """search() keeps a region's device table alive for the annotation seam; crisprhawk.py searches
+    every region before annotating any, so the total is capped and the oldest links are released."""
+    from crispr_hawk_b200.search_guides import _LiveTables
+
+    class Res:
+        def __init__(self):
+            self.closed = False
+
+        def close(self):
+            self.closed = True
+
+    live = _LiveTables(cap_bytes=100)
+    links = [dict(res=Res()) for _ in range(5)]
+    keep = [lk["res"] for lk in links]
+    for lk in links[:3]:
+        live.add(lk, 40)
+    assert keep[0].closed and links[0]["res"] is None  # 120 > 100: the oldest went
+    assert not keep[1].closed and not keep[2].closed and live.total == 80
+    links[1]["res"].close()
+    links[1]["res"] = None  # annotated (annotation._columns releases the table itself)
+    live.add(links[3], 40)
+    assert live.total == 80 and not keep[2].closed and not keep[3].closed
+    live.add(links[4], 500)  # one table larger than the cap stays (the newest is never dropped)
+    assert keep[2].closed and keep[3].closed and not keep[4].closed and len(live.links) == 1
