@@ -21,9 +21,6 @@
 
 namespace hawk {
 
-__device__ __forceinline__ bool is_upper(uint8_t c) { return c >= 'A' && c <= 'Z'; }
-__device__ __forceinline__ uint8_t to_upper(uint8_t c) { return (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
-
 struct AnnotVarArgs {
   BatchView B;
   ScanConst K;
@@ -45,75 +42,16 @@ template <int PASS>
 __global__ void __launch_bounds__(256) annot_variants_kernel(const __grid_constant__ AnnotVarArgs A) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= A.n) return;
-  const int32_t h = A.hap[r];
-  const int s = A.strand[r];
-  const int32_t pivot = A.pos[r] + A.K.geom[s].c0;
-  const int32_t stop = A.stop[r];
   const uint8_t* core = A.text + (size_t)r * A.text_stride + HAWK_GUIDESEQPAD;
-  const int C = A.K.C;
-  const int64_t v0 = A.V.var_off[h], v1 = A.V.var_off[h + 1];
-  uint32_t found = 0;
   int64_t out = PASS ? (int64_t)A.off[r] : 0;
-  if (v1 > v0) {
-    // segment holding the core's first base
-    const int64_t s0 = A.B.seg_off[h], s1 = A.B.seg_off[h + 1];
-    int64_t k = s0, hi = s1;
-    while (hi - k > 1) {
-      const int64_t mid = (k + hi) >> 1;
-      if (A.B.seg_rel[mid] <= pivot) k = mid; else hi = mid;
-    }
-    int32_t p = A.B.seg_gen[k] + (A.B.seg_step[k] ? (pivot - A.B.seg_rel[k]) : 0);
-    // first variant at or after the core's first coordinate
-    int64_t j = v0, jh = v1;
-    while (j < jh) {
-      const int64_t mid = (j + jh) >> 1;
-      if (A.V.var_pos[mid] + A.V.pos_base < p) j = mid + 1; else jh = mid;
-    }
-    int64_t last = -1;
-    for (int i = 0; i < C && j < v1; ++i) {
-      const int32_t idx = pivot + i;
-      while (k + 1 < s1 && A.B.seg_rel[k + 1] <= idx) ++k;
-      p = A.B.seg_gen[k] + (A.B.seg_step[k] ? (idx - A.B.seg_rel[k]) : 0);
-      while (j < v1 && A.V.var_pos[j] + A.V.pos_base < p) ++j;
-      int offset = 0;  // annotation.py:264: reset per base, carried over the variants of one base
-      for (int64_t jj = j; jj < v1 && A.V.var_pos[jj] + A.V.pos_base == p; ++jj) {
-        const int32_t rl = A.V.var_reflen[jj], al = A.V.var_altlen[jj];
-        const uint8_t* alt = A.V.alt_pool + A.V.var_altoff[jj];
-        const bool is_snv = rl == al;
-        if (!is_snv) offset = rl < al ? al - rl : 0;
-        const int seglen = (i + offset + 1 <= C ? offset + 1 : C - i);
-        const uint8_t* seg = core + i;
-        bool ok = false;
-        if (!is_snv) {  // _check_insertion (:197-226)
-          if (i == 0) {
-            int up = -1;  // _find_insertion_stop: first upper-case character, 0 when none
-            for (int t = 0; t < seglen; ++t)
-              if (is_upper(seg[t])) { up = t; break; }
-            if (up == 0) atomicExch(&A.flags[0], 1);  // the reference asserts here
-            const int kk = up < 0 ? 0 : up;
-            bool e = kk <= al;
-            for (int t = 0; e && t < kk; ++t) e = alt[al - kk + t] == to_upper(seg[t]);
-            ok = e;
-          }
-          if (!ok && p == stop) {
-            bool e = seglen <= al;
-            for (int t = 0; e && t < seglen; ++t) e = alt[t] == to_upper(seg[t]);
-            ok = e;
-          }
-        }
-        if (!ok) {  // _check_snv (:229-243): all lower-case and equal to the ALT allele
-          bool e = seglen == al;
-          for (int t = 0; e && t < seglen; ++t) e = !is_upper(seg[t]) && alt[t] == to_upper(seg[t]);
-          ok = e;
-        }
-        if (ok && jj != last) {  // a set: the bases of one insertion share the anchor's coordinate
-          last = jj;
-          if (PASS) A.idx[out++] = (int32_t)(jj - v0);
-          ++found;
-        }
-      }
-    }
-  }
+  bool would_assert = false;
+  const uint32_t found = annot_row_variants(
+      A.B, A.K, A.V, A.hap[r], A.strand[r], A.pos[r], A.stop[r], core,
+      [&](int32_t j) {
+        if (PASS) A.idx[out++] = j;
+      },
+      &would_assert);
+  if (would_assert) atomicExch(&A.flags[0], 1);
   if (!PASS) A.cnt[r] = found;
 }
 
@@ -128,29 +66,6 @@ struct AnnotTextArgs {
   int32_t* gc_den;
 };
 
-// complement of one IUPAC letter, case kept (utils.py:46-79); other bytes unchanged
-__device__ __forceinline__ uint8_t rc_char(uint8_t c) {
-  const uint8_t u = to_upper(c);
-  uint8_t o;
-  switch (u) {
-    case 'A': o = 'T'; break;
-    case 'C': o = 'G'; break;
-    case 'G': o = 'C'; break;
-    case 'T': o = 'A'; break;
-    case 'U': o = 'A'; break;
-    case 'R': o = 'Y'; break;
-    case 'Y': o = 'R'; break;
-    case 'M': o = 'K'; break;
-    case 'K': o = 'M'; break;
-    case 'H': o = 'D'; break;
-    case 'D': o = 'H'; break;
-    case 'B': o = 'V'; break;
-    case 'V': o = 'B'; break;
-    default: o = u; break;  // N, S, W
-  }
-  return (uint8_t)(o | (c & 0x20));
-}
-
 // one thread per 16-byte word of the output text (coalesced 128-bit stores; the source bytes of
 // a row are shared by its words through L1); the row's first word also counts G/C
 __global__ void __launch_bounds__(256) annot_text_kernel(const __grid_constant__ AnnotTextArgs A) {
@@ -164,27 +79,9 @@ __global__ void __launch_bounds__(256) annot_text_kernel(const __grid_constant__
   const uint8_t* src = A.text + (size_t)r * A.text_stride;
   uint32_t word[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (int b = 0; b < 16; ++b) {
-    const int i = 16 * w + b;
-    uint8_t c = 0;
-    if (i < W) c = s ? rc_char(src[W - 1 - i]) : src[i];
-    word[b >> 2] |= (uint32_t)c << (8 * (b & 3));
-  }
+  for (int b = 0; b < 16; ++b) word[b >> 2] |= (uint32_t)annot_text_byte(src, W, s, 16 * w + b) << (8 * (b & 3));
   reinterpret_cast<uint4*>(A.rc_text + (size_t)r * A.text_stride)[w] = make_uint4(word[0], word[1], word[2], word[3]);
-  if (w == 0) {
-    // guide part of the forward core: right' = right XOR strand (search_guides.py:538)
-    const bool rp = (A.K.right != 0) != (s == 1);
-    const int g0 = HAWK_GUIDESEQPAD + (rp ? A.K.P : 0);
-    int num = 0, den = 0;
-    for (int i = 0; i < A.K.G; ++i) {
-      const uint8_t u = to_upper(src[g0 + i]);
-      const int gc = (u == 'G') | (u == 'C') | (u == 'S');
-      num += gc;
-      den += gc | (u == 'A') | (u == 'T') | (u == 'W');
-    }
-    A.gc_num[r] = num;
-    A.gc_den[r] = den;
-  }
+  if (w == 0) annot_gc_counts(A.K, s, src, &A.gc_num[r], &A.gc_den[r]);
 }
 
 int launch_annot_variants(cudaStream_t st, const BatchView& B, const ScanConst& K, const VariantView& V,

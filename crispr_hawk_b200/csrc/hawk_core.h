@@ -648,6 +648,143 @@ HAWK_HD int64_t find_ref_partner(const BatchView& B, const ScanConst& K, const u
   return lo;  // caller checks lo < end and start equality
 }
 
+// ---- N2: post-search pure functions on one guide row (annotation.py:27-51, 197-281, 513-541) ----
+// Variant table of a batch: haplotype h carries variants [var_off[h], var_off[h+1]), sorted by
+// position, in the reference's normalised form (variant.py:456-486): var_pos + pos_base = genomic
+// coordinate of the anchor, REF / ALT allele lengths, ALT text = alt_pool[var_altoff .. + altlen).
+struct VariantView {
+  const int64_t* var_off;
+  const int32_t* var_pos;
+  const int32_t* var_reflen;
+  const int32_t* var_altlen;
+  const int64_t* var_altoff;
+  const uint8_t* alt_pool;
+  int32_t pos_base;
+};
+
+HAWK_HD bool ascii_is_upper(uint8_t c) { return c >= 'A' && c <= 'Z'; }
+HAWK_HD uint8_t ascii_to_upper(uint8_t c) { return (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
+
+// complement of one IUPAC letter, case kept (utils.py:46-79); other bytes unchanged
+HAWK_HD uint8_t rc_char(uint8_t c) {
+  const uint8_t u = ascii_to_upper(c);
+  uint8_t o;
+  switch (u) {
+    case 'A': o = 'T'; break;
+    case 'C': o = 'G'; break;
+    case 'G': o = 'C'; break;
+    case 'T': o = 'A'; break;
+    case 'U': o = 'A'; break;
+    case 'R': o = 'Y'; break;
+    case 'Y': o = 'R'; break;
+    case 'M': o = 'K'; break;
+    case 'K': o = 'M'; break;
+    case 'H': o = 'D'; break;
+    case 'D': o = 'H'; break;
+    case 'B': o = 'V'; break;
+    case 'V': o = 'B'; break;
+    default: o = u; break;  // N, S, W
+  }
+  return (uint8_t)(o | (c & 0x20));
+}
+
+// byte i of the text reverse_guides leaves in a guide of strand s (window of W characters)
+HAWK_HD uint8_t annot_text_byte(const uint8_t* src, int W, int s, int i) {
+  if (i >= W) return 0;
+  return s ? rc_char(src[W - 1 - i]) : src[i];
+}
+
+// gc_content: G+C+S and A+C+G+T+S+W counts of the guide without its PAM (forward text; the
+// counts are invariant under reverse complement)
+HAWK_HD void annot_gc_counts(const ScanConst& K, int s, const uint8_t* src, int32_t* num_out, int32_t* den_out) {
+  const bool rp = (K.right != 0) != (s == 1);  // right' = right XOR strand (search_guides.py:538)
+  const int g0 = HAWK_GUIDESEQPAD + (rp ? K.P : 0);
+  int num = 0, den = 0;
+  for (int i = 0; i < K.G; ++i) {
+    const uint8_t u = ascii_to_upper(src[g0 + i]);
+    const int gc = (u == 'G') | (u == 'C') | (u == 'S');
+    num += gc;
+    den += gc | (u == 'A') | (u == 'T') | (u == 'W');
+  }
+  *num_out = num;
+  *den_out = den;
+}
+
+// polish_guide_variants (annotation.py:246-281) for one row: walks the core's G + P bases,
+// genomic coordinate through the run-length posmap (segment pointer advanced incrementally),
+// variant at that coordinate by a monotone walk of the haplotype's sorted table, then
+// _check_insertion / _check_snv (:197-243) on the window text. emit(j) receives the
+// haplotype-local index of every variant kept (a set: once each); returns their number.
+// *would_assert is set when the reference's _find_insertion_stop assert would fire.
+template <class Emit>
+HAWK_HD uint32_t annot_row_variants(const BatchView& B, const ScanConst& K, const VariantView& V, int32_t h, int s,
+                                    int32_t pos, int32_t stop, const uint8_t* core, Emit&& emit, bool* would_assert) {
+  const int32_t pivot = pos + K.geom[s].c0;
+  const int C = K.C;
+  const int64_t v0 = V.var_off[h], v1 = V.var_off[h + 1];
+  uint32_t found = 0;
+  if (v1 <= v0) return 0;
+  // segment holding the core's first base
+  const int64_t s0 = B.seg_off[h], s1 = B.seg_off[h + 1];
+  int64_t k = s0, hi = s1;
+  while (hi - k > 1) {
+    const int64_t mid = (k + hi) >> 1;
+    if (B.seg_rel[mid] <= pivot) k = mid; else hi = mid;
+  }
+  int32_t p = B.seg_gen[k] + (B.seg_step[k] ? (pivot - B.seg_rel[k]) : 0);
+  // first variant at or after the core's first coordinate
+  int64_t j = v0, jh = v1;
+  while (j < jh) {
+    const int64_t mid = (j + jh) >> 1;
+    if (V.var_pos[mid] + V.pos_base < p) j = mid + 1; else jh = mid;
+  }
+  int64_t last = -1;
+  for (int i = 0; i < C && j < v1; ++i) {
+    const int32_t idx = pivot + i;
+    while (k + 1 < s1 && B.seg_rel[k + 1] <= idx) ++k;
+    p = B.seg_gen[k] + (B.seg_step[k] ? (idx - B.seg_rel[k]) : 0);
+    while (j < v1 && V.var_pos[j] + V.pos_base < p) ++j;
+    int offset = 0;  // annotation.py:264: reset per base, carried over the variants of one base
+    for (int64_t jj = j; jj < v1 && V.var_pos[jj] + V.pos_base == p; ++jj) {
+      const int32_t rl = V.var_reflen[jj], al = V.var_altlen[jj];
+      const uint8_t* alt = V.alt_pool + V.var_altoff[jj];
+      const bool is_snv = rl == al;
+      if (!is_snv) offset = rl < al ? al - rl : 0;
+      const int seglen = (i + offset + 1 <= C ? offset + 1 : C - i);
+      const uint8_t* seg = core + i;
+      bool ok = false;
+      if (!is_snv) {  // _check_insertion (:197-226)
+        if (i == 0) {
+          int up = -1;  // _find_insertion_stop: first upper-case character, 0 when none
+          for (int t = 0; t < seglen; ++t)
+            if (ascii_is_upper(seg[t])) { up = t; break; }
+          if (up == 0) *would_assert = true;  // the reference asserts here
+          const int kk = up < 0 ? 0 : up;
+          bool e = kk <= al;
+          for (int t = 0; e && t < kk; ++t) e = alt[al - kk + t] == ascii_to_upper(seg[t]);
+          ok = e;
+        }
+        if (!ok && p == stop) {
+          bool e = seglen <= al;
+          for (int t = 0; e && t < seglen; ++t) e = alt[t] == ascii_to_upper(seg[t]);
+          ok = e;
+        }
+      }
+      if (!ok) {  // _check_snv (:229-243): all lower-case and equal to the ALT allele
+        bool e = seglen == al;
+        for (int t = 0; e && t < seglen; ++t) e = !ascii_is_upper(seg[t]) && alt[t] == ascii_to_upper(seg[t]);
+        ok = e;
+      }
+      if (ok && jj != last) {  // a set: the bases of one insertion share the anchor's coordinate
+        last = jj;
+        emit((int32_t)(jj - v0));
+        ++found;
+      }
+    }
+  }
+  return found;
+}
+
 // ---- unphased resolution (search_guides.py:175-257) -------------------------------
 // Column descriptor of one window position.
 struct Column {

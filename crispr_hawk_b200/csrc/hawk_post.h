@@ -48,19 +48,6 @@ struct RowMap {
   int32_t hap_add;     // other haplotypes: index + hap_add
 };
 
-// Variant table of a batch (N2): haplotype h carries variants [var_off[h], var_off[h+1]), sorted by
-// position, in the reference's normalised form (variant.py:456-486): var_pos + pos_base = genomic
-// coordinate of the anchor, REF / ALT allele lengths, ALT text = alt_pool[var_altoff .. + altlen).
-struct VariantView {
-  const int64_t* var_off;
-  const int32_t* var_pos;
-  const int32_t* var_reflen;
-  const int32_t* var_altlen;
-  const int64_t* var_altoff;
-  const uint8_t* alt_pool;
-  int32_t pos_base;
-};
-
 // annot_kernels.cu (N2: post-search pure functions on the guide table)
 int launch_annot_variants(cudaStream_t st, const BatchView& B, const ScanConst& K, const VariantView& V,
                           const int32_t* hap, const uint8_t* strand, const int32_t* pos, const int32_t* stop,

@@ -226,4 +226,38 @@ void hawkcheck_fetch_hits(void* tp, int s, uint64_t* out) {
 }
 void hawkcheck_free(void* t) { delete (CheckTable*)t; }
 
+
+// N2 on the CPU: the kernels' own per-row logic (annot_row_variants, annot_text_byte,
+// annot_gc_counts of hawk_core.h) over a guide table, serially. gv_off has n + 1 entries, gv_idx
+// room for n * (G + P) indices; returns the number of variant references or -1 when the
+// reference's assert would fire.
+int64_t hawkcheck_annotate(const int64_t* seg_off, const int32_t* seg_rel, const int32_t* seg_gen,
+                           const uint8_t* seg_step, const int64_t* var_off, const int32_t* var_pos,
+                           const int32_t* var_reflen, const int32_t* var_altlen, const int64_t* var_altoff,
+                           const uint8_t* alt_pool, const hawk_params* params, int64_t n, const int32_t* hap,
+                           const uint8_t* strand, const int32_t* pos, const int32_t* stop, const uint8_t* text,
+                           int32_t text_stride, uint8_t* rc_text, int32_t* gc_num, int32_t* gc_den, int64_t* gv_off,
+                           int32_t* gv_idx) {
+  BatchView B{};
+  B.seg_off = seg_off;
+  B.seg_rel = seg_rel;
+  B.seg_gen = seg_gen;
+  B.seg_step = seg_step;
+  const ScanConst K = make_scan_const(*params, 0);
+  const VariantView V{var_off, var_pos, var_reflen, var_altlen, var_altoff, alt_pool, 0};
+  const int W = K.C + 2 * HAWK_GUIDESEQPAD;
+  int64_t out = 0;
+  bool would_assert = false;
+  gv_off[0] = 0;
+  for (int64_t r = 0; r < n; ++r) {
+    const uint8_t* src = text + (size_t)r * text_stride;
+    annot_row_variants(B, K, V, hap[r], strand[r], pos[r], stop[r], src + HAWK_GUIDESEQPAD,
+                       [&](int32_t j) { gv_idx[out++] = j; }, &would_assert);
+    gv_off[r + 1] = out;
+    for (int i = 0; i < text_stride; ++i) rc_text[(size_t)r * text_stride + i] = annot_text_byte(src, W, strand[r], i);
+    annot_gc_counts(K, strand[r], src, &gc_num[r], &gc_den[r]);
+  }
+  return would_assert ? -1 : out;
+}
+
 }  // extern "C"

@@ -97,3 +97,36 @@ def search(pam, region, haps, guidelen, right, variants_present, phased, raw=Fal
         return tab
     finally:
         L.hawkcheck_free(t)
+
+
+def annotate(table, haps, pam, guidelen, right):
+    """N2 through the kernels' own per-row logic compiled for the CPU (hawkcheck_annotate):
+    same columns as _cabi.Result.annotate, for a table in emission order."""
+    L = lib()
+    L.hawkcheck_annotate.restype = C.c_int64
+    fwd, rc = pam_patterns(pam)
+    params = _cabi.make_params(fwd, rc, guidelen, right, False)
+    seg = marshal.segment_table(haps)
+    vt = marshal.variant_table(haps)
+    n, w = len(table["hap"]), table["text"].shape[1] if len(table["hap"]) else guidelen + len(fwd) + 20
+    stride = (w + 15) // 16 * 16
+    text = np.zeros((n, stride), np.uint8)
+    text[:, :w] = table["text"]
+    rc_text = np.zeros((n, stride), np.uint8)
+    num, den = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    off = np.zeros(n + 1, np.int64)
+    idx = np.zeros(max(1, n * (guidelen + len(fwd))), np.int32)
+    pool = vt.alt_pool if len(vt.alt_pool) else np.zeros(1, np.uint8)
+    total = L.hawkcheck_annotate(
+        _p(seg.seg_off), _p(seg.seg_rel), _p(seg.seg_gen), _p(seg.seg_step), _p(vt.var_off),
+        _p(vt.var_pos if len(vt.var_pos) else np.zeros(1, np.int32)),
+        _p(vt.var_reflen if len(vt.var_reflen) else np.zeros(1, np.int32)),
+        _p(vt.var_altlen if len(vt.var_altlen) else np.zeros(1, np.int32)),
+        _p(vt.var_altoff if len(vt.var_altoff) else np.zeros(1, np.int64)), _p(pool), C.byref(params), C.c_int64(n),
+        _p(np.ascontiguousarray(table["hap"], np.int32)), _p(np.ascontiguousarray(table["strand"], np.uint8)),
+        _p(np.ascontiguousarray(table["pos"], np.int32)), _p(np.ascontiguousarray(table["stop"], np.int32)), _p(text),
+        C.c_int32(stride), _p(rc_text), _p(num), _p(den), _p(off), _p(idx),
+    )  # fmt: skip
+    if total < 0:
+        raise AssertionError("the reference's _find_insertion_stop assert would fire")
+    return {"rc_text": rc_text[:, :w], "gc_num": num, "gc_den": den, "gv_off": off, "gv_idx": idx[:total], "vt": vt}

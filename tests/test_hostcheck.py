@@ -90,3 +90,46 @@ def test_pack_every_byte_value():
             assert nib == O.IUPAC_BITS[ch.upper()] and low == int(ch.islower()), b
         else:
             assert nib == 0 and low == 0, b
+
+
+def _annot_cases():
+    import gzip
+    import json
+    import os
+
+    from tests.helpers import GOLDEN_DIR
+
+    with gzip.open(os.path.join(GOLDEN_DIR, "annot.json.gz"), "rb") as fh:
+        annot = json.loads(fh.read().decode())
+    return [(c, annot[c["name"]]) for c in all_golden_cases() if c["name"] in annot]
+
+
+@pytest.mark.parametrize("case,want", _annot_cases(), ids=[c["name"] for c, _ in _annot_cases()])
+def test_n2_row_logic_on_cpu_matches_reference_annotation(case, want):
+    """The per-row code the N2 kernels execute (annot_row_variants / annot_text_byte /
+    annot_gc_counts in hawk_core.h), compiled for the CPU, against the reference's own
+    annotation outputs."""
+    from crispr_hawk_b200.annotation import format_af
+
+    region, haps = fixture_objects(case)
+    if not haps:
+        pytest.skip("no haplotypes")
+    tab = hostcheck.search(case["pam"], region, haps, case["guidelen"], case["right"], case["variants_present"],
+                           case["phased"])  # fmt: skip
+    ann = hostcheck.annotate(tab, haps, case["pam"], case["guidelen"], case["right"])
+    order = np.argsort(tab["bucket"], kind="stable").tolist()
+    assert len(order) == len(want)
+    right = case["right"]
+    for k, i in enumerate(order):
+        h = haps[int(tab["hap"][i])]
+        s = int(tab["strand"][i])
+        if h.variants == "NA":
+            v, afs = "NA", "NA"
+        else:
+            ids = sorted(ann["vt"].ids[int(tab["hap"][i])][j] for j in ann["gv_idx"][ann["gv_off"][i] : ann["gv_off"][i + 1]])
+            v = ",".join(ids)
+            vals = [format_af(h.afs[x]) if str(h.afs[x]) != "nan" else "NA" for x in v.split(",")]
+            afs = "NA" if not vals or (len(set(vals)) == 1 and vals[0] == "NA") else ",".join(vals)
+        rp = ((not right) if s == 1 else bool(right)) != (s == 1)
+        got = [v, afs, ann["rc_text"][i].tobytes().decode("ascii"), rp, str(int(ann["gc_num"][i]) / int(ann["gc_den"][i]))]
+        assert got == want[k], f"guide {k}"
