@@ -171,11 +171,14 @@ class Workload:
         ann = res.annotate(batch, buffers=bufs)
         out = {"rows": int(n), "variant_refs": int(len(ann["gv_idx"]))}
         for key, kw in (("variants_ms", dict(want_text=False)), ("text_gc_ms", dict(want_variants=False))):
-            torch.cuda.synchronize(self.device)
-            t0 = time.perf_counter()
-            for _ in range(reps):
+            best = None
+            for _ in range(max(1, reps)):
+                torch.cuda.synchronize(self.device)
+                t0 = time.perf_counter()
                 res.annotate(batch, buffers=bufs, **kw)
-            out[key] = 1e3 * (time.perf_counter() - t0) / reps
+                dt = 1e3 * (time.perf_counter() - t0)
+                best = dt if best is None else min(best, dt)
+            out[key] = best  # best of `reps` calls: the 0.8 GB going down is sensitive to the host's state
         if oracle is not None and n:
             if getattr(self, "_edits_out2", None) is None or len(self._edits_out2["hap"]) < n:
                 self._edits_out2 = _cabi.alloc_table(int(n * 1.05) + 1024, ts, pinned=True)
