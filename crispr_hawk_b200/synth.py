@@ -323,6 +323,9 @@ CONFIGS = {
                ins=0.05, max_indel=10, pam="NGG", guidelen=20, right=False),
     "c3": dict(bed_len=1_000_000, n_alt_hap=5008, n_sites=10_000, mean_alts=1000, seed=2, snv=0.90,
                ins=0.05, max_indel=10, pam="TTTV", guidelen=23, right=True),
+    # unphased (gnomAD-style pseudo-samples): generated by synth_unphased.make_unphased_cohort
+    "c4": dict(bed_len=10_000_000, unphased=True, pitch=8, seed=4, snv=0.88, multi=0.05, max_indel=5, n_samples=10,
+               pam="NNGRRT", guidelen=21, right=False),
     "c5shard": dict(bed_len=50_000_000, n_alt_hap=625, n_sites=500_000, mean_alts=50_000, seed=5,
                     snv=0.90, ins=0.05, max_indel=10, pam="NGG", guidelen=20, right=False),
 }  # fmt: skip
@@ -331,6 +334,11 @@ CONFIGS = {
 def config_cohort(name: str, scale: float = 1.0, seed_offset: int = 0, n_alt_hap: Optional[int] = None,
                   hap_block: int = 0) -> Cohort:
     k = CONFIGS[name]
+    if k.get("unphased"):
+        from . import synth_unphased
+
+        return synth_unphased.make_unphased_cohort(max(200, int(k["bed_len"] * scale)), k["seed"] + seed_offset, k["pitch"],
+                                                   k["snv"], k["multi"], k["max_indel"], k["n_samples"])  # fmt: skip
     bed_len = max(200, int(k["bed_len"] * scale))
     n_sites = max(1, int(k["n_sites"] * scale))
     mean = k["mean_alts"] * scale

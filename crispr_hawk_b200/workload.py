@@ -11,7 +11,7 @@ from typing import Optional
 
 import numpy as np
 
-from . import _cabi, marshal, synth
+from . import _cabi, marshal, synth, synth_unphased
 from .pam import pam_patterns
 
 
@@ -240,3 +240,81 @@ class Workload:
         seg = marshal.SegmentTable(seg_off.astype(np.int64), self.d.seg.seg_rel[take], self.d.seg.seg_gen[take],
                                    self.d.seg.seg_step[take])  # fmt: skip
         return buf, off, lens, self.a[idx], self.b[idx], self.d.is_ref[idx], seg
+
+
+class UnphasedWorkload:
+    """BASELINE config 4: an unphased cohort (synth_unphased) -- REF, the per-sample IUPAC SNV
+    haplotypes and the per-indel window haplotypes -- searched with `variants_present and not
+    phased` semantics (is_pamhit_valid + resolve_guide, search_guides.py:473-479). Same two ways
+    of running the path as `Workload`; the texts (a few hundred MB) are built on the host by the
+    generator and uploaded once."""
+
+    def __init__(self, cohort: synth_unphased.UnphasedCohort, pam: str, guidelen: int, right: bool,
+                 ctx: Optional[_cabi.Context] = None, device: Optional[int] = None,
+                 uset: Optional[synth_unphased.UnphasedSet] = None):  # fmt: skip
+        """`uset`: search these haplotypes (a subset / reordering of the cohort's) instead of all."""
+        import torch
+
+        self.torch = torch
+        self.cohort = cohort
+        self.pam, self.guidelen, self.right = pam, guidelen, right
+        self.device = torch.cuda.current_device() if device is None else device
+        self.ctx = ctx or _cabi.Context.default(self.device)
+        self.d = uset if uset is not None else synth_unphased.derive_unphased(cohort)
+        self.fwd, self.rc = pam_patterns(pam)
+        self.params = _cabi.make_params(self.fwd, self.rc, guidelen, right, True)
+        self.a, self.b = self.d.scan_bounds(cohort, len(self.fwd))
+        self.scanned_bp = int((self.b.astype(np.int64) - self.a).clip(min=0).sum())
+        self.ascii_dev = torch.from_numpy(self.d.ascii).to(torch.device("cuda", self.device))
+        self.batch = None
+
+    def prepare_resident(self) -> None:
+        self.batch = _cabi.Batch(self.ctx, None, self.d.slot_off, self.d.lens, device_ptr=self.ascii_dev.data_ptr())
+        self.batch.set_posmap(self.d.seg)
+        self.batch.set_alleles(self.d.alleles)
+
+    def step_resident(self) -> _cabi.Result:
+        """encode (K1) + unphased search; texts resident in HBM, table stays on the device."""
+        if self.batch is None:
+            self.prepare_resident()
+        self.batch.repack(self.ascii_dev.data_ptr())
+        return _cabi.search(self.ctx, self.batch, self.params, self.a, self.b, self.d.is_ref)
+
+    def host_buffers(self):
+        torch = self.torch
+        if not hasattr(self, "_host"):
+            pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+            A, S = self.d.alleles, self.d.seg
+            self._host = {
+                "ascii": pin(self.d.ascii), "out": None,
+                "seg": marshal.SegmentTable(pin(S.seg_off), pin(S.seg_rel), pin(S.seg_gen), pin(S.seg_step)),
+                "alleles": marshal.AlleleTable(pin(A.va_off), pin(A.va_idx), pin(A.va_ent_off), pin(A.va_ref)),
+            }  # fmt: skip
+        return self._host
+
+    def step_host(self, n_groups: int = 0):
+        """Everything starts and ends in host memory: texts, position maps and variant_alleles
+        tables go up, the batch is packed and searched, the guide table comes down (the calls
+        `encode_haplotypes` + `search` make through the C-ABI). Returns (table, h2d, d2h bytes)."""
+        hb = self.host_buffers()
+        t0 = self.ctx.traffic()
+        batch = _cabi.Batch(self.ctx, hb["ascii"], self.d.slot_off, self.d.lens)
+        batch.set_posmap(hb["seg"])
+        batch.set_alleles(hb["alleles"])
+        res = _cabi.search(self.ctx, batch, self.params, self.a, self.b, self.d.is_ref)
+        n, w = res.n_guides, res.text_stride
+        if hb["out"] is None or len(hb["out"]["hap"]) < n:
+            hb["out"] = _cabi.alloc_table(int(n * 1.05) + 1024, w, pinned=True)
+        table = res.table(hb["out"])
+        res.close()
+        batch.close()
+        t1 = self.ctx.traffic()
+        return table, t1[0] - t0[0], t1[1] - t0[1]
+
+    step_host_twocall = step_host
+
+    def oracle_subset(self, hap_indices):
+        """The flat arrays of a subset of haplotypes (oracle/c_oracle.search's inputs)."""
+        u = self.d.take(hap_indices)
+        a, b = u.scan_bounds(self.cohort, len(self.fwd))
+        return u, a, b

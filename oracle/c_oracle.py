@@ -22,7 +22,7 @@ class _Table(C.Structure):
         ("strand", C.POINTER(C.c_uint8)), ("text", C.POINTER(C.c_uint8)),
         ("window", C.c_int),
         ("n_hits", C.c_int64 * 2), ("hits", C.POINTER(C.c_uint64) * 2),
-        ("scanned_bp", C.c_int64),
+        ("scanned_bp", C.c_int64), ("status", C.c_int),
     ]  # fmt: skip
 
 
@@ -37,6 +37,7 @@ def lib():
             subprocess.run(["make", "-s", "-C", HERE], check=True)
         _lib = C.CDLL(LIB)
         _lib.oracle_search.restype = C.POINTER(_Table)
+        _lib.oracle_search2.restype = C.POINTER(_Table)
         _lib.oracle_table_free.argtypes = [C.POINTER(_Table)]
         _lib.oracle_encode.restype = C.c_int64
         _lib.oracle_max_threads.restype = C.c_int
@@ -80,9 +81,15 @@ def encode_into(buf: np.ndarray) -> None:
         raise ValueError(f"non-IUPAC character at {bad}")
 
 
+class OracleKeyError(KeyError):
+    """The reference's bare KeyError: ambiguity code without variant_alleles entry (:207-213)."""
+
+
 def search(ascii_slots, slot_off, lens, scan_start, scan_stop, is_ref, seg, pam_fwd, pam_rc, G, right,
-           threads=1, raw_only=False):  # fmt: skip
-    """Returns dict(hap,strand,pos,start,stop,text) in FINAL order + raw hit lists."""
+           threads=1, raw_only=False, unphased=False, alleles=None):  # fmt: skip
+    """Returns dict(hap,strand,pos,start,stop,text) in FINAL order + raw hit lists.
+    `unphased` (variants_present and not phased, search_guides.py:473-479) needs `alleles`, the
+    flattened variant_alleles tables (crispr_hawk_b200.marshal.AlleleTable)."""
     f = np.asarray(pam_fwd, np.uint8)
     r = np.asarray(pam_rc, np.uint8)
     a = np.ascontiguousarray(scan_start, np.int32)
@@ -90,13 +97,27 @@ def search(ascii_slots, slot_off, lens, scan_start, scan_stop, is_ref, seg, pam_
     ir = np.ascontiguousarray(is_ref, np.uint8)
     lens = np.ascontiguousarray(lens, np.int32)
     slot_off = np.ascontiguousarray(slot_off, np.int64)
-    tp = lib().oracle_search(
+    if unphased:
+        va = [np.ascontiguousarray(x, dt) for x, dt in ((alleles.va_off, np.int64), (alleles.va_idx, np.int32),
+                                                        (alleles.va_ent_off, np.int64), (alleles.va_ref, np.uint8))]  # fmt: skip
+        vap = [_p(x) for x in va]
+    else:
+        vap = [None] * 4
+    tp = lib().oracle_search2(
         _p(ascii_slots), _p(slot_off), _p(lens), _p(a), _p(b), _p(ir), C.c_int32(len(lens)),
         _p(seg.seg_off), _p(seg.seg_rel), _p(seg.seg_gen), _p(seg.seg_step), _p(f), _p(r),
         C.c_int(len(f)), C.c_int(G), C.c_int(1 if right else 0), C.c_int(threads),
-        C.c_int(1 if raw_only else 0),
+        C.c_int(1 if raw_only else 0), C.c_int(1 if unphased else 0), *vap,
     )  # fmt: skip
+    if not tp:
+        raise ValueError("oracle_search2: window too long")
     t = tp.contents
+    if t.status:
+        status = int(t.status)
+        lib().oracle_table_free(tp)
+        if status == 1:
+            raise OracleKeyError("ambiguity code without variant_alleles entry")
+        raise ValueError({2: "duplicate REF guide", 3: "expansion above 2^24 strings"}.get(status, f"status {status}"))
     n, w = t.n_rows, t.window
 
     def arr(ptr, count, dtype):

@@ -1,5 +1,5 @@
 """Pin the C restatement (oracle/scan_oracle.c) against the reference-generated golden
-vectors (phased and variant-free cases; the unphased branch lives in the Python oracle)."""
+vectors: phased, variant-free and unphased (resolve_guide) cases."""
 
 import numpy as np
 import pytest
@@ -9,7 +9,7 @@ from crispr_hawk_b200.pam import pam_patterns
 from oracle import c_oracle
 from tests.helpers import all_golden_cases, fixture_objects, golden_guides, split_hits
 
-CASES = [c for c in all_golden_cases() if c["phased"] or not c["variants_present"]]
+CASES = all_golden_cases()
 
 
 def run_c_oracle(case, threads=2):
@@ -20,8 +20,10 @@ def run_c_oracle(case, threads=2):
     bounds = [marshal.scan_bounds(h, region.start, region.stop, len(fwd)) for h in haps]
     is_ref = [h.samples == "REF" for h in haps]
     seg = marshal.segment_table(haps)
+    unphased = bool(case["variants_present"] and not case["phased"])
     return haps, c_oracle.search(buf, off, lens, [b[0] for b in bounds], [b[1] for b in bounds], is_ref,
-                                 seg, fwd, rc, case["guidelen"], case["right"], threads=threads)  # fmt: skip
+                                 seg, fwd, rc, case["guidelen"], case["right"], threads=threads,
+                                 unphased=unphased, alleles=marshal.allele_table(haps) if unphased else None)  # fmt: skip
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
