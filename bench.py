@@ -144,6 +144,8 @@ def cpu_sample(workload: str, n_alt: int, scale: float):
     from crispr_hawk_b200 import marshal, synth
 
     k = synth.CONFIGS[workload]
+    if k.get("unphased"):
+        return cpu_sample_unphased(workload, scale)
     c = synth.config_cohort(workload, scale, n_alt_hap=n_alt)
     d = synth.derive(c)
     texts = synth.materialize_host(c)
@@ -157,9 +159,35 @@ def cpu_sample(workload: str, n_alt: int, scale: float):
                 G=k["guidelen"], right=k["right"], pam=k["pam"])  # fmt: skip
 
 
+def cpu_sample_unphased(workload: str, scale: float):
+    """Config 4's CPU sample: the same generator on a region `CPU_C4_FRACTION` of the size (all
+    of its haplotypes: REF, the IUPAC SNV haplotypes, every indel-window haplotype)."""
+    from crispr_hawk_b200 import synth, synth_unphased
+    from crispr_hawk_b200.pam import pam_patterns
+
+    k = synth.CONFIGS[workload]
+    c = synth.config_cohort(workload, scale * CPU_C4_FRACTION)
+    u = synth_unphased.derive_unphased(c)
+    fwd, rc = pam_patterns(k["pam"])
+    a, b = u.scan_bounds(c, len(fwd))
+    bp = int((b.astype(np.int64) - a).clip(min=0).sum())
+    return dict(cohort=c, u=u, buf=u.ascii, off=u.slot_off, lens=u.lens, fwd=fwd, rc=rc, a=a, b=b, bp=bp,
+                G=k["guidelen"], right=k["right"], pam=k["pam"], unphased=True, n_hap=u.n_hap)  # fmt: skip
+
+
+CPU_C4_FRACTION = 0.1
+
+
 def cpu_step(s, threads):
     from oracle import c_oracle
 
+    if s.get("unphased"):
+        # encode happens inside the search (per haplotype, in the OpenMP loop)
+        t0 = time.perf_counter()
+        u = s["u"]
+        out = c_oracle.search(s["buf"], s["off"], s["lens"], s["a"], s["b"], u.is_ref, u.seg, s["fwd"], s["rc"], s["G"],
+                              s["right"], threads=threads, unphased=True, alleles=u.alleles)  # fmt: skip
+        return time.perf_counter() - t0, len(out["hap"]), 0
     t0 = time.perf_counter()
     enc_bad = 0
     # encoder.encode over every haplotype (scalar table lookup), then search
@@ -179,13 +207,20 @@ def python_port_rate(workload: str, scale: float, budget_s: float = 6.0):
     from oracle import hawk_oracle as O
 
     k = synth.CONFIGS[workload]
-    c = synth.make_cohort(20_000, 3, 200, 20, seed=77, snv_frac=k["snv"], ins_frac=k["ins"], max_indel=k["max_indel"])
-    haps = synth.synth_haplotypes(c)
-    a, b = synth.scan_bounds(c, len(k["pam"]))
+    if k.get("unphased"):
+        from crispr_hawk_b200 import synth_unphased as SU
+
+        c = SU.make_unphased_cohort(3000, 77, k["pitch"], k["snv"], k["multi"], k["max_indel"], k["n_samples"])
+        haps = SU.unphased_haplotypes(c)
+        a, b = SU.derive_unphased(c).scan_bounds(c, len(k["pam"]))
+    else:
+        c = synth.make_cohort(20_000, 3, 200, 20, seed=77, snv_frac=k["snv"], ins_frac=k["ins"], max_indel=k["max_indel"])
+        haps = synth.synth_haplotypes(c)
+        a, b = synth.scan_bounds(c, len(k["pam"]))
     bp = int((b.astype(np.int64) - a).sum())
     t0 = time.perf_counter()
     ohaps = [O.OracleHap.from_object(h) for h in haps]
-    n = len(O.search(k["pam"], c.region_start, c.region_stop, ohaps, k["guidelen"], k["right"], True, True))
+    n = len(O.search(k["pam"], c.region_start, c.region_stop, ohaps, k["guidelen"], k["right"], True, not k.get("unphased")))
     dt = time.perf_counter() - t0
     return bp / dt, bp, n
 
@@ -199,6 +234,8 @@ def run_reference_arm(args, rank, world):
     # size the sample so one step is a few seconds of CPU work on all threads
     n_alt = max(threads * 2, 16) - 1  # REF + n_alt = a multiple of the thread count: no idle tail in the OpenMP loop
     s = cpu_sample(args.workload, n_alt, args.scale)
+    if s.get("unphased"):
+        n_alt = s["n_hap"] - 1
     times = []
     for i in range(args.warmup + args.steps):
         dt, n, _ = cpu_step(s, threads)
@@ -207,6 +244,9 @@ def run_reference_arm(args, rank, world):
     ms = 1e3 * sum(times) / len(times)
     value = s["bp"] / (ms / 1e3)
     sample = f"{n_alt + 1} haplotypes (REF + first {n_alt}) of workload {args.workload} x {s['bp'] // (n_alt + 1)} bp, encode + search, per step"
+    if s.get("unphased"):
+        sample = (f"workload {args.workload} on a region {CPU_C4_FRACTION:g} of the size: all {s['n_hap']} haplotypes, "
+                  f"{s['bp']:,} hap-bp, encode + unphased search, per step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -226,9 +266,12 @@ def workload_config(args, scanned_bp, n_hap, sample=False):
     from crispr_hawk_b200 import synth
 
     k = synth.CONFIGS[args.workload]
+    bed = int(k['bed_len'] * args.scale * (CPU_C4_FRACTION if sample and k.get("unphased") else 1.0))
+    kind = ("unphased (10 population pseudo-samples, 1 site / %d bp): REF + IUPAC SNV haplotypes + indel-window haplotypes,"
+            % k["pitch"]) if k.get("unphased") else "phased,"
     return {
         "workload": f"{args.workload}: {k['pam']} / {k['guidelen']} nt / {'right' if k['right'] else 'left'}, "
-                    f"{int(k['bed_len'] * args.scale):,} bp region, phased, {n_hap} haplotypes per rank"
+                    f"{bed:,} bp region, {kind} {n_hap} haplotypes per rank"
                     + (" (CPU sample)" if sample else ""),
         "haplotypes_per_rank": n_hap, "scanned_bp_per_rank_per_step": scanned_bp,
         "l2": "n/a (CPU arm)" if sample else ("inputs exceed L2 (no flush needed)" if scanned_bp > 400e6 else "L2 flushed between steps"),
@@ -257,14 +300,23 @@ def run_product_arm(args, rank, world, local_rank):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from crispr_hawk_b200 import _cabi, synth
-    from crispr_hawk_b200.workload import Workload
+    from crispr_hawk_b200.workload import UnphasedWorkload, Workload
 
     lib = _cabi.load_library()
     k = synth.CONFIGS[args.workload]
-    n_alt = args.haplotypes or k["n_alt_hap"]
-    cohort = synth.config_cohort(args.workload, args.scale, n_alt_hap=n_alt, hap_block=rank)
+    unphased = bool(k.get("unphased"))
     ctx = _cabi.Context.default(local_rank)
-    wl = Workload(cohort, k["pam"], k["guidelen"], k["right"], ctx, local_rank)
+    if unphased:
+        # every rank searches a region of its own (same shape, its own seed): regions are the
+        # reference's unit of work (crisprhawk.py:84-115 loops over them)
+        cohort = synth.config_cohort(args.workload, args.scale, seed_offset=1000 * rank)
+        wl = UnphasedWorkload(cohort, k["pam"], k["guidelen"], k["right"], ctx, local_rank)
+        n_hap_rank = wl.d.n_hap
+    else:
+        n_alt = args.haplotypes or k["n_alt_hap"]
+        cohort = synth.config_cohort(args.workload, args.scale, n_alt_hap=n_alt, hap_block=rank)
+        wl = Workload(cohort, k["pam"], k["guidelen"], k["right"], ctx, local_rank)
+        n_hap_rank = cohort.n_hap
     wl.prepare_resident()
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     flush = None
@@ -365,14 +417,21 @@ def run_product_arm(args, rank, world, local_rank):
                                "note": "the PAM match proper: sparse sector reads around variants, bound by DRAM traffic"}  # fmt: skip
     kernels["candidate_kernels"] = {"ms": cand_ms}
     kernels["expand_kernel"] = {"ms": expand_ms}
-    kernels["table_pipeline"] = {"ms": post_ms}
-    dom = "pack_kernel" if pack_ms >= scan_ms else "scan_k2_total"
+    table_bytes = wl.table_algorithmic_bytes(n_guides, hits_total)
+    kernels["table_pipeline"] = {
+        "ms": post_ms, "algorithmic_bytes": table_bytes, "gbs": gbs(table_bytes, post_ms),
+        "note": "everything downstream of the hit lists (coordinates, unphased resolution, redundancy filter, rows, "
+                "bucket ids); algorithmic bytes = guide rows written + hit records read + window planes read",
+    }  # fmt: skip
+    dom = max((("pack_kernel", pack_ms), ("scan_k2_total", scan_ms), ("table_pipeline", post_ms)), key=lambda t: t[1])[0]
     ach = kernels[dom]["gbs"] or 0.0
     roofline = {
         "kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": traffic(dom), "peak_source": peak_src,
+        "traffic": traffic(dom), "traffic_source": "profiles/traffic.json (ncu --set full capture of this workload)" if traffic(dom) else None,
+        "peak_source": peak_src,
         "scan_kernel_frac": (kernels["scan_k2_total"]["gbs"] or 0.0) / peak,
         "pack_kernel_frac": (kernels["pack_kernel"]["gbs"] or 0.0) / peak,
+        "table_pipeline_frac": (kernels["table_pipeline"]["gbs"] or 0.0) / peak,
         "match_kernel_dram_frac": (kernels["match_kernel"]["dram_gbs"] or 0.0) / peak if profiled else None,
     }  # fmt: skip
 
@@ -399,6 +458,9 @@ def run_product_arm(args, rank, world, local_rank):
                "ms_per_step": e_ms, "steps": e2e_steps, "rows_per_step": int(len(table["hap"])),
                "call": "hawk_search_stream: one C-ABI call, haplotype groups pipelined, H2D / compute / D2H overlapped",
                "input": "haplotype texts (pinned ASCII slot space), the reference's own input to this path"}  # fmt: skip
+        if unphased:
+            e2e["call"] = ("hawk_batch_create + hawk_batch_set_posmap + hawk_batch_set_alleles + hawk_search + "
+                           "hawk_result_fetch (the streamed call is phased / variant-free only)")
 
         def timed(fn, reps):
             fn()
@@ -413,6 +475,7 @@ def run_product_arm(args, rank, world, local_rank):
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             return float(tt.item()), out
 
+    if e2e is not None and not unphased:
         # the same as two calls with nothing overlapped (encode_haplotypes, then search + fetch)
         two_ms, (_, h2d_b, d2h_b) = timed(wl.step_host_twocall, max(1, e2e_steps - 1))
         e2e["two_calls_no_overlap"] = {"value": total_bp / (two_ms / 1e3), "unit": UNIT, "ms_per_step": two_ms,
@@ -428,7 +491,7 @@ def run_product_arm(args, rank, world, local_rank):
 
     # ---- final merge (N > 1): per-rank tables gathered to rank 0 over NCCL, rows resident in HBM ----
     final_merge = None
-    if world > 1 and not args.no_e2e:
+    if world > 1 and not args.no_e2e and not unphased:
         from crispr_hawk_b200 import shard
 
         wl.prepare_resident()
@@ -458,7 +521,7 @@ def run_product_arm(args, rank, world, local_rank):
 
     # ---- next rows of the scope table on the same workload (rank 0, N = 1 only) ----
     next_rows = None
-    if rank == 0 and world == 1 and not args.no_e2e:
+    if rank == 0 and world == 1 and not args.no_e2e and not unphased:
         from oracle import annot_oracle
 
         m = wl.annotate_measure(oracle=annot_oracle)
@@ -482,6 +545,8 @@ def run_product_arm(args, rank, world, local_rank):
         threads = c_oracle.max_threads()
         n_cpu = max(threads * 2, 16) - 1  # REF + n_cpu = a multiple of the thread count
         s = cpu_sample(args.workload, n_cpu, args.scale)
+        if s.get("unphased"):
+            n_cpu = s["n_hap"] - 1
         cpu_step(s, threads)
         reps, acc = 0, 0.0
         while acc < 8.0 and reps < 20:
@@ -492,8 +557,9 @@ def run_product_arm(args, rank, world, local_rank):
         py_rate, py_bp, _ = python_port_rate(args.workload, args.scale)
         cpu = {
             "value": s["bp"] * reps / acc, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n_cpu + 1} haplotypes (REF + first {n_cpu}) of the same workload, {s['bp']:,} hap-bp per pass, "
-                      f"{reps} passes, encode + search (oracle/scan_oracle.c, OpenMP)",
+            "sample": (f"the same workload on a region {CPU_C4_FRACTION:g} of the size, all {n_cpu + 1} haplotypes, " if unphased
+                       else f"{n_cpu + 1} haplotypes (REF + first {n_cpu}) of the same workload, ")
+                      + f"{s['bp']:,} hap-bp per pass, {reps} passes, encode + search (oracle/scan_oracle.c, OpenMP)",
             "single_thread_value": (s["bp"] / one_dt) if one_dt else None,
             "python_port_value": py_rate, "python_port_sample_bp": py_bp,
         }  # fmt: skip
@@ -503,7 +569,7 @@ def run_product_arm(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args, wl.scanned_bp, cohort.n_hap),
+            "config": workload_config(args, wl.scanned_bp, n_hap_rank),
             "guides_per_step": total_guides, "hits_per_step_rank0": hits_total,
             "job_guides_in_timed_region": int(job_counts[0].item()),
             "device_ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,

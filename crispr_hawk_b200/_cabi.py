@@ -13,7 +13,7 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HAWKSCAN_LIB", os.path.join(PKG_DIR, "libhawkscan.so"))
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 HAWK_MAX_PAM = 16
 HAWK_F_UNPHASED = 1
 
@@ -84,6 +84,9 @@ SIGNATURES = {
     "hawk_batch_create": (C.c_int, [_P, _U8P, _I64P, _I32P, C.c_int32, C.POINTER(_P), _I64P]),
     "hawk_batch_create_dev": (C.c_int, [_P, _P, _I64P, _I32P, C.c_int32, C.POINTER(_P), _I64P]),
     "hawk_batch_repack_dev": (C.c_int, [_P, _P, _I64P]),
+    "hawk_encode_search_dev": (
+        C.c_int, [_P, _P, _P, C.POINTER(HawkParams), _I32P, _I32P, _U8P, C.POINTER(_P), _I64P],
+    ),
     "hawk_batch_create_from_edits": (
         C.c_int,
         [_P, _U8P, C.c_int64, C.c_int32, C.c_int32, _I64P, _I32P, _I32P, _I32P, _I64P, _U8P, C.c_int64,
@@ -92,6 +95,7 @@ SIGNATURES = {
     "hawk_batch_layout": (C.c_int, [_P, _I64P, _I32P]),
     "hawk_ctx_stream": (C.c_void_p, [_P]),
     "hawk_ctx_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "hawk_ctx_set_fused": (C.c_int, [_P, C.c_int32]),
     "hawk_ctx_profile": (C.c_int, [_P, C.POINTER(C.c_double), _I64P]),
     "hawk_materialize_dev": (
         C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P],
@@ -236,6 +240,10 @@ class Context:
     def stream(self) -> int:
         """cudaStream_t of the context as an integer (for torch.cuda.ExternalStream)."""
         return int(self.lib.hawk_ctx_stream(self.handle) or 0)
+
+    def set_fused(self, mode: int) -> None:
+        """hawk_ctx_set_fused: 0 staged, 1 fused kernel, 2 by haplotype shape (default)."""
+        check(self.lib.hawk_ctx_set_fused(self.handle, int(mode)))
 
     def set_profiling(self, enabled: bool) -> None:
         check(self.lib.hawk_ctx_set_profiling(self.handle, 1 if enabled else 0))
@@ -478,6 +486,22 @@ def search(ctx: Context, batch: Batch, params: HawkParams, scan_start, scan_stop
                             ptr(b, C.c_int32), ptr(r, C.c_uint8), C.byref(h)),
         "hawk_search",
     )  # fmt: skip
+    return Result(ctx.lib, h)
+
+
+def encode_search(ctx: Context, batch: Batch, device_ptr: int, params: HawkParams, scan_start, scan_stop, is_ref) -> Result:
+    """hawk_encode_search_dev: re-encode `batch` from device-resident texts and search it in one
+    pass (K1 + K2 fused)."""
+    a = np.ascontiguousarray(scan_start, dtype=np.int32)
+    b = np.ascontiguousarray(scan_stop, dtype=np.int32)
+    r = np.ascontiguousarray(is_ref, dtype=np.uint8)
+    h, bad = _P(), C.c_int64(-1)
+    rc = ctx.lib.hawk_encode_search_dev(ctx.handle, batch.handle, C.c_void_p(device_ptr), C.byref(params),
+                                        ptr(a, C.c_int32), ptr(b, C.c_int32), ptr(r, C.c_uint8), C.byref(h), C.byref(bad))  # fmt: skip
+    if rc != HAWK_OK:
+        err = HawkLibraryError(ctx.lib.hawk_last_error().decode(), rc)
+        err.bad_slot = bad.value
+        raise err
     return Result(ctx.lib, h)
 
 

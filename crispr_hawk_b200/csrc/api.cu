@@ -443,10 +443,25 @@ extern "C" int hawk_batch_repack_dev(hawk_batch* b, const uint8_t* d_ascii, int6
     if (bad_slot) *bad_slot = bad;
     return hawk_fail(HAWK_EIUPAC, "non-IUPAC character at slot %lld", (long long)bad);
   }
+  b->sparse = false;
   return HAWK_OK;
 }
 
+extern "C" int hawk_encode_search_dev(hawk_ctx* c, hawk_batch* b, const uint8_t* d_ascii, const hawk_params* params,
+                                      const int32_t* scan_start, const int32_t* scan_stop, const uint8_t* is_ref,
+                                      hawk_result** out, int64_t* bad_slot) {
+  if (!b || !d_ascii || ((uintptr_t)d_ascii & 15))
+    return hawk_fail(HAWK_EINVAL, "hawk_encode_search_dev: bad arguments (texts must be 16-byte aligned device memory)");
+  return hawk_search_impl(c, b, params, scan_start, scan_stop, is_ref, nullptr, out, d_ascii, bad_slot);
+}
+
 extern "C" void* hawk_ctx_stream(hawk_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+extern "C" int hawk_ctx_set_fused(hawk_ctx* c, int32_t mode) {
+  if (!c || mode < 0 || mode > 2) return hawk_fail(HAWK_EINVAL, "hawk_ctx_set_fused: mode must be 0, 1 or 2");
+  c->fused_mode = mode;
+  return HAWK_OK;
+}
 
 extern "C" int hawk_ctx_set_profiling(hawk_ctx* c, int32_t enabled) {
   if (!c) return hawk_fail(HAWK_EINVAL, "hawk_ctx_set_profiling: null context");
@@ -482,6 +497,7 @@ extern "C" int hawk_batch_destroy(hawk_batch* b) {
 extern "C" int hawk_batch_export_nibbles(hawk_batch* b, int32_t hap, uint8_t* nibbles, uint8_t* lower) {
   if (!b || hap < 0 || hap >= b->n_hap || !nibbles)
     return hawk_fail(HAWK_EINVAL, "hawk_batch_export_nibbles: bad arguments");
+  if (b->sparse) return hawk_fail(HAWK_EINVAL, "hawk_batch_export_nibbles: the batch keeps planes only around variant bases");
   hawk_ctx* c = b->ctx;
   CKCUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
@@ -656,6 +672,140 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
   return HAWK_OK;
 }
 
+// chunks either side of a variant chunk whose planes the stages after the scan can read: a hit
+// needs a variant base inside its core, and its padded window reaches G + PAD before / C + PAD - 1
+// behind the PAM position, so no base further than G + C + PAD - 1 from a variant base is read
+static int fused_reach(const ScanConst& K) { return (31 + K.G + K.C + HAWK_GUIDESEQPAD - 1) >> 5; }
+
+// K1 + K2 fused (fused_kernels.cu): the texts are read once, planes are stored only where later
+// stages read them, hit entries come out per warp sub-range; one host round trip (hit totals,
+// the first non-IUPAC slot, the overflow flag), then the entries become the two record streams.
+static int run_scan_fused(hawk_ctx* c, hawk_batch* b, const uint8_t* d_ascii, const hawk_params* params,
+                          const int32_t* scan_start, const int32_t* scan_stop, const uint8_t* is_ref, ScanInputs& in,
+                          ScanOut& out, int64_t* bad_slot, bool* fell_back) {
+  cudaStream_t st = c->stream;
+  Trace tr;
+  const int32_t n_hap = b->n_hap;
+  const ScanConst K = make_scan_const(*params, 0);
+  const int64_t n_chunks = b->total_slots / HAWK_CHUNK;
+  *fell_back = false;
+  auto al8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
+  const size_t o_a = 0, o_b = o_a + al8((size_t)n_hap * 4), o_ref = o_b + al8((size_t)n_hap * 4),
+               o_tot = o_ref + al8((size_t)n_hap), total_bytes = o_tot + 64;
+  char* hp = (char*)c->pinned_get(total_bytes);
+  if (!hp) return hawk_fail(HAWK_ENOMEM, "pinned staging allocation failed");
+  out.scanned_bp = 0;
+  for (int32_t h = 0; h < n_hap; ++h) {
+    int64_t a = scan_start[h] < 0 ? 0 : scan_start[h], e = scan_stop[h];
+    if (e > a) out.scanned_bp += e - a;
+  }
+  memcpy(hp + o_a, scan_start, (size_t)n_hap * 4);
+  memcpy(hp + o_b, scan_stop, (size_t)n_hap * 4);
+  memcpy(hp + o_ref, is_ref, (size_t)n_hap);
+  uint64_t* tot0 = (uint64_t*)(hp + o_tot);  // [1..2] hit totals, [3] overflow flag, [4] first bad slot
+  memset(tot0, 0, 64);
+  tot0[4] = (uint64_t)INT64_MAX;
+  CK(in.buf.alloc(c, total_bytes));
+  CK(c->small_h2d(in.buf.p, hp, total_bytes));
+  char* dp = (char*)in.buf.p;
+  in.a = (int32_t*)(dp + o_a);
+  in.b = (int32_t*)(dp + o_b);
+  in.is_ref = (uint8_t*)(dp + o_ref);
+  uint64_t* d_tot = (uint64_t*)(dp + o_tot);
+  for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(c, 16));
+  // segment capacities: host total (allocation), device prefix (addresses)
+  const int64_t n_sub = fused_sub_ranges(n_chunks);
+  const int all_dense = K.unphased;
+  int64_t n_dense = all_dense ? n_sub : 0;
+  if (!all_dense) {
+    int64_t last = -1;
+    for (int32_t h = 0; h < n_hap; ++h) {
+      if (!is_ref[h]) continue;
+      const int64_t t0 = (b->slot_off[h] >> 5) - HAWK_SLOT_GAP / HAWK_CHUNK;
+      const int64_t t1 = h + 1 < n_hap ? (b->slot_off[h + 1] >> 5) - HAWK_SLOT_GAP / HAWK_CHUNK : n_chunks;
+      int64_t s0 = t0 / FUSED_SUB, s1 = (t1 - 1) / FUSED_SUB;
+      if (s0 <= last) s0 = last + 1;
+      if (s1 >= s0) {
+        n_dense += s1 - s0 + 1;
+        last = s1;
+      }
+    }
+  }
+  const size_t total_cap = (size_t)(n_sub - n_dense) * (FUSED_SUB / 4) + (size_t)n_dense * FUSED_SUB;
+  DevBuf d_hs, d_cap, d_segbase, d_tiles, d_entries, d_cnt, d_base;
+  CK(d_hs.alloc(c, (size_t)(n_hap > 0 ? n_hap : 1) * sizeof(HapScan)));
+  CK(d_cap.alloc(c, (size_t)(n_sub + 1) * 4));
+  CK(d_segbase.alloc(c, (size_t)(n_sub + 1) * 8));
+  CK(d_tiles.alloc(c, ((size_t)scan_tiles(n_sub) + 2) * 8));
+  CK(d_entries.alloc(c, (total_cap ? total_cap : 1) * 16));
+  CK(d_cnt.alloc(c, (size_t)(n_sub + 1) * 4 * 3));
+  CK(d_base.alloc(c, (size_t)(n_sub + 1) * 8 * 2));
+  uint32_t* cnt_ent = d_cnt.as<uint32_t>();
+  uint32_t* cnt_h0 = cnt_ent + (n_sub + 1);
+  uint32_t* cnt_h1 = cnt_h0 + (n_sub + 1);
+  uint64_t* base0 = d_base.as<uint64_t>();
+  uint64_t* base1 = base0 + (n_sub + 1);
+  tr.tick("fused: upload");
+  ProfScope prof_scope(c);
+  BatchView B = batch_view(b, in.a, in.b, in.is_ref);
+  hawk_prof_begin(st, 1);
+  CK(launch_hapscan(st, B, K, d_hs.as<HapScan>()));
+  CK(launch_fused_caps(st, b->d_slot_off.as<int64_t>(), in.is_ref, n_hap, n_chunks, all_dense, d_cap.as<uint32_t>()));
+  CK(exclusive_scan_u32(st, d_cap.as<uint32_t>(), n_sub, d_segbase.as<uint64_t>(), d_tiles.as<uint64_t>(), nullptr));
+  hawk_prof_end(st);
+  FusedLaunch L{};
+  L.ascii = d_ascii;
+  L.n_chunks = n_chunks;
+  L.q = b->q.p;
+  L.v = b->v.as<uint32_t>();
+  L.nz = b->nz.as<uint32_t>();
+  L.slot_off = b->d_slot_off.as<int64_t>();
+  L.n_hap = n_hap;
+  L.hs = d_hs.as<HapScan>();
+  L.K = K;
+  L.reach = fused_reach(K);
+  L.store_all = 0;
+  L.seg_base = d_segbase.as<uint64_t>();
+  L.seg_cap = d_cap.as<uint32_t>();
+  L.entries = d_entries.p;
+  L.cnt_ent = cnt_ent;
+  L.cnt_hit0 = cnt_h0;
+  L.cnt_hit1 = cnt_h1;
+  L.overflow = (uint32_t*)(d_tot + 3);
+  L.bad = (int64_t*)(d_tot + 4);
+  cudaEvent_t ev;
+  c->mark(0, &ev);
+  int rc = launch_fused_scan(st, L);
+  c->close_mark();
+  CK(rc);
+  b->sparse = true;
+  b->sparse_reach = L.reach;
+  hawk_prof_begin(st, 1);
+  CK(exclusive_scan_u32(st, cnt_h0, n_sub, base0, d_tiles.as<uint64_t>(), d_tot + 1));
+  CK(exclusive_scan_u32(st, cnt_h1, n_sub, base1, d_tiles.as<uint64_t>(), d_tot + 2));
+  hawk_prof_end(st);
+  uint64_t totals[8];
+  CK(c->small_d2h_sync(totals, d_tot, 64));
+  tr.tick("fused: scan + sync");
+  if ((int64_t)totals[4] != INT64_MAX) {
+    if (bad_slot) *bad_slot = (int64_t)totals[4];
+    return hawk_fail(HAWK_EIUPAC, "non-IUPAC character at slot %lld", (long long)totals[4]);
+  }
+  if (totals[3]) {  // a segment overflowed (variants denser than one chunk in four): staged K2 on the kept planes
+    *fell_back = true;
+    return HAWK_OK;
+  }
+  out.n[0] = (int64_t)totals[1];
+  out.n[1] = (int64_t)totals[2];
+  for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(c, (size_t)(out.n[s] > 0 ? out.n[s] : 1) * 8));
+  hawk_prof_begin(st, 3);
+  CK(launch_fused_expand(st, d_entries.p, d_segbase.as<uint64_t>(), cnt_ent, base0, base1, n_sub,
+                         out.hits[0].as<uint64_t>(), out.hits[1].as<uint64_t>()));
+  hawk_prof_end(st);
+  tr.tick("fused: expand launched");
+  return HAWK_OK;
+}
+
 static int check_scan_args(hawk_ctx* c, hawk_batch* b, const hawk_params* p, const int32_t* a,
                            const int32_t* e, hawk_result** out) {
   if (!c || !b || !p || !out || (b->n_hap > 0 && (!a || !e)))
@@ -675,6 +825,7 @@ extern "C" int hawk_pam_search(hawk_ctx* c, hawk_batch* b, const hawk_params* pa
                                const int32_t* scan_start, const int32_t* scan_stop,
                                hawk_result** out) {
   CK(check_scan_args(c, b, params, scan_start, scan_stop, out));
+  if (b->sparse) return hawk_fail(HAWK_EINVAL, "hawk_pam_search: the batch keeps planes only around variant bases; re-encode it");
   CKCUDA(cudaSetDevice(c->device));
   hawk_result* r = new (std::nothrow) hawk_result();
   if (!r) return hawk_fail(HAWK_ENOMEM, "hawk_pam_search: host allocation");
@@ -829,8 +980,10 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
 }
 
 int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const int32_t* scan_start,
-                     const int32_t* scan_stop, const uint8_t* is_ref, const StreamLink* link, hawk_result** out) {
+                     const int32_t* scan_stop, const uint8_t* is_ref, const StreamLink* link, hawk_result** out,
+                     const uint8_t* fused_text, int64_t* bad_slot) {
   CK(check_scan_args(c, b, params, scan_start, scan_stop, out));
+  if (bad_slot) *bad_slot = -1;
   if (b->n_hap > 0 && !is_ref) return hawk_fail(HAWK_EINVAL, "hawk_search: is_ref missing");
   if (!b->has_posmap) return hawk_fail(HAWK_EINVAL, "hawk_search: call hawk_batch_set_posmap first");
   const bool unphased = (params->flags & HAWK_F_UNPHASED) != 0;
@@ -863,7 +1016,29 @@ int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, cons
   ScanOut so;
   do {
     Trace tr;
-    if ((rc = run_scan(c, b, params, scan_start, scan_stop, is_ref, 0, in, so))) break;
+    bool staged = true;
+    if (fused_text) {
+      // The fused kernel is flat over the slot space: it wins when the haplotypes are short (an
+      // unphased cohort's ~200-base indel windows: the staged K2 spends a thread block per
+      // haplotype) and currently loses ~0.2 ms per 5 G bases on long ones, where its extra
+      // integer work per chunk outweighs the plane writes it saves (K1 is bound by the integer
+      // pipe, not by HBM -- DESIGN.md section 3).
+      const int64_t n_chunks_all = b->total_slots / HAWK_CHUNK;
+      const bool short_haps = K.unphased || (int64_t)b->n_hap * 2048 > n_chunks_all;
+      const bool use_fused = c->fused_mode == 1 || (c->fused_mode == 2 && short_haps);
+      if (K.small && use_fused && b->total_slots > 0) {
+        bool fell_back = false;
+        if ((rc = run_scan_fused(c, b, fused_text, params, scan_start, scan_stop, is_ref, in, so, bad_slot, &fell_back))) break;
+        staged = fell_back;
+      } else {
+        if ((rc = hawk_batch_repack_dev(b, fused_text, bad_slot))) break;
+      }
+    } else if (b->sparse && (!K.small || ((31 + K.G + K.C + HAWK_GUIDESEQPAD - 1) >> 5) > b->sparse_reach)) {
+      rc = hawk_fail(HAWK_EINVAL, "hawk_search: this batch keeps planes only around variant bases "
+                     "(hawk_encode_search_dev) and this guide / PAM geometry reaches further; re-encode it");
+      break;
+    }
+    if (staged && (rc = run_scan(c, b, params, scan_start, scan_stop, is_ref, 0, in, so))) break;
     tr.tick("run_scan total");
     r->scanned_bp = so.scanned_bp;
     cudaEvent_t ev_post;

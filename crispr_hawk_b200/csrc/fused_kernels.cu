@@ -1,0 +1,441 @@
+// fused_kernels.cu -- K1 + K2 in one pass over the haplotype texts (sm_100a).
+//
+// pack_kernel (scan_kernels.cu) writes 0.625 B of planes per base for every base, and the
+// staged K2 then reads back only the few per cent of them that lie next to a variant base.
+// Here one kernel reads the ASCII once, builds the plane words in registers and
+//   * stores them only where a later stage can read them: chunks within `reach` chunks of a
+//     chunk that holds a variant (lower-case) base, and every chunk of a REF haplotype
+//     (what rows_fast / gather_fast / the REF partner comparison touch);
+//   * finds the candidate chunks (a variant base within reach of a guide core, or REF) from
+//     the case words of the neighbouring chunks, which the same warp holds in registers;
+//   * matches the PAM on both strands for the candidates with the fused filters
+//     (search_guides.py:32-131, :395-420, :468-471 -- scan_chunk_small of hawk_core.h, the same
+//     code the staged match_kernel runs) and appends {haplotype, chunk, hit masks} entries to a
+//     per-warp segment in chunk order.
+// A second, small kernel turns the entries into the sorted (hap << 32 | pos) record streams at
+// exact prefix offsets, like the staged expand_kernel.
+//
+// Work decomposition is FLAT over the slot space: warp w owns the chunks
+// [w * FUSED_SUB, (w + 1) * FUSED_SUB) whatever haplotypes they belong to (a per-warp cursor maps
+// chunks to haplotypes), so 5,009 haplotypes of 1 Mb and 428,529 haplotypes of 200 bases cost the
+// same per base. A warp streams its sub-range 32 chunks (1 KB of text) per iteration, software-
+// pipelined by one iteration: iteration i is packed, then iteration i - 1 -- whose neighbours on
+// both sides are now in registers -- is finalised (store decision, candidate decision). One
+// extra iteration either side of the sub-range is packed as halo (1.6 % of the work).
+// Candidates are queued per warp and matched 32 at a time, every lane busy, although only a few
+// per cent of the chunks are candidates; the matcher reads the planes back through L2 (they
+// were stored a moment ago by this warp).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hawk_core.h"
+#include "hawk_kernels.h"
+#include "hawk_post.h"
+
+namespace hawk {
+
+// first chunk of haplotype h's territory (its leading zero gap included); T(n_hap) = n_chunks
+__device__ __forceinline__ int64_t territory(const int64_t* __restrict__ slot_off, int32_t n_hap, int64_t n_chunks,
+                                             int32_t h) {
+  return h >= n_hap ? n_chunks : (__ldg(&slot_off[h]) >> 5) - (HAWK_SLOT_GAP / HAWK_CHUNK);
+}
+
+struct FusedArgs {
+  const uint4* ascii;
+  int64_t n_chunks;
+  uint4* q;
+  uint32_t* v;
+  uint32_t* nz;
+  const int64_t* slot_off;
+  int32_t n_hap;
+  const HapScan* hs;
+  ScanConst K;
+  int32_t reach;      // planes are kept for chunks within `reach` chunks of a variant chunk (1..3)
+  const uint64_t* seg_base;  // per sub-range: first entry slot, capacity
+  const uint32_t* seg_cap;
+  uint4* entries;       // {haplotype, chunk (haplotype-relative), hits strand 0, hits strand 1}
+  uint32_t* cnt_ent;    // per sub-range: entries, hits per strand
+  uint32_t* cnt_hit0;
+  uint32_t* cnt_hit1;
+  uint32_t* overflow;   // set when a segment was too small (the caller falls back to the staged K2)
+  unsigned long long* bad;
+};
+
+struct Planes5 {
+  uint32_t a, c, g, t, v;
+};
+
+struct Raw8 {
+  uint32_t w[8];
+};
+
+template <bool WIDE>
+__device__ __forceinline__ void load_raw(const uint4* __restrict__ p, Raw8& r) {
+  if (WIDE) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                   "=r"(r.w[7])
+                 : "l"(p));
+  } else {
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    r.w[0] = a.x, r.w[1] = a.y, r.w[2] = a.z, r.w[3] = a.w;
+    r.w[4] = b.x, r.w[5] = b.y, r.w[6] = b.z, r.w[7] = b.w;
+  }
+}
+
+// haplotype whose territory holds the chunks being finalised, everything relative to the
+// sub-range start s (32-bit): warp-uniform
+struct HapCursor {
+  int32_t h;
+  int32_t t_next;      // first chunk of the next territory
+  int32_t c_lo, c_hi;  // chunks that can hold a scanned position: [c_lo, c_hi)
+  int32_t is_ref;
+};
+
+template <bool WIDE, int REACH>
+__global__ void __launch_bounds__(FUSED_WARPS * 32, 32 / FUSED_WARPS) fused_scan_kernel(const __grid_constant__ FusedArgs A) {
+  __shared__ uint16_t q_off[FUSED_WARPS][64];  // candidate queue (ring): chunk offset in the sub-range
+  __shared__ int32_t q_hap[FUSED_WARPS][64];   // ... and its haplotype
+  const int lane = threadIdx.x & 31, warp = FUSED_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5);
+  const int64_t sub = (int64_t)blockIdx.x * FUSED_WARPS + warp;
+  const int64_t s = sub * FUSED_SUB;
+  if (s >= A.n_chunks) return;  // uniform over the warp; no block-wide barrier below
+  const int32_t n = (int32_t)(s + FUSED_SUB < A.n_chunks ? FUSED_SUB : A.n_chunks - s);  // chunks owned
+  const int32_t n_avail = (int32_t)(A.n_chunks - s < FUSED_SUB + 32 ? A.n_chunks - s : FUSED_SUB + 32);  // + halo
+  const int32_t n_iter = (n + 31) >> 5;
+  const ScanConst& K = A.K;
+  BatchView B{};
+  B.q = reinterpret_cast<const Planes*>(A.q);
+  B.v = A.v;
+  const uint4* const asc = A.ascii + 2 * s + 2 * lane;  // this lane's chunk of iteration 0
+  uint4* const qs = A.q + s + lane;
+  uint32_t* const vs = A.v + s + lane;
+  uint32_t* const nzs = A.nz + (s >> 5);
+  const uint32_t lane_bit = 1u << lane, lanes_below = lane_bit - 1u;
+
+  auto load_cursor = [&](int32_t h) {
+    HapCursor cu;
+    cu.h = h;
+    const int64_t tn = territory(A.slot_off, A.n_hap, A.n_chunks, h + 1) - s;
+    cu.t_next = tn > (int64_t)(FUSED_SUB + 64) ? FUSED_SUB + 64 : (int32_t)tn;
+    const HapScan* H = A.hs + h;
+    const int64_t c0 = H->chunk0 - s;  // may be far below zero; the clamps keep the interval test exact
+    const int32_t a = H->a, b = H->b;
+    int64_t lo = c0 + (a >> 5), hi = b > a ? c0 + ((b + 31) >> 5) : lo;
+    if (lo < -64) lo = -64;
+    if (hi < -64) hi = -64;
+    if (lo > FUSED_SUB + 64) lo = FUSED_SUB + 64;
+    if (hi > FUSED_SUB + 64) hi = FUSED_SUB + 64;
+    cu.c_lo = (int32_t)lo;
+    cu.c_hi = (int32_t)hi;
+    cu.is_ref = H->is_ref;
+    return cu;
+  };
+  HapCursor cur;
+  {
+    int32_t lo = 0, hi = A.n_hap;  // T(lo) <= s < T(hi)
+    while (hi - lo > 1) {
+      const int32_t mid = (lo + hi) >> 1;
+      if (territory(A.slot_off, A.n_hap, A.n_chunks, mid) <= s) lo = mid; else hi = mid;
+    }
+    cur = load_cursor(lo);
+  }
+
+  uint4* const seg = A.entries + A.seg_base[sub];
+  const uint32_t cap = A.seg_cap[sub];
+  uint32_t n_ent = 0, n_h0 = 0, n_h1 = 0;
+  uint32_t qhead = 0, qn = 0;
+  uint32_t nz_mine = 0;  // lane l: the nz word of iteration (32 m + l), stored 32 words at a time
+
+  // match the oldest `take` (<= 32) queued candidates, append the ones with hits to the segment
+  auto flush = [&](uint32_t take) {
+    __syncwarp();  // the planes / case words below were stored by other lanes of this warp
+    uint32_t m0 = 0, m1 = 0;
+    int32_t h = 0, c = 0;
+    if ((uint32_t)lane < take) {
+      const uint32_t slot = (qhead + lane) & 63u;
+      h = q_hap[warp][slot];
+      const HapScan H = A.hs[h];
+      c = (int32_t)(s + q_off[warp][slot] - H.chunk0);
+      const bool use_v = !H.is_ref;
+      uint32_t w0 = 0, w1 = 0, w2 = 0;
+      bool go = true;
+      if (use_v) {
+        const uint32_t* vp = A.v + H.chunk0 + c;
+        w0 = vp[-1] & K.prev_mask;
+        w1 = vp[0];
+        w2 = vp[1] & K.next_mask;
+        go = (w0 | w1 | w2) != 0;
+      }
+      if (go) {
+        uint32_t out[2], raw[2];
+        scan_chunk_small(B, K, H, c, w0, w1, w2, use_v, out, raw);
+        m0 = out[0];
+        m1 = out[1];
+      }
+    }
+    const uint32_t has = __ballot_sync(0xFFFFFFFFu, (m0 | m1) != 0);
+    if ((m0 | m1) != 0) {
+      const uint32_t at = n_ent + __popc(has & lanes_below);
+      if (at < cap) seg[at] = make_uint4((uint32_t)h, (uint32_t)c, m0, m1);
+    }
+    n_ent += __popc(has);
+    uint32_t k0 = __popc(m0), k1 = __popc(m1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      k0 += __shfl_xor_sync(0xFFFFFFFFu, k0, o);
+      k1 += __shfl_xor_sync(0xFFFFFFFFu, k1, o);
+    }
+    n_h0 += k0;
+    n_h1 += k1;
+    qhead = (qhead + take) & 63u;
+    qn -= take;
+  };
+
+  // text of iteration `it` (chunk 32 it + lane of the sub-range; -1 and n_iter are the halo)
+  auto fetch = [&](int32_t it, Raw8& r) {
+    if (32 * it + 32 <= n_avail) {  // uniform; only the tail of the slot space fails it
+      load_raw<WIDE>(asc + 64 * it, r);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r.w[k] = 0u;
+      if (32 * it + lane < n_avail) load_raw<WIDE>(asc + 64 * it, r);
+    }
+  };
+  // ... -> planes; returns the "case word non-zero" ballot
+  auto pack = [&](int32_t it, const Raw8& r, Planes5& o) -> uint32_t {
+    const PackedChunk k = pack_chunk_lean(r.w);
+    o.a = k.a, o.c = k.c, o.g = k.g, o.t = k.t, o.v = k.v;
+    if (k.invalid) {
+      const int32_t cl = 32 * it + lane;
+      if (cl >= 0 && cl < n) atomicMin(A.bad, (unsigned long long)((s + cl) * 32 + (__ffs(k.invalid) - 1)));
+    }
+    return __ballot_sync(0xFFFFFFFFu, k.v != 0);
+  };
+
+  // finalise iteration j: P are its planes, nzp / nzc / nzn the ballots of iterations j - 1, j, j + 1
+  auto finalise = [&](int32_t j, const Planes5& P, uint32_t nzp, uint32_t nzc, uint32_t nzn) {
+    const int32_t cl0 = 32 * j;
+    if (lane == (j & 31)) nz_mine = nzc;
+    if ((j & 31) == 31) nzs[j - 31 + lane] = nz_mine;
+    // variant chunk within one chunk (candidate) / within REACH chunks (planes are kept)
+    const uint32_t near1 = nzc | __funnelshift_l(nzp, nzc, 1) | __funnelshift_r(nzc, nzn, 1);
+    uint32_t keep_bits = near1;
+    if (REACH >= 2) keep_bits |= __funnelshift_l(nzp, nzc, 2) | __funnelshift_r(nzc, nzn, 2);
+    if (REACH >= 3) keep_bits |= __funnelshift_l(nzp, nzc, 3) | __funnelshift_r(nzc, nzn, 3);
+    uint32_t cand_bits = near1;
+    while (cl0 >= cur.t_next) cur = load_cursor(cur.h + 1);  // uniform
+    int32_t h_l = cur.h;
+    if (cl0 + 31 < cur.t_next) {
+      // the whole iteration lies in one haplotype's territory (the common case): uniform masks
+      if (cur.is_ref) cand_bits = keep_bits = 0xFFFFFFFFu;
+      if (cl0 < cur.c_lo || cl0 + 32 > cur.c_hi) cand_bits &= interval_mask(cur.c_lo, cur.c_hi, cl0);
+    } else {
+      // short haplotypes: the 32 chunks straddle territories, every lane finds its own
+      const int64_t cg = s + cl0 + lane;
+      while (h_l + 1 < A.n_hap && cg >= territory(A.slot_off, A.n_hap, A.n_chunks, h_l + 1)) ++h_l;
+      const HapScan* H = A.hs + h_l;
+      const int64_t crel = cg - H->chunk0;
+      const int32_t a = H->a, b = H->b;
+      const bool ref = H->is_ref != 0;
+      const bool c = b > a && crel >= (a >> 5) && crel < ((b + 31) >> 5) && (ref || (near1 & lane_bit));
+      cand_bits = __ballot_sync(0xFFFFFFFFu, c);
+      keep_bits |= __ballot_sync(0xFFFFFFFFu, ref);
+    }
+    if (cl0 + 32 > n) {  // the last iteration of the slot space
+      const uint32_t valid = (1u << (n - cl0)) - 1u;
+      keep_bits &= valid;
+      cand_bits &= valid;
+    }
+    if (keep_bits & lane_bit) {
+      qs[cl0] = make_uint4(P.a, P.c, P.g, P.t);
+      vs[cl0] = P.v;
+    }
+    // matches of older candidates: all their neighbour chunks have been stored by now
+    if (qn >= 32) flush(32);
+    if (cand_bits & lane_bit) {
+      const uint32_t slot = (qhead + qn + __popc(cand_bits & lanes_below)) & 63u;
+      q_off[warp][slot] = (uint16_t)(cl0 + lane);
+      q_hap[warp][slot] = h_l;
+    }
+    qn += __popc(cand_bits);
+  };
+
+  // the neighbour chunks this warp's matcher reads but another warp owns
+  auto store_edge = [&](int32_t it, const Planes5& P, int which_lane) {
+    if (lane == which_lane && 32 * it + lane < n_avail) {
+      qs[32 * it] = make_uint4(P.a, P.c, P.g, P.t);
+      vs[32 * it] = P.v;
+    }
+  };
+
+  Planes5 pa{0u, 0u, 0u, 0u, 0u}, pb;
+  Raw8 raw;
+  uint32_t nz_pp = 0, nz_p = 0, nz_c;  // ballots of iterations i - 2, i - 1, i
+  if (s > 0) {  // leading halo
+    fetch(-1, raw);
+    nz_p = pack(-1, raw, pb);
+    store_edge(-1, pb, 31);
+  }
+  // Software pipeline, unrolled by two so the plane registers never move: the text of iteration
+  // i + 1 is requested, iteration i is packed, then iteration i - 1 (neighbours on both sides now
+  // known) is finalised. Iteration n_iter is the trailing halo.
+  fetch(0, raw);
+  nz_c = pack(0, raw, pa);
+  fetch(1, raw);
+  nz_pp = nz_p;
+  nz_p = nz_c;
+  int32_t i = 1;
+  for (; i + 1 <= n_iter; i += 2) {
+    nz_c = pack(i, raw, pb);
+    fetch(i + 1, raw);
+    finalise(i - 1, pa, nz_pp, nz_p, nz_c);
+    nz_pp = nz_p;
+    nz_p = nz_c;
+    nz_c = pack(i + 1, raw, pa);
+    fetch(i + 2, raw);
+    if (i + 1 == n_iter) store_edge(i + 1, pa, 0);
+    finalise(i, pb, nz_pp, nz_p, nz_c);
+    nz_pp = nz_p;
+    nz_p = nz_c;
+  }
+  if (i <= n_iter) {  // i == n_iter: pack the trailing halo, finalise the last owned iteration
+    nz_c = pack(i, raw, pb);
+    store_edge(i, pb, 0);
+    finalise(i - 1, pa, nz_pp, nz_p, nz_c);
+  }
+  if (n_iter & 31) {  // nz words of the last, partial group of 32 iterations
+    const int32_t j0 = n_iter & ~31;
+    if (lane < (n_iter & 31)) nzs[j0 + lane] = nz_mine;
+  }
+  while (qn > 0) flush(qn < 32 ? qn : 32);
+  if (lane == 0) {
+    A.cnt_ent[sub] = n_ent;
+    A.cnt_hit0[sub] = n_h0;
+    A.cnt_hit1[sub] = n_h1;
+    if (n_ent > cap) atomicOr(A.overflow, 1u);
+  }
+}
+
+// capacity of every sub-range's entry segment: all of its chunks when it overlaps a REF haplotype
+// (every chunk of REF is a candidate) or when every haplotype is dense (unphased cohorts), else a
+// quarter of them
+__global__ void fused_caps_kernel(const int64_t* __restrict__ slot_off, const uint8_t* __restrict__ is_ref, int32_t n_hap,
+                                  int64_t n_chunks, int64_t n_sub, int32_t all_dense, uint32_t* __restrict__ cap) {
+  const int64_t sub = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sub >= n_sub) return;
+  const int64_t s = sub * FUSED_SUB, e = s + FUSED_SUB < n_chunks ? s + FUSED_SUB : n_chunks;
+  bool dense = all_dense != 0;
+  if (!dense) {
+    int32_t lo = 0, hi = n_hap;
+    while (hi - lo > 1) {
+      const int32_t mid = (lo + hi) >> 1;
+      if (territory(slot_off, n_hap, n_chunks, mid) <= s) lo = mid; else hi = mid;
+    }
+    for (int32_t h = lo; h < n_hap && territory(slot_off, n_hap, n_chunks, h) < e; ++h)
+      if (is_ref[h]) dense = true;
+  }
+  cap[sub] = dense ? (uint32_t)FUSED_SUB : (uint32_t)(FUSED_SUB / 4);
+}
+
+// entries -> (hap << 32 | pos) records at exact offsets; one warp per sub-range
+__global__ void __launch_bounds__(128) fused_expand_kernel(const uint4* __restrict__ entries,
+                                                           const uint64_t* __restrict__ seg_base,
+                                                           const uint32_t* __restrict__ cnt_ent,
+                                                           const uint64_t* __restrict__ base0,
+                                                           const uint64_t* __restrict__ base1, int64_t n_sub,
+                                                           uint64_t* __restrict__ hits0, uint64_t* __restrict__ hits1) {
+  const int lane = threadIdx.x & 31;
+  const int64_t sub = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (sub >= n_sub) return;
+  const uint4* seg = entries + seg_base[sub];
+  const uint32_t n = cnt_ent[sub];
+  uint64_t run0 = base0[sub], run1 = base1[sub];
+  for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+    const uint32_t k = k0 + lane;
+    uint4 en = make_uint4(0u, 0u, 0u, 0u);
+    if (k < n) en = seg[k];
+    const uint32_t pk = (uint32_t)__popc(en.z) | ((uint32_t)__popc(en.w) << 16);
+    uint32_t incl = pk;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += y;
+    }
+    const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31), excl = incl - pk;
+    const uint64_t p0 = ((uint64_t)en.x << 32) | ((uint64_t)en.y << 5);
+    uint64_t a = run0 + (excl & 0xFFFFu), b = run1 + (excl >> 16);
+    uint32_t bits = en.z;
+    while (bits) {
+      const int jb = __ffs(bits) - 1;
+      bits &= bits - 1;
+      hits0[a++] = p0 + (uint32_t)jb;
+    }
+    bits = en.w;
+    while (bits) {
+      const int jb = __ffs(bits) - 1;
+      bits &= bits - 1;
+      hits1[b++] = p0 + (uint32_t)jb;
+    }
+    run0 += tot & 0xFFFFu;
+    run1 += tot >> 16;
+  }
+}
+
+int64_t fused_sub_ranges(int64_t n_chunks) { return (n_chunks + FUSED_SUB - 1) / FUSED_SUB; }
+
+int launch_fused_caps(cudaStream_t st, const int64_t* slot_off, const uint8_t* is_ref, int32_t n_hap, int64_t n_chunks,
+                      int32_t all_dense, uint32_t* cap) {
+  const int64_t n_sub = fused_sub_ranges(n_chunks);
+  if (n_sub <= 0) return HAWK_OK;
+  fused_caps_kernel<<<(unsigned)((n_sub + 127) / 128), 128, 0, st>>>(slot_off, is_ref, n_hap, n_chunks, n_sub, all_dense, cap);
+  hawk_note_launch(1);
+  return hawk_check_cuda(cudaGetLastError(), "fused_caps_kernel launch");
+}
+
+int launch_fused_scan(cudaStream_t st, const FusedLaunch& L) {
+  const int64_t n_sub = fused_sub_ranges(L.n_chunks);
+  if (n_sub <= 0) return HAWK_OK;
+  FusedArgs A{};
+  A.ascii = (const uint4*)L.ascii;
+  A.n_chunks = L.n_chunks;
+  A.q = (uint4*)L.q;
+  A.v = L.v;
+  A.nz = L.nz;
+  A.slot_off = L.slot_off;
+  A.n_hap = L.n_hap;
+  A.hs = L.hs;
+  A.K = L.K;
+  A.reach = L.reach;
+  A.seg_base = L.seg_base;
+  A.seg_cap = L.seg_cap;
+  A.entries = (uint4*)L.entries;
+  A.cnt_ent = L.cnt_ent;
+  A.cnt_hit0 = L.cnt_hit0;
+  A.cnt_hit1 = L.cnt_hit1;
+  A.overflow = L.overflow;
+  A.bad = (unsigned long long*)L.bad;
+  const unsigned blocks = (unsigned)((n_sub + FUSED_WARPS - 1) / FUSED_WARPS);
+  const bool wide = ((uintptr_t)L.ascii & 31) == 0;
+  if (L.reach < 1 || L.reach > 3) return hawk_fail(HAWK_EINVAL, "fused scan: reach %d out of range", L.reach);
+#define HAWK_FUSED_LAUNCH(W, R) fused_scan_kernel<W, R><<<blocks, FUSED_WARPS * 32, 0, st>>>(A)
+  if (wide) {
+    if (L.reach == 1) HAWK_FUSED_LAUNCH(true, 1); else if (L.reach == 2) HAWK_FUSED_LAUNCH(true, 2); else HAWK_FUSED_LAUNCH(true, 3);
+  } else {
+    if (L.reach == 1) HAWK_FUSED_LAUNCH(false, 1); else if (L.reach == 2) HAWK_FUSED_LAUNCH(false, 2); else HAWK_FUSED_LAUNCH(false, 3);
+  }
+#undef HAWK_FUSED_LAUNCH
+  hawk_note_launch(1);
+  return hawk_check_cuda(cudaGetLastError(), "fused_scan_kernel launch");
+}
+
+int launch_fused_expand(cudaStream_t st, const void* entries, const uint64_t* seg_base, const uint32_t* cnt_ent,
+                        const uint64_t* base0, const uint64_t* base1, int64_t n_sub, uint64_t* hits0, uint64_t* hits1) {
+  if (n_sub <= 0) return HAWK_OK;
+  fused_expand_kernel<<<(unsigned)((n_sub + 3) / 4), 128, 0, st>>>((const uint4*)entries, seg_base, cnt_ent, base0, base1,
+                                                                  n_sub, hits0, hits1);
+  hawk_note_launch(1);
+  return hawk_check_cuda(cudaGetLastError(), "fused_expand_kernel launch");
+}
+
+}  // namespace hawk

@@ -173,6 +173,47 @@ HAWK_HD PackedChunk pack_chunk(const uint32_t* words) {
   return o;
 }
 
+// 4x4 byte-matrix transpose of four words (row = word, column = byte): eight byte permutes
+HAWK_HD void transpose4x4_bytes(uint32_t& w0, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
+  const uint32_t t0 = byte_perm(w0, w1, 0x5140), t1 = byte_perm(w2, w3, 0x5140);
+  const uint32_t t2 = byte_perm(w0, w1, 0x7362), t3 = byte_perm(w2, w3, 0x7362);
+  w0 = byte_perm(t0, t1, 0x5410);
+  w1 = byte_perm(t0, t1, 0x7632);
+  w2 = byte_perm(t2, t3, 0x5410);
+  w3 = byte_perm(t2, t3, 0x7632);
+}
+
+// pack_chunk with fewer ALU-pipe instructions (the pack is bound by that pipe, not by HBM):
+// the per-plane byte gathers become two 4x4 byte transposes (16 permutes instead of 24), the
+// planes are not masked by "is a letter" (a non-letter other than NUL sets `invalid`, and a
+// batch with an invalid byte is refused as a whole; NUL has letter number 0 -> zero planes),
+// the case word is bit 5 as it stands, and the validity word takes 7 boolean ops. Same result
+// as pack_chunk on every NUL / IUPAC byte, and the same `invalid` word on every input.
+HAWK_HD PackedChunk pack_chunk_lean(const uint32_t* words) {
+  uint32_t lo[4], hi[4];
+  HAWK_UNROLL
+  for (int g = 0; g < 4; ++g) {
+    lo[g] = words[2 * g];
+    hi[g] = words[2 * g + 1];
+    transpose8x8(lo[g], hi[g]);
+  }
+  transpose4x4_bytes(lo[0], lo[1], lo[2], lo[3]);  // -> bit planes 0..3 of the 32 characters
+  transpose4x4_bytes(hi[0], hi[1], hi[2], hi[3]);  // -> bit planes 4..7
+  PackedChunk o;
+  o.a = table5<letter_table(0)>(lo[0], lo[1], lo[2], lo[3], hi[0]);
+  o.c = table5<letter_table(1)>(lo[0], lo[1], lo[2], lo[3], hi[0]);
+  o.g = table5<letter_table(2)>(lo[0], lo[1], lo[2], lo[3], hi[0]);
+  o.t = table5<letter_table(3)>(lo[0], lo[1], lo[2], lo[3], hi[0]);
+  o.v = hi[1];
+  const uint32_t or_a = lop3<0xFE>(lo[0], lo[1], lo[2]), or_b = lop3<0xFE>(lo[3], hi[0], hi[1]);
+  const uint32_t or_7 = lop3<0xFE>(or_a, or_b, hi[2]);      // bits 0..6: any set
+  const uint32_t alpha = ~hi[3] & hi[2];                    // 0x40..0x7F
+  const uint32_t acg = lop3<0xFE>(o.a, o.c, o.g);
+  const uint32_t ok = lop3<0xA8>(acg, o.t, alpha);          // (acg | t) & alpha: an IUPAC letter
+  o.invalid = lop3<0x54>(or_7, hi[3], ok);                  // (or_7 | b7) & ~ok: not NUL, not a letter
+  return o;
+}
+
 // nibble -> IUPAC letter (inverse of the table above), upper-case
 HAWK_HD char nibble_letter(uint32_t n) {
   // "?ACMGRSVTWYHKDBN" as two 64-bit immediates (no local array, no stack frame)

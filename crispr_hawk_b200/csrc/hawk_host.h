@@ -108,6 +108,9 @@ struct hawk_ctx {
   bool bulk_h2d = false;  // a streamed search owns the H2D copy engine: uploads go through the SMs
   // bytes the host layer moved across PCIe since the context was created (hawk_ctx_traffic)
   int64_t h2d_bytes = 0, d2h_bytes = 0;
+  // hawk_encode_search_dev: 0 = K1 then the staged K2, 1 = the fused kernel whenever the guide
+  // geometry allows, 2 = choose by haplotype shape (hawk_ctx_set_fused)
+  int fused_mode = 2;
   // optional per-kernel timing (hawk_ctx_set_profiling)
   bool profiling = false;
   struct Span { cudaEvent_t a, b; int kind; };
@@ -179,6 +182,10 @@ struct hawk_batch {
   DevBuf seg_off, seg_rel, seg_gen, seg_step;
   DevBuf va_off, va_idx, va_ent_off, va_ref;
   bool has_posmap = false, has_alleles = false;
+  // planes are kept only around variant bases and for REF haplotypes (hawk_encode_search_dev):
+  // valid for searches whose windows reach at most `sparse_reach` chunks from a variant chunk
+  bool sparse = false;
+  int32_t sparse_reach = 0;
   // N2: the haplotypes' variant tables (hawk_batch_set_variants, or kept from the edit lists)
   DevBuf var_off, var_pos, var_rl, var_al, var_ao, var_pool;
   int32_t var_pos_base = 0;
@@ -223,5 +230,8 @@ struct StreamLink {
 
 int batch_create_impl(hawk_ctx* c, const uint8_t* ascii, bool ascii_on_device, const int64_t* slot_off,
                       const int32_t* len, int32_t n_hap, hawk_batch** out, int64_t* bad_slot);
+// `fused_text`: device-resident texts of the batch's layout; the batch is re-encoded from them
+// inside the search (fused K1 + K2 when the guide geometry allows, else K1 then the staged K2)
 int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const int32_t* scan_start,
-                     const int32_t* scan_stop, const uint8_t* is_ref, const StreamLink* link, hawk_result** out);
+                     const int32_t* scan_stop, const uint8_t* is_ref, const StreamLink* link, hawk_result** out,
+                     const uint8_t* fused_text = nullptr, int64_t* bad_slot = nullptr);

@@ -77,6 +77,35 @@ int launch_gather_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, 
 int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n_max,
                        const uint64_t* totals, const uint32_t* key_table, int32_t key_min, int64_t* bucket);
 
+// fused_kernels.cu: K1 + K2 in one pass over the texts (flat over the slot space)
+constexpr int FUSED_WARPS = 1;    // warps per CTA (one: the warp index is then provably uniform -> uniform datapath)
+constexpr int FUSED_SUB = 4096;   // chunks per warp sub-range (128 KB of text)
+struct FusedLaunch {
+  const uint8_t* ascii;
+  int64_t n_chunks;
+  void* q;
+  uint32_t* v;
+  uint32_t* nz;
+  const int64_t* slot_off;
+  int32_t n_hap;
+  const HapScan* hs;
+  ScanConst K;
+  int32_t reach, store_all;
+  const uint64_t* seg_base;
+  const uint32_t* seg_cap;
+  void* entries;
+  uint32_t *cnt_ent, *cnt_hit0, *cnt_hit1, *overflow;
+  int64_t* bad;
+};
+int64_t fused_sub_ranges(int64_t n_chunks);
+int launch_fused_caps(cudaStream_t st, const int64_t* slot_off, const uint8_t* is_ref, int32_t n_hap, int64_t n_chunks,
+                      int32_t all_dense, uint32_t* cap);
+int launch_fused_scan(cudaStream_t st, const FusedLaunch& L);
+int launch_fused_expand(cudaStream_t st, const void* entries, const uint64_t* seg_base, const uint32_t* cnt_ent,
+                        const uint64_t* base0, const uint64_t* base1, int64_t n_sub, uint64_t* hits0, uint64_t* hits1);
+// scan2_kernels.cu: per-haplotype scan geometry
+int launch_hapscan(cudaStream_t st, const BatchView& B, const ScanConst& K, HapScan* hs);
+
 // synth_kernels.cu: edit lists -> lengths, output positions, posmap segments (two passes)
 int launch_derive(cudaStream_t st, int32_t n_hap, const int64_t* edit_off, const int32_t* pos, const int32_t* reflen,
                   const int32_t* altlen, const int64_t* altoff, int64_t ref_len, int64_t alt_pool_len,

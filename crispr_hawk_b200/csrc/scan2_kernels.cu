@@ -61,6 +61,13 @@ __global__ void sblock_table_kernel(const int64_t* __restrict__ sblock_off, int3
   blk_tab[b] = make_int2(lo, (int32_t)(b - sblock_off[lo]) * S2_T);
 }
 
+int launch_hapscan(cudaStream_t st, const BatchView& B, const ScanConst& K, HapScan* hs) {
+  if (B.n_hap <= 0) return HAWK_OK;
+  hapscan_kernel<<<(B.n_hap + 127) / 128, 128, 0, st>>>(B, K, hs);
+  hawk_note_launch(1);
+  return hawk_check_cuda(cudaGetLastError(), "hapscan_kernel launch");
+}
+
 struct SliceCtx {
   int32_t h;
   int32_t c32;   // first chunk of this thread's slice (haplotype-relative)

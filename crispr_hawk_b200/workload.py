@@ -52,15 +52,27 @@ class Workload:
         """1 B ASCII read + 0.5 B planes + 0.125 B case bits written per slot."""
         return 1.625 * self.d.total_slots
 
+    def table_algorithmic_bytes(self, n_rows: int, n_hits: int) -> float:
+        """Guide-table pipeline: rows written (25 B of columns + the padded text row), hit records
+        read (8 B), window planes read per hit (0.625 B per window base)."""
+        w = self.guidelen + len(self.fwd) + 2 * marshal.GUIDESEQPAD
+        return n_rows * (25.0 + (w + 15) // 16 * 16) + n_hits * (8.0 + 0.625 * w)
+
     # ---- the hot path, inputs resident in HBM ----
     def prepare_resident(self) -> None:
         self.batch = _cabi.Batch(self.ctx, None, self.d.slot_off, self.d.lens, device_ptr=self.ascii_dev.data_ptr())
         self.batch.set_posmap(self.d.seg)
 
-    def step_resident(self) -> _cabi.Result:
-        """encode (K1) + search (K2 + post-scan pipeline); table stays on the device."""
+    def step_resident(self, fused=None) -> _cabi.Result:
+        """encode + search over the texts resident in HBM; the table stays on the device.
+        `fused`: True = hawk_encode_search_dev with the fused K1 + K2 kernel forced, None = the
+        same call choosing by haplotype shape (the default of the library), False = the two
+        calls hawk_batch_repack_dev (K1) + hawk_search (staged K2)."""
         if self.batch is None:
             self.prepare_resident()
+        if fused is None or fused:
+            self.ctx.set_fused(2 if fused is None else 1)
+            return _cabi.encode_search(self.ctx, self.batch, self.ascii_dev.data_ptr(), self.params, self.a, self.b, self.d.is_ref)
         self.batch.repack(self.ascii_dev.data_ptr())
         return _cabi.search(self.ctx, self.batch, self.params, self.a, self.b, self.d.is_ref)
 
@@ -273,10 +285,14 @@ class UnphasedWorkload:
         self.batch.set_posmap(self.d.seg)
         self.batch.set_alleles(self.d.alleles)
 
-    def step_resident(self) -> _cabi.Result:
-        """encode (K1) + unphased search; texts resident in HBM, table stays on the device."""
+    def step_resident(self, fused=None) -> _cabi.Result:
+        """encode + unphased search; texts resident in HBM, table stays on the device (see
+        Workload.step_resident for `fused`)."""
         if self.batch is None:
             self.prepare_resident()
+        if fused is None or fused:
+            self.ctx.set_fused(2 if fused is None else 1)
+            return _cabi.encode_search(self.ctx, self.batch, self.ascii_dev.data_ptr(), self.params, self.a, self.b, self.d.is_ref)
         self.batch.repack(self.ascii_dev.data_ptr())
         return _cabi.search(self.ctx, self.batch, self.params, self.a, self.b, self.d.is_ref)
 
@@ -312,6 +328,20 @@ class UnphasedWorkload:
         return table, t1[0] - t0[0], t1[1] - t0[1]
 
     step_host_twocall = step_host
+
+    # ---- sizes for the roofline (algorithmic bytes) ----
+    def pack_algorithmic_bytes(self) -> float:
+        return 1.625 * self.d.total_slots
+
+    def scan_algorithmic_bytes(self, n_hits: int) -> float:
+        """Every haplotype of an unphased cohort is dense in variant bases (IUPAC codes every few
+        bases), so every scanned base is read: 0.5 B/bp planes, 0.125 B/bp case plane for the
+        non-REF haplotypes, 8 B per emitted hit record."""
+        bp = (self.b.astype(np.int64) - self.a).clip(min=0)
+        ref_bp = int(bp[self.d.is_ref.astype(bool)].sum())
+        return 0.5 * self.scanned_bp + 0.125 * (self.scanned_bp - ref_bp) + 8.0 * n_hits
+
+    table_algorithmic_bytes = Workload.table_algorithmic_bytes
 
     def oracle_subset(self, hap_indices):
         """The flat arrays of a subset of haplotypes (oracle/c_oracle.search's inputs)."""

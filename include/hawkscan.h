@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define HAWK_ABI_VERSION 2
+#define HAWK_ABI_VERSION 3
 #define HAWK_SLOT_ALIGN 128 /* bases; haplotypes start on a 64-byte plane boundary */
 #define HAWK_SLOT_GAP 128   /* unused (zero) slots before the first and after every haplotype */
 #define HAWK_CHUNK 32       /* bases per chunk (one uint4 of planes, one uint32 of case bits) */
@@ -274,6 +274,23 @@ int hawk_result_fetch_variants(hawk_result *result, int32_t *gv_idx /* gv_total 
 /* Re-run K1 into an existing batch from device-resident texts of the same layout (the
  * coordinate maps / allele tables attached to the batch are kept). */
 int hawk_batch_repack_dev(hawk_batch *batch, const uint8_t *d_ascii, int64_t *bad_slot);
+
+/* encode_haplotypes + search (crisprhawk.py:64-115) in ONE pass over device-resident texts: K1
+ * and K2 fused. The batch is re-encoded from `d_ascii` (its own layout, 16-byte aligned, device
+ * memory) and searched at once: the texts are read a single time, the PAM is matched while the
+ * plane words are still in registers, and planes are stored only where the rest of the pipeline
+ * reads them (around variant bases and for REF haplotypes). The result equals
+ * hawk_batch_repack_dev + hawk_search. Afterwards the batch is *sparse*: it serves this result
+ * (hawk_result_annotate) and further hawk_search calls whose guide + PAM are not longer; anything
+ * else (hawk_pam_search, hawk_batch_export_nibbles, longer guides) needs hawk_batch_repack_dev
+ * first and says so. Guides longer than 32 nt (or guide + PAM > 33) take K1 then the staged K2. */
+int hawk_encode_search_dev(hawk_ctx *ctx, hawk_batch *batch, const uint8_t *d_ascii, const hawk_params *params,
+                           const int32_t *scan_start, const int32_t *scan_stop, const uint8_t *is_ref,
+                           hawk_result **result, int64_t *bad_slot);
+/* Which kernels hawk_encode_search_dev runs: 0 = K1, then the staged K2 (the batch stays dense);
+ * 1 = the fused kernel whenever the guide geometry allows; 2 (default) = by haplotype shape --
+ * fused for unphased cohorts and short haplotypes, staged for long ones. Results are identical. */
+int hawk_ctx_set_fused(hawk_ctx *ctx, int32_t mode);
 
 /* The context's cudaStream_t (so callers can time with events on the stream the kernels
  * run on) and optional per-kernel timing: with profiling on, every K1 / K2 launch of the

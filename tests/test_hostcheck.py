@@ -133,3 +133,31 @@ def test_n2_row_logic_on_cpu_matches_reference_annotation(case, want):
         rp = ((not right) if s == 1 else bool(right)) != (s == 1)
         got = [v, afs, ann["rc_text"][i].tobytes().decode("ascii"), rp, str(int(ann["gc_num"][i]) / int(ann["gc_den"][i]))]
         assert got == want[k], f"guide {k}"
+
+
+def test_lean_pack_equals_pack_on_every_byte():
+    """pack_chunk_lean (the fused kernel's K1) vs pack_chunk: all 256 byte values in every lane
+    position, random mixes of IUPAC letters / NUL / junk."""
+    import ctypes as C
+
+    import numpy as np
+
+    from tests import hostcheck
+
+    lib = hostcheck.lib()
+    lib.hawkcheck_pack_lean_diff.restype = C.c_int64
+    rng = np.random.default_rng(5)
+    letters = np.frombuffer(b"ACGTRYSWKMBDHVNacgtryswkmbdhvn", np.uint8)
+    parts = []
+    for lane in range(32):  # every byte value at every position of an otherwise valid chunk
+        blk = letters[rng.integers(0, len(letters), (256, 32))]
+        blk[:, lane] = np.arange(256)
+        parts.append(blk)
+    parts.append(letters[rng.integers(0, len(letters), (4096, 32))])
+    mix = letters[rng.integers(0, len(letters), (4096, 32))]
+    mix[rng.random(mix.shape) < 0.2] = 0
+    parts.append(mix)
+    parts.append(rng.integers(0, 256, (4096, 32)).astype(np.uint8))
+    parts.append(np.zeros((4, 32), np.uint8))
+    buf = np.ascontiguousarray(np.concatenate(parts).reshape(-1))
+    assert lib.hawkcheck_pack_lean_diff(buf.ctypes.data_as(C.c_void_p), C.c_int64(len(buf) // 32)) == 0
