@@ -973,6 +973,112 @@ static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const Bat
   return HAWK_OK;
 }
 
+// unphased pipeline downstream of the scan (resolve_kernels.cu): two passes over the hits, one
+// host round trip (row total + error flag) between them
+static int search_unphased(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const BatchView& B, ScanOut& so, int32_t ref_h,
+                           hawk_result* r) {
+  cudaStream_t st = c->stream;
+  Trace tr;
+  const int64_t n_hits[2] = {so.n[0], so.n[1]};
+  const uint64_t* recs[2] = {so.hits[0].as<uint64_t>(), so.hits[1].as<uint64_t>()};
+  RefInfo ref{ref_h, 1, 0, 0};
+  DevBuf d_refrange, d_refbm[2], start[2], stop[2], cnt[2], rpivot[2], blk_sum[2], blk_base[2], d_tot, d_kb;
+  CK(d_refrange.alloc(c, 32, true));
+  CK(launch_ref_range(st, recs[0], n_hits[0], recs[1], n_hits[1], ref_h, d_refrange.as<int64_t>()));
+  size_t bm_words = 1;
+  if (ref_h >= 0) {
+    ref.g0 = b->first_gen[ref_h];
+    ref.len = b->len[ref_h];
+    bm_words = (size_t)(ref.len + 31) / 32 + 1;
+  }
+  for (int s = 0; s < 2; ++s) CK(d_refbm[s].alloc(c, bm_words * 4, true));
+  if (ref_h >= 0)
+    CK(launch_ref_bitmap(st, recs[0], recs[1], d_refrange.as<int64_t>(), d_refbm[0].as<uint32_t>(), d_refbm[1].as<uint32_t>()));
+  int64_t n_blk[2];
+  CK(d_tot.alloc(c, 32, true));  // [0..1] kept rows per strand, [2] error code
+  for (int s = 0; s < 2; ++s) {
+    n_blk[s] = resolve_blocks(n_hits[s]);
+    CK(start[s].alloc(c, (size_t)n_hits[s] * 4));
+    CK(stop[s].alloc(c, (size_t)n_hits[s] * 4));
+    CK(cnt[s].alloc(c, (size_t)n_hits[s] * 4));
+    CK(rpivot[s].alloc(c, (size_t)n_hits[s] * 4));
+    CK(blk_sum[s].alloc(c, (size_t)(n_blk[s] + 1) * 8));
+    CK(blk_base[s].alloc(c, (size_t)(n_blk[s] + 1) * 8));
+  }
+  const uint32_t* bm[2] = {d_refbm[0].as<uint32_t>(), d_refbm[1].as<uint32_t>()};
+  int32_t* st_[2] = {start[0].as<int32_t>(), start[1].as<int32_t>()};
+  int32_t* sp_[2] = {stop[0].as<int32_t>(), stop[1].as<int32_t>()};
+  uint32_t* cn_[2] = {cnt[0].as<uint32_t>(), cnt[1].as<uint32_t>()};
+  int32_t* rp_[2] = {rpivot[0].as<int32_t>(), rpivot[1].as<int32_t>()};
+  uint64_t* bs_[2] = {blk_sum[0].as<uint64_t>(), blk_sum[1].as<uint64_t>()};
+  uint64_t* bb_[2] = {blk_base[0].as<uint64_t>(), blk_base[1].as<uint64_t>()};
+  CK(launch_resolve_count(st, B, K, recs, n_hits, ref, bm, st_, sp_, cn_, rp_, bs_, (int*)(d_tot.as<uint64_t>() + 2)));
+  {
+    const uint64_t* in_[2] = {bs_[0], bs_[1]};
+    CK(launch_blk_prefix64(st, in_, n_blk, bb_, d_tot.as<uint64_t>()));
+  }
+  uint64_t tot[4] = {0, 0, 0, 0};
+  CK(c->small_d2h_sync(tot, d_tot.p, 32));
+  tr.tick("resolve: count + sync");
+  const int err = (int)(int32_t)(uint32_t)tot[2];
+  if (err == HAWK_EALLELES)
+    return hawk_fail(HAWK_EALLELES, "ambiguity code inside a guide window has no variant_alleles entry");
+  if (err == HAWK_ECAPACITY)
+    return hawk_fail(HAWK_ECAPACITY, "resolve_guide expansion of one hit exceeds %llu strings", (unsigned long long)HAWK_MAX_EXPANSION);
+  const int64_t n = (int64_t)(tot[0] + tot[1]);
+  if (n >= 0xFFFFFFFFll) return hawk_fail(HAWK_ECAPACITY, "unphased search: more than 2^32 guide rows");
+  const int W = K.C + 2 * HAWK_GUIDESEQPAD;
+  r->n_guides = n;
+  r->text_stride = (W + 15) / 16 * 16;
+  CK(r->hap.alloc(c, (size_t)n * 4));
+  CK(r->strand.alloc(c, (size_t)n));
+  CK(r->pos.alloc(c, (size_t)n * 4));
+  CK(r->start.alloc(c, (size_t)n * 4));
+  CK(r->stop.alloc(c, (size_t)n * 4));
+  CK(r->bucket.alloc(c, (size_t)n * 8));
+  CK(r->text.alloc(c, (size_t)n * r->text_stride));
+  if (n > 0) {
+    CK(d_kb.alloc(c, (size_t)(b->n_hap + 1) * 16));
+    const uint32_t* cc_[2] = {cn_[0], cn_[1]};
+    const uint64_t* cb_[2] = {bb_[0], bb_[1]};
+    CK(launch_hap_offsets_cnt(st, recs, n_hits, cc_, cb_, d_tot.as<uint64_t>(), b->n_hap, d_kb.as<uint64_t>()));
+    const int64_t key_span = b->gmax >= b->gmin ? ((int64_t)b->gmax - b->gmin + 1) * 2 : 0;
+    const bool direct = key_span > 0 && key_span <= HAWK_DIRECT_KEY_SPAN;
+    DevBuf key_table;
+    if (direct) {
+      CK(key_table.alloc(c, (size_t)key_span * 4));
+      CKCUDA(cudaMemsetAsync(key_table.p, 0xFF, (size_t)key_span * 4, st));
+    }
+    const int32_t* cs_[2] = {st_[0], st_[1]};
+    const int32_t* ce_[2] = {sp_[0], sp_[1]};
+    const int32_t* cr_[2] = {rp_[0], rp_[1]};
+    const uint64_t* kb_[2] = {d_kb.as<uint64_t>() + (size_t)(b->n_hap + 1), d_kb.as<uint64_t>()};
+    CK(launch_resolve_write(st, B, K, recs, n_hits, cs_, ce_, cc_, cr_, cb_, kb_, ref_h, r->text_stride,
+                            r->hap.as<int32_t>(), r->strand.as<uint8_t>(), r->pos.as<int32_t>(), r->start.as<int32_t>(),
+                            r->stop.as<int32_t>(), r->text.as<uint8_t>(), direct ? key_table.as<uint32_t>() : nullptr, b->gmin));
+    if (direct) {
+      CK(launch_bucket_read(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n, d_tot.as<uint64_t>(),
+                            key_table.as<uint32_t>(), b->gmin, r->bucket.as<int64_t>()));
+    } else {
+      uint64_t tsize = 1024;
+      while (tsize < (uint64_t)n * 2) tsize <<= 1;
+      DevBuf keys, vals;
+      CK(keys.alloc(c, tsize * 8));
+      CK(vals.alloc(c, tsize * 8));
+      CKCUDA(cudaMemsetAsync(keys.p, 0xFF, tsize * 8, st));
+      CKCUDA(cudaMemsetAsync(vals.p, 0xFF, tsize * 8, st));
+      CK(launch_buckets(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n, keys.as<unsigned long long>(),
+                        vals.as<unsigned long long>(), tsize, r->bucket.as<int64_t>()));
+    }
+    c->close_mark();
+    CKCUDA(cudaStreamSynchronize(st));  // the temporaries above are released on return
+  } else {
+    c->close_mark();
+  }
+  tr.tick("resolve: write + sync");
+  return HAWK_OK;
+}
+
 extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params,
                            const int32_t* scan_start, const int32_t* scan_stop,
                            const uint8_t* is_ref, hawk_result** out) {
@@ -1049,6 +1155,17 @@ int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, cons
       if ((rc = search_fast(c, b, K, B, so, ref_h, link, r))) break;
       r->params = *params;
       r->is_table = true;
+      for (int s = 0; s < 2; ++s) {
+        r->n_hits[s] = n_hits[s];
+        r->hits[s].move_from(so.hits[s]);
+      }
+      break;
+    }
+    // windows of the scan's fast form (<= 80 characters) and a REF whose coordinates are linear
+    // (always, for an unphased cohort) take the two-pass pipeline over the hit stream
+    static const bool old_unphased = getenv("HAWK_OLD_UNPHASED") != nullptr;
+    if (!old_unphased && K.small && W <= 80 && (ref_h < 0 || b->linear[ref_h])) {
+      if ((rc = search_unphased(c, b, K, B, so, ref_h, r))) break;
       for (int s = 0; s < 2; ++s) {
         r->n_hits[s] = n_hits[s];
         r->hits[s].move_from(so.hits[s]);

@@ -106,6 +106,23 @@ int launch_fused_expand(cudaStream_t st, const void* entries, const uint64_t* se
 // scan2_kernels.cu: per-haplotype scan geometry
 int launch_hapscan(cudaStream_t st, const BatchView& B, const ScanConst& K, HapScan* hs);
 
+// resolve_kernels.cu: unphased guide-table pipeline over the hit stream
+int64_t resolve_blocks(int64_t n);
+int launch_resolve_count(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* const recs[2],
+                         const int64_t n[2], const RefInfo& ref, const uint32_t* const ref_bm[2], int32_t* const start[2],
+                         int32_t* const stop[2], uint32_t* const cnt[2], int32_t* const rpivot[2],
+                         uint64_t* const blk_sum[2], int* err);
+int launch_blk_prefix64(cudaStream_t st, const uint64_t* const sum[2], const int64_t n_blk[2], uint64_t* const base[2],
+                        uint64_t* totals);
+int launch_hap_offsets_cnt(cudaStream_t st, const uint64_t* const recs[2], const int64_t n[2], const uint32_t* const cnt[2],
+                           const uint64_t* const base[2], const uint64_t* totals, int32_t n_hap, uint64_t* kb);
+int launch_resolve_write(cudaStream_t st, const BatchView& B, const ScanConst& K, const uint64_t* const recs[2],
+                         const int64_t n[2], const int32_t* const start[2], const int32_t* const stop[2],
+                         const uint32_t* const cnt[2], const int32_t* const rpivot[2], const uint64_t* const blk_base[2],
+                         const uint64_t* const kb_other[2], int32_t ref_h, int32_t text_stride, int32_t* o_hap,
+                         uint8_t* o_strand, int32_t* o_pos, int32_t* o_start, int32_t* o_stop, uint8_t* o_text,
+                         uint32_t* key_table, int32_t key_min);
+
 // synth_kernels.cu: edit lists -> lengths, output positions, posmap segments (two passes)
 int launch_derive(cudaStream_t st, int32_t n_hap, const int64_t* edit_off, const int32_t* pos, const int32_t* reflen,
                   const int32_t* altlen, const int64_t* altoff, int64_t ref_len, int64_t alt_pool_len,
