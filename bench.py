@@ -404,13 +404,21 @@ def run_product_arm(args, rank, world, local_rank):
     profiled = args.workload == "c2" and args.scale == 1.0 and not args.haplotypes
     traffic = lambda k: TRAFFIC.get(k) if profiled else None  # noqa: E731
     gbs = lambda nbytes, ms: nbytes / ms / 1e6 if ms and nbytes else None  # noqa: E731
-    kernels["pack_kernel"] = {"ms": pack_ms, "algorithmic_bytes": pack_bytes, "gbs": gbs(pack_bytes, pack_ms),
-                              "dram_traffic": traffic("pack_kernel"), "launches_per_step": 1}  # fmt: skip
+    fused = wl.fused_auto()
+    k1_name = "fused_scan_kernel" if fused else "pack_kernel"
+    if fused:
+        # K1 + K2 in one kernel: 1 B/slot of text read, planes written where later stages read them
+        # (an unphased cohort is dense in variant bases: all of them), 16 B per chunk with a hit
+        pack_bytes += 16.0 * hits_total / 2
+    kernels["pack_kernel"] = {"name": k1_name, "ms": pack_ms, "algorithmic_bytes": pack_bytes, "gbs": gbs(pack_bytes, pack_ms),
+                              "dram_traffic": traffic(k1_name), "launches_per_step": 1}  # fmt: skip
     kernels["scan_k2_total"] = {
         "ms": scan_ms, "algorithmic_bytes": scan_bytes, "gbs": gbs(scan_bytes, scan_ms),
-        "note": "all K2 kernels (hapscan, block table, cand_count, match_kernel, expand_kernel, prefix sums); "
-                "algorithmic bytes by the SURVEY 8(d) formula, which still charges the whole 0.125 B/bp case plane "
-                "although the nz summary lets K2 skip it",
+        "note": ("fused path: the PAM match runs inside fused_scan_kernel (see pack_kernel); this entry is the segment "
+                 "bookkeeping + fused_expand_kernel only" if fused else
+                 "all K2 kernels (hapscan, block table, cand_count, match_kernel, expand_kernel, prefix sums); "
+                 "algorithmic bytes by the SURVEY 8(d) formula, which still charges the whole 0.125 B/bp case plane "
+                 "although the nz summary lets K2 skip it"),
     }  # fmt: skip
     kernels["match_kernel"] = {"ms": match_ms, "dram_traffic": traffic("match_kernel"),
                                "dram_gbs": gbs(traffic("match_kernel"), match_ms),
@@ -426,7 +434,7 @@ def run_product_arm(args, rank, world, local_rank):
     dom = max((("pack_kernel", pack_ms), ("scan_k2_total", scan_ms), ("table_pipeline", post_ms)), key=lambda t: t[1])[0]
     ach = kernels[dom]["gbs"] or 0.0
     roofline = {
-        "kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        "kernel": kernels[dom].get("name", dom), "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
         "traffic": traffic(dom), "traffic_source": "profiles/traffic.json (ncu --set full capture of this workload)" if traffic(dom) else None,
         "peak_source": peak_src,
         "scan_kernel_frac": (kernels["scan_k2_total"]["gbs"] or 0.0) / peak,
@@ -489,35 +497,90 @@ def run_product_arm(args, rank, world, local_rank):
         n1b_ms, _ = timed(wl.step_edits_twocall, max(1, e2e_steps - 1))
         e2e["from_edit_lists"]["two_calls_no_overlap_ms"] = n1b_ms
 
-    # ---- final merge (N > 1): per-rank tables gathered to rank 0 over NCCL, rows resident in HBM ----
-    final_merge = None
-    if world > 1 and not args.no_e2e and not unphased:
+    # ---- final merge (N > 1): every rank pushes its rows into rank 0's buffer over NVLink ----
+    def measure_merge(w, result, hap_add, with_text):
+        """Three merges (the first one warms the IPC mapping); best of the other two."""
         from crispr_hawk_b200 import shard
 
-        wl.prepare_resident()
-        res = wl.step_resident()
         dev = f"cuda:{local_rank}"
-        key_min, key_span = cohort.region_start, cohort.region_stop - cohort.region_start + 1
-        m_ms = []
-        for _ in range(3):  # first pass warms NCCL's point-to-point channels
+        key_min, key_span = w.cohort.region_start, w.cohort.region_stop - w.cohort.region_start + 1
+        m_ms, out = [], None
+        session = shard.MergeSession(ctx, rank, world, dev)
+        for _ in range(3):  # the first merge sets the session up (allocation + CUDA IPC mapping, ~40 ms once)
             barrier()
             t0 = time.perf_counter()
-            merged = shard.merge_tables_device(res, ctx, rank * n_alt, rank, world, dev, key_min, key_span)
+            merged = shard.merge_tables_device(result, ctx, hap_add, rank, world, dev, key_min, key_span,
+                                               with_text=with_text, session=session)
             barrier()
             m_ms.append(1e3 * (time.perf_counter() - t0))
+            if rank == 0:
+                out = {"rows": int(merged["hap"].shape[0]), "received_bytes": int(merged.received_bytes),
+                       "first_merge_ms_with_session_setup": m_ms[0]}
+            del merged
+        session.close()
+        if rank != 0:
+            return None
+        best = min(m_ms[1:])
+        out.update(ms=best, gbs=out["received_bytes"] / (best / 1e3) / 1e9, with_text=with_text)
+        return out
+
+    final_merge = None
+    if world > 1 and not args.no_e2e and not unphased:
+        wl.prepare_resident()
+        res = wl.step_resident()
+        full = measure_merge(wl, res, rank * n_alt, True)
+        slim = measure_merge(wl, res, rank * n_alt, False)
         if rank == 0:
-            rows = int(merged["hap"].shape[0])
-            recv = (rows - res.n_guides) * (17 + res.text_stride)
-            final_merge = {"ms": min(m_ms[1:]), "rows": rows, "received_bytes": int(recv),
-                           "gbs": recv / (min(m_ms[1:]) / 1e3) / 1e9,
-                           "what": "ranks > 0 send their guide rows (REF rows dropped) to rank 0 with NCCL send/recv over "
-                                   "NVLink, tables resident in device memory on both ends; rank 0 recomputes the first-seen "
-                                   "bucket ids on the device (hawk_first_seen_dev). Outside the timed step: nothing "
-                                   "downstream consumes the merged table at this rate"}  # fmt: skip
-        del merged
+            final_merge = dict(full)
+            final_merge["rows_only"] = slim
+            final_merge["what"] = (
+                "one-sided push over NVLink: rank 0 owns ONE buffer for the merged table (CUDA IPC), every other rank "
+                "writes its guide rows (REF rows dropped, haplotype indices shifted) straight into its slice, all ranks "
+                "at once (hawk_result_push); rank 0 then computes the first-seen bucket ids in place "
+                "(hawk_first_seen_dev). rows_only: the same without the window text (17 B per row; the host that owns "
+                "the haplotype texts slices it). Outside the timed step")
         res.close()
         wl.batch.close()
         wl.batch = None
+
+    # ---- the chromosome-scale configuration (BASELINE config 5) on the same ranks: one 626-haplotype
+    # block of a 50 Mb region per GPU (N x 31.3 G haplotype-bp per step), steps + the merge ----
+    c5 = None
+    if world > 1 and not args.no_e2e and not args.no_c5 and args.workload == "c2" and args.scale == 1.0:
+        del wl
+        torch.cuda.empty_cache()
+        k5 = synth.CONFIGS["c5shard"]
+        cohort5 = synth.config_cohort("c5shard", 1.0, hap_block=rank)
+        wl5 = Workload(cohort5, k5["pam"], k5["guidelen"], k5["right"], ctx, local_rank)
+        wl5.prepare_resident()
+        for _ in range(2):
+            wl5.step_resident().close()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n5 = 5
+        e0.record(stream)
+        for _ in range(n5):
+            r5 = wl5.step_resident()
+            g5 = r5.n_guides
+            r5.close()
+        e1.record(stream)
+        barrier()
+        t5 = torch.tensor([e0.elapsed_time(e1) / n5], dtype=torch.float64, device=f"cuda:{local_rank}")
+        b5 = torch.tensor([wl5.scanned_bp, g5], dtype=torch.int64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        dist.all_reduce(b5)
+        r5 = wl5.step_resident()
+        wl5.ascii_dev = None  # the texts are not needed for the merge: make room for the merged table
+        torch.cuda.empty_cache()
+        m5 = measure_merge(wl5, r5, rank * k5["n_alt_hap"], False)
+        r5.close()
+        if rank == 0:
+            ms5 = float(t5.item())
+            c5 = {"workload": f"c5: NGG / 20 nt, 50,000,000 bp region, {k5['n_alt_hap'] + 1} haplotypes per rank "
+                              f"({world * k5['n_alt_hap']} + REF over the job)",
+                  "scanned_bp_per_step": int(b5[0].item()), "guides_per_step": int(b5[1].item()), "ms_per_step": ms5,
+                  "value": int(b5[0].item()) / (ms5 / 1e3), "unit": UNIT, "steps": n5, "final_merge_rows_only": m5}  # fmt: skip
+        wl = wl5
 
     # ---- next rows of the scope table on the same workload (rank 0, N = 1 only) ----
     next_rows = None
@@ -573,7 +636,7 @@ def run_product_arm(args, rank, world, local_rank):
             "guides_per_step": total_guides, "hits_per_step_rank0": hits_total,
             "job_guides_in_timed_region": int(job_counts[0].item()),
             "device_ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "final_merge": final_merge, "next_rows": next_rows,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "final_merge": final_merge, "c5": c5, "next_rows": next_rows,
             "gpu_launches": int(launches), "clocks": clocks, "profile_steps": prof_steps,
         }  # fmt: skip
         emit(line)
@@ -605,15 +668,18 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="N > 1: skip the chromosome-scale (config 5) block")
     ap.add_argument("--no-clocks", action="store_true", help="do not run nvidia-smi beside the timed region")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        # the CPU arm builds and loads the checker only: libhawkscan.so is never opened here
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+        return run_reference_arm(args, rank, world)
     import __graft_entry__ as entry
 
     entry.build()  # every rank: serialised by a file lock, a no-op when the libraries are up to date
-    if args.impl == "reference":
-        return run_reference_arm(args, rank, world)
     return run_product_arm(args, rank, world, local_rank)
 
 

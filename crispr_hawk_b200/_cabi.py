@@ -56,7 +56,7 @@ class HawkTableOut(C.Structure):
         ("pos", C.POINTER(C.c_int32)),
         ("start", C.POINTER(C.c_int32)),
         ("stop", C.POINTER(C.c_int32)),
-        ("bucket", C.POINTER(C.c_int64)),
+        ("bucket", C.POINTER(C.c_uint32)),
         ("text", C.POINTER(C.c_uint8)),
         ("capacity", C.c_int64),
         ("text_stride", C.c_int32),
@@ -96,6 +96,7 @@ SIGNATURES = {
     "hawk_ctx_stream": (C.c_void_p, [_P]),
     "hawk_ctx_set_profiling": (C.c_int, [_P, C.c_int32]),
     "hawk_ctx_set_fused": (C.c_int, [_P, C.c_int32]),
+    "hawk_ctx_sync": (C.c_int, [_P]),
     "hawk_ctx_profile": (C.c_int, [_P, C.POINTER(C.c_double), _I64P]),
     "hawk_materialize_dev": (
         C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P],
@@ -108,10 +109,16 @@ SIGNATURES = {
     "hawk_pam_search": (C.c_int, [_P, _P, C.POINTER(HawkParams), _I32P, _I32P, C.POINTER(_P)]),
     "hawk_result_destroy": (C.c_int, [_P]),
     "hawk_result_info": (C.c_int, [_P, _I64P, _I64P, _I32P, _I32P, _I64P]),
-    "hawk_result_fetch": (C.c_int, [_P, _I32P, _U8P, _I32P, _I32P, _I32P, _I64P, _U8P]),
+    "hawk_result_fetch": (C.c_int, [_P, _I32P, _U8P, _I32P, _I32P, _I32P, _U32P, _U8P]),
     "hawk_result_fetch_hits": (C.c_int, [_P, C.c_int32, _U64P]),
     "hawk_result_device_columns": (C.c_int, [_P, C.POINTER(_P)]),
     "hawk_first_seen_dev": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P]),
+    "hawk_merge_layout": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _I64P, _I64P]),
+    "hawk_peer_alloc": (C.c_int, [_P, C.c_int64, C.POINTER(_P), _U8P]),
+    "hawk_peer_free": (C.c_int, [_P, _P]),
+    "hawk_peer_open": (C.c_int, [_P, _U8P, C.POINTER(_P)]),
+    "hawk_peer_close": (C.c_int, [_P, _P]),
+    "hawk_result_push": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, C.c_int64, C.c_int32, _I64P]),
     "hawk_pack_dev": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P]),
     "hawk_scan_plan": (C.c_int64, [_I32P, _I32P, C.c_int32, _I64P]),
     "hawk_scan_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
@@ -410,13 +417,13 @@ class Result:
             out = {
                 "hap": np.empty(n, np.int32), "strand": np.empty(n, np.uint8), "pos": np.empty(n, np.int32),
                 "start": np.empty(n, np.int32), "stop": np.empty(n, np.int32),
-                "bucket": np.empty(n, np.int64), "text": np.empty((n, ts), np.uint8),
+                "bucket": np.empty(n, np.uint32), "text": np.empty((n, ts), np.uint8),
             }  # fmt: skip
         check(
             self.lib.hawk_result_fetch(
                 self.handle, ptr(out["hap"], C.c_int32), ptr(out["strand"], C.c_uint8),
                 ptr(out["pos"], C.c_int32), ptr(out["start"], C.c_int32), ptr(out["stop"], C.c_int32),
-                ptr(out["bucket"], C.c_int64), ptr(out["text"], C.c_uint8),
+                ptr(out["bucket"], C.c_uint32), ptr(out["text"], C.c_uint8),
             ),  # fmt: skip
             "hawk_result_fetch",
         )
@@ -519,7 +526,7 @@ def pam_search(ctx: Context, batch: Batch, params: HawkParams, scan_start, scan_
 
 # --------------------------------------------------------------------------- streamed search
 TABLE_COLUMNS = (("hap", np.int32), ("strand", np.uint8), ("pos", np.int32), ("start", np.int32),
-                 ("stop", np.int32), ("bucket", np.int64))  # fmt: skip
+                 ("stop", np.int32), ("bucket", np.uint32))  # fmt: skip
 
 
 def text_stride(params: HawkParams) -> int:
@@ -533,8 +540,8 @@ def alloc_table(capacity: int, stride: int, pinned: bool = False):
         import torch
 
         mk = lambda dt, k=1: torch.empty(max(capacity * k, 1), dtype=dt, pin_memory=True).numpy()  # noqa: E731
-        tdt = {np.int32: torch.int32, np.uint8: torch.uint8, np.int64: torch.int64}
-        out = {name: mk(tdt[dt]) for name, dt in TABLE_COLUMNS}
+        tdt = {np.int32: torch.int32, np.uint8: torch.uint8, np.int64: torch.int64, np.uint32: torch.int32}
+        out = {name: mk(tdt[dt]).view(dt) for name, dt in TABLE_COLUMNS}
         out["text"] = mk(torch.uint8, stride)
     else:
         out = {name: np.empty(max(capacity, 1), dt) for name, dt in TABLE_COLUMNS}
@@ -548,7 +555,7 @@ def _table_out(buffers, stride: int) -> HawkTableOut:
     cap = min(cap, len(buffers["text"].reshape(-1)) // stride)
     t.hap, t.strand, t.pos = ptr(buffers["hap"], C.c_int32), ptr(buffers["strand"], C.c_uint8), ptr(buffers["pos"], C.c_int32)
     t.start, t.stop = ptr(buffers["start"], C.c_int32), ptr(buffers["stop"], C.c_int32)
-    t.bucket, t.text = ptr(buffers["bucket"], C.c_int64), ptr(buffers["text"].reshape(-1), C.c_uint8)
+    t.bucket, t.text = ptr(buffers["bucket"], C.c_uint32), ptr(buffers["text"].reshape(-1), C.c_uint8)
     t.capacity, t.text_stride = cap, stride
     return t
 

@@ -457,6 +457,13 @@ extern "C" int hawk_encode_search_dev(hawk_ctx* c, hawk_batch* b, const uint8_t*
 
 extern "C" void* hawk_ctx_stream(hawk_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
+extern "C" int hawk_ctx_sync(hawk_ctx* c) {
+  if (!c) return hawk_fail(HAWK_EINVAL, "hawk_ctx_sync: null context");
+  CKCUDA(cudaSetDevice(c->device));
+  CKCUDA(cudaStreamSynchronize(c->stream));
+  return HAWK_OK;
+}
+
 extern "C" int hawk_ctx_set_fused(hawk_ctx* c, int32_t mode) {
   if (!c || mode < 0 || mode > 2) return hawk_fail(HAWK_EINVAL, "hawk_ctx_set_fused: mode must be 0, 1 or 2");
   c->fused_mode = mode;
@@ -904,7 +911,7 @@ static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const Bat
   CK(r->pos.alloc(c, (size_t)n_max * 4));
   CK(r->start.alloc(c, (size_t)n_max * 4));
   CK(r->stop.alloc(c, (size_t)n_max * 4));
-  CK(r->bucket.alloc(c, (size_t)n_max * 8));
+  CK(r->bucket.alloc(c, (size_t)n_max * 4));
   CK(r->text.alloc(c, (size_t)n_max * r->text_stride));
   uint64_t kept[2] = {0, 0};
   if (n_max > 0) {
@@ -943,7 +950,7 @@ static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const Bat
     }
     if (direct)
       CK(launch_bucket_read(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n_max, d_tot.as<uint64_t>(),
-                            key_table, key_min, r->bucket.as<int64_t>()));
+                            key_table, key_min, r->bucket.as<uint32_t>()));
     c->close_mark();
     if (link) {
       int64_t rr[4];
@@ -964,7 +971,7 @@ static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const Bat
       CKCUDA(cudaMemsetAsync(keys.p, 0xFF, tsize * 8, st));
       CKCUDA(cudaMemsetAsync(vals.p, 0xFF, tsize * 8, st));
       CK(launch_buckets(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n, keys.as<unsigned long long>(),
-                        vals.as<unsigned long long>(), tsize, r->bucket.as<int64_t>()));
+                        vals.as<unsigned long long>(), tsize, r->bucket.as<uint32_t>()));
       CKCUDA(cudaStreamSynchronize(st));  // keys / vals are released on return
     }
   } else {
@@ -1035,7 +1042,7 @@ static int search_unphased(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const
   CK(r->pos.alloc(c, (size_t)n * 4));
   CK(r->start.alloc(c, (size_t)n * 4));
   CK(r->stop.alloc(c, (size_t)n * 4));
-  CK(r->bucket.alloc(c, (size_t)n * 8));
+  CK(r->bucket.alloc(c, (size_t)n * 4));
   CK(r->text.alloc(c, (size_t)n * r->text_stride));
   if (n > 0) {
     CK(d_kb.alloc(c, (size_t)(b->n_hap + 1) * 16));
@@ -1058,7 +1065,7 @@ static int search_unphased(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const
                             r->stop.as<int32_t>(), r->text.as<uint8_t>(), direct ? key_table.as<uint32_t>() : nullptr, b->gmin));
     if (direct) {
       CK(launch_bucket_read(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n, d_tot.as<uint64_t>(),
-                            key_table.as<uint32_t>(), b->gmin, r->bucket.as<int64_t>()));
+                            key_table.as<uint32_t>(), b->gmin, r->bucket.as<uint32_t>()));
     } else {
       uint64_t tsize = 1024;
       while (tsize < (uint64_t)n * 2) tsize <<= 1;
@@ -1068,7 +1075,7 @@ static int search_unphased(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const
       CKCUDA(cudaMemsetAsync(keys.p, 0xFF, tsize * 8, st));
       CKCUDA(cudaMemsetAsync(vals.p, 0xFF, tsize * 8, st));
       CK(launch_buckets(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n, keys.as<unsigned long long>(),
-                        vals.as<unsigned long long>(), tsize, r->bucket.as<int64_t>()));
+                        vals.as<unsigned long long>(), tsize, r->bucket.as<uint32_t>()));
     }
     c->close_mark();
     CKCUDA(cudaStreamSynchronize(st));  // the temporaries above are released on return
@@ -1257,7 +1264,11 @@ int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, cons
     if ((rc = r->pos.alloc(c, (size_t)n * 4))) break;
     if ((rc = r->start.alloc(c, (size_t)n * 4))) break;
     if ((rc = r->stop.alloc(c, (size_t)n * 4))) break;
-    if ((rc = r->bucket.alloc(c, (size_t)n * 8))) break;
+    if (n >= 0xFFFFFFFFll) {
+      rc = hawk_fail(HAWK_ECAPACITY, "search: more than 2^32 guide rows");
+      break;
+    }
+    if ((rc = r->bucket.alloc(c, (size_t)n * 4))) break;
     if ((rc = r->text.alloc(c, (size_t)n * r->text_stride))) break;
     if (n > 0) {
       GatherLaunch g;
@@ -1292,7 +1303,7 @@ int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, cons
       if ((rc = hawk_check_cuda(cudaMemsetAsync(vals.p, 0xFF, tsize * 8, st), "bucket vals memset"))) break;
       if ((rc = launch_buckets(st, r->start.as<int32_t>(), r->strand.as<uint8_t>(), n,
                                keys.as<unsigned long long>(), vals.as<unsigned long long>(), tsize,
-                               r->bucket.as<int64_t>())))
+                               r->bucket.as<uint32_t>())))
         break;
     }
     c->close_mark();
@@ -1335,20 +1346,20 @@ extern "C" int hawk_result_info(hawk_result* r, int64_t* n_guides, int64_t* n_hi
 }
 
 extern "C" int hawk_result_fetch(hawk_result* r, int32_t* hap, uint8_t* strand, int32_t* pos,
-                                 int32_t* start, int32_t* stop, int64_t* bucket, uint8_t* text) {
+                                 int32_t* start, int32_t* stop, uint32_t* bucket, uint8_t* text) {
   if (!r) return hawk_fail(HAWK_EINVAL, "hawk_result_fetch: null result");
   CKCUDA(cudaSetDevice(r->ctx->device));
   cudaStream_t st = r->ctx->stream;
   size_t n = (size_t)r->n_guides;
   if (n == 0) return HAWK_OK;
   r->ctx->d2h_bytes += (int64_t)(n * ((hap ? 4 : 0) + (strand ? 1 : 0) + (pos ? 4 : 0) + (start ? 4 : 0) + (stop ? 4 : 0) +
-                                     (bucket ? 8 : 0) + (text ? (size_t)r->text_stride : 0)));
+                                     (bucket ? 4 : 0) + (text ? (size_t)r->text_stride : 0)));
   if (hap) CKCUDA(cudaMemcpyAsync(hap, r->hap.p, n * 4, cudaMemcpyDeviceToHost, st));
   if (strand) CKCUDA(cudaMemcpyAsync(strand, r->strand.p, n, cudaMemcpyDeviceToHost, st));
   if (pos) CKCUDA(cudaMemcpyAsync(pos, r->pos.p, n * 4, cudaMemcpyDeviceToHost, st));
   if (start) CKCUDA(cudaMemcpyAsync(start, r->start.p, n * 4, cudaMemcpyDeviceToHost, st));
   if (stop) CKCUDA(cudaMemcpyAsync(stop, r->stop.p, n * 4, cudaMemcpyDeviceToHost, st));
-  if (bucket) CKCUDA(cudaMemcpyAsync(bucket, r->bucket.p, n * 8, cudaMemcpyDeviceToHost, st));
+  if (bucket) CKCUDA(cudaMemcpyAsync(bucket, r->bucket.p, n * 4, cudaMemcpyDeviceToHost, st));
   if (text) CKCUDA(cudaMemcpyAsync(text, r->text.p, n * (size_t)r->text_stride, cudaMemcpyDeviceToHost, st));
   CKCUDA(cudaStreamSynchronize(st));
   return HAWK_OK;

@@ -75,7 +75,7 @@ int launch_gather_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, 
                        int32_t text_stride, int32_t* o_hap, uint8_t* o_strand, int32_t* o_pos, int32_t* o_start,
                        int32_t* o_stop, uint8_t* o_text, uint32_t* key_table, int32_t key_min, const RowMap& rm);
 int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n_max,
-                       const uint64_t* totals, const uint32_t* key_table, int32_t key_min, int64_t* bucket);
+                       const uint64_t* totals, const uint32_t* key_table, int32_t key_min, uint32_t* bucket);
 
 // fused_kernels.cu: K1 + K2 in one pass over the texts (flat over the slot space)
 constexpr int FUSED_WARPS = 1;    // warps per CTA (one: the warp index is then provably uniform -> uniform datapath)
@@ -149,7 +149,7 @@ int launch_expand_write(cudaStream_t st, const BatchView& B, const ScanConst& K,
 int launch_gather(cudaStream_t st, const GatherLaunch& g);
 int launch_buckets(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n,
                    unsigned long long* keys, unsigned long long* vals, uint64_t table_size,
-                   int64_t* bucket);
+                   uint32_t* bucket);
 int launch_export_nibbles(cudaStream_t st, const void* q, const uint32_t* v, int64_t chunk0,
                           int32_t len, uint8_t* nib, uint8_t* lower);
 

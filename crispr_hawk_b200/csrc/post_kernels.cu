@@ -382,13 +382,13 @@ __global__ void bucket_insert_kernel(const int32_t* __restrict__ start,
 __global__ void bucket_lookup_kernel(const int32_t* __restrict__ start,
                                      const uint8_t* __restrict__ strand, int64_t n,
                                      const unsigned long long* keys, const unsigned long long* vals,
-                                     uint64_t mask, int64_t* __restrict__ bucket) {
+                                     uint64_t mask, uint32_t* __restrict__ bucket) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned long long key = ((unsigned long long)(uint32_t)start[i] << 1) | strand[i];
   uint64_t slot = mix64(key) & mask;
   while (keys[slot] != key) slot = (slot + 1) & mask;
-  bucket[i] = (int64_t)vals[slot];
+  bucket[i] = (uint32_t)vals[slot];
 }
 
 // ---------------------------------------------------------------- nibble export
@@ -471,7 +471,7 @@ int launch_gather(cudaStream_t st, const GatherLaunch& g) {
 
 int launch_buckets(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n,
                    unsigned long long* keys, unsigned long long* vals, uint64_t table_size,
-                   int64_t* bucket) {
+                   uint32_t* bucket) {
   if (n <= 0) return HAWK_OK;
   bucket_insert_kernel<<<grid_for(n, 256), 256, 0, st>>>(start, strand, n, keys, vals,
                                                          table_size - 1);

@@ -208,7 +208,7 @@ int run_groups(hawk_ctx* c, const Plan& P, const hawk_params* params, const int3
       cp(out->pos ? out->pos + base : nullptr, r->pos.p, m * 4);
       cp(out->start ? out->start + base : nullptr, r->start.p, m * 4);
       cp(out->stop ? out->stop + base : nullptr, r->stop.p, m * 4);
-      cp(out->bucket ? out->bucket + base : nullptr, r->bucket.p, m * 8);
+      cp(out->bucket ? out->bucket + base : nullptr, r->bucket.p, m * 4);
       cp(out->text ? out->text + (size_t)base * stride : nullptr, r->text.p, m * (size_t)stride);
       if ((rc = hawk_check_cuda(ce, "guide table D2H"))) {
         hawk_result_destroy(r);

@@ -276,26 +276,35 @@ __global__ void __launch_bounds__(ROW_T) gather_fast_kernel(const __grid_constan
 
 __global__ void bucket_read_kernel(const int32_t* __restrict__ start, const uint8_t* __restrict__ strand,
                                    const uint64_t* __restrict__ totals, const uint32_t* __restrict__ key_table,
-                                   int32_t key_min, int64_t* __restrict__ bucket) {
+                                   int32_t key_min, uint32_t* __restrict__ bucket) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)(totals[0] + totals[1])) return;
-  bucket[i] = (int64_t)key_table[((uint32_t)(start[i] - key_min) << 1) | strand[i]];
+  bucket[i] = key_table[((uint32_t)(start[i] - key_min) << 1) | strand[i]];
 }
 
 // first-seen table of a finished table (final merge of per-rank tables): key -> smallest row
+// a start outside [key_min, key_min + key_span) (or a strand other than 0 / 1) is reported through
+// `bad` instead of indexing the table out of bounds
 __global__ void first_seen_mark_kernel(const int32_t* __restrict__ start, const uint8_t* __restrict__ strand, int64_t n,
-                                       int32_t key_min, uint32_t* __restrict__ key_table) {
+                                       int32_t key_min, int64_t key_span, uint32_t* __restrict__ key_table,
+                                       uint32_t* __restrict__ bad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  atomicMin(&key_table[((uint32_t)(start[i] - key_min) << 1) | strand[i]], (uint32_t)i);
+  const int64_t k = (int64_t)start[i] - key_min;
+  if (k < 0 || k >= key_span || strand[i] > 1) {
+    atomicOr(bad, 1u);
+    return;
+  }
+  atomicMin(&key_table[((uint32_t)k << 1) | strand[i]], (uint32_t)i);
 }
 
 __global__ void first_seen_read_kernel(const int32_t* __restrict__ start, const uint8_t* __restrict__ strand, int64_t n,
-                                       int32_t key_min, const uint32_t* __restrict__ key_table,
-                                       int64_t* __restrict__ bucket) {
+                                       int32_t key_min, int64_t key_span, const uint32_t* __restrict__ key_table,
+                                       uint32_t* __restrict__ bucket) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  bucket[i] = (int64_t)key_table[((uint32_t)(start[i] - key_min) << 1) | strand[i]];
+  const int64_t k = (int64_t)start[i] - key_min;
+  bucket[i] = (k < 0 || k >= key_span || strand[i] > 1) ? 0xFFFFFFFFu : key_table[((uint32_t)k << 1) | strand[i]];
 }
 
 // ---------------------------------------------------------------- launch wrappers
@@ -377,7 +386,7 @@ int launch_gather_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, 
 }
 
 int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* strand, int64_t n_max,
-                       const uint64_t* totals, const uint32_t* key_table, int32_t key_min, int64_t* bucket) {
+                       const uint64_t* totals, const uint32_t* key_table, int32_t key_min, uint32_t* bucket) {
   if (n_max <= 0) return HAWK_OK;
   bucket_read_kernel<<<blocks_for(n_max, 256), 256, 0, st>>>(start, strand, totals, key_table, key_min, bucket);
   hawk_note_launch(1);
@@ -388,17 +397,30 @@ int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* str
 
 // device layer: bucket ids of a table that already sits in device memory
 extern "C" int hawk_first_seen_dev(void* stream, const int32_t* d_start, const uint8_t* d_strand, int64_t n,
-                                   int32_t key_min, int64_t key_span, uint32_t* d_key_table, int64_t* d_bucket) {
-  if (n < 0 || key_span < 0 || n >= 0xFFFFFFFFll) return hawk_fail(HAWK_EINVAL, "hawk_first_seen_dev: bad sizes");
+                                   int32_t key_min, int64_t key_span, uint32_t* d_key_table, uint32_t* d_bucket) {
+  if (n < 0 || key_span < 0 || n >= 0xFFFFFFFFll || key_span > 0x7FFFFFFFll)
+    return hawk_fail(HAWK_EINVAL, "hawk_first_seen_dev: bad sizes");
   if (n == 0) return HAWK_OK;
   if (!d_start || !d_strand || !d_key_table || !d_bucket || key_span == 0)
     return hawk_fail(HAWK_EINVAL, "hawk_first_seen_dev: null buffer");
   cudaStream_t st = (cudaStream_t)stream;
+  // the word behind the table (entry 2 * key_span) is the out-of-range flag
   cudaError_t e = cudaMemsetAsync(d_key_table, 0xFF, (size_t)key_span * 2 * 4, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_key_table + 2 * key_span, 0, 4, st);
   if (e != cudaSuccess) return hawk_check_cuda(e, "key table memset");
   const unsigned blocks = (unsigned)((n + 255) / 256);
-  hawk::first_seen_mark_kernel<<<blocks, 256, 0, st>>>(d_start, d_strand, n, key_min, d_key_table);
-  hawk::first_seen_read_kernel<<<blocks, 256, 0, st>>>(d_start, d_strand, n, key_min, d_key_table, d_bucket);
+  hawk::first_seen_mark_kernel<<<blocks, 256, 0, st>>>(d_start, d_strand, n, key_min, key_span, d_key_table,
+                                                       d_key_table + 2 * key_span);
+  hawk::first_seen_read_kernel<<<blocks, 256, 0, st>>>(d_start, d_strand, n, key_min, key_span, d_key_table, d_bucket);
   hawk_note_launch(2);
-  return hawk_check_cuda(cudaGetLastError(), "first_seen kernels launch");
+  int rc = hawk_check_cuda(cudaGetLastError(), "first_seen kernels launch");
+  if (rc != HAWK_OK) return rc;
+  uint32_t bad = 0;
+  e = cudaMemcpyAsync(&bad, d_key_table + 2 * key_span, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return hawk_check_cuda(e, "first_seen flag read");
+  if (bad)
+    return hawk_fail(HAWK_EINVAL, "hawk_first_seen_dev: a row's start lies outside [key_min, key_min + key_span) "
+                     "(or its strand is not 0 / 1)");
+  return HAWK_OK;
 }

@@ -72,7 +72,7 @@ def first_seen_buckets(start: np.ndarray, strand: np.ndarray) -> np.ndarray:
     head = np.ones(len(sk), bool)
     head[1:] = sk[1:] != sk[:-1]
     first = order[head]  # stable sort: first element of every run is the smallest index
-    bucket = np.empty(len(key), np.int64)
+    bucket = np.empty(len(key), np.uint32)
     bucket[order] = first[np.cumsum(head) - 1]
     return bucket
 
@@ -124,7 +124,7 @@ class _DevArray:
 
 
 _COLS_T = (("hap", "int32"), ("strand", "uint8"), ("pos", "int32"), ("start", "int32"), ("stop", "int32"))
-_TYPESTR = {"int32": "<i4", "uint8": "|u1"}
+_TYPESTR = {"int32": "<i4", "uint8": "|u1", "uint32": "<u4"}
 
 
 def result_tensors(res, device: str):
@@ -142,69 +142,157 @@ def result_tensors(res, device: str):
     return out
 
 
+class MergeSession:
+    """The gathering rank's buffer for merged tables, allocated once and mapped by every other
+    rank through CUDA IPC (hawk_peer_alloc / hawk_peer_open). Mapping a peer's memory costs
+    ~10 ms and freeing exported memory ~20 ms, so the buffer is kept across merges and only
+    re-made (a collective) when a merge needs more room. A merged table is a view of this
+    buffer: valid until the session's next merge or close()."""
+
+    def __init__(self, ctx, rank: int, world: int, device: str, group=None):
+        self.ctx, self.rank, self.world, self.device, self.group = ctx, rank, world, device, group
+        self.capacity, self.base = 0, None
+
+    def ensure(self, nbytes: int):
+        """Collective: afterwards every rank holds a pointer to >= nbytes of rank 0's buffer."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _cabi
+
+        if nbytes <= self.capacity:
+            return self.base
+        self.close()
+        lib = self.ctx.lib
+        want = int(nbytes * 1.25) + (1 << 20)
+        base = C.c_void_p()
+        handle = torch.zeros(64, dtype=torch.uint8)
+        if self.rank == 0:
+            hbuf = (C.c_uint8 * 64)()
+            _cabi.check(lib.hawk_peer_alloc(self.ctx.handle, want, C.byref(base), hbuf), "hawk_peer_alloc")
+            handle = torch.tensor(list(hbuf), dtype=torch.uint8)
+        if self.world > 1:
+            hdev = handle.to(self.device)
+            dist.broadcast(hdev, src=0, group=self.group)
+            handle = hdev.cpu()
+        if self.rank > 0:
+            hbuf = (C.c_uint8 * 64)(*handle.tolist())
+            _cabi.check(lib.hawk_peer_open(self.ctx.handle, hbuf, C.byref(base)), "hawk_peer_open")
+        self.base, self.capacity = base, want
+        return base
+
+    def close(self):
+        """Collective when the session holds a buffer (peers unmap before the owner frees)."""
+        if self.base is None:
+            return
+        import torch.distributed as dist
+
+        lib = self.ctx.lib
+        if self.rank > 0:
+            lib.hawk_peer_close(self.ctx.handle, self.base)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if self.rank == 0:
+            lib.hawk_peer_free(self.ctx.handle, self.base)
+        self.base, self.capacity = None, 0
+
+
+class MergedTable(dict):
+    """The merged guide table on the gathering rank: {column: torch tensor} over the session's
+    device buffer (valid until the session's next merge / close)."""
+
+    def __init__(self, session, cols):
+        super().__init__(cols)
+        self.session = session
+
+    def close(self):
+        """Drop the views; a table that made its own (temporary) session also frees the buffer."""
+        self.clear()
+        if self.session is not None and self.session.world == 1:
+            self.session.close()
+        self.session = None
+
+
+_MERGE_COLS = (("hap", "<i4", 4), ("strand", "|u1", 1), ("pos", "<i4", 4), ("start", "<i4", 4), ("stop", "<i4", 4),
+               ("bucket", "<u4", 4))  # fmt: skip
+
+
 def merge_tables_device(res, ctx, hap_offset: int, rank: int, world: int, device: str, key_min: int, key_span: int,
-                        group=None):  # fmt: skip
-    """Final merge with the tables resident on the GPUs: every rank's guide table stays in the
-    library's device memory, ranks > 0 send their rows (without the REF rows, which every rank
-    emits first and rank 0 owns) to rank 0 over NCCL (NVLink), column by column; rank 0
-    concatenates in rank order -- the reference's emission order, rank blocks being contiguous
-    haplotype ranges -- and recomputes the first-seen bucket ids on the device
-    (hawk_first_seen_dev). `hap_offset`: added to the local index of this rank's non-REF
-    haplotypes (local 0 = REF stays 0). Returns {column: torch tensor} on rank 0, None elsewhere.
-    The caller keeps `res` alive until the merge is done."""
+                        group=None, with_text: bool = True, session: Optional[MergeSession] = None):  # fmt: skip
+    """Final merge with the tables resident on the GPUs, as a one-sided push over NVLink: rank 0
+    owns ONE buffer for the merged table, mapped by every other rank (MergeSession: CUDA IPC,
+    set up once and reused); every rank writes its rows (ranks > 0 without the REF rows, which
+    every rank emits first and rank 0 owns; haplotype indices shifted by `hap_offset`) straight
+    into its slice -- all ranks at once, no receive calls (hawk_result_push). Rank blocks are
+    contiguous haplotype ranges, so the concatenation in rank order is the reference's emission
+    order; rank 0 then recomputes the first-seen bucket ids in place (hawk_first_seen_dev).
+    `with_text=False` leaves the window text behind (the host that owns the haplotype texts can
+    slice it, as search_guides.py:134-160 does). Returns a MergedTable on rank 0, None elsewhere
+    (`.session` keeps the buffer; pass it to the next merge, close() it at the end -- both
+    collectives). Every rank returns only after its own rows have landed (stream synchronised)
+    and a barrier, so `res` may be closed right away."""
     import ctypes as C
 
     import torch
     import torch.distributed as dist
 
+    from . import _cabi
+
+    lib = ctx.lib
     torch.cuda.synchronize(device)  # the table was written on the library's stream
     t = result_tensors(res, device)
     n, ts = res.n_guides, res.text_stride
     n_ref = int((t["hap"] == 0).sum().item()) if (rank > 0 and n) else 0  # REF rows: a prefix
-    lo = n_ref
     counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    mine = torch.tensor([n - lo], dtype=torch.int64, device=device)
+    mine = torch.tensor([n - n_ref], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_gather(counts, mine, group=group)
     else:
         counts = [mine]
     sizes = [int(c.item()) for c in counts]
-    if rank > 0:
-        if n - lo > 0:
-            hap = t["hap"][lo:] + int(hap_offset)
-            # plain blocking sends, one column after the other: every transfer gets the whole
-            # NVLink path to rank 0 (a batched isend/irecv group of the same columns measured
-            # 4x slower: 23 ms vs 5.3 ms for 0.95 GB between two B200s)
-            for name, _ in _COLS_T:
-                dist.send((hap if name == "hap" else t[name][lo:]).contiguous(), dst=0, group=group)
-            dist.send(t["text"][lo:].contiguous(), dst=0, group=group)
-        return None
     total = sum(sizes)
-    merged = {name: torch.empty(total, dtype=getattr(torch, dt), device=device) for name, dt in _COLS_T}
-    merged["text"] = torch.empty((total, ts), dtype=torch.uint8, device=device)
-    at = 0
-    for r in range(world):
-        m = sizes[r]
-        if r == 0:
-            for name, _ in _COLS_T:
-                merged[name][:m] = t[name]  # rank 0: local indices are global already (hap_offset 0)
-            merged["text"][:m] = t["text"]
-        elif m:
-            for name, _ in _COLS_T:
-                dist.recv(merged[name][at : at + m], src=r, group=group)
-            dist.recv(merged["text"][at : at + m], src=r, group=group)
-        at += m
-    merged["bucket"] = torch.empty(total, dtype=torch.int64, device=device)
+    at = sum(sizes[:rank])
+    off = (C.c_int64 * 7)()
+    nbytes = C.c_int64()
+    _cabi.check(lib.hawk_merge_layout(total, ts, 1 if with_text else 0, off, C.byref(nbytes)), "hawk_merge_layout")
+    temporary = session is None
+    session = session or MergeSession(ctx, rank, world, device, group)
+    base = session.ensure(nbytes.value)
+    pushed = C.c_int64()
+    _cabi.check(lib.hawk_result_push(res.handle, n_ref, int(hap_offset) if rank > 0 else 0, 0, base, total, at,
+                                     1 if with_text else 0, C.byref(pushed)), "hawk_result_push")  # fmt: skip
+    torch.cuda.synchronize(device)  # hawk_result_push runs on the library's stream
+    _cabi.check(lib.hawk_ctx_sync(ctx.handle), "hawk_ctx_sync")
+    if world > 1:
+        dist.barrier(group=group)  # every rank's rows are in rank 0's memory
+    if temporary and world > 1:
+        # no session to keep: the peers unmap now, rank 0's table owns the buffer from here on
+        if rank > 0:
+            lib.hawk_peer_close(ctx.handle, base)
+            session.base, session.capacity = None, 0
+        dist.barrier(group=group)
+        session.world = 1  # closing it later is no longer a collective
+    if rank > 0:
+        return None
+    cols = {}
+    for k, (name, typestr, width) in enumerate(_MERGE_COLS):
+        cols[name] = (torch.as_tensor(_DevArray(base.value + off[k], (total,), typestr), device=device) if total
+                      else torch.empty(0, dtype=torch.int32, device=device))  # fmt: skip
+    if with_text:
+        cols["text"] = (torch.as_tensor(_DevArray(base.value + off[6], (total, ts), "|u1"), device=device) if total
+                        else torch.empty((0, ts), dtype=torch.uint8, device=device))  # fmt: skip
+    merged = MergedTable(session, cols)
+    merged.received_bytes = (total - sizes[0]) * (17 + (ts if with_text else 0))
     if total:
-        table = torch.empty(2 * int(key_span), dtype=torch.int32, device=device)
+        if getattr(session, "_key_table", None) is None or session._key_table.numel() < 2 * int(key_span) + 1:
+            session._key_table = torch.empty(2 * int(key_span) + 1, dtype=torch.int32, device=device)
         stream = torch.cuda.current_stream(device).cuda_stream
-        from . import _cabi
-
         _cabi.check(
-            ctx.lib.hawk_first_seen_dev(C.c_void_p(stream), C.c_void_p(merged["start"].data_ptr()),
-                                        C.c_void_p(merged["strand"].data_ptr()), total, int(key_min), int(key_span),
-                                        C.c_void_p(table.data_ptr()), C.c_void_p(merged["bucket"].data_ptr())),
+            lib.hawk_first_seen_dev(C.c_void_p(stream), C.c_void_p(base.value + off[3]), C.c_void_p(base.value + off[1]),
+                                    total, int(key_min), int(key_span), C.c_void_p(session._key_table.data_ptr()),
+                                    C.c_void_p(base.value + off[5])),
             "hawk_first_seen_dev",
         )  # fmt: skip
-        torch.cuda.synchronize(device)
     return merged

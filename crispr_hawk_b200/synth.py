@@ -119,6 +119,9 @@ class Derived:
     is_ref: np.ndarray  # uint8
     variant_bases: int  # lower-case bases over all haplotypes
 
+    def n_hap_total(self) -> int:
+        return len(self.lens)
+
 
 def derive(c: Cohort) -> Derived:
     if "d" in c._derived:

@@ -164,6 +164,9 @@ class UnphasedSet:
     def n_hap(self) -> int:
         return len(self.lens)
 
+    def n_hap_total(self) -> int:
+        return len(self.lens)
+
     def take(self, idx) -> "UnphasedSet":
         """The haplotypes `idx` (any order) as a set of their own: what a search over exactly
         those haplotypes is fed (oracle subsets of a full-size run, the reference's ordering)."""

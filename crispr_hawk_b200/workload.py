@@ -52,6 +52,11 @@ class Workload:
         """1 B ASCII read + 0.5 B planes + 0.125 B case bits written per slot."""
         return 1.625 * self.d.total_slots
 
+    def fused_auto(self) -> bool:
+        """Whether hawk_encode_search_dev picks the fused K1 + K2 kernel for this workload
+        (api.cu: unphased cohorts and short haplotypes)."""
+        return bool(self.params.flags & _cabi.HAWK_F_UNPHASED) or self.d.n_hap_total() * 2048 > self.d.total_slots // 32
+
     def table_algorithmic_bytes(self, n_rows: int, n_hits: int) -> float:
         """Guide-table pipeline: rows written (25 B of columns + the padded text row), hit records
         read (8 B), window planes read per hit (0.625 B per window base)."""
@@ -342,6 +347,7 @@ class UnphasedWorkload:
         return 0.5 * self.scanned_bp + 0.125 * (self.scanned_bp - ref_bp) + 8.0 * n_hits
 
     table_algorithmic_bytes = Workload.table_algorithmic_bytes
+    fused_auto = Workload.fused_auto
 
     def oracle_subset(self, hap_indices):
         """The flat arrays of a subset of haplotypes (oracle/c_oracle.search's inputs)."""

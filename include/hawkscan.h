@@ -159,7 +159,7 @@ int hawk_result_info(hawk_result *result, int64_t *n_guides, int64_t *n_hits, in
  * window text (extract_guide_sequence / resolved string), `text_stride` bytes per
  * row of which the first `window` are the text. Any pointer may be NULL. */
 int hawk_result_fetch(hawk_result *result, int32_t *hap, uint8_t *strand, int32_t *pos,
-                      int32_t *start, int32_t *stop, int64_t *bucket, uint8_t *text);
+                      int32_t *start, int32_t *stop, uint32_t *bucket, uint8_t *text);
 /* Borrowed DEVICE addresses of the table's columns (hap, strand, pos, start, stop, bucket,
  * text; n_guides rows each, text_stride bytes per text row), valid until the result is
  * destroyed and ordered on the context's stream: lets a multi-GPU caller gather the per-rank
@@ -213,7 +213,7 @@ typedef struct hawk_table_out {
   int32_t *pos;
   int32_t *start;
   int32_t *stop;
-  int64_t *bucket;
+  uint32_t *bucket;   /* row indices: a table holds fewer than 2^32 rows */
   uint8_t *text;       /* capacity * text_stride bytes */
   int64_t capacity;    /* rows every non-NULL column can hold */
   int32_t text_stride; /* must equal hawk_table_text_stride(pam_len, guide_len) */
@@ -298,6 +298,8 @@ int hawk_ctx_set_fused(hawk_ctx *ctx, int32_t mode);
  * ms[0] = K1 pack_kernel, ms[1] = K2 candidate kernels + prefix sums, ms[2] = guide-table
  * pipeline, ms[3] = K2 expand_kernel, ms[4] = K2 match_kernel; n[i] = bracketed regions. */
 void *hawk_ctx_stream(hawk_ctx *ctx);
+/* wait for everything queued on the context's stream (the asynchronous calls of this header) */
+int hawk_ctx_sync(hawk_ctx *ctx);
 int hawk_ctx_set_profiling(hawk_ctx *ctx, int32_t enabled);
 int hawk_ctx_profile(hawk_ctx *ctx, double *ms /* [5] */, int64_t *n /* [5] */);
 
@@ -347,9 +349,34 @@ int hawk_scan_expand_dev(void *stream, int32_t n_hap, int64_t n_sblocks, int64_t
  * search_guides.py:306-337): d_bucket[i] = smallest row index sharing row i's (start, strand)
  * key. The final step of the multi-GPU merge, after the per-rank tables were concatenated in
  * rank order. Keys are direct addresses: key_span = largest start - key_min + 1;
- * d_key_table holds 2 * key_span uint32 (any content); n < 2^32. */
+ * d_key_table holds 2 * key_span + 1 uint32 (any content); n < 2^32. Synchronises the stream
+ * before returning; a start outside [key_min, key_min + key_span) returns HAWK_EINVAL (the
+ * bucket column is then undefined) instead of touching memory outside the table. */
 int hawk_first_seen_dev(void *stream, const int32_t *d_start, const uint8_t *d_strand, int64_t n,
-                        int32_t key_min, int64_t key_span, uint32_t *d_key_table, int64_t *d_bucket);
+                        int32_t key_min, int64_t key_span, uint32_t *d_key_table, uint32_t *d_bucket);
+
+/* ---- multi-GPU final merge: one-sided push over NVLink ---------------------------------------
+ * One process per GPU, rank blocks = contiguous haplotype ranges of one region, every rank with
+ * REF as its local haplotype 0 (remove_redundant_guides needs it). The merged table lives in ONE
+ * buffer owned by the gathering rank: hawk_merge_layout gives the byte offset of every column
+ * (hap i32, strand u8, pos i32, start i32, stop i32, bucket u32, text u8 x text_stride; each
+ * column padded to 256 bytes; text is optional) and the size to allocate; hawk_peer_alloc
+ * allocates it and exports a 64-byte CUDA IPC handle, which the caller ships to the other ranks
+ * by any means (bench.py: one torch.distributed broadcast); they map it with hawk_peer_open and
+ * write their rows into their slice with hawk_result_push -- rows [row_lo, n_guides) of a
+ * result (row_lo = number of leading REF rows, which the gathering rank owns) to row offset
+ * `at`, haplotype indices shifted by hap_add on the way (index hap_keep excepted) -- all peers
+ * at the same time, stores going over NVLink straight into the owner's HBM. After a barrier the
+ * owner runs hawk_first_seen_dev on its columns. hawk_result_push is asynchronous on the
+ * context's stream; hawk_peer_close synchronises it first. */
+int hawk_merge_layout(int64_t total_rows, int32_t text_stride, int32_t with_text, int64_t *off /* [7] */,
+                      int64_t *bytes);
+int hawk_peer_alloc(hawk_ctx *ctx, int64_t bytes, void **d_ptr, uint8_t *handle /* [64] */);
+int hawk_peer_free(hawk_ctx *ctx, void *d_ptr);
+int hawk_peer_open(hawk_ctx *ctx, const uint8_t *handle /* [64] */, void **d_ptr);
+int hawk_peer_close(hawk_ctx *ctx, void *d_ptr);
+int hawk_result_push(hawk_result *result, int64_t row_lo, int32_t hap_add, int32_t hap_keep, void *d_buffer,
+                     int64_t total_rows, int64_t at, int32_t with_text, int64_t *pushed_bytes);
 
 /* N1 (next row): materialise haplotype texts on the device from the reference text and
  * per-haplotype sorted, non-overlapping edit lists (haplotype.py:106-121,185-252

@@ -121,7 +121,7 @@ def test_streamed_workload_equals_resident(name, scale, n_alt):
             for col in COLS:
                 assert np.array_equal(got[col], want[col]), (step.__name__, n_groups, col)
             assert np.array_equal(got["text"], want["text"]), (step.__name__, n_groups)
-            assert d2h >= len(want["hap"]) * (25 + stride)
+            assert d2h >= len(want["hap"]) * (21 + stride)
         assert wl.last_stream.n_hits == n_hits and wl.last_stream.scanned_bp == wl.scanned_bp
     assert h2d < wl.d.total_slots // 2  # edit lists (one group): a fraction of the texts crosses PCIe
     got, h2d, d2h = wl.step_host_twocall()
@@ -150,3 +150,32 @@ def test_device_resident_merge_single_rank():
         assert np.array_equal(m[col].cpu().numpy(), want[col]), col
     assert np.array_equal(m["text"].cpu().numpy()[:, : want["text"].shape[1]], want["text"])
     res.close()
+
+
+def test_first_seen_rejects_out_of_range_start():
+    """hawk_first_seen_dev with a start outside [key_min, key_min + key_span): HAWK_EINVAL, no
+    write outside the key table (the words behind it keep their canary)."""
+    import ctypes as C
+
+    import torch
+
+    lib = _cabi.load_library()
+    dev = f"cuda:{torch.cuda.current_device()}"
+    key_min, key_span = 1000, 64
+    start = torch.tensor([1000, 1005, 1063, 1005], dtype=torch.int32, device=dev)
+    strand = torch.tensor([0, 1, 0, 1], dtype=torch.uint8, device=dev)
+    table = torch.full((2 * key_span + 1 + 64,), 0x5A5A5A5A, dtype=torch.int32, device=dev)
+    bucket = torch.zeros(4, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run(s):
+        return lib.hawk_first_seen_dev(C.c_void_p(stream), C.c_void_p(s.data_ptr()), C.c_void_p(strand.data_ptr()), 4, key_min,
+                                       key_span, C.c_void_p(table.data_ptr()), C.c_void_p(bucket.data_ptr()))  # fmt: skip
+
+    assert run(start) == _cabi.HAWK_OK
+    assert bucket.cpu().tolist() == [0, 1, 2, 1]
+    for bad in (999, 1064, 1000 + (1 << 20), -5):
+        s2 = start.clone()
+        s2[2] = bad
+        assert run(s2) == _cabi.HAWK_EINVAL
+        assert table[2 * key_span + 1 :].cpu().eq(0x5A5A5A5A).all()

@@ -50,12 +50,15 @@ res = wl.step_resident()
 key_min, key_span = cohort.region_start, cohort.region_stop - cohort.region_start + 1
 
 
+session = shard.MergeSession(ctx, rank, world, dev)
+
+
 def merge():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    m = shard.merge_tables_device(res, ctx, rank * n_alt, rank, world, dev, key_min, key_span)
+    m = shard.merge_tables_device(res, ctx, rank * n_alt, rank, world, dev, key_min, key_span, session=session)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
