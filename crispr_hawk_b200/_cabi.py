@@ -384,6 +384,11 @@ class Batch:
         )
         self.has_variants = True
 
+    def device_bytes(self) -> int:
+        """Device memory of the packed planes (0.625 B per slot + the chunk slack)."""
+        total = int(self.slot_off[-1]) if len(self.slot_off) else 0
+        return total * 5 // 8 + 1024
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.hawk_batch_destroy(self.handle)
@@ -406,10 +411,28 @@ class Result:
         self.n_guides, self.n_hits, self.window, self.scanned_bp = n.value, (hits[0], hits[1]), w.value, bp.value
         self.text_stride = ts.value or w.value
 
-    def table(self, buffers=None):
+    def device_bytes(self) -> int:
+        """Device memory the table's columns and hit lists hold (rows x 21 B + text + 8 B per hit)."""
+        rows = max(int(self.n_guides), int(self.n_hits[0] + self.n_hits[1]))  # columns are sized for every hit kept
+        return rows * (21 + self.text_stride + 8)
+
+    def table(self, buffers=None, want_text: bool = True):
         """Download the guide table. `buffers`: optional dict of preallocated (e.g. pinned)
-        1-D numpy arrays with at least n rows each; views of them are returned."""
+        1-D numpy arrays with at least n rows each; views of them are returned.
+        `want_text=False`: the window-text column stays on the device (no "text" key)."""
         n, w, ts = self.n_guides, self.window, self.text_stride
+        if not want_text:
+            out = ({k: buffers[k][:n] for k in ("hap", "strand", "pos", "start", "stop", "bucket")} if buffers is not None else
+                   {"hap": np.empty(n, np.int32), "strand": np.empty(n, np.uint8), "pos": np.empty(n, np.int32),
+                    "start": np.empty(n, np.int32), "stop": np.empty(n, np.int32), "bucket": np.empty(n, np.uint32)})  # fmt: skip
+            check(
+                self.lib.hawk_result_fetch(
+                    self.handle, ptr(out["hap"], C.c_int32), ptr(out["strand"], C.c_uint8), ptr(out["pos"], C.c_int32),
+                    ptr(out["start"], C.c_int32), ptr(out["stop"], C.c_int32), ptr(out["bucket"], C.c_uint32), None,
+                ),  # fmt: skip
+                "hawk_result_fetch",
+            )
+            return out
         if buffers is not None:
             out = {k: buffers[k][:n] for k in ("hap", "strand", "pos", "start", "stop", "bucket")}
             out["text"] = buffers["text"][: n * ts].reshape(n, ts)

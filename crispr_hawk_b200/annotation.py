@@ -101,15 +101,28 @@ def _fallback(name, *args):
     return fn(*args)
 
 
+def _stage(guides, cols, order, apply):
+    """Run one per-guide step: a lazy GuideList takes it as a stage (objects that exist are
+    updated now, the others when they are built); a plain list is walked as the reference does."""
+    if hasattr(guides, "add_stage"):
+        guides.add_stage(lambda g, k: apply(g, int(order[k])))
+    else:
+        for g, i in zip(guides, order.tolist()):
+            apply(g, i)
+    return guides
+
+
 def _annotate_variants(guides, verbosity: int, debug: bool):
     """annotation.py:284-315."""
     got = _columns(guides, debug)
     if got is None:
         return _fallback("_annotate_variants", guides, verbosity, debug)
     cols, order = got
-    for g, i in zip(guides, order.tolist()):
+
+    def apply(g, i):
         g.variants = cols["variants"][i]
-    return guides
+
+    return _stage(guides, cols, order, apply)
 
 
 def annotate_variants_afs(guides, verbosity: int):
@@ -118,9 +131,11 @@ def annotate_variants_afs(guides, verbosity: int):
     if got is None:
         return _fallback("annotate_variants_afs", guides, verbosity)
     cols, order = got
-    for g, i in zip(guides, order.tolist()):
+
+    def apply(g, i):
         g.afs_str = cols["afs_str"][i].split(",")  # the setter joins again (guide.py:311-328)
-    return guides
+
+    return _stage(guides, cols, order, apply)
 
 
 def reverse_guides(guides, verbosity: int):
@@ -129,12 +144,14 @@ def reverse_guides(guides, verbosity: int):
     if got is None:
         return _fallback("reverse_guides", guides, verbosity)
     cols, order = got
-    for g, i in zip(guides, order.tolist()):
+
+    def apply(g, i):
         if g.strand == 1:
             g._sequence = cols["sequence"][i]
             g._right = cols["right"][i]
             (getattr(g, "_compute_pamguide_sequences", None) or g._split)()  # guide.py:255
-    return guides
+
+    return _stage(guides, cols, order, apply)
 
 
 def gc_content(guides, verbosity: int, debug: bool):
@@ -143,9 +160,11 @@ def gc_content(guides, verbosity: int, debug: bool):
     if got is None:
         return _fallback("gc_content", guides, verbosity, debug)
     cols, order = got
-    for g, i in zip(guides, order.tolist()):
+
+    def apply(g, i):
         g.gc = float(cols["gc"][i])  # the setter stores str(value) (guide.py:598-618)
-    return guides
+
+    return _stage(guides, cols, order, apply)
 
 
 SEAM = ("_annotate_variants", "annotate_variants_afs", "reverse_guides", "gc_content")

@@ -96,6 +96,9 @@ def encode(sequence: str, verbosity: int, debug: bool) -> List[int]:
 
 
 def encode_region(haplotypes, verbosity: int, debug: bool) -> PackedRegion:
+    pack = getattr(haplotypes[0], "_region_pack", None) if len(haplotypes) else None
+    if pack is not None and pack.matches(haplotypes):
+        return pack  # N1: the haplotypes were materialised on the device from edit lists, packed already
     texts = [marshal.hap_text(h) for h in haplotypes]
     return PackedRegion(pack_texts(texts, debug), texts)
 

@@ -80,6 +80,9 @@ class _LazySeq:
     def __len__(self) -> int:
         return len(self._hap)
 
+    def __str__(self) -> str:  # haplotypes_table writes f"{hap.sequence}" (haplotypes.py:836-841)
+        return self._hap.text()
+
 
 class EditHaplotype:
     def __init__(self, batch: "_cabi.Batch", index: int, length: int, posmap: SegmentMap, start: int, stop: int,
@@ -182,3 +185,103 @@ def build_phased(ref_text: str, region_start: int, hap_edits: Sequence[Sequence[
     packed = PackedRegion(batch, [None] * n)
     packed.owners = [id(h) for h in haps]
     return haps, packed
+
+
+# --------------------------------------------------------------------------- drop-in seam (N1)
+# Mirror of crisprhawk.haplotypes.add_variants_phased (haplotypes.py:716-751): the reference's
+# own VariantRecord lists in, haplotypes out -- but as EditHaplotypes over ONE device batch
+# built from edit lists, instead of one host rewrite of the sequence and of two
+# len(haplotype)-entry dicts per variant (haplotype.py:106-159, 185-252). install() rebinds
+# it in `crisprhawk.haplotypes`; `add_variants` (:754-792) finds it through the module globals.
+class UnsupportedShape(Exception):
+    """The region's records do not have the shape the device builder takes; the reference's
+    own builder is used for it."""
+
+
+_reference_add_variants_phased = None  # set by install()
+
+
+def _copy_edits(variants, ref_text: str, region_start: int):
+    """One chromosome copy: `_sort_variants` order for the ids (SNPs by position, then indels by
+    position, haplotype.py:494-512), position order for the edits; REF alleles checked against
+    the reference text like haplotype.py:206-210."""
+    snps = sorted((v for v in variants if v.vtype[0] == "snp"), key=lambda v: v.position)
+    indels = sorted((v for v in variants if v.vtype[0] != "snp"), key=lambda v: v.position)
+    ordered = snps + indels
+    ids = [v.id[0] for v in ordered]
+    afs = {v.id[0]: v.afs[0] for v in ordered}
+    edits = sorted((Edit(int(v.position), v.ref, v.alt[0]) for v in ordered), key=lambda e: e.pos)
+    end = region_start + len(ref_text)
+    last_stop = -1
+    for e in edits:
+        if len(e.ref) > 1 and len(e.alt) > 1:
+            raise UnsupportedShape("complex substitution")
+        if e.pos <= last_stop:
+            raise UnsupportedShape("records overlap on one chromosome copy")
+        if e.pos < region_start or e.pos + len(e.ref) > end:
+            raise UnsupportedShape("record runs past the region")
+        i = e.pos - region_start
+        if ref_text[i : i + len(e.ref)] != e.ref:
+            raise ValueError(
+                f"Mismatching reference alleles in VCF and reference sequence "
+                f"at position {e.pos} ({ref_text[i : i + len(e.ref)]} - {e.ref})"
+            )  # haplotype.py:206-210
+        if e.ref[0].upper() != e.alt[0].upper() and (len(e.ref) > 1 or len(e.alt) > 1):
+            raise UnsupportedShape("indel without an anchor base")
+        last_stop = e.pos + len(e.ref) - 1
+    return tuple((e.pos, e.ref, e.alt) for e in edits), edits, ",".join(ids), afs
+
+
+def plan_phased(ref_text: str, region_start: int, samples: Sequence[str], variants):
+    """compute_haplotypes_phased (:143-171) + _solve_haplotypes_phased (:297-333) +
+    collapse_haplotypes (:274-294) on edit lists: returns the collapsed haplotypes as dicts
+    {edits, samples, variants, afs}, REF first, in the reference's first-seen order. Haplotype
+    copies are merged when their edit lists are equal -- the reference merges on equal
+    sequences, which differs only for un-normalised indel records spelling the same text."""
+    per_sample = {s: ([], []) for s in samples}
+    for v in variants:
+        for copy in (0, 1):
+            for smp in v.samples[0][copy]:
+                per_sample[smp][copy].append(v)
+    groups: Dict[tuple, dict] = {(): dict(edits=[], members=[], variants="NA", afs={})}
+    for smp in samples:
+        c0, c1 = per_sample[smp]
+        if not c0 and not c1:
+            continue  # samples without variants are dropped (:170)
+        built = [_copy_edits(c, ref_text, region_start) for c in (c0, c1)]
+        if built[0][0] == built[1][0]:  # ishomozygous (:228): one haplotype, S:1|1 (haplotype.py:331-354)
+            entries = [(built[0], f"{smp}:1|1")]
+        else:
+            entries = [(built[0], f"{smp}:1|0"), (built[1], f"{smp}:0|1")]
+        for (key, edits, ids, afs), label in entries:
+            g = groups.get(key)
+            if g is None:
+                g = groups[key] = dict(edits=edits, members=[], variants=ids, afs=afs)
+            g["members"].append(label)
+    out = []
+    for key, g in groups.items():
+        is_ref = key == ()
+        out.append(dict(edits=g["edits"], samples="REF" if is_ref else ",".join(dict.fromkeys(g["members"])),
+                        variants="NA" if is_ref else g["variants"], afs={} if is_ref else g["afs"]))  # fmt: skip
+    return out
+
+
+def add_variants_phased(haplotypes, region, vcfs, variants, phased: bool, debug: bool):
+    """Drop-in for crisprhawk.haplotypes.add_variants_phased (haplotypes.py:716-751)."""
+    ref_text = region.sequence.sequence
+    try:
+        if len(haplotypes) != 1 or not ref_text.isupper():
+            raise UnsupportedShape("not a single reference haplotype")
+        plan = plan_phased(ref_text, region.start, vcfs[region.contig].samples, variants)
+    except UnsupportedShape:
+        if _reference_add_variants_phased is None:
+            raise
+        return _reference_add_variants_phased(haplotypes, region, vcfs, variants, phased, debug)
+    haps, packed = build_phased(ref_text, region.start, [p["edits"] for p in plan], [p["samples"] for p in plan],
+                                [p["variants"] for p in plan], [p["afs"] for p in plan],
+                                [f"hap{i}" for i in range(len(plan))], contig=region.contig)  # fmt: skip
+    ref_afs = getattr(haplotypes[0], "afs", None)
+    if ref_afs is not None:
+        haps[0].afs = ref_afs
+    haps[0]._region_pack = packed  # crispr_hawk_b200.encoder.encode_region hands it to search()
+    return haps

@@ -12,7 +12,8 @@ from . import encoder, search_guides
 _saved = {}
 
 
-def install(module: Optional[object] = None, annotation_module: Optional[object] = None, annotation: bool = True):
+def install(module: Optional[object] = None, annotation_module: Optional[object] = None, annotation: bool = True,
+            haplotypes_module: Optional[object] = None, haplotypes: bool = True):
     """Rebind in `crisprhawk.crisprhawk` (or the given module object). Returns it.
 
     With `annotation` (N2) the four per-guide loops `annotation.annotate_guides` runs right
@@ -22,6 +23,7 @@ def install(module: Optional[object] = None, annotation_module: Optional[object]
     every other list to the reference's own functions."""
     from . import _cabi
     from . import annotation as ann
+    from . import haplotypes as hapmod
 
     _cabi.load_library()  # fail loudly now, not in the middle of a run
     drv = module or importlib.import_module("crisprhawk.crisprhawk")
@@ -40,11 +42,35 @@ def install(module: Optional[object] = None, annotation_module: Optional[object]
                 if _saved[amod][n] is not None:
                     ann._reference[n] = _saved[amod][n]
                 setattr(amod, n, getattr(ann, n))
+    if haplotypes:
+        # N1: the phased branch of haplotype assembly (haplotypes.py:716-751) builds its haplotypes
+        # on the device from edit lists; shapes it does not take go to the reference's builder
+        hmod = haplotypes_module
+        if hmod is None and module is None:
+            hmod = importlib.import_module("crisprhawk.haplotypes")
+        if hmod is not None and hmod not in _saved:
+            _saved[hmod] = {"add_variants_phased": getattr(hmod, "add_variants_phased", None)}
+            hapmod._reference_add_variants_phased = _saved[hmod]["add_variants_phased"]
+            hmod.add_variants_phased = hapmod.add_variants_phased
     return drv
 
 
-def uninstall(module: Optional[object] = None, annotation_module: Optional[object] = None) -> None:
+def uninstall(module: Optional[object] = None, annotation_module: Optional[object] = None,
+              haplotypes_module: Optional[object] = None) -> None:
     from . import annotation as ann
+    from . import haplotypes as hapmod
+
+    hmod = haplotypes_module
+    if hmod is None and module is None:
+        try:
+            hmod = importlib.import_module("crisprhawk.haplotypes")
+        except Exception:
+            hmod = None
+    if hmod is not None:
+        for name, fn in _saved.pop(hmod, {}).items():
+            if fn is not None:
+                setattr(hmod, name, fn)
+        hapmod._reference_add_variants_phased = None
 
     drv = module or importlib.import_module("crisprhawk.crisprhawk")
     for name, fn in _saved.pop(drv, {}).items():

@@ -29,15 +29,23 @@ class _LiveTables:
     before it annotates any). Bounded: beyond `cap_bytes` of table memory the oldest links are
     released -- their lists then go to the reference's own annotation functions."""
 
-    def __init__(self, cap_bytes: int = 16 << 30):
+    def __init__(self, cap_bytes=None):
         self.cap_bytes, self.total, self.links = cap_bytes, 0, []
+
+    def _cap(self) -> int:
+        if self.cap_bytes is None:  # half of the device's memory, asked once
+            try:
+                self.cap_bytes = int(_cabi.Context.default().info()["total_mem"]) // 2
+            except Exception:
+                self.cap_bytes = 16 << 30
+        return self.cap_bytes
 
     def add(self, link: dict, nbytes: int) -> None:
         self.links = [(lk, nb) for lk, nb in self.links if lk.get("res") is not None]
         self.total = sum(nb for _, nb in self.links)
         self.links.append((link, nbytes))
         self.total += nbytes
-        while self.total > self.cap_bytes and len(self.links) > 1:
+        while self.total > self._cap() and len(self.links) > 1:
             old, nb = self.links.pop(0)
             if old.get("res") is not None:
                 old["res"].close()
@@ -49,15 +57,86 @@ LIVE_TABLES = _LiveTables()
 
 
 class GuideList(list):
-    """`search()`'s return value for phased / variant-free searches: a plain list of Guide
-    objects (buckets in first-seen order) that also carries the device-resident guide table it
-    was built from (`hawk`: table columns, `_cabi.Result`, batch, haplotypes, table order), for
-    the N2 mirrors in crispr_hawk_b200.annotation. Any list operation that builds a new list
-    drops the link, which is the safe direction."""
+    """`search()`'s return value: the reference's `List[Guide]` (buckets in first-seen order,
+    search_guides.py:306-369) whose Guide objects are built on first access -- N3, the guide
+    table as the wire format. The list carries the table it came from (`hawk`: columns,
+    `_cabi.Result`, batch, haplotypes, table order) for the N2 mirrors in
+    crispr_hawk_b200.annotation, which register their columns as *stages* here instead of
+    touching every object: a Guide built later gets the stages applied at birth, one built
+    earlier is updated when a stage arrives. Indexing, slicing and iteration build only what
+    they touch; every other list operation (`+`, `sort`, `copy`, `in`, pickling ...) builds the
+    remaining objects first and then behaves like the plain list it is."""
 
-    def __init__(self, guides, hawk):
-        super().__init__(guides)
-        self.hawk = hawk
+    def __init__(self, n: int, make, hawk=None):
+        super().__init__([None] * n)
+        self._make, self._pending, self.hawk = make, n, hawk
+        self._stages = []  # [(apply(guide, final_index), ...)] in the order annotate_guides ran them
+
+    # ---- element access: build on demand ----
+    def _build(self, k: int):
+        g = self._make(k)
+        for apply in self._stages:
+            apply(g, k)
+        list.__setitem__(self, k, g)
+        self._pending -= 1
+        return g
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[j] for j in range(*k.indices(len(self)))]
+        g = list.__getitem__(self, k)
+        if g is None and self._pending:
+            g = self._build(k if k >= 0 else k + len(self))
+        return g
+
+    def __iter__(self):
+        for k in range(len(self)):
+            yield self[k]
+
+    def add_stage(self, apply) -> None:
+        """Register one of annotate_guides' per-guide steps: applied now to the guides that
+        exist, at construction to the others."""
+        if self._pending:
+            for k in range(len(self)):
+                g = list.__getitem__(self, k)
+                if g is not None:
+                    apply(g, k)
+            self._stages.append(apply)
+        else:
+            for k, g in enumerate(list.__iter__(self)):
+                apply(g, k)
+
+    def realise(self) -> "GuideList":
+        """Build every remaining Guide (afterwards this is an ordinary list)."""
+        if self._pending:
+            for k in range(len(self)):
+                if list.__getitem__(self, k) is None:
+                    self._build(k)
+            self._stages = []
+        return self
+
+    @property
+    def built(self) -> int:
+        return len(self) - self._pending
+
+
+def _realised(name):
+    base = getattr(list, name)
+
+    def method(self, *a, **kw):
+        self.realise()
+        return base(self, *a, **kw)
+
+    method.__name__ = name
+    return method
+
+
+for _name in ("__add__", "__radd__", "__iadd__", "__mul__", "__rmul__", "__imul__", "__contains__", "__reversed__", "__eq__",
+              "__ne__", "__lt__", "__le__", "__gt__", "__ge__", "__reduce_ex__", "__repr__", "__setitem__", "__delitem__", "copy", "count",
+              "index", "sort", "reverse", "pop", "remove", "insert", "append", "extend", "clear"):  # fmt: skip
+    if hasattr(list, _name):
+        setattr(GuideList, _name, _realised(_name))
+GuideList.__hash__ = None
 
 
 def _packed_for(haplotypes, haplotypes_bits, verbosity: int, debug: bool) -> PackedRegion:
@@ -101,8 +180,12 @@ def pam_search(pam, region, haplotypes, haplotypes_bits, verbosity: int, debug: 
 
 
 def search_table(pam, region, haplotypes, haplotypes_bits, guidelen: int, right: bool,
-                 variants_present: bool, phased: bool, verbosity: int = 0, debug: bool = False):  # fmt: skip
-    """Run the device pipeline and return (table dict, Result) without building Guides."""
+                 variants_present: bool, phased: bool, verbosity: int = 0, debug: bool = False,
+                 want_text: bool = True):  # fmt: skip
+    """Run the device pipeline and return (table dict, Result) without building Guides.
+    `want_text=False` leaves the window-text column on the device (48 of the 69 bytes a row
+    takes across PCIe): for a phased / variant-free search it is a slice of the haplotype text
+    the caller already holds (search_guides.py:134-160)."""
     packed = _packed_for(haplotypes, haplotypes_bits, verbosity, debug)
     batch = packed.batch
     unphased = bool(variants_present and not phased)
@@ -126,7 +209,7 @@ def search_table(pam, region, haplotypes, haplotypes_bits, guidelen: int, right:
             )  # fmt: skip
         raise
     res.batch_ref = batch  # the batch the table was computed from (kept alive with the result)
-    return res.table(), res
+    return res.table(want_text=want_text), res
 
 
 def search(pam, region, haplotypes, haplotypes_bits, guidelen: int, right: bool,
@@ -135,8 +218,10 @@ def search(pam, region, haplotypes, haplotypes_bits, guidelen: int, right: bool,
     if verbosity >= 3:
         pam_search(pam, region, haplotypes, haplotypes_bits, verbosity, debug)
     start_t = time()
+    unphased = bool(variants_present and not phased)
+    # unphased rows hold resolved strings; otherwise the text is a window of the haplotype's own
     table, res = search_table(pam, region, haplotypes, haplotypes_bits, guidelen, right,
-                              variants_present, phased, verbosity, debug)  # fmt: skip
+                              variants_present, phased, verbosity, debug, want_text=unphased)  # fmt: skip
     Guide = guide_class()
     pamlen = len(pam_patterns(pam)[0])
     span = guidelen + pamlen
@@ -144,26 +229,37 @@ def search(pam, region, haplotypes, haplotypes_bits, guidelen: int, right: bool,
     # order (:306-369): a stable sort of the emission-ordered table by bucket id
     order = np.argsort(table["bucket"], kind="stable")
     hap_i, strand, pos = table["hap"], table["strand"], table["pos"]
-    starts, stops = table["start"].tolist(), table["stop"].tolist()
-    texts = table["text"]
-    guides = []
-    for i in order.tolist():
-        h = haplotypes[hap_i[i]]
+    starts, stops = table["start"], table["stop"]
+    texts = table.get("text")
+    hap_texts = {}
+
+    def make(k: int):
+        """The k-th guide of the reference's list (guide.py:64-120 arguments, :488-503)."""
+        i = int(order[k])
+        hi = int(hap_i[i])
+        h = haplotypes[hi]
         s = int(strand[i])
+        p = int(pos[i])
         rp = (not right) if s == 1 else bool(right)  # :538
-        pivot = int(pos[i]) if rp else int(pos[i]) - guidelen
+        pivot = p if rp else p - guidelen
         pm = h.posmap
         gpm = {j: pm[pivot + j] for j in range(span)}  # retrieve_guide_posmap :283-303
-        guides.append(
-            Guide(starts[i], stops[i], texts[i].tobytes().decode("ascii"), guidelen, pamlen, s,
-                  h.samples, h.variants, h.afs, gpm, debug, rp, h.id)
-        )  # fmt: skip
+        if texts is not None:
+            seq = texts[i].tobytes().decode("ascii")
+        else:  # extract_guide_sequence :134-160
+            t = hap_texts.get(hi)
+            if t is None:
+                t = hap_texts[hi] = marshal.hap_text(h)
+            w0 = pivot - GUIDESEQPAD
+            seq = t[w0 : w0 + span + 2 * GUIDESEQPAD]
+        return Guide(int(starts[i]), int(stops[i]), seq, guidelen, pamlen, s, h.samples, h.variants, h.afs, gpm, debug, rp, h.id)
+
     print_verbosity(f"Guides retrieved in {time() - start_t:.2f}s", verbosity, 3)
-    if not (variants_present and not phased):
+    if not unphased:
         # N2 seam: the device-resident table travels with the list, so the mirrors of
         # annotation.py's per-guide loops (crispr_hawk_b200.annotation) can run on it
         link = dict(table=table, res=res, batch=res.batch_ref, haplotypes=haplotypes, right=bool(right), order=order)
-        LIVE_TABLES.add(link, int(res.n_guides) * (25 + int(res.text_stride)))
-        return GuideList(guides, link)
+        LIVE_TABLES.add(link, res.device_bytes() + getattr(res.batch_ref, "device_bytes", lambda: 0)())
+        return GuideList(len(order), make, link)
     res.close()
-    return guides
+    return GuideList(len(order), make, None)

@@ -55,8 +55,6 @@ def unpack_nibbles(q, v, off, lens, h):
 
 def search(pam, region, haps, guidelen, right, variants_present, phased, raw=False):
     texts = [marshal.hap_text(h) for h in haps]
-    q, v, off, lens, bad = pack(texts)
-    assert bad == -1
     fwd, rc = pam_patterns(pam)
     unphased = bool(variants_present and not phased)
     params = _cabi.make_params(fwd, rc, guidelen, right, unphased)
@@ -64,8 +62,16 @@ def search(pam, region, haps, guidelen, right, variants_present, phased, raw=Fal
     a = np.array([b[0] for b in bounds], np.int32)
     b = np.array([b[1] for b in bounds], np.int32)
     is_ref = np.array([h.samples == "REF" for h in haps], np.uint8)
-    seg = marshal.segment_table(haps)
-    va = marshal.allele_table(haps)
+    return search_flat(texts, params, a, b, is_ref, marshal.segment_table(haps), marshal.allele_table(haps), raw)
+
+
+def search_flat(texts, params, a, b, is_ref, seg, va, raw=False):
+    """The same from the flat arrays the C-ABI takes (tests/fake_backend.py feeds these)."""
+    q, v, off, lens, bad = pack(texts)
+    assert bad == -1
+    a, b = np.ascontiguousarray(a, np.int32), np.ascontiguousarray(b, np.int32)
+    is_ref = np.ascontiguousarray(is_ref, np.uint8)
+    haps = texts
     L = lib()
     t = L.hawkcheck_search(
         _p(q), _p(v), _p(off), _p(lens), _p(a), _p(b), _p(is_ref), C.c_int32(len(haps)),
@@ -102,12 +108,16 @@ def search(pam, region, haps, guidelen, right, variants_present, phased, raw=Fal
 def annotate(table, haps, pam, guidelen, right):
     """N2 through the kernels' own per-row logic compiled for the CPU (hawkcheck_annotate):
     same columns as _cabi.Result.annotate, for a table in emission order."""
-    L = lib()
-    L.hawkcheck_annotate.restype = C.c_int64
     fwd, rc = pam_patterns(pam)
     params = _cabi.make_params(fwd, rc, guidelen, right, False)
-    seg = marshal.segment_table(haps)
-    vt = marshal.variant_table(haps)
+    return annotate_flat(table, params, marshal.segment_table(haps), marshal.variant_table(haps))
+
+
+def annotate_flat(table, params, seg, vt):
+    L = lib()
+    L.hawkcheck_annotate.restype = C.c_int64
+    guidelen = params.guide_len
+    fwd = [0] * params.pam_len
     n, w = len(table["hap"]), table["text"].shape[1] if len(table["hap"]) else guidelen + len(fwd) + 20
     stride = (w + 15) // 16 * 16
     text = np.zeros((n, stride), np.uint8)

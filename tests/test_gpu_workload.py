@@ -71,7 +71,7 @@ def test_workload_table_matches_c_oracle(name, scale, n_alt):
     for kcol in COLS + ("bucket",):
         assert np.array_equal(t2[kcol], table[kcol])
     assert np.array_equal(t2["text"], table["text"])
-    assert h2d > wl.d.total_slots and d2h >= len(table["hap"]) * (25 + (wl.guidelen + len(wl.fwd) + 20 + 15) // 16 * 16)
+    assert h2d > wl.d.total_slots and d2h >= len(table["hap"]) * (21 + (wl.guidelen + len(wl.fwd) + 20 + 15) // 16 * 16)
     # raw pam_search semantics on the same batch
     raw = _cabi.pam_search(wl.ctx, wl.batch, wl.params, wl.a, wl.b)
     for s in (0, 1):

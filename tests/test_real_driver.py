@@ -1,0 +1,228 @@
+"""install() against the GENUINE reference driver: `crisprhawk.crisprhawk.encode_haplotypes`,
+`guides_search` (crisprhawk.py:64-115) and `annotation.annotate_guides` (annotation.py:545-600)
+run unmodified, once as they are and once with crispr_hawk_b200 installed, and must leave the
+same Guide objects behind -- every field. The build container has the reference but no GPU, so
+the device layer is the kernels' own core compiled for the CPU (tests/fake_backend.py); the
+kernels themselves are compared with the same reference outputs on the GPU box
+(tests/test_gpu_parity.py, tests/test_gpu_annot.py)."""
+
+import sys
+import types
+
+import pytest
+
+import crispr_hawk_b200 as hawk
+from crispr_hawk_b200 import search_guides
+from oracle import refshim
+from tests import fake_backend
+from tests.synth_cases import config1_cases, kat_cases, make_case, random_cases
+
+pytestmark = pytest.mark.ref
+
+
+def load_driver():
+    """`import crisprhawk.crisprhawk` with the out-of-scope first-party modules it pulls in
+    (scorers, graphics, off-target search, converter: SURVEY.md 8c) replaced by stubs."""
+    refshim.load()
+    for name, attrs in {
+        "crisprhawk.scoring": dict(scoring_guides=lambda guides, *a: guides),
+        "crisprhawk.scoring_envs": dict(ScoringEnvs=object),
+        "crisprhawk.graphical_reports": dict(compute_graphical_reports=lambda *a: None),
+        "crisprhawk.candidate_guides": dict(candidate_guides_analysis=lambda *a: None),
+        "crisprhawk.search_offtargets": dict(offtargets_search=lambda guides, *a: guides),
+        "crisprhawk.converter": dict(convert_gnomad_vcf=lambda *a: None),
+        "crisprhawk.crisprme_data": dict(prepare_data_crisprme=lambda *a: None),
+    }.items():
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+    import crisprhawk.crisprhawk as drv
+
+    return drv
+
+
+def guide_fields(g):
+    pm = g.posmap
+    # collapsed sample strings are joined from a Python set in the reference (haplotypes.py:258): compare as sets
+    return (g.start, g.stop, g.strand, g.sequence, g.guidelen, g.pamlen, bool(g.right), frozenset(g.samples.split(",")), g.variants, g.afs_str,
+            g.gc, g.hapid, g.guide_id, g.pam, g.guide, tuple(pm[j] for j in range(len(pm))), g.afs is not None)  # fmt: skip
+
+
+def run_driver(drv, case):
+    region, haps = refshim.build_case(case.ref_text, case.bed_start, case.bed_stop, case.vcf_lines, case.samples, case.phased)
+    args = types.SimpleNamespace(guidelen=case.guidelen, right=case.right, verbosity=0, debug=True, annotations=[],
+                                 gene_annotations=[], annotation_colnames=[], gene_annotation_colnames=[])  # fmt: skip
+    pam = drv.encode_pam(case.pam, case.right, 0, True)
+    bits = drv.encode_haplotypes({region: haps}, args)
+    guides = drv.guides_search(pam, {region: haps}, bits, case.variants_present, case.phased, args)
+    returned = guides[region]
+    guides = drv.annotate_guides(guides, args)
+    return region, returned, guides[region]
+
+
+CASES = [c for c in config1_cases() if c.phased] + [kat_cases()[0], kat_cases()[2]] + [
+    make_case(100 + k, phased=True, pam=p, guidelen=g, right=r) for k, (p, g, r) in enumerate([("NGG", 20, False), ("TTTV", 23, True), ("NNGRRT", 21, False)])
+]  # fmt: skip
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
+def test_installed_driver_leaves_the_same_guides(case, monkeypatch):
+    drv = load_driver()
+    _, _, want = run_driver(drv, case)
+    want = [guide_fields(g) for g in want]
+    fake_backend.activate(monkeypatch)
+    hawk.install()
+    try:
+        assert drv.search is search_guides.search
+        _, returned, got = run_driver(drv, case)
+        assert isinstance(returned, search_guides.GuideList)
+        assert got is returned  # the seam returns the list it was given (the reference builds no new one either)
+        assert returned.built == 0 or len(returned) == 0  # nothing touched an object so far: all stages are pending
+        assert [guide_fields(g) for g in got] == want
+        assert got.built == len(got)
+    finally:
+        hawk.uninstall()
+    assert drv.search is not search_guides.search
+
+
+def test_evicted_tables_fall_back_to_the_reference_functions(monkeypatch):
+    """LIVE_TABLES forced small: the first region's table is released before it is annotated and
+    its list takes the reference's own annotation functions -- same guides all the same."""
+    drv = load_driver()
+    case = config1_cases()[0]
+    case2 = make_case(7, bed_len=900, n_sites=20, n_samples=5, phased=True, bed_start=50001)  # another region
+    _, _, want = run_driver(drv, case)
+    want = [guide_fields(g) for g in want]
+    _, _, want2 = run_driver(drv, case2)
+    want2 = [guide_fields(g) for g in want2]
+    fake_backend.activate(monkeypatch)
+    monkeypatch.setattr(search_guides, "LIVE_TABLES", search_guides._LiveTables(cap_bytes=1))
+    hawk.install()
+    try:
+        region, haps = refshim.build_case(case.ref_text, case.bed_start, case.bed_stop, case.vcf_lines, case.samples, True)
+        region2, haps2 = refshim.build_case(case2.ref_text, case2.bed_start, case2.bed_stop, case2.vcf_lines, case2.samples, True)
+        args = types.SimpleNamespace(guidelen=20, right=False, verbosity=0, debug=True, annotations=[], gene_annotations=[])
+        pam = drv.encode_pam("NGG", False, 0, True)
+        hh = {region: haps, region2: haps2}
+        guides = drv.guides_search(pam, hh, drv.encode_haplotypes(hh, args), True, True, args)
+        first, second = guides[region], guides[region2]
+        assert first.hawk["res"] is None and second.hawk["res"] is not None  # the older table was evicted
+        guides = drv.annotate_guides(guides, args)
+        assert [guide_fields(g) for g in guides[region]] == want
+        assert [guide_fields(g) for g in guides[region2]] == want2
+    finally:
+        hawk.uninstall()
+
+
+def test_lazy_list_behaves_like_the_list_it_replaces(monkeypatch):
+    drv = load_driver()
+    case = config1_cases()[0]
+    fake_backend.activate(monkeypatch)
+    hawk.install()
+    try:
+        _, guides, _ = run_driver(drv, case)
+    finally:
+        hawk.uninstall()
+    n = len(guides)
+    assert n > 100 and guides.built == 0 and "None" not in repr(guides)[:200] and guides.built == n  # repr builds
+    fake_backend.activate(monkeypatch)
+    region, haps = refshim.build_case(case.ref_text, case.bed_start, case.bed_stop, case.vcf_lines, case.samples, True)
+    pam = hawk.PAM("NGG", False, True)
+    pam.encode(0)
+    lazy = hawk.search(pam, region, haps, hawk.encode_region(haps, 0, True), 20, False, True, True, 0, True)
+    assert lazy.built == 0
+    g5 = lazy[5]
+    assert lazy.built == 1 and lazy[5] is g5 and lazy[-1] is lazy[n - 1] and lazy.built == 2
+    assert [g.guide_id for g in lazy[2:4]] == [guides[2].guide_id, guides[3].guide_id] and lazy.built == 4
+    both = lazy + []  # any whole-list operation builds the rest first
+    assert lazy.built == n and type(both) is list and all(g is not None for g in both)
+    assert [g.guide_id for g in lazy] == [g.guide_id for g in guides]
+    assert sorted(lazy, key=lambda g: g.start)[0].start == min(g.start for g in guides)
+
+
+# --------------------------------------------------------------------------- N1 through install()
+N1_CASES = config1_cases() + [kat_cases()[2]] + random_cases(5)
+
+
+def hap_fields(h):
+    pm = h.posmap
+    return (h.sequence.sequence, tuple(pm[i] for i in range(len(h))), h.start, h.stop, frozenset(h.samples.split(",")),
+            h.variants, dict(h.afs))  # fmt: skip
+
+
+@pytest.mark.parametrize("case", N1_CASES, ids=[c.name for c in N1_CASES])
+def test_haplotype_seam_equals_reference_builder(case, monkeypatch):
+    """install() rebinds crisprhawk.haplotypes.add_variants_phased: the reference's VariantRecord
+    lists become device-built EditHaplotypes. Same haplotypes (text, position map, bounds, sample
+    sets, variant ids, allele frequencies, order) and the same search() output as the reference's
+    own builder; unphased regions fall through to it untouched."""
+    ref = refshim.load()
+    load_driver()
+    region, want_haps = refshim.build_case(case.ref_text, case.bed_start, case.bed_stop, case.vcf_lines, case.samples, case.phased)
+    _, _, want = refshim.run_search(region, want_haps, case.pam, case.guidelen, case.right, case.variants_present, case.phased)
+    fake_backend.activate(monkeypatch)
+    hawk.install()
+    try:
+        from crispr_hawk_b200 import haplotypes as HN
+
+        assert ref.haplotypes.add_variants_phased is HN.add_variants_phased
+        region2, haps = refshim.build_case(case.ref_text, case.bed_start, case.bed_stop, case.vcf_lines, case.samples, case.phased)
+        if case.phased and case.vcf_lines:
+            assert all(isinstance(h, HN.EditHaplotype) for h in haps)
+        assert [hap_fields(h) for h in haps] == [hap_fields(h) for h in want_haps]
+        for h, w in zip(haps, want_haps):
+            assert marshal_bounds(h, region2, 3) == tuple(ref.search_guides.compute_scan_start_stop(w, region.start, region.stop, 3))
+        pam = hawk.PAM(case.pam, case.right, True)
+        pam.encode(0)
+        bits = hawk.encode_region(haps, 0, True)
+        if case.phased and case.vcf_lines:
+            assert bits is haps[0]._region_pack  # no text ever goes back up: the batch built from the edits is searched
+        got = hawk.search(pam, region2, haps, bits, case.guidelen, case.right, case.variants_present, case.phased, 0, True)
+    finally:
+        hawk.uninstall()
+    assert ref.haplotypes.add_variants_phased is not HN.add_variants_phased
+
+    def fields(g):
+        pm = g.posmap
+        return (g.start, g.stop, g.strand, g.sequence, bool(g.right), frozenset(g.samples.split(",")), g.variants, g.hapid,
+                tuple(pm[j] for j in range(len(pm))), g.guide_id)  # fmt: skip
+
+    assert [fields(g) for g in got] == [fields(g) for g in want]
+
+
+def marshal_bounds(h, region, pamlen):
+    from crispr_hawk_b200 import marshal
+
+    return tuple(marshal.scan_bounds(h, region.start, region.stop, pamlen))
+
+
+def test_unsupported_shapes_go_to_the_reference_builder(monkeypatch):
+    """Two records overlapping on one chromosome copy: not an edit list the device builder
+    takes -> the reference's own add_variants_phased builds the region."""
+    ref = refshim.load()
+    load_driver()
+    text = kat_cases()[0].ref_text
+    lines = ["chr1\t1020\t.\t" + text[119:123] + "\t" + text[119] + "\t.\tPASS\tAF=0.2\tGT\t1|0\t0|1",
+             "chr1\t1021\t.\t" + text[120] + "\t" + ("A" if text[120] != "A" else "C") + "\t.\tPASS\tAF=0.2\tGT\t1|0\t0|0"]  # fmt: skip
+    fake_backend.activate(monkeypatch)
+    hawk.install()
+    try:
+        from crispr_hawk_b200 import haplotypes as HN
+
+        try:
+            _, haps = refshim.build_case(text, 1001, 1080, lines, ["S1", "S2"], True)
+        except Exception as e:  # whatever the reference itself does with such records is what happens
+            haps = e
+        hawk.uninstall()
+        try:
+            _, want = refshim.build_case(text, 1001, 1080, lines, ["S1", "S2"], True)
+        except Exception as e:
+            want = e
+        if isinstance(want, Exception):
+            assert type(haps) is type(want)
+        else:
+            assert not any(isinstance(h, HN.EditHaplotype) for h in haps)
+            assert [hap_fields(h) for h in haps] == [hap_fields(h) for h in want]
+    finally:
+        hawk.uninstall()
