@@ -279,6 +279,105 @@ def workload_config(args, scanned_bp, n_hap, sample=False):
     }  # fmt: skip
 
 
+
+# --------------------------------------------------------------------------- Python seam legs
+def api_search_leg():
+    """`crispr_hawk_b200.search()` -- Python haplotype objects in, the reference's List[Guide] out
+    -- beside the pure-Python port of the reference's search (oracle/hawk_oracle.py, the
+    reference's own cost model) on the same objects; guides compared field by field."""
+    import crispr_hawk_b200 as hawk
+    from crispr_hawk_b200 import synth
+    from oracle import hawk_oracle as O
+
+    out = {}
+    for label, name, scale, n_alt in (("config1_5kb_x21", "c1", 1.0, 20), ("c2_100kb_x65", "c2", 0.1, 64)):
+        k = synth.CONFIGS[name]
+        c = synth.config_cohort(name, scale, n_alt_hap=n_alt)
+        haps = synth.synth_haplotypes(c)
+        region = synth.SynthRegion(c)
+        a, b = synth.scan_bounds(c, len(k["pam"]))
+        pam = hawk.PAM(k["pam"], k["right"], True)
+        pam.encode(0)
+
+        def run():
+            return hawk.search(pam, region, haps, hawk.encode_region(haps, 0, True), k["guidelen"], k["right"], True, True, 0, True)
+
+        run()
+        t0 = time.perf_counter()
+        guides = run()
+        t_list = time.perf_counter() - t0
+        guides[0]
+        t_first = time.perf_counter() - t0
+        guides.realise()
+        t_all = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        want = O.search(k["pam"], c.region_start, c.region_stop, [O.OracleHap.from_object(h) for h in haps], k["guidelen"],
+                        k["right"], True, True)  # fmt: skip
+        t_py = time.perf_counter() - t0
+        same = [(g.start, g.stop, g.strand, g.sequence, g.hapid) for g in guides] == [(g.start, g.stop, g.strand, g.sequence, g.hapid) for g in want]
+        if not same:
+            raise AssertionError(f"api_search {label}: guides differ from the Python port")
+        out[label] = {"hap_bp": int((b.astype(np.int64) - a).clip(min=0).sum()), "guides": len(guides),
+                      "search_returns_ms": 1e3 * t_list, "first_guide_ms": 1e3 * t_first, "all_guides_built_ms": 1e3 * t_all,
+                      "python_port_ms": 1e3 * t_py, "speedup_all_guides_built": t_py / t_all}  # fmt: skip
+    out["what"] = ("encode_region + search through the public Python API (host texts up, table without the text column "
+                   "down, lazy GuideList); all_guides_built forces every Guide object like a report writer would")
+    return out
+
+
+def variant_records_leg(n_samples: int = 200):
+    """N1 through the seam install() binds (crispr_hawk_b200.haplotypes.add_variants_phased): the
+    reference's VariantRecord lists of config 2's region for `n_samples` phased samples ->
+    haplotypes built on the device from edit lists -> search()."""
+    import types
+
+    import crispr_hawk_b200 as hawk
+    from crispr_hawk_b200 import haplotypes as HN
+    from crispr_hawk_b200 import synth
+
+    k = synth.CONFIGS["c2"]
+    c = synth.config_cohort("c2", 1.0, n_alt_hap=2 * n_samples)
+    ref = c.ref.tobytes().decode()
+    pool = c.alt_pool.tobytes().decode()
+    names = [f"S{i + 1}" for i in range(n_samples)]
+    carriers = [(set(), set()) for _ in range(len(c.site_pos))]
+    for h in range(1, c.n_hap):
+        smp, copy = names[(h - 1) // 2], (h - 1) % 2
+        for site in c.hap_sites[c.hap_off[h] : c.hap_off[h + 1]].tolist():
+            carriers[site][copy].add(smp)
+    records = []
+    for site in range(len(c.site_pos)):
+        if not (carriers[site][0] or carriers[site][1]):
+            continue
+        p, rl, al, ao = int(c.site_pos[site]), int(c.site_reflen[site]), int(c.site_altlen[site]), int(c.site_altoff[site])
+        r, a = ref[p : p + rl], pool[ao : ao + al]
+        records.append(types.SimpleNamespace(position=c.region_start + p, ref=r, alt=[a], afs=[0.1], samples=[carriers[site]],
+                                             vtype=["snp" if rl == 1 and al == 1 else "indel"],
+                                             id=[f"chr1-{c.region_start + p}-{r}/{a}"]))  # fmt: skip
+    region = synth.SynthRegion(c)
+    region.sequence = types.SimpleNamespace(sequence=ref)
+    vcfs = {"chr1": types.SimpleNamespace(samples=names)}
+    pam = hawk.PAM(k["pam"], k["right"], True)
+    pam.encode(0)
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        haps = HN.add_variants_phased([types.SimpleNamespace(afs={})], region, vcfs, records, True, True)
+        t_build = time.perf_counter() - t0
+        guides = hawk.search(pam, region, haps, hawk.encode_region(haps, 0, True), k["guidelen"], k["right"], True, True, 0, True)
+        t_all = time.perf_counter() - t0
+        guides[len(guides) // 2]
+        if best is None or t_all < best[1]:
+            best = (t_build, t_all, len(haps), len(guides))
+    bp = sum(len(h) - 200 - len(k["pam"]) for h in haps)
+    return {"samples": n_samples, "records": len(records), "haplotypes": best[2], "guides": best[3], "hap_bp": int(bp),
+            "haplotypes_built_ms": 1e3 * best[0], "build_plus_search_ms": 1e3 * best[1],
+            "value": bp / best[1], "unit": UNIT,
+            "what": "VariantRecord lists -> edit lists (host metadata) -> hawk_batch_create_from_edits -> search(); the "
+                    "reference's own add_variants_phased rewrites the sequence and two 1,000,200-entry dicts per variant "
+                    "and haplotype for the same input"}  # fmt: skip
+
+
 # --------------------------------------------------------------------------- product arm
 def run_product_arm(args, rank, world, local_rank):
     import torch
@@ -354,6 +453,7 @@ def run_product_arm(args, rank, world, local_rank):
     sampler = None if args.no_clocks else ClockSampler(local_rank).start()
     for _ in range(max(args.warmup, 3)):
         n_guides, n_hits = one_step()
+    exchange_counts()  # the collective / first device tensor of this process is set up outside the timed region
     barrier()
     launches0 = lib.hawk_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -362,9 +462,14 @@ def run_product_arm(args, rank, world, local_rank):
     w0 = time.time()
     ev0.record(stream)
     tally_host[0] = tally_host[1] = 0
+    step_wall = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         n_guides, n_hits = one_step()
+        step_wall.append(1e3 * (time.perf_counter() - ts))
+    ts = time.perf_counter()
     job_counts = exchange_counts()
+    exchange_ms = 1e3 * (time.perf_counter() - ts)
     ev1.record(stream)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -600,6 +705,12 @@ def run_product_arm(args, rank, world, local_rank):
                         "each also compared with the device result",
         }}  # fmt: skip
 
+    # ---- the Python side of the seam (rank 0, N = 1 only): what a user of the drop-in sees ----
+    if rank == 0 and world == 1 and not args.no_e2e and not unphased:
+        next_rows = dict(next_rows or {})
+        next_rows["api_search"] = api_search_leg()
+        next_rows["from_variant_records"] = variant_records_leg()
+
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -636,6 +747,8 @@ def run_product_arm(args, rank, world, local_rank):
             "guides_per_step": total_guides, "hits_per_step_rank0": hits_total,
             "job_guides_in_timed_region": int(job_counts[0].item()),
             "device_ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
+            "step_wall_ms": {"min": min(step_wall), "median": statistics.median(step_wall), "max": max(step_wall),
+                             "argmax": step_wall.index(max(step_wall)), "count_exchange_ms": exchange_ms},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "final_merge": final_merge, "c5": c5, "next_rows": next_rows,
             "gpu_launches": int(launches), "clocks": clocks, "profile_steps": prof_steps,
         }  # fmt: skip

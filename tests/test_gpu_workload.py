@@ -72,7 +72,8 @@ def test_workload_table_matches_c_oracle(name, scale, n_alt):
         assert np.array_equal(t2[kcol], table[kcol])
     assert np.array_equal(t2["text"], table["text"])
     assert h2d > wl.d.total_slots and d2h >= len(table["hap"]) * (21 + (wl.guidelen + len(wl.fwd) + 20 + 15) // 16 * 16)
-    # raw pam_search semantics on the same batch
+    # raw pam_search semantics on the same batch (re-encoded in full: a fused search leaves it sparse)
+    wl.batch.repack(wl.ascii_dev.data_ptr())
     raw = _cabi.pam_search(wl.ctx, wl.batch, wl.params, wl.a, wl.b)
     for s in (0, 1):
         assert np.array_equal(raw.hits(s), want["hits"][s])
