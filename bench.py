@@ -601,6 +601,12 @@ def run_product_arm(args, rank, world, local_rank):
                                   "rows_per_step": int(len(table2["hap"])), "call": "hawk_search_stream_edits"}  # fmt: skip
         n1b_ms, _ = timed(wl.step_edits_twocall, max(1, e2e_steps - 1))
         e2e["from_edit_lists"]["two_calls_no_overlap_ms"] = n1b_ms
+        # ... and with the window-text column left on the device (hawk_table_out.text = NULL): 21 B per row
+        # come down instead of 69; the text is a slice of the haplotype the host can rebuild lazily
+        n1c_ms, (table3, h2d3, d2h3) = timed(lambda: wl.step_edits(want_text=False), e2e_steps)
+        e2e["from_edit_lists"]["rows_only"] = {"value": total_bp / (n1c_ms / 1e3), "unit": UNIT, "ms_per_step": n1c_ms,
+                                               "h2d_bytes_per_step": int(h2d3), "d2h_bytes_per_step": int(d2h3),
+                                               "rows_per_step": int(len(table3["hap"]))}  # fmt: skip
 
     # ---- final merge (N > 1): every rank pushes its rows into rank 0's buffer over NVLink ----
     def measure_merge(w, result, hap_add, with_text):

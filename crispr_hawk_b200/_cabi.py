@@ -556,36 +556,40 @@ def text_stride(params: HawkParams) -> int:
     return int(load_library().hawk_table_text_stride(params.pam_len, params.guide_len))
 
 
-def alloc_table(capacity: int, stride: int, pinned: bool = False):
+def alloc_table(capacity: int, stride: int, pinned: bool = False, want_text: bool = True):
     """Host columns for `capacity` guide rows (pinned through torch when asked: the streamed
-    search overlaps its copies only with page-locked memory)."""
+    search overlaps its copies only with page-locked memory). `want_text=False`: no text column
+    (hawk_table_out.text = NULL: the rows come down at 21 bytes each instead of 21 + stride)."""
     if pinned:
         import torch
 
         mk = lambda dt, k=1: torch.empty(max(capacity * k, 1), dtype=dt, pin_memory=True).numpy()  # noqa: E731
         tdt = {np.int32: torch.int32, np.uint8: torch.uint8, np.int64: torch.int64, np.uint32: torch.int32}
         out = {name: mk(tdt[dt]).view(dt) for name, dt in TABLE_COLUMNS}
-        out["text"] = mk(torch.uint8, stride)
+        out["text"] = mk(torch.uint8, stride) if want_text else None
     else:
         out = {name: np.empty(max(capacity, 1), dt) for name, dt in TABLE_COLUMNS}
-        out["text"] = np.empty(max(capacity * stride, 1), np.uint8)
+        out["text"] = np.empty(max(capacity * stride, 1), np.uint8) if want_text else None
     return out
 
 
 def _table_out(buffers, stride: int) -> HawkTableOut:
     t = HawkTableOut()
     cap = min(len(buffers[name]) for name, _ in TABLE_COLUMNS)
-    cap = min(cap, len(buffers["text"].reshape(-1)) // stride)
+    text = buffers.get("text")
+    if text is not None:
+        cap = min(cap, len(text.reshape(-1)) // stride)
     t.hap, t.strand, t.pos = ptr(buffers["hap"], C.c_int32), ptr(buffers["strand"], C.c_uint8), ptr(buffers["pos"], C.c_int32)
     t.start, t.stop = ptr(buffers["start"], C.c_int32), ptr(buffers["stop"], C.c_int32)
-    t.bucket, t.text = ptr(buffers["bucket"], C.c_uint32), ptr(buffers["text"].reshape(-1), C.c_uint8)
+    t.bucket, t.text = ptr(buffers["bucket"], C.c_uint32), (ptr(text.reshape(-1), C.c_uint8) if text is not None else None)
     t.capacity, t.text_stride = cap, stride
     return t
 
 
 def _table_views(buffers, n: int, stride: int, window: int):
     out = {name: buffers[name][:n] for name, _ in TABLE_COLUMNS}
-    out["text"] = buffers["text"].reshape(-1)[: n * stride].reshape(n, stride)[:, :window]
+    if buffers.get("text") is not None:
+        out["text"] = buffers["text"].reshape(-1)[: n * stride].reshape(n, stride)[:, :window]
     return out
 
 
@@ -600,7 +604,7 @@ class StreamResult:
         return self.table_
 
 
-def _run_stream(call, params: HawkParams, buffers, pinned: bool, what: str) -> StreamResult:
+def _run_stream(call, params: HawkParams, buffers, pinned: bool, what: str, want_text: bool = True) -> StreamResult:
     """Run `call(table_out_ptr, n, hits, bp)`; on HAWK_ECAPACITY grow the buffers and repeat."""
     stride = text_stride(params)
     window = params.pam_len + params.guide_len + 20
@@ -608,13 +612,13 @@ def _run_stream(call, params: HawkParams, buffers, pinned: bool, what: str) -> S
         # count first: one pass without output sizes the table exactly
         n, hits, bp = C.c_int64(), (C.c_int64 * 2)(), C.c_int64()
         check(call(None, n, hits, bp), what)
-        buffers = alloc_table(n.value, stride, pinned)
+        buffers = alloc_table(n.value, stride, pinned, want_text)
     for _ in range(2):
         t = _table_out(buffers, stride)
         n, hits, bp = C.c_int64(), (C.c_int64 * 2)(), C.c_int64()
         rc = call(C.byref(t), n, hits, bp)
         if rc == HAWK_ECAPACITY and n.value > t.capacity:
-            buffers = alloc_table(int(n.value * 1.05) + 1024, stride, pinned)
+            buffers = alloc_table(int(n.value * 1.05) + 1024, stride, pinned, want_text)
             continue
         check(rc, what)
         return StreamResult(_table_views(buffers, n.value, stride, window), n.value, (hits[0], hits[1]), bp.value,
@@ -651,7 +655,7 @@ def search_stream(ctx: Context, ascii_slots: np.ndarray, slot_off, lens, seg, pa
 
 def search_stream_edits(ctx: Context, ref_ascii, region_start: int, edit_off, edit_pos, edit_reflen, edit_altlen,
                         edit_altoff, alt_pool, params: HawkParams, scan_start, scan_stop, is_ref,
-                        n_groups: int = 0, buffers=None, pinned: bool = False) -> StreamResult:  # fmt: skip
+                        n_groups: int = 0, buffers=None, pinned: bool = False, want_text: bool = True) -> StreamResult:  # fmt: skip
     """hawk_search_stream_edits: reference text + edit lists in, host guide table out."""
     ref = np.ascontiguousarray(ref_ascii, dtype=np.uint8)
     eo = np.ascontiguousarray(edit_off, dtype=np.int64)
@@ -672,7 +676,7 @@ def search_stream_edits(ctx: Context, ref_ascii, region_start: int, edit_off, ed
             C.byref(n), hits, C.byref(bp),
         )  # fmt: skip
 
-    return _run_stream(call, params, buffers, pinned, "hawk_search_stream_edits")
+    return _run_stream(call, params, buffers, pinned, "hawk_search_stream_edits", want_text)
 
 
 def stream_plan(slot_off, is_ref, n_groups: int = 0):

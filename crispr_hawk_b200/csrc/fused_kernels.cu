@@ -93,7 +93,7 @@ struct HapCursor {
 };
 
 template <bool WIDE, int REACH>
-__global__ void __launch_bounds__(FUSED_WARPS * 32, 32 / FUSED_WARPS) fused_scan_kernel(const __grid_constant__ FusedArgs A) {
+__global__ void __launch_bounds__(FUSED_WARPS * 32, 24 / FUSED_WARPS) fused_scan_kernel(const __grid_constant__ FusedArgs A) {
   __shared__ uint16_t q_off[FUSED_WARPS][64];  // candidate queue (ring): chunk offset in the sub-range
   __shared__ int32_t q_hap[FUSED_WARPS][64];   // ... and its haplotype
   const int lane = threadIdx.x & 31, warp = FUSED_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5);
@@ -213,6 +213,17 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, 32 / FUSED_WARPS) fused_scan
     return __ballot_sync(0xFFFFFFFFu, k.v != 0);
   };
 
+  // iterations [fast_lo, fast_hi) lie entirely inside the current (non-REF) haplotype's scan range
+  // and territory and inside the sub-range: no boundary of any kind -- the common case by far
+  int32_t fast_lo = 0, fast_hi = 0;
+  auto set_fast_window = [&]() {
+    int32_t hi = cur.c_hi < cur.t_next ? cur.c_hi : cur.t_next;
+    if (n < hi) hi = n;
+    fast_lo = cur.c_lo <= 0 ? 0 : (cur.c_lo + 31) >> 5;
+    fast_hi = cur.is_ref ? fast_lo : (hi >> 5);
+  };
+  set_fast_window();
+
   // finalise iteration j: P are its planes, nzp / nzc / nzn the ballots of iterations j - 1, j, j + 1
   auto finalise = [&](int32_t j, const Planes5& P, uint32_t nzp, uint32_t nzc, uint32_t nzn) {
     const int32_t cl0 = 32 * j;
@@ -224,41 +235,51 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, 32 / FUSED_WARPS) fused_scan
     if (REACH >= 2) keep_bits |= __funnelshift_l(nzp, nzc, 2) | __funnelshift_r(nzc, nzn, 2);
     if (REACH >= 3) keep_bits |= __funnelshift_l(nzp, nzc, 3) | __funnelshift_r(nzc, nzn, 3);
     uint32_t cand_bits = near1;
-    while (cl0 >= cur.t_next) cur = load_cursor(cur.h + 1);  // uniform
     int32_t h_l = cur.h;
-    if (cl0 + 31 < cur.t_next) {
-      // the whole iteration lies in one haplotype's territory (the common case): uniform masks
-      if (cur.is_ref) cand_bits = keep_bits = 0xFFFFFFFFu;
-      if (cl0 < cur.c_lo || cl0 + 32 > cur.c_hi) cand_bits &= interval_mask(cur.c_lo, cur.c_hi, cl0);
-    } else {
-      // short haplotypes: the 32 chunks straddle territories, every lane finds its own
-      const int64_t cg = s + cl0 + lane;
-      while (h_l + 1 < A.n_hap && cg >= territory(A.slot_off, A.n_hap, A.n_chunks, h_l + 1)) ++h_l;
-      const HapScan* H = A.hs + h_l;
-      const int64_t crel = cg - H->chunk0;
-      const int32_t a = H->a, b = H->b;
-      const bool ref = H->is_ref != 0;
-      const bool c = b > a && crel >= (a >> 5) && crel < ((b + 31) >> 5) && (ref || (near1 & lane_bit));
-      cand_bits = __ballot_sync(0xFFFFFFFFu, c);
-      keep_bits |= __ballot_sync(0xFFFFFFFFu, ref);
+    if (j < fast_lo || j >= fast_hi) {  // a boundary somewhere in these 32 chunks
+      while (cl0 >= cur.t_next) {  // uniform
+        cur = load_cursor(cur.h + 1);
+        set_fast_window();
+      }
+      h_l = cur.h;
+      if (cl0 + 31 < cur.t_next) {
+        // one haplotype's territory: uniform masks
+        if (cur.is_ref) cand_bits = keep_bits = 0xFFFFFFFFu;
+        cand_bits &= interval_mask(cur.c_lo, cur.c_hi, cl0);
+      } else {
+        // short haplotypes: the 32 chunks straddle territories, every lane finds its own
+        const int64_t cg = s + cl0 + lane;
+        while (h_l + 1 < A.n_hap && cg >= territory(A.slot_off, A.n_hap, A.n_chunks, h_l + 1)) ++h_l;
+        const HapScan* H = A.hs + h_l;
+        const int64_t crel = cg - H->chunk0;
+        const int32_t a = H->a, b = H->b;
+        const bool ref = H->is_ref != 0;
+        const bool c = b > a && crel >= (a >> 5) && crel < ((b + 31) >> 5) && (ref || (near1 & lane_bit));
+        cand_bits = __ballot_sync(0xFFFFFFFFu, c);
+        keep_bits |= __ballot_sync(0xFFFFFFFFu, ref);
+      }
+      if (cl0 + 32 > n) {  // the last iteration of the slot space
+        const uint32_t valid = (1u << (n - cl0)) - 1u;
+        keep_bits &= valid;
+        cand_bits &= valid;
+      }
     }
-    if (cl0 + 32 > n) {  // the last iteration of the slot space
-      const uint32_t valid = (1u << (n - cl0)) - 1u;
-      keep_bits &= valid;
-      cand_bits &= valid;
-    }
-    if (keep_bits & lane_bit) {
-      qs[cl0] = make_uint4(P.a, P.c, P.g, P.t);
-      vs[cl0] = P.v;
+    if (keep_bits) {  // uniform
+      if (keep_bits & lane_bit) {
+        qs[cl0] = make_uint4(P.a, P.c, P.g, P.t);
+        vs[cl0] = P.v;
+      }
     }
     // matches of older candidates: all their neighbour chunks have been stored by now
     if (qn >= 32) flush(32);
-    if (cand_bits & lane_bit) {
-      const uint32_t slot = (qhead + qn + __popc(cand_bits & lanes_below)) & 63u;
-      q_off[warp][slot] = (uint16_t)(cl0 + lane);
-      q_hap[warp][slot] = h_l;
+    if (cand_bits) {  // uniform
+      if (cand_bits & lane_bit) {
+        const uint32_t slot = (qhead + qn + __popc(cand_bits & lanes_below)) & 63u;
+        q_off[warp][slot] = (uint16_t)(cl0 + lane);
+        q_hap[warp][slot] = h_l;
+      }
+      qn += __popc(cand_bits);
     }
-    qn += __popc(cand_bits);
   };
 
   // the neighbour chunks this warp's matcher reads but another warp owns
@@ -269,40 +290,26 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, 32 / FUSED_WARPS) fused_scan
     }
   };
 
-  Planes5 pa{0u, 0u, 0u, 0u, 0u}, pb;
+  Planes5 prev{0u, 0u, 0u, 0u, 0u}, now;
   Raw8 raw;
   uint32_t nz_pp = 0, nz_p = 0, nz_c;  // ballots of iterations i - 2, i - 1, i
   if (s > 0) {  // leading halo
     fetch(-1, raw);
-    nz_p = pack(-1, raw, pb);
-    store_edge(-1, pb, 31);
+    nz_p = pack(-1, raw, now);
+    store_edge(-1, now, 31);
   }
-  // Software pipeline, unrolled by two so the plane registers never move: the text of iteration
-  // i + 1 is requested, iteration i is packed, then iteration i - 1 (neighbours on both sides now
-  // known) is finalised. Iteration n_iter is the trailing halo.
+  // Software pipeline: the text of iteration i + 1 is requested, iteration i is packed, then
+  // iteration i - 1 (neighbours on both sides now known) is finalised. Iteration n_iter is the
+  // trailing halo.
   fetch(0, raw);
-  nz_c = pack(0, raw, pa);
-  fetch(1, raw);
-  nz_pp = nz_p;
-  nz_p = nz_c;
-  int32_t i = 1;
-  for (; i + 1 <= n_iter; i += 2) {
-    nz_c = pack(i, raw, pb);
+  for (int32_t i = 0; i <= n_iter; ++i) {
+    nz_c = pack(i, raw, now);
     fetch(i + 1, raw);
-    finalise(i - 1, pa, nz_pp, nz_p, nz_c);
+    if (i == n_iter) store_edge(i, now, 0);
+    if (i > 0) finalise(i - 1, prev, nz_pp, nz_p, nz_c);
+    prev = now;
     nz_pp = nz_p;
     nz_p = nz_c;
-    nz_c = pack(i + 1, raw, pa);
-    fetch(i + 2, raw);
-    if (i + 1 == n_iter) store_edge(i + 1, pa, 0);
-    finalise(i, pb, nz_pp, nz_p, nz_c);
-    nz_pp = nz_p;
-    nz_p = nz_c;
-  }
-  if (i <= n_iter) {  // i == n_iter: pack the trailing halo, finalise the last owned iteration
-    nz_c = pack(i, raw, pb);
-    store_edge(i, pb, 0);
-    finalise(i - 1, pa, nz_pp, nz_p, nz_c);
   }
   if (n_iter & 31) {  // nz words of the last, partial group of 32 iterations
     const int32_t j0 = n_iter & ~31;

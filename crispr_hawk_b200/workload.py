@@ -137,7 +137,7 @@ class Workload:
             self._edits_out = None
         return self._edits
 
-    def step_edits(self, n_groups: int = 0):
+    def step_edits(self, n_groups: int = 0, want_text: bool = True):
         """N1 path through ONE call (hawk_search_stream_edits): only the reference text and the
         per-haplotype edit lists start on the host; texts are materialised on the device group
         by group, then K1, K2 and the table pipeline as usual, while the previous group's guide
@@ -145,10 +145,11 @@ class Workload:
         c = self.cohort
         e = self._edit_buffers()
         t0 = self.ctx.traffic()
+        key = "_edits_out" if want_text else "_edits_out_slim"
         res = _cabi.search_stream_edits(self.ctx, e["ref"], c.region_start, e["off"], e["pos"], e["rl"], e["al"], e["ao"],
                                         e["pool"], self.params, self.a, self.b, self.d.is_ref, n_groups=n_groups,
-                                        buffers=self._edits_out, pinned=True)  # fmt: skip
-        self._edits_out = res.buffers
+                                        buffers=getattr(self, key, None), pinned=True, want_text=want_text)  # fmt: skip
+        setattr(self, key, res.buffers)
         t1 = self.ctx.traffic()
         return res.table(), t1[0] - t0[0], t1[1] - t0[1]
 
