@@ -506,8 +506,8 @@ def run_product_arm(args, rank, world, local_rank):
     scan_ms = cand_ms + match_ms + expand_ms  # all of K2
     pack_bytes = wl.pack_algorithmic_bytes()
     scan_bytes = wl.scan_algorithmic_bytes(hits_total)
-    profiled = args.workload == "c2" and args.scale == 1.0 and not args.haplotypes
-    traffic = lambda k: TRAFFIC.get(k) if profiled else None  # noqa: E731
+    profiled = args.workload in TRAFFIC and args.scale == 1.0 and not args.haplotypes
+    traffic = lambda k: TRAFFIC.get(args.workload, {}).get(k) if profiled else None  # noqa: E731
     gbs = lambda nbytes, ms: nbytes / ms / 1e6 if ms and nbytes else None  # noqa: E731
     fused = wl.fused_auto()
     k1_name = "fused_scan_kernel" if fused else "pack_kernel"
@@ -540,12 +540,12 @@ def run_product_arm(args, rank, world, local_rank):
     ach = kernels[dom]["gbs"] or 0.0
     roofline = {
         "kernel": kernels[dom].get("name", dom), "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": traffic(dom), "traffic_source": "profiles/traffic.json (ncu --set full capture of this workload)" if traffic(dom) else None,
+        "traffic": traffic(kernels[dom].get("name", dom)), "traffic_source": "profiles/traffic.json (ncu --set full capture of this workload)" if traffic(kernels[dom].get("name", dom)) else None,
         "peak_source": peak_src,
         "scan_kernel_frac": (kernels["scan_k2_total"]["gbs"] or 0.0) / peak,
         "pack_kernel_frac": (kernels["pack_kernel"]["gbs"] or 0.0) / peak,
         "table_pipeline_frac": (kernels["table_pipeline"]["gbs"] or 0.0) / peak,
-        "match_kernel_dram_frac": (kernels["match_kernel"]["dram_gbs"] or 0.0) / peak if profiled else None,
+        "match_kernel_dram_frac": (kernels["match_kernel"]["dram_gbs"] or 0.0) / peak if profiled and not fused else None,
     }  # fmt: skip
 
     # ---- e2e: host buffers in, host table out ----
