@@ -31,7 +31,6 @@
 namespace hawk {
 
 constexpr int RES_T = 128;   // hits per block (count and write must agree)
-constexpr int RES_MAXA = 12; // ambiguous columns per hit handled from registers / local arrays
 
 // window bits [w0, w0 + 96) of a per-chunk bit plane accessor, as three words
 template <class F>
@@ -68,23 +67,63 @@ struct ResCountArgs {
   int* err;
 };
 
-struct AmbCol {
-  uint64_t chars;   // candidate characters, 8 bits each (count <= 8), in the reference's order
-  uint32_t eq;      // bit d: candidate d equals the REF base at this core column (pad columns: all ones)
-  uint8_t j, cnt;
-};
-
-// Column `j` of the window starting at haplotype index w0: candidates as packed characters.
-// Returns false on a missing variant_alleles entry. cnt > 8 (three or more allele entries at a
-// site) leaves `chars` unset: the caller takes column_char instead.
+// Column `j` of the window starting at haplotype index w0 (load_column of hawk_core.h with a
+// cursor): the ambiguous columns of one window are visited in ascending order and every one of
+// them is a site of the haplotype's variant_alleles table, so the table is binary-searched once
+// per hit (`site` < 0) and walked forward afterwards. Returns false on a missing entry.
 __device__ __forceinline__ bool decode_amb_column(const BatchView& B, const ScanConst& K, int32_t h, int64_t chunk0,
-                                                  int32_t w0, int j, int s, int W, Column& c, uint32_t& cnt) {
+                                                  int32_t w0, int j, int s, int W, Column& c, uint32_t& cnt,
+                                                  int64_t& site) {
   const bool rp = K.geom[s].c0 == 0;
   const int k0 = rp ? HAWK_GUIDESEQPAD : W - HAWK_GUIDESEQPAD - K.P;  // search_guides.py:252
   const uint32_t pam_code = (j >= k0 && j < k0 + K.P) ? K.pat[s][j - k0] : 0u;
-  if (!load_column(B, h, chunk0, w0 + j, pam_code, c)) return false;
-  cnt = column_count(c);
+  const int32_t idx = w0 + j;
+  c.nib = nibble_at(B.q, chunk0, idx);
+  c.lower = lower_at(B.v, chunk0, idx);
+  c.allowed = pam_code ? (c.nib & pam_code) : c.nib;
+  const int64_t end = B.va_off[h + 1];
+  if (site < 0) {
+    int64_t lo = B.va_off[h], hi = end;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (B.va_idx[mid] < idx) lo = mid + 1; else hi = mid;
+    }
+    site = lo;
+  } else {
+    while (site < end && B.va_idx[site] < idx) ++site;
+  }
+  if (site >= end || B.va_idx[site] != idx) return false;
+  c.e0 = B.va_ent_off[site];
+  c.m = (int32_t)(B.va_ent_off[site + 1] - c.e0);
+  cnt = (uint32_t)popc32(c.allowed) * (uint32_t)c.m;
   return true;
+}
+
+// the same without a cursor (columns visited in any order)
+__device__ __forceinline__ bool decode_amb_column(const BatchView& B, const ScanConst& K, int32_t h, int64_t chunk0,
+                                                  int32_t w0, int j, int s, int W, Column& c, uint32_t& cnt) {
+  int64_t site = -1;
+  return decode_amb_column(B, K, h, chunk0, w0, j, s, W, c, cnt, site);
+}
+
+// Candidates of an ambiguous column as packed characters (<= 8), in the reference's order -- bases
+// ascending A, C, G, T, then the site's allele entries; upper-case iff the base equals the entry's
+// REF allele (search_guides.py:207-213) -- and the set of candidates whose base is `refnib`.
+__device__ __forceinline__ void column_candidates(const BatchView& B, const Column& c, uint32_t refnib, uint64_t& chars,
+                                                  uint32_t& eq) {
+  chars = 0;
+  eq = 0;
+  uint32_t d = 0, allowed = c.allowed;
+  while (allowed) {
+    const uint32_t base = allowed & (~allowed + 1u);
+    allowed &= allowed - 1u;
+    const uint32_t up = (uint32_t)(uint8_t)nibble_letter(base);
+    for (int32_t e = 0; e < c.m; ++e, ++d) {
+      const uint32_t ch = (B.va_ref[c.e0 + e] == base) ? up : up + 32u;
+      chars |= (uint64_t)ch << (8 * d);
+      if (base == refnib) eq |= 1u << d;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(RES_T) resolve_count_kernel(const __grid_constant__ ResCountArgs A) {
@@ -139,6 +178,7 @@ __global__ void __launch_bounds__(RES_T) resolve_count_kernel(const __grid_const
         if (diff & ~ab & keep) equal = 0;
       }
     }
+    int64_t site = -1;
     for (int w = 0; w < 3 && total; ++w) {
       uint32_t bits = amb[w];
       while (bits) {
@@ -146,7 +186,7 @@ __global__ void __launch_bounds__(RES_T) resolve_count_kernel(const __grid_const
         bits &= bits - 1;
         Column c;
         uint32_t cnt;
-        if (!decode_amb_column(B, K, h, chunk0, w0, j, s, W, c, cnt)) {
+        if (!decode_amb_column(B, K, h, chunk0, w0, j, s, W, c, cnt, site)) {
           atomicExch(A.err, HAWK_EALLELES);
           total = 0;
           break;
@@ -284,9 +324,37 @@ __device__ __forceinline__ uint32_t r_chars4(uint32_t pa, uint32_t pc, uint32_t 
   return ((x0 & ~m) | (x1 & m)) | (r_spread4((pv >> i) & 0xFu) << 5);
 }
 
+// Per-hit descriptor of the row-balanced writer, in shared memory: up to RES_DCOLS ambiguous
+// columns, each with <= 8 candidate characters.
+constexpr int RES_DCOLS = 8;
+struct HitDesc {
+  uint64_t chars[RES_DCOLS];  // candidate characters of column a, 8 bits each
+  uint8_t j[RES_DCOLS];       // window column
+  uint8_t cnt[RES_DCOLS];     // candidates
+  uint8_t eq[RES_DCOLS];      // bit d: candidate d equals the REF base there (pad columns: all candidates)
+  uint32_t inv[RES_DCOLS];    // ceil(2^32 / cnt): t / cnt = umulhi(t, inv) for t < 2^24, cnt <= 8
+  uint32_t total;             // strings of the hit (0: the hit takes the one-thread path below)
+  uint32_t drops;             // 1: a REF partner exists and some string equals it
+  int32_t n_amb;
+  int32_t h, pos, start, stop;
+  uint64_t f;                 // first table row of the hit
+};
+
+// Row-balanced writer: a warp takes 32 consecutive hits; every lane describes its own hit in
+// shared memory (window text from the planes, candidate characters of the ambiguous columns),
+// then the warp's strings -- product index r over all its hits -- are dealt to the lanes round
+// robin: owner hit by a 5-step search in the warp's prefix of string counts, digits from the
+// mixed-radix index (last column fastest), and the row's place from the number of redundant
+// strings before it, which is a rank in the product of the per-column "equals REF" digit sets.
+// Hits with more than RES_DCOLS ambiguous columns or a site with > 8 candidates (rare) are
+// written by their own lane afterwards, one string at a time.
 template <int N16>  // text_stride / 16: 3..5
 __global__ void __launch_bounds__(RES_T) resolve_write_kernel(const __grid_constant__ ResWriteArgs A) {
-  __shared__ uint64_t wsum[RES_T / 32];
+  constexpr int NW = RES_T / 32;
+  __shared__ uint64_t wsum[NW];
+  __shared__ HitDesc desc[NW][32];
+  __shared__ uint4 base_txt[NW][32][N16];
+  __shared__ uint32_t tot_excl[NW][33];
   const int s = blockIdx.x & 1;
   const int64_t blk = blockIdx.x >> 1;
   const ResWriteStrand S = A.S[s];
@@ -308,18 +376,27 @@ __global__ void __launch_bounds__(RES_T) resolve_write_kernel(const __grid_const
   __syncthreads();
   uint64_t wbase = 0;
   for (int k = 0; k < warp; ++k) wbase += wsum[k];
-  if (mine == 0) return;
-  const uint64_t rec = S.recs[i];
-  const int32_t h = (int32_t)(rec >> 32), pos = (int32_t)(rec & 0xFFFFFFFFu);
-  uint64_t f = S.blk_base[blk] + wbase + (incl - mine) + S.kb_other[h + (s == 1 ? 1 : 0)];
-  const int32_t st = S.start[i], sp = S.stop[i];
-  if (A.key_table) atomicMin(&A.key_table[((uint32_t)(st - A.key_min) << 1) | (uint32_t)s], (uint32_t)f);
-  const int64_t chunk0 = B.slot_off[h] >> 5;
-  const int32_t w0 = pos + K.geom[s].w0;
-  // window text of the haplotype itself (codes as they stand), N16 x 16 bytes in registers
-  uint4 base[N16];
-  uint32_t amb[3];
-  {
+
+  HitDesc& D = desc[warp][lane];
+  D.total = 0;
+  D.n_amb = 0;
+  D.drops = 0;
+  bool slow = false;
+  uint32_t amb[3] = {0u, 0u, 0u};
+  int64_t chunk0 = 0, rchunk0 = 0;
+  int32_t w0 = 0, rpivot = -1;
+  if (mine != 0) {
+    const uint64_t rec = S.recs[i];
+    const int32_t h = (int32_t)(rec >> 32), pos = (int32_t)(rec & 0xFFFFFFFFu);
+    D.h = h;
+    D.pos = pos;
+    D.start = S.start[i];
+    D.stop = S.stop[i];
+    D.f = S.blk_base[blk] + wbase + (incl - mine) + S.kb_other[h + (s == 1 ? 1 : 0)];
+    if (A.key_table) atomicMin(&A.key_table[((uint32_t)(D.start - A.key_min) << 1) | (uint32_t)s], (uint32_t)D.f);
+    chunk0 = B.slot_off[h] >> 5;
+    w0 = pos + K.geom[s].w0;
+    // window text of the haplotype itself (codes as they stand)
     const int64_t c = chunk0 + (w0 >> 5);
     const uint32_t sh = (uint32_t)(w0 & 31);
     const uint4 q0 = *reinterpret_cast<const uint4*>(&B.q[c]), q1 = *reinterpret_cast<const uint4*>(&B.q[c + 1]),
@@ -348,105 +425,161 @@ __global__ void __launch_bounds__(RES_T) resolve_write_kernel(const __grid_const
         else if (left < 4) word &= (1u << (8 * left)) - 1u;
         wd[q] = word;
       }
-      base[p] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+      base_txt[warp][lane][p] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
     }
+    // ambiguous columns, first column first (= most significant digit of the product index)
+    rpivot = S.rpivot[i];
+    rchunk0 = A.ref_h >= 0 ? (B.slot_off[A.ref_h] >> 5) : 0;
+    uint64_t total = 1;
+    int n_amb = 0;
+    int64_t site = -1;
+    for (int w = 0; w < 3; ++w) {
+      uint32_t bits = amb[w];
+      while (bits) {
+        const int j = 32 * w + __ffs(bits) - 1;
+        bits &= bits - 1;
+        Column c2;
+        uint32_t cnt;
+        decode_amb_column(B, K, h, chunk0, w0, j, s, W, c2, cnt, site);
+        total *= cnt;
+        if (n_amb < RES_DCOLS && cnt <= 8) {
+          const int cj = j - HAWK_GUIDESEQPAD;
+          const bool core = rpivot >= 0 && cj >= 0 && cj < K.C;
+          uint64_t chars;
+          uint32_t eq;
+          column_candidates(B, c2, core ? nibble_at(B.q, rchunk0, (int64_t)rpivot + cj) : 0u, chars, eq);
+          if (!core) eq = (1u << cnt) - 1u;  // outside the core every candidate "equals"
+          D.chars[n_amb] = chars;
+          D.j[n_amb] = (uint8_t)j;
+          D.cnt[n_amb] = (uint8_t)cnt;
+          D.eq[n_amb] = (uint8_t)eq;
+          D.inv[n_amb] = (uint32_t)((0x100000000ull + cnt - 1) / cnt);
+        } else {
+          slow = true;
+        }
+        ++n_amb;
+      }
+    }
+    D.n_amb = n_amb;
+    D.drops = rpivot >= 0 ? 1u : 0u;
+    D.total = slow ? 0u : (uint32_t)total;
   }
-  // ambiguous columns, first column first (= most significant digit of the product index)
-  AmbCol col[RES_MAXA];
-  int n_amb = 0;
-  bool simple = true;  // every column fits the packed form
-  const int32_t rpivot = S.rpivot[i];
-  const int64_t rchunk0 = A.ref_h >= 0 ? (B.slot_off[A.ref_h] >> 5) : 0;
-  uint64_t total = 1;
-  for (int w = 0; w < 3; ++w) {
-    uint32_t bits = amb[w];
-    while (bits) {
-      const int j = 32 * w + __ffs(bits) - 1;
-      bits &= bits - 1;
-      Column c;
-      uint32_t cnt;
-      decode_amb_column(B, K, h, chunk0, w0, j, s, W, c, cnt);
-      total *= cnt;
-      if (n_amb < RES_MAXA && cnt <= 8) {
-        AmbCol& a = col[n_amb];
-        a.j = (uint8_t)j;
-        a.cnt = (uint8_t)cnt;
-        a.chars = 0;
-        a.eq = 0xFFFFFFFFu;
-        uint32_t refnib = 0;
-        const int cj = j - HAWK_GUIDESEQPAD;
-        const bool core = cj >= 0 && cj < K.C;
-        if (core && rpivot >= 0) {
-          refnib = nibble_at(B.q, rchunk0, (int64_t)rpivot + cj);
-          a.eq = 0;
-        }
-        for (uint32_t d = 0; d < cnt; ++d) {
-          const char ch = column_char(B, c, d);
-          a.chars |= (uint64_t)(uint8_t)ch << (8 * d);
-          if (core && rpivot >= 0 && (iupac_entry((uint8_t)ch) & 15u) == refnib) a.eq |= 1u << d;
-        }
+  // the warp's strings, dealt to the lanes
+  uint32_t tincl = D.total;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, tincl, d);
+    if (lane >= d) tincl += y;
+  }
+  tot_excl[warp][lane] = tincl - D.total;
+  if (lane == 31) tot_excl[warp][32] = tincl;
+  __syncwarp();
+  const uint32_t T = tot_excl[warp][32];
+  for (uint32_t r = lane; r < T; r += 32) {
+    // owner: last hit with tot_excl <= r
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1)
+      if (tot_excl[warp][lo + step] <= r) lo += step;
+    const HitDesc& H = desc[warp][lo];
+    uint32_t t = r - tot_excl[warp][lo];
+    // digits (last column fastest) and, when a REF partner exists, the redundancy rank
+    uint32_t digit[RES_DCOLS];
+#pragma unroll
+    for (int a = RES_DCOLS - 1; a >= 0; --a) {
+      if (a < H.n_amb) {
+        const uint32_t c = H.cnt[a], q = c == 1 ? t : __umulhi(t, H.inv[a]);  // 2^32 / 1 does not fit
+        digit[a] = t - q * c;
+        t = q;
       } else {
-        simple = false;
-      }
-      ++n_amb;
-    }
-  }
-  uint8_t* const text0 = A.o_text + f * (uint64_t)A.text_stride;
-  if (simple) {
-    uint32_t digit[RES_MAXA];
-#pragma unroll
-    for (int a = 0; a < RES_MAXA; ++a) digit[a] = 0;
-    uint64_t k = 0;
-    for (uint64_t t = 0; t < total; ++t) {
-      // redundant with the REF guide: every core column chose the REF base (search_guides.py:356-369)
-      bool drop = rpivot >= 0;
-      for (int a = 0; a < n_amb && drop; ++a) drop = (col[a].eq >> digit[a]) & 1u;
-      if (!drop) {
-        const uint64_t row = f + k;
-        A.o_hap[row] = h;
-        A.o_strand[row] = (uint8_t)s;
-        A.o_pos[row] = pos;
-        A.o_start[row] = st;
-        A.o_stop[row] = sp;
-        uint8_t* dst = text0 + k * (uint64_t)A.text_stride;
-#pragma unroll
-        for (int p = 0; p < N16; ++p) reinterpret_cast<uint4*>(dst)[p] = base[p];
-        for (int a = 0; a < n_amb; ++a) dst[col[a].j] = (uint8_t)(col[a].chars >> (8 * digit[a]));
-        ++k;
-      }
-      for (int a = n_amb - 1; a >= 0; --a) {  // odometer, last column fastest
-        if (++digit[a] < col[a].cnt) break;
         digit[a] = 0;
       }
     }
-  } else {
-    // rare shapes (more than RES_MAXA ambiguous columns, or a site with three or more allele
-    // entries): one string at a time, columns re-derived per string
+    uint32_t dropped_before = 0;
+    bool drop = false;
+    if (H.drops) {
+      uint32_t suffix[RES_DCOLS + 1];  // product of |eq| over the columns behind a
+      suffix[RES_DCOLS] = 1;
+#pragma unroll
+      for (int a = RES_DCOLS - 1; a >= 0; --a) suffix[a] = suffix[a + 1] * (a < H.n_amb ? (uint32_t)__popc(H.eq[a]) : 1u);
+      drop = true;
+#pragma unroll
+      for (int a = 0; a < RES_DCOLS; ++a) {
+        if (a < H.n_amb && drop) {
+          const uint32_t e = H.eq[a];
+          dropped_before += (uint32_t)__popc(e & ((1u << digit[a]) - 1u)) * suffix[a + 1];
+          if (!((e >> digit[a]) & 1u)) drop = false;
+        }
+      }
+    }
+    if (drop) continue;  // redundant with the REF guide (search_guides.py:356-369)
+    const uint64_t row = H.f + (r - tot_excl[warp][lo]) - dropped_before;
+    A.o_hap[row] = H.h;
+    A.o_strand[row] = (uint8_t)s;
+    A.o_pos[row] = H.pos;
+    A.o_start[row] = H.start;
+    A.o_stop[row] = H.stop;
+    uint8_t* const dst8 = A.o_text + row * (uint64_t)A.text_stride;
+    uint4* const dst = reinterpret_cast<uint4*>(dst8);
+#pragma unroll
+    for (int p = 0; p < N16; ++p) dst[p] = base_txt[warp][lo][p];
+#pragma unroll
+    for (int a = 0; a < RES_DCOLS; ++a)
+      if (a < H.n_amb) dst8[H.j[a]] = (uint8_t)(H.chars[a] >> (8 * digit[a]));  // same thread, program order
+  }
+  if (!slow || mine == 0) return;
+  // rare shapes (more than RES_DCOLS ambiguous columns, or a site with more than 8 candidates):
+  // one string at a time by the hit's own lane, columns re-derived per string
+  {
+    const int32_t h = D.h, pos = D.pos, st = D.start, sp = D.stop;
+    uint64_t total = 1;
+    for (int w = 0; w < 3; ++w) {
+      uint32_t bits = amb[w];
+      while (bits) {
+        const int j = 32 * w + __ffs(bits) - 1;
+        bits &= bits - 1;
+        Column c2;
+        uint32_t cnt;
+        decode_amb_column(B, K, h, chunk0, w0, j, s, W, c2, cnt);
+        total *= cnt;
+      }
+    }
+    uint8_t* const text0 = A.o_text + D.f * (uint64_t)A.text_stride;
     uint64_t k = 0;
     for (uint64_t t = 0; t < total; ++t) {
-      uint8_t* dst = text0 + k * (uint64_t)A.text_stride;
-#pragma unroll
-      for (int p = 0; p < N16; ++p) reinterpret_cast<uint4*>(dst)[p] = base[p];
-      uint64_t rem = t;
+      // two passes over the columns: decide first, write only a string that stays (a redundant
+      // one must not touch the slot behind the hit's last row: it belongs to the next hit)
       bool same = rpivot >= 0;
-      for (int w = 2; w >= 0; --w) {
-        uint32_t bits = amb[w];
-        while (bits) {
-          const int j = 32 * w + 31 - __clz(bits);  // last column first: least significant digit
-          bits &= ~(1u << (j & 31));
-          Column c;
-          uint32_t cnt;
-          decode_amb_column(B, K, h, chunk0, w0, j, s, W, c, cnt);
-          const char ch = column_char(B, c, (uint32_t)(rem % cnt));
-          rem /= cnt;
-          dst[j] = (uint8_t)ch;
-          const int cj = j - HAWK_GUIDESEQPAD;
-          if (same && cj >= 0 && cj < K.C)
-            same = (iupac_entry((uint8_t)ch) & 15u) == nibble_at(B.q, rchunk0, (int64_t)rpivot + cj);
+      uint8_t* dst = text0 + k * (uint64_t)A.text_stride;
+      for (int pass = same ? 0 : 1; pass < 2; ++pass) {
+        if (pass == 1) {
+          if (same) break;
+#pragma unroll
+          for (int p = 0; p < N16; ++p) reinterpret_cast<uint4*>(dst)[p] = base_txt[warp][lane][p];
+        }
+        uint64_t rem = t;
+        for (int w = 2; w >= 0; --w) {
+          uint32_t bits = amb[w];
+          while (bits) {
+            const int j = 32 * w + 31 - __clz(bits);  // last column first: least significant digit
+            bits &= ~(1u << (j & 31));
+            Column c2;
+            uint32_t cnt;
+            decode_amb_column(B, K, h, chunk0, w0, j, s, W, c2, cnt);
+            const char ch = column_char(B, c2, (uint32_t)(rem % cnt));
+            rem /= cnt;
+            if (pass == 1) {
+              dst[j] = (uint8_t)ch;
+            } else {
+              const int cj = j - HAWK_GUIDESEQPAD;
+              if (same && cj >= 0 && cj < K.C)
+                same = (iupac_entry((uint8_t)ch) & 15u) == nibble_at(B.q, rchunk0, (int64_t)rpivot + cj);
+            }
+          }
         }
       }
       if (!same) {
-        const uint64_t row = f + k;
+        const uint64_t row = D.f + k;
         A.o_hap[row] = h;
         A.o_strand[row] = (uint8_t)s;
         A.o_pos[row] = pos;
