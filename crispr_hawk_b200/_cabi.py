@@ -105,6 +105,7 @@ SIGNATURES = {
     "hawk_batch_export_nibbles": (C.c_int, [_P, C.c_int32, _U8P, _U8P]),
     "hawk_batch_set_posmap": (C.c_int, [_P, _I64P, _I32P, _I32P, _U8P]),
     "hawk_batch_set_alleles": (C.c_int, [_P, _I64P, _I32P, _I64P, _U8P]),
+    "hawk_batch_set_scan": (C.c_int, [_P, _I32P, _I32P, _U8P]),
     "hawk_search": (C.c_int, [_P, _P, C.POINTER(HawkParams), _I32P, _I32P, _U8P, C.POINTER(_P)]),
     "hawk_pam_search": (C.c_int, [_P, _P, C.POINTER(HawkParams), _I32P, _I32P, C.POINTER(_P)]),
     "hawk_result_destroy": (C.c_int, [_P]),
@@ -372,6 +373,15 @@ class Batch:
         )
         self.has_alleles = True
 
+    def set_scan(self, scan_start, scan_stop, is_ref):
+        """hawk_batch_set_scan: attach the scan bounds; searches may then pass None for them."""
+        a = np.ascontiguousarray(scan_start, dtype=np.int32)
+        b = np.ascontiguousarray(scan_stop, dtype=np.int32)
+        r = np.ascontiguousarray(is_ref, dtype=np.uint8)
+        check(self.lib.hawk_batch_set_scan(self.handle, ptr(a, C.c_int32), ptr(b, C.c_int32), ptr(r, C.c_uint8)),
+              "hawk_batch_set_scan")  # fmt: skip
+        self.has_scan = True
+
     def set_variants(self, vt):
         """N2: the haplotypes' variant tables (marshal.VariantTable) for Result.annotate."""
         check(
@@ -506,10 +516,10 @@ class Result:
             pass
 
 
-def search(ctx: Context, batch: Batch, params: HawkParams, scan_start, scan_stop, is_ref) -> Result:
-    a = np.ascontiguousarray(scan_start, dtype=np.int32)
-    b = np.ascontiguousarray(scan_stop, dtype=np.int32)
-    r = np.ascontiguousarray(is_ref, dtype=np.uint8)
+def search(ctx: Context, batch: Batch, params: HawkParams, scan_start=None, scan_stop=None, is_ref=None) -> Result:
+    a = None if scan_start is None else np.ascontiguousarray(scan_start, dtype=np.int32)
+    b = None if scan_stop is None else np.ascontiguousarray(scan_stop, dtype=np.int32)
+    r = None if is_ref is None else np.ascontiguousarray(is_ref, dtype=np.uint8)
     h = _P()
     check(
         ctx.lib.hawk_search(ctx.handle, batch.handle, C.byref(params), ptr(a, C.c_int32),
@@ -519,12 +529,13 @@ def search(ctx: Context, batch: Batch, params: HawkParams, scan_start, scan_stop
     return Result(ctx.lib, h)
 
 
-def encode_search(ctx: Context, batch: Batch, device_ptr: int, params: HawkParams, scan_start, scan_stop, is_ref) -> Result:
+def encode_search(ctx: Context, batch: Batch, device_ptr: int, params: HawkParams, scan_start=None, scan_stop=None,
+                  is_ref=None) -> Result:  # fmt: skip
     """hawk_encode_search_dev: re-encode `batch` from device-resident texts and search it in one
-    pass (K1 + K2 fused)."""
-    a = np.ascontiguousarray(scan_start, dtype=np.int32)
-    b = np.ascontiguousarray(scan_stop, dtype=np.int32)
-    r = np.ascontiguousarray(is_ref, dtype=np.uint8)
+    pass. Bounds None: the ones attached with Batch.set_scan."""
+    a = None if scan_start is None else np.ascontiguousarray(scan_start, dtype=np.int32)
+    b = None if scan_stop is None else np.ascontiguousarray(scan_stop, dtype=np.int32)
+    r = None if is_ref is None else np.ascontiguousarray(is_ref, dtype=np.uint8)
     h, bad = _P(), C.c_int64(-1)
     rc = ctx.lib.hawk_encode_search_dev(ctx.handle, batch.handle, C.c_void_p(device_ptr), C.byref(params),
                                         ptr(a, C.c_int32), ptr(b, C.c_int32), ptr(r, C.c_uint8), C.byref(h), C.byref(bad))  # fmt: skip

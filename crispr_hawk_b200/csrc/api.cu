@@ -613,39 +613,115 @@ struct ScanOut {
 // next stage (candidates, then hits), everything else is stream-ordered
 struct ScanInputs {  // per-search arrays on the device, carved out of one upload
   DevBuf buf;
+  bool cached = false;  // the bounds are the batch's own (hawk_batch_set_scan): nothing to upload
   int32_t *a = nullptr, *b = nullptr;
   uint8_t* is_ref = nullptr;
   int64_t* sblock_off = nullptr;
 };
+
+static inline size_t al8z(size_t x) { return (x + 7) & ~(size_t)7; }
+struct ScanLayout {
+  size_t o_sb, o_a, o_b, o_ref, bytes;
+  explicit ScanLayout(int32_t n_hap) {
+    o_sb = 0;
+    o_a = o_sb + (size_t)(n_hap + 1) * 8;
+    o_b = o_a + al8z((size_t)n_hap * 4);
+    o_ref = o_b + al8z((size_t)n_hap * 4);
+    bytes = o_ref + al8z((size_t)n_hap);
+  }
+};
+
+// sub-ranges of the fused kernel that overlap a REF haplotype's territory (full-size entry segments)
+static int64_t count_dense_subs(const hawk_batch* b, const uint8_t* is_ref) {
+  const int64_t n_chunks = b->total_slots / HAWK_CHUNK;
+  int64_t n_dense = 0, last = -1;
+  for (int32_t h = 0; h < b->n_hap; ++h) {
+    if (!is_ref[h]) continue;
+    const int64_t t0 = (b->slot_off[h] >> 5) - HAWK_SLOT_GAP / HAWK_CHUNK;
+    const int64_t t1 = h + 1 < b->n_hap ? (b->slot_off[h + 1] >> 5) - HAWK_SLOT_GAP / HAWK_CHUNK : n_chunks;
+    int64_t s0 = t0 / FUSED_SUB, s1 = (t1 - 1) / FUSED_SUB;
+    if (s0 <= last) s0 = last + 1;
+    if (s1 >= s0) {
+      n_dense += s1 - s0 + 1;
+      last = s1;
+    }
+  }
+  return n_dense;
+}
+
+extern "C" int hawk_batch_set_scan(hawk_batch* b, const int32_t* scan_start, const int32_t* scan_stop,
+                                   const uint8_t* is_ref) {
+  if (!b || (b->n_hap > 0 && (!scan_start || !scan_stop || !is_ref)))
+    return hawk_fail(HAWK_EINVAL, "hawk_batch_set_scan: bad arguments");
+  hawk_ctx* c = b->ctx;
+  CKCUDA(cudaSetDevice(c->device));
+  const int32_t n = b->n_hap;
+  b->has_scan = false;
+  b->h_scan_a.assign(scan_start, scan_start + n);
+  b->h_scan_b.assign(scan_stop, scan_stop + n);
+  b->h_scan_ref.assign(is_ref, is_ref + n);
+  const ScanLayout L(n);
+  std::vector<char> host(L.bytes, 0);
+  b->scan_sblocks = hawk_scan_plan(scan_start, scan_stop, n, (int64_t*)(host.data() + L.o_sb));
+  b->scan_bp = 0;
+  b->scan_ref_h = -1;
+  b->scan_n_ref = 0;
+  for (int32_t h = 0; h < n; ++h) {
+    const int64_t a = scan_start[h] < 0 ? 0 : scan_start[h], e = scan_stop[h];
+    if (e > a) b->scan_bp += e - a;
+    if (is_ref[h]) {
+      if (b->scan_ref_h < 0) b->scan_ref_h = h;
+      ++b->scan_n_ref;
+    }
+  }
+  if (n > 0) {
+    memcpy(host.data() + L.o_a, scan_start, (size_t)n * 4);
+    memcpy(host.data() + L.o_b, scan_stop, (size_t)n * 4);
+    memcpy(host.data() + L.o_ref, is_ref, (size_t)n);
+  }
+  b->scan_dense_subs = count_dense_subs(b, is_ref);
+  CK(b->d_scan.alloc(c, L.bytes));
+  CKCUDA(cudaMemcpyAsync(b->d_scan.p, host.data(), L.bytes, cudaMemcpyHostToDevice, c->stream));
+  CKCUDA(cudaStreamSynchronize(c->stream));
+  c->h2d_bytes += (int64_t)L.bytes;
+  b->has_scan = true;
+  return HAWK_OK;
+}
 
 static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const int32_t* scan_start,
                     const int32_t* scan_stop, const uint8_t* is_ref, int raw, ScanInputs& in, ScanOut& out) {
   cudaStream_t st = c->stream;
   Trace tr;
   const int32_t n_hap = b->n_hap;
-  auto al8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
-  const size_t o_sb = 0, o_a = o_sb + (size_t)(n_hap + 1) * 8, o_b = o_a + al8((size_t)n_hap * 4),
-               o_ref = o_b + al8((size_t)n_hap * 4), total_bytes = o_ref + al8((size_t)n_hap);
-  char* hp = (char*)c->pinned_get(total_bytes);
-  if (!hp) return hawk_fail(HAWK_ENOMEM, "pinned staging allocation failed");
-  const int64_t n_sblocks = hawk_scan_plan(scan_start, scan_stop, n_hap, (int64_t*)(hp + o_sb));
-  out.scanned_bp = 0;
-  for (int32_t h = 0; h < n_hap; ++h) {
-    int64_t a = scan_start[h] < 0 ? 0 : scan_start[h], e = scan_stop[h];
-    if (e > a) out.scanned_bp += e - a;
+  const ScanLayout L(n_hap);
+  int64_t n_sblocks;
+  char* dp;
+  if (in.cached) {
+    n_sblocks = b->scan_sblocks;
+    out.scanned_bp = b->scan_bp;
+    dp = (char*)b->d_scan.p;
+  } else {
+    char* hp = (char*)c->pinned_get(L.bytes);
+    if (!hp) return hawk_fail(HAWK_ENOMEM, "pinned staging allocation failed");
+    n_sblocks = hawk_scan_plan(scan_start, scan_stop, n_hap, (int64_t*)(hp + L.o_sb));
+    out.scanned_bp = 0;
+    for (int32_t h = 0; h < n_hap; ++h) {
+      int64_t a = scan_start[h] < 0 ? 0 : scan_start[h], e = scan_stop[h];
+      if (e > a) out.scanned_bp += e - a;
+    }
+    if (n_hap > 0) {
+      memcpy(hp + L.o_a, scan_start, (size_t)n_hap * 4);
+      memcpy(hp + L.o_b, scan_stop, (size_t)n_hap * 4);
+      memcpy(hp + L.o_ref, is_ref, (size_t)n_hap);
+    }
+    CK(in.buf.alloc(c, L.bytes));
+    CK(c->small_h2d(in.buf.p, hp, L.bytes));
+    dp = (char*)in.buf.p;
   }
-  if (n_hap > 0) {
-    memcpy(hp + o_a, scan_start, (size_t)n_hap * 4);
-    memcpy(hp + o_b, scan_stop, (size_t)n_hap * 4);
-    memcpy(hp + o_ref, is_ref, (size_t)n_hap);
-  }
-  CK(in.buf.alloc(c, total_bytes));
-  CK(c->small_h2d(in.buf.p, hp, total_bytes));
-  char* dp = (char*)in.buf.p;
-  in.sblock_off = (int64_t*)(dp + o_sb);
-  in.a = (int32_t*)(dp + o_a);
-  in.b = (int32_t*)(dp + o_b);
-  in.is_ref = (uint8_t*)(dp + o_ref);
+  in.sblock_off = (int64_t*)(dp + L.o_sb);
+  in.a = (int32_t*)(dp + L.o_a);
+  in.b = (int32_t*)(dp + L.o_b);
+  in.is_ref = (uint8_t*)(dp + L.o_ref);
   for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(c, 16));
   if (n_sblocks == 0) return HAWK_OK;
   DevBuf d_ws, d_mws, d_masks;
@@ -696,48 +772,47 @@ static int run_scan_fused(hawk_ctx* c, hawk_batch* b, const uint8_t* d_ascii, co
   const ScanConst K = make_scan_const(*params, 0);
   const int64_t n_chunks = b->total_slots / HAWK_CHUNK;
   *fell_back = false;
-  auto al8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
-  const size_t o_a = 0, o_b = o_a + al8((size_t)n_hap * 4), o_ref = o_b + al8((size_t)n_hap * 4),
-               o_tot = o_ref + al8((size_t)n_hap), total_bytes = o_tot + 64;
-  char* hp = (char*)c->pinned_get(total_bytes);
-  if (!hp) return hawk_fail(HAWK_ENOMEM, "pinned staging allocation failed");
-  out.scanned_bp = 0;
-  for (int32_t h = 0; h < n_hap; ++h) {
-    int64_t a = scan_start[h] < 0 ? 0 : scan_start[h], e = scan_stop[h];
-    if (e > a) out.scanned_bp += e - a;
-  }
-  memcpy(hp + o_a, scan_start, (size_t)n_hap * 4);
-  memcpy(hp + o_b, scan_stop, (size_t)n_hap * 4);
-  memcpy(hp + o_ref, is_ref, (size_t)n_hap);
-  uint64_t* tot0 = (uint64_t*)(hp + o_tot);  // [1..2] hit totals, [3] overflow flag, [4] first bad slot
-  memset(tot0, 0, 64);
-  tot0[4] = (uint64_t)INT64_MAX;
-  CK(in.buf.alloc(c, total_bytes));
-  CK(c->small_h2d(in.buf.p, hp, total_bytes));
-  char* dp = (char*)in.buf.p;
-  in.a = (int32_t*)(dp + o_a);
-  in.b = (int32_t*)(dp + o_b);
-  in.is_ref = (uint8_t*)(dp + o_ref);
-  uint64_t* d_tot = (uint64_t*)(dp + o_tot);
-  for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(c, 16));
-  // segment capacities: host total (allocation), device prefix (addresses)
+  // [1..2] hit totals, [3] overflow flag, [4] first bad slot
+  uint64_t tot0[8] = {0, 0, 0, 0, (uint64_t)INT64_MAX, 0, 0, 0};
   const int64_t n_sub = fused_sub_ranges(n_chunks);
   const int all_dense = K.unphased;
-  int64_t n_dense = all_dense ? n_sub : 0;
-  if (!all_dense) {
-    int64_t last = -1;
+  int64_t n_dense;
+  uint64_t* d_tot;
+  if (in.cached) {  // the batch's own bounds (hawk_batch_set_scan): only the totals block goes up
+    const ScanLayout L(n_hap);
+    char* dp = (char*)b->d_scan.p;
+    in.a = (int32_t*)(dp + L.o_a);
+    in.b = (int32_t*)(dp + L.o_b);
+    in.is_ref = (uint8_t*)(dp + L.o_ref);
+    out.scanned_bp = b->scan_bp;
+    n_dense = all_dense ? n_sub : b->scan_dense_subs;
+    CK(in.buf.alloc(c, 64));
+    CK(c->small_h2d(in.buf.p, tot0, 64));
+    d_tot = (uint64_t*)in.buf.p;
+  } else {
+    const size_t o_a = 0, o_b = o_a + al8z((size_t)n_hap * 4), o_ref = o_b + al8z((size_t)n_hap * 4),
+                 o_tot = o_ref + al8z((size_t)n_hap), total_bytes = o_tot + 64;
+    char* hp = (char*)c->pinned_get(total_bytes);
+    if (!hp) return hawk_fail(HAWK_ENOMEM, "pinned staging allocation failed");
+    out.scanned_bp = 0;
     for (int32_t h = 0; h < n_hap; ++h) {
-      if (!is_ref[h]) continue;
-      const int64_t t0 = (b->slot_off[h] >> 5) - HAWK_SLOT_GAP / HAWK_CHUNK;
-      const int64_t t1 = h + 1 < n_hap ? (b->slot_off[h + 1] >> 5) - HAWK_SLOT_GAP / HAWK_CHUNK : n_chunks;
-      int64_t s0 = t0 / FUSED_SUB, s1 = (t1 - 1) / FUSED_SUB;
-      if (s0 <= last) s0 = last + 1;
-      if (s1 >= s0) {
-        n_dense += s1 - s0 + 1;
-        last = s1;
-      }
+      int64_t a = scan_start[h] < 0 ? 0 : scan_start[h], e = scan_stop[h];
+      if (e > a) out.scanned_bp += e - a;
     }
+    memcpy(hp + o_a, scan_start, (size_t)n_hap * 4);
+    memcpy(hp + o_b, scan_stop, (size_t)n_hap * 4);
+    memcpy(hp + o_ref, is_ref, (size_t)n_hap);
+    memcpy(hp + o_tot, tot0, 64);
+    CK(in.buf.alloc(c, total_bytes));
+    CK(c->small_h2d(in.buf.p, hp, total_bytes));
+    char* dp = (char*)in.buf.p;
+    in.a = (int32_t*)(dp + o_a);
+    in.b = (int32_t*)(dp + o_b);
+    in.is_ref = (uint8_t*)(dp + o_ref);
+    d_tot = (uint64_t*)(dp + o_tot);
+    n_dense = all_dense ? n_sub : count_dense_subs(b, is_ref);
   }
+  for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(c, 16));
   const size_t total_cap = (size_t)(n_sub - n_dense) * (FUSED_SUB / 4) + (size_t)n_dense * FUSED_SUB;
   DevBuf d_hs, d_cap, d_segbase, d_tiles, d_entries, d_cnt, d_base;
   CK(d_hs.alloc(c, (size_t)(n_hap > 0 ? n_hap : 1) * sizeof(HapScan)));
@@ -1095,6 +1170,13 @@ extern "C" int hawk_search(hawk_ctx* c, hawk_batch* b, const hawk_params* params
 int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const int32_t* scan_start,
                      const int32_t* scan_stop, const uint8_t* is_ref, const StreamLink* link, hawk_result** out,
                      const uint8_t* fused_text, int64_t* bad_slot) {
+  // NULL bounds: the ones attached to the batch (hawk_batch_set_scan), already on the device
+  const bool cached = b && !scan_start && !scan_stop && !is_ref && b->has_scan;
+  if (cached) {
+    scan_start = b->h_scan_a.data();
+    scan_stop = b->h_scan_b.data();
+    is_ref = b->h_scan_ref.data();
+  }
   CK(check_scan_args(c, b, params, scan_start, scan_stop, out));
   if (bad_slot) *bad_slot = -1;
   if (b->n_hap > 0 && !is_ref) return hawk_fail(HAWK_EINVAL, "hawk_search: is_ref missing");
@@ -1106,11 +1188,16 @@ int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, cons
   CKCUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   int32_t ref_h = -1, n_ref = 0;
-  for (int32_t h = 0; h < b->n_hap; ++h)
-    if (is_ref[h]) {
-      if (ref_h < 0) ref_h = h;
-      ++n_ref;
-    }
+  if (cached) {
+    ref_h = b->scan_ref_h;
+    n_ref = b->scan_n_ref;
+  } else {
+    for (int32_t h = 0; h < b->n_hap; ++h)
+      if (is_ref[h]) {
+        if (ref_h < 0) ref_h = h;
+        ++n_ref;
+      }
+  }
   if (n_ref > 1)
     return hawk_fail(HAWK_EDUPREF, "hawk_search: %d haplotypes are labelled REF; the reference aborts on "
                      "the duplicate REF guides this produces (search_guides.py:328-334)", n_ref);
@@ -1124,6 +1211,7 @@ int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, cons
 
   int rc = HAWK_OK;
   ScanInputs in;
+  in.cached = cached;
   DevBuf d_refrange, d_err;
   DevBuf start[2], stop[2], keep[2], kept_excl[2], tile_sums, cnt[2], off[2], text_pre[2], row_hit[2];
   ScanOut so;

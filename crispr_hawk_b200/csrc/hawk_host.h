@@ -190,6 +190,14 @@ struct hawk_batch {
   DevBuf var_off, var_pos, var_rl, var_al, var_ao, var_pool;
   int32_t var_pos_base = 0;
   bool has_variants = false;
+  // scan bounds attached to the batch (hawk_batch_set_scan): searches that pass NULL bounds use
+  // these device-resident copies instead of uploading n_hap-sized arrays per call
+  bool has_scan = false;
+  std::vector<int32_t> h_scan_a, h_scan_b;
+  std::vector<uint8_t> h_scan_ref;
+  DevBuf d_scan;  // [sblock_off (n_hap + 1) x 8 | scan_start | scan_stop | is_ref]
+  int64_t scan_bp = 0, scan_sblocks = 0, scan_dense_subs = 0;
+  int32_t scan_ref_h = -1, scan_n_ref = 0;
   // host-side facts about the coordinate maps (hawk_batch_set_posmap)
   std::vector<int64_t> h_seg_off;
   std::vector<int32_t> first_gen;   // posmap(0) per haplotype

@@ -67,6 +67,7 @@ class Workload:
     def prepare_resident(self) -> None:
         self.batch = _cabi.Batch(self.ctx, None, self.d.slot_off, self.d.lens, device_ptr=self.ascii_dev.data_ptr())
         self.batch.set_posmap(self.d.seg)
+        self.batch.set_scan(self.a, self.b, self.d.is_ref)  # bounds are batch metadata: uploaded once
 
     def step_resident(self, fused=None) -> _cabi.Result:
         """encode + search over the texts resident in HBM; the table stays on the device.
@@ -77,9 +78,9 @@ class Workload:
             self.prepare_resident()
         if fused is None or fused:
             self.ctx.set_fused(2 if fused is None else 1)
-            return _cabi.encode_search(self.ctx, self.batch, self.ascii_dev.data_ptr(), self.params, self.a, self.b, self.d.is_ref)
+            return _cabi.encode_search(self.ctx, self.batch, self.ascii_dev.data_ptr(), self.params)
         self.batch.repack(self.ascii_dev.data_ptr())
-        return _cabi.search(self.ctx, self.batch, self.params, self.a, self.b, self.d.is_ref)
+        return _cabi.search(self.ctx, self.batch, self.params)
 
     # ---- the hot path through host buffers ----
     def host_buffers(self):
@@ -290,6 +291,7 @@ class UnphasedWorkload:
         self.batch = _cabi.Batch(self.ctx, None, self.d.slot_off, self.d.lens, device_ptr=self.ascii_dev.data_ptr())
         self.batch.set_posmap(self.d.seg)
         self.batch.set_alleles(self.d.alleles)
+        self.batch.set_scan(self.a, self.b, self.d.is_ref)  # bounds are batch metadata: uploaded once
 
     def step_resident(self, fused=None) -> _cabi.Result:
         """encode + unphased search; texts resident in HBM, table stays on the device (see
@@ -298,9 +300,9 @@ class UnphasedWorkload:
             self.prepare_resident()
         if fused is None or fused:
             self.ctx.set_fused(2 if fused is None else 1)
-            return _cabi.encode_search(self.ctx, self.batch, self.ascii_dev.data_ptr(), self.params, self.a, self.b, self.d.is_ref)
+            return _cabi.encode_search(self.ctx, self.batch, self.ascii_dev.data_ptr(), self.params)
         self.batch.repack(self.ascii_dev.data_ptr())
-        return _cabi.search(self.ctx, self.batch, self.params, self.a, self.b, self.d.is_ref)
+        return _cabi.search(self.ctx, self.batch, self.params)
 
     def host_buffers(self):
         torch = self.torch

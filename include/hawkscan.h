@@ -126,6 +126,15 @@ int hawk_batch_set_posmap(hawk_batch *batch, const int64_t *seg_off, const int32
 int hawk_batch_set_alleles(hawk_batch *batch, const int64_t *va_off, const int32_t *va_idx,
                            const int64_t *va_ent_off, const uint8_t *va_ref);
 
+/* Scan bounds as batch metadata (like the coordinate maps): scan_start / scan_stop are the
+ * haplotype-relative bounds of compute_scan_start_stop (search_guides.py:49-84) for the PAM length
+ * that will be searched, is_ref[h] = (samples == "REF"). Once attached, hawk_search /
+ * hawk_encode_search_dev may be called with scan_start = scan_stop = is_ref = NULL and use these
+ * device-resident copies: a cohort of 4.3e5 indel-window haplotypes otherwise spends a
+ * millisecond per search re-staging and re-uploading three n_hap-sized arrays. */
+int hawk_batch_set_scan(hawk_batch *batch, const int32_t *scan_start, const int32_t *scan_stop,
+                        const uint8_t *is_ref);
+
 /* Replaces search_guides.py:510-548 (search) up to, not including, the
  * construction of Python Guide objects. scan_start/scan_stop are the
  * haplotype-relative bounds of compute_scan_start_stop (:49-84); is_ref[h] =
