@@ -137,6 +137,7 @@ SIGNATURES = {
     "hawk_batch_set_variants": (C.c_int, [_P, _I64P, _I32P, _I32P, _I32P, _I64P, _U8P, C.c_int64]),
     "hawk_result_annotate": (C.c_int, [_P, _P, _U8P, _I32P, _I32P, _I64P, _I64P]),
     "hawk_result_fetch_variants": (C.c_int, [_P, _I32P]),
+    "hawk_result_collapse": (C.c_int, [_P, _U8P, C.c_int32, _U32P, _U8P, _I32P]),
     "hawk_table_text_stride": (C.c_int32, [C.c_int32, C.c_int32]),
     "hawk_stream_plan": (C.c_int32, [_I64P, C.c_int32, _U8P, C.c_int32, _I32P, _I32P, C.c_int32]),
     "hawk_search_stream": (
@@ -492,6 +493,15 @@ class Result:
             check(self.lib.hawk_result_fetch_variants(self.handle, ptr(idx, C.c_int32)), "hawk_result_fetch_variants")
         return {"rc_text": rc.reshape(n, ts)[:, :w] if want_text else None, "gc_num": num, "gc_den": den,
                 "gv_off": off, "gv_idx": idx}  # fmt: skip
+
+    def collapse(self, is_ref):
+        """hawk_result_collapse: (perm, head, collision) -- rows ordered by (start, stop, group),
+        head[k] = 1 where a report row (group) starts."""
+        r = np.ascontiguousarray(is_ref, dtype=np.uint8)
+        perm, head, col = np.empty(self.n_guides, np.uint32), np.empty(self.n_guides, np.uint8), C.c_int32(0)
+        check(self.lib.hawk_result_collapse(self.handle, ptr(r, C.c_uint8), len(r), ptr(perm, C.c_uint32), ptr(head, C.c_uint8),
+                                            C.byref(col)), "hawk_result_collapse")  # fmt: skip
+        return perm, head, bool(col.value)
 
     def device_columns(self):
         """Borrowed device addresses {column: int} of the table (hawk_result_device_columns)."""

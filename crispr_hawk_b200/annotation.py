@@ -71,6 +71,24 @@ def annotate_table(table: Dict[str, np.ndarray], res, batch, haplotypes, right: 
     return {"variants": variants, "afs_str": afs_str, "sequence": seq, "right": rp, "gc": gc}
 
 
+def report_groups(table, res, haplotypes):
+    """Row groups of reports._collapse_report_entries (reports.py:958-1008) from the resident
+    table: `hawk_result_collapse`, then the split into index arrays (report_rows.groups_of)."""
+    from . import report_rows
+
+    is_ref = np.array([h.samples == "REF" for h in haplotypes], dtype=np.uint8)
+    perm, head, collision = res.collapse(is_ref)
+    key_of = None
+    if collision:
+        hap, strand, start, stop = table["hap"], table["strand"], table["start"], table["stop"]
+        core = res.table()["text"][:, 10 : 10 + res.window - 20]  # GUIDESEQPAD either side
+
+        def key_of(i):
+            return (int(start[i]), int(stop[i]), int(strand[i]), int(is_ref[hap[i]]), core[i].tobytes())
+
+    return report_rows.groups_of(perm, head, collision, key_of)
+
+
 # --------------------------------------------------------------------------- drop-in seam (N2)
 # Mirrors of the four per-guide loops annotation.annotate_guides runs right after search()
 # (annotation.py:563-572), same names, signatures and return values. On a list that came from
@@ -88,6 +106,7 @@ def _columns(guides, debug: bool):
         if link.get("res") is None or not getattr(link["res"], "handle", None):
             return None
         link["cols"] = annotate_table(link["table"], link["res"], link["batch"], link["haplotypes"], link["right"], debug=debug)
+        link["groups"] = report_groups(link["table"], link["res"], link["haplotypes"])  # for the report's row collapse
         link["res"].close()  # the table has served its purpose: release the device memory
         link["res"] = None
     return link["cols"], link["order"]

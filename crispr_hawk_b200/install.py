@@ -13,15 +13,20 @@ _saved = {}
 
 
 def install(module: Optional[object] = None, annotation_module: Optional[object] = None, annotation: bool = True,
-            haplotypes_module: Optional[object] = None, haplotypes: bool = True):
+            haplotypes_module: Optional[object] = None, haplotypes: bool = True,
+            reports_module: Optional[object] = None, reports: bool = True):
     """Rebind in `crisprhawk.crisprhawk` (or the given module object). Returns it.
 
     With `annotation` (N2) the four per-guide loops `annotation.annotate_guides` runs right
     after `search()` -- `_annotate_variants`, `annotate_variants_afs`, `reverse_guides`,
     `gc_content` (annotation.py:563-572) -- are rebound in `crisprhawk.annotation` (or the
     given module object) too; they act on lists returned by this package's `search` and hand
-    every other list to the reference's own functions."""
+    every other list to the reference's own functions. With `reports` (N2, second half)
+    `reports._process_data` and `reports._collapse_report_entries` (reports.py:476-531, 958-1008)
+    are rebound the same way: the row collapse uses the groups the device computed over the
+    resident table instead of a pandas groupby."""
     from . import _cabi
+    from . import report_rows as rep
     from . import annotation as ann
     from . import haplotypes as hapmod
 
@@ -52,13 +57,36 @@ def install(module: Optional[object] = None, annotation_module: Optional[object]
             _saved[hmod] = {"add_variants_phased": getattr(hmod, "add_variants_phased", None)}
             hapmod._reference_add_variants_phased = _saved[hmod]["add_variants_phased"]
             hmod.add_variants_phased = hapmod.add_variants_phased
+    if reports:
+        rmod = reports_module
+        if rmod is None and module is None:
+            rmod = importlib.import_module("crisprhawk.reports")
+        if rmod is not None and rmod not in _saved:
+            _saved[rmod] = {n: getattr(rmod, n, None) for n in rep.SEAM}
+            for n in rep.SEAM:
+                if _saved[rmod][n] is not None:
+                    rep._reference[n] = _saved[rmod][n]
+                    setattr(rmod, n, getattr(rep, n))
     return drv
 
 
 def uninstall(module: Optional[object] = None, annotation_module: Optional[object] = None,
-              haplotypes_module: Optional[object] = None) -> None:
+              haplotypes_module: Optional[object] = None, reports_module: Optional[object] = None) -> None:
     from . import annotation as ann
     from . import haplotypes as hapmod
+    from . import report_rows as rep
+
+    rmod = reports_module
+    if rmod is None and module is None:
+        try:
+            rmod = importlib.import_module("crisprhawk.reports")
+        except Exception:
+            rmod = None
+    if rmod is not None:
+        for name, fn in _saved.pop(rmod, {}).items():
+            if fn is not None:
+                setattr(rmod, name, fn)
+            rep._reference.pop(name, None)
 
     hmod = haplotypes_module
     if hmod is None and module is None:

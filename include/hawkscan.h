@@ -280,6 +280,17 @@ int hawk_result_annotate(hawk_result *result, hawk_batch *batch, uint8_t *rc_tex
                          int32_t *gc_den, int64_t *gv_off, int64_t *gv_total);
 int hawk_result_fetch_variants(hawk_result *result, int32_t *gv_idx /* gv_total */);
 
+/* N2, the row collapse of the report (reports._collapse_report_entries, reports.py:958-1008, for
+ * the score-free column set): rows of a phased / variant-free hawk_search result that agree in
+ * (start, stop, strand, origin = is_ref of the haplotype, guide + PAM text incl. case) form one
+ * report row. perm[k] = table row at position k of the order (start, stop, group), ties in
+ * emission order (what pandas' "first" aggregations see); head[k] = 1 where a group starts.
+ * *collision = 1 if two different keys shared a 64-bit hash (never merged: heads are confirmed
+ * on the bytes; the groups of such a key may then be split in two runs). The host orders the
+ * groups like pandas sorts the groupby keys and joins the strings (crispr_hawk_b200/report_rows.py). */
+int hawk_result_collapse(hawk_result *result, const uint8_t *is_ref, int32_t n_hap, uint32_t *perm /* n_guides */,
+                         uint8_t *head /* n_guides */, int32_t *collision);
+
 /* Re-run K1 into an existing batch from device-resident texts of the same layout (the
  * coordinate maps / allele tables attached to the batch are kept). */
 int hawk_batch_repack_dev(hawk_batch *batch, const uint8_t *d_ascii, int64_t *bad_slot);

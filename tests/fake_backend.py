@@ -101,6 +101,15 @@ class FakeResult:
     def annotate(self, batch, **kw):
         return hostcheck.annotate_flat(self.tab, self.params, batch.seg, batch.vt)
 
+    def collapse(self, is_ref):
+        """hawk_result_collapse: rows ordered by (start, stop, group), ties in emission order."""
+        t, core = self.tab, slice(10, 10 + self.window - 20)
+        keys = [(int(t["start"][i]), int(t["stop"][i]), int(t["strand"][i]), int(is_ref[t["hap"][i]]), t["text"][i, core].tobytes())
+                for i in range(self.n_guides)]  # fmt: skip
+        perm = np.array(sorted(range(self.n_guides), key=lambda i: (keys[i], i)), dtype=np.uint32)
+        head = np.array([k == 0 or keys[perm[k]] != keys[perm[k - 1]] for k in range(self.n_guides)], dtype=np.uint8)
+        return perm, head, False
+
     def close(self):
         self.closed, self.handle = True, None
 

@@ -226,3 +226,45 @@ def test_unsupported_shapes_go_to_the_reference_builder(monkeypatch):
             assert [hap_fields(h) for h in haps] == [hap_fields(h) for h in want]
     finally:
         hawk.uninstall()
+
+
+# --------------------------------------------------------------------------- N2: report rows
+def run_report(drv, case):
+    """reports.report_guides' two steps (reports.py:1029-1056) on the driver's annotated guides."""
+    import crisprhawk.reports as R
+
+    region, _, guides = run_driver(drv, case)
+    pam = drv.encode_pam(case.pam, case.right, 0, True)
+    rep = R._construct_report({region: guides}, pam, [], [], [], [], False, False)[region]
+    return rep, (R._collapse_report_entries(rep, pam, [], [], False) if not rep.empty else rep)
+
+
+REPORT_CASES = [c for c in CASES if c.name.startswith(("C1", "kat"))][:4] + CASES[-3:] + [
+    make_case(120, phased=True, pam="NNGRRT", guidelen=21, right=False, bed_len=1500, n_sites=60, n_samples=8, indel_frac=0.4)
+]  # fmt: skip
+
+
+@pytest.mark.parametrize("case", REPORT_CASES, ids=[c.name for c in REPORT_CASES])
+def test_installed_report_collapse_equals_the_reference(case, monkeypatch):
+    """The genuine `_construct_report` + `_collapse_report_entries`, plain and with the package
+    installed (the collapse then uses the device-computed groups): identical DataFrames."""
+    drv = load_driver()
+    import crisprhawk.reports as R
+
+    _, want = run_report(drv, case)
+    fake_backend.activate(monkeypatch)
+    hawk.install()
+    try:
+        assert R._collapse_report_entries.__module__ == "crispr_hawk_b200.report_rows"
+        rep, got = run_report(drv, case)
+        assert rep.empty or "hawk_groups" in rep.attrs  # the device groups were used, not the pandas groupby
+        assert list(got.columns) == list(want.columns)
+        assert len(got) == len(want) <= len(rep)
+        # sample strings of N1-built haplotypes are joined in a different (set) order upstream: normalise
+        for df in (got, want):
+            if "samples" in df:
+                df["samples"] = [",".join(sorted(s.split(","))) for s in df["samples"]]
+        assert got.equals(want), got.compare(want)
+    finally:
+        hawk.uninstall()
+    assert R._collapse_report_entries.__module__ == "crisprhawk.reports"
