@@ -24,11 +24,11 @@ def test_collapsed_rows_match_reference_report(case):
 
 
 def test_device_groups_equal_a_host_grouping_at_scale():
-    """c2-shaped cohort (NGG, 20 nt), ~1 M rows: every group of the device order holds exactly
+    """c2-shaped cohort (NGG, 20 nt), some 0.5 M rows: every group of the device order holds exactly
     the rows sharing (start, stop, strand, origin, core text); groups ascend by (start, stop);
     rows inside a group ascend (emission order)."""
     k = synth.CONFIGS["c2"]
-    c = synth.config_cohort("c2", 0.1, n_alt_hap=400)
+    c = synth.config_cohort("c2", 0.1, n_alt_hap=2000)
     wl = Workload(c, k["pam"], k["guidelen"], k["right"])
     res = wl.step_resident()
     table = res.table()
@@ -37,7 +37,7 @@ def test_device_groups_equal_a_host_grouping_at_scale():
     perm, head, collision = res.collapse(is_ref)
     res.close()
     n = len(table["hap"])
-    assert n > 500_000 and not collision
+    assert n > 300_000 and not collision
     assert np.array_equal(np.sort(perm), np.arange(n))
     core = table["text"][:, 10 : 10 + wl.guidelen + len(wl.fwd)]
     key = np.concatenate([table["start"].astype(">u4").view(np.uint8).reshape(n, 4), table["stop"].astype(">u4").view(np.uint8).reshape(n, 4),
