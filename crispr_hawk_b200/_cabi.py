@@ -96,6 +96,7 @@ SIGNATURES = {
     "hawk_ctx_stream": (C.c_void_p, [_P]),
     "hawk_ctx_set_profiling": (C.c_int, [_P, C.c_int32]),
     "hawk_ctx_set_fused": (C.c_int, [_P, C.c_int32]),
+    "hawk_ctx_set_edit_planes": (C.c_int, [_P, C.c_int32]),
     "hawk_ctx_sync": (C.c_int, [_P]),
     "hawk_ctx_profile": (C.c_int, [_P, C.POINTER(C.c_double), _I64P]),
     "hawk_materialize_dev": (
@@ -253,6 +254,10 @@ class Context:
     def set_fused(self, mode: int) -> None:
         """hawk_ctx_set_fused: 0 staged, 1 fused kernel, 2 by haplotype shape (default)."""
         check(self.lib.hawk_ctx_set_fused(self.handle, int(mode)))
+
+    def set_edit_planes(self, mode: int) -> None:
+        """hawk_ctx_set_edit_planes: 1 planes around the edits only (default), 0 texts + K1."""
+        check(self.lib.hawk_ctx_set_edit_planes(self.handle, int(mode)))
 
     def set_profiling(self, enabled: bool) -> None:
         check(self.lib.hawk_ctx_set_profiling(self.handle, 1 if enabled else 0))

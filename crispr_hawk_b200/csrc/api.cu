@@ -233,8 +233,8 @@ extern "C" int hawk_layout(const int32_t* len, int32_t n_hap, int64_t* slot_off,
 // ------------------------------------------------------------------ batch
 int batch_create_impl(hawk_ctx* c, const uint8_t* ascii, bool ascii_on_device,
                              const int64_t* slot_off, const int32_t* len, int32_t n_hap,
-                             hawk_batch** out, int64_t* bad_slot) {
-  if (!c || !out || n_hap < 0 || (n_hap > 0 && (!ascii || !slot_off || !len)))
+                             hawk_batch** out, int64_t* bad_slot, bool defer_planes) {
+  if (!c || !out || n_hap < 0 || (n_hap > 0 && ((!ascii && !defer_planes) || !slot_off || !len)))
     return hawk_fail(HAWK_EINVAL, "hawk_batch_create: bad arguments");
   CKCUDA(cudaSetDevice(c->device));
   if (bad_slot) *bad_slot = -1;
@@ -266,7 +266,9 @@ int batch_create_impl(hawk_ctx* c, const uint8_t* ascii, bool ascii_on_device,
     if ((rc = hawk_check_cuda(cudaMemsetAsync(b->v.as<uint8_t>() + used * 4, 0, (n_chunks - used) * 4, st), "slack memset"))) break;
     if ((rc = upload(c, b->d_slot_off, b->slot_off.data(), (size_t)(n_hap + 1) * 8))) break;
     if ((rc = upload(c, b->d_len, b->len.data(), (size_t)n_hap * 4))) break;
-    if (!ascii) {  // no haplotypes: the slot space is the leading gap only
+    if (defer_planes) {
+      // the caller fills the planes later (hawk_edits_ensure)
+    } else if (!ascii) {  // no haplotypes: the slot space is the leading gap only
       if ((rc = hawk_check_cuda(cudaMemsetAsync(b->q.p, 0, n_chunks * 16, st), "gap memset"))) break;
       if ((rc = hawk_check_cuda(cudaMemsetAsync(b->v.p, 0, n_chunks * 4, st), "gap memset"))) break;
     } else if (total > 0) {
@@ -350,6 +352,35 @@ extern "C" int hawk_batch_create_from_edits(hawk_ctx* c, const uint8_t* ref_asci
   CK(launch_derive(st, n_hap, d_eoff.as<int64_t>(), d_pos.as<int32_t>(), d_rl.as<int32_t>(), d_al.as<int32_t>(),
                    d_ao.as<int64_t>(), ref_len, alt_pool_len, region_start, d_op.as<int32_t>(), d_len.as<int32_t>(),
                    d_segcnt.as<int32_t>(), d_bad.as<int32_t>(), nullptr, nullptr, nullptr, nullptr, 0));
+  // the reference's own planes (the windows around the edits are cut from them) and the ALT pool
+  // check; anything unusual -- a non-IUPAC character, lower-case (soft-masked) reference bases,
+  // which every haplotype would inherit as variant bases -- goes the long way round (texts + K1)
+  DevBuf d_refq, d_refv, d_refnz, d_flags;
+  const int64_t ref_chunks = (ref_len + HAWK_CHUNK - 1) / HAWK_CHUNK;
+  bool windows_ok = c->edit_planes == 1 && n_hap > 0 && getenv("HAWK_DENSE_EDITS") == nullptr;
+  std::vector<uint32_t> ref_nz;
+  unsigned long long flags[2] = {~0ull, ~0ull};  // first bad reference slot, first bad pool offset
+  if (windows_ok) {
+    // text padded with zeros to whole chunks (+ one chunk the funnel shifts may read)
+    DevBuf d_reftext;
+    const size_t padded = (size_t)(ref_chunks + 1) * HAWK_CHUNK;
+    CK(d_reftext.alloc(c, padded));
+    CKCUDA(cudaMemsetAsync(d_reftext.as<uint8_t>() + ref_len, 0, padded - (size_t)ref_len, st));
+    CKCUDA(cudaMemcpyAsync(d_reftext.p, d_ref.p, (size_t)ref_len, cudaMemcpyDeviceToDevice, st));
+    CK(d_refq.alloc(c, (size_t)(ref_chunks + 1) * 16));
+    CK(d_refv.alloc(c, (size_t)(ref_chunks + 1) * 4));
+    const size_t nzw = (size_t)(ref_chunks + 1 + 31) / 32;
+    CK(d_refnz.alloc(c, nzw * 4, true));
+    CK(upload(c, d_flags, flags, 16));
+    CK(hawk_pack_dev(st, d_reftext.as<uint8_t>(), (int64_t)padded, d_refq.p, d_refv.as<uint32_t>(), d_refnz.as<uint32_t>(),
+                     d_flags.as<int64_t>()));
+    CK(launch_pool_check(st, d_pool.as<uint8_t>(), alt_pool_len, d_flags.as<unsigned long long>() + 1));
+    ref_nz.resize(nzw);
+    CK(c->small_d2h_sync(ref_nz.data(), d_refnz.p, nzw * 4));
+    CK(c->small_d2h_sync(flags, d_flags.p, 16));
+    for (uint32_t w : ref_nz) windows_ok = windows_ok && w == 0;
+    windows_ok = windows_ok && flags[0] == ~0ull && flags[1] == ~0ull;
+  }
   std::vector<int32_t> len(n_hap), seg_count(n_hap);
   int32_t bad_hap = INT32_MAX;
   if (n_hap) {
@@ -368,13 +399,38 @@ extern "C" int hawk_batch_create_from_edits(hawk_ctx* c, const uint8_t* ref_asci
   seg_off[0] = 0;
   for (int32_t h = 0; h < n_hap; ++h) seg_off[h + 1] = seg_off[h] + seg_count[h];
   CK(upload(c, d_so, slot_off.data(), (size_t)(n_hap + 1) * 8));
-  CK(d_ascii.alloc(c, (size_t)total));
-  CK(hawk_materialize_dev(st, d_ref.as<uint8_t>(), ref_len, d_eoff.as<int64_t>(), d_pos.as<int32_t>(),
-                          d_rl.as<int32_t>(), d_al.as<int32_t>(), d_ao.as<int64_t>(), d_op.as<int32_t>(),
-                          d_pool.as<uint8_t>(), d_so.as<int64_t>(), d_len.as<int32_t>(), n_hap, total, n_edits,
-                          n_hap ? *std::max_element(len.begin(), len.end()) : 0, d_ascii.as<uint8_t>()));
   hawk_batch* b = nullptr;
-  CK(batch_create_impl(c, d_ascii.as<uint8_t>(), true, slot_off.data(), len.data(), n_hap, &b, bad_slot));
+  if (windows_ok) {
+    // planes only where a search reads them, built at the first search (hawk_edits_ensure)
+    CK(batch_create_impl(c, nullptr, true, slot_off.data(), len.data(), n_hap, &b, bad_slot, true));
+    b->edits_lazy = true;
+    b->ref_len = ref_len;
+    b->ref_chunks = ref_chunks;
+    b->n_edits = n_edits;
+    b->has_edits.resize(n_hap);
+    std::vector<int32_t> plain;
+    for (int32_t h = 0; h < n_hap; ++h) {
+      b->has_edits[h] = edit_off[h + 1] > edit_off[h];
+      if (!b->has_edits[h]) plain.push_back(h);
+    }
+    b->n_plain = (int32_t)plain.size();
+    int rc = b->n_plain ? upload(c, b->d_plain, plain.data(), plain.size() * 4) : HAWK_OK;
+    if (rc) {
+      hawk_batch_destroy(b);
+      return rc;
+    }
+    b->ref_text.move_from(d_ref);
+    b->ref_q.move_from(d_refq);
+    b->ref_v.move_from(d_refv);
+    b->edit_outpos.move_from(d_op);
+  } else {
+    CK(d_ascii.alloc(c, (size_t)total));
+    CK(hawk_materialize_dev(st, d_ref.as<uint8_t>(), ref_len, d_eoff.as<int64_t>(), d_pos.as<int32_t>(),
+                            d_rl.as<int32_t>(), d_al.as<int32_t>(), d_ao.as<int64_t>(), d_op.as<int32_t>(),
+                            d_pool.as<uint8_t>(), d_so.as<int64_t>(), d_len.as<int32_t>(), n_hap, total, n_edits,
+                            n_hap ? *std::max_element(len.begin(), len.end()) : 0, d_ascii.as<uint8_t>()));
+    CK(batch_create_impl(c, d_ascii.as<uint8_t>(), true, slot_off.data(), len.data(), n_hap, &b, bad_slot));
+  }
   tr.tick("edits: materialise + pack");
   // pass 1: the run-length coordinate maps, straight into the batch
   const size_t n_seg = (size_t)seg_off[n_hap];
@@ -413,6 +469,56 @@ extern "C" int hawk_batch_create_from_edits(hawk_ctx* c, const uint8_t* ref_asci
   return HAWK_OK;
 }
 
+int hawk_edits_ensure(hawk_batch* b, int need) {
+  if (!b || !b->edits_lazy) return HAWK_OK;
+  if (need > HAWK_SLOT_GAP / HAWK_CHUNK) need = HAWK_EDITS_DENSE;  // a window may not cross into the next haplotype
+  if (need != HAWK_EDITS_DENSE && b->edits_reach >= need) return HAWK_OK;
+  hawk_ctx* c = b->ctx;
+  CKCUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  if (b->total_slots == 0) return HAWK_OK;
+  Trace tr;
+  if (need == HAWK_EDITS_DENSE) {
+    // every text, then K1 (synth_kernels.cu, scan_kernels.cu)
+    DevBuf d_ascii, d_bad;
+    CK(d_ascii.alloc(c, (size_t)b->total_slots));
+    int32_t max_len = 0;
+    for (int32_t l : b->len) max_len = l > max_len ? l : max_len;
+    CK(hawk_materialize_dev(st, b->ref_text.as<uint8_t>(), b->ref_len, b->var_off.as<int64_t>(), b->var_pos.as<int32_t>(),
+                            b->var_rl.as<int32_t>(), b->var_al.as<int32_t>(), b->var_ao.as<int64_t>(),
+                            b->edit_outpos.as<int32_t>(), b->var_pool.as<uint8_t>(), b->d_slot_off.as<int64_t>(),
+                            b->d_len.as<int32_t>(), b->n_hap, b->total_slots, b->n_edits, max_len, d_ascii.as<uint8_t>()));
+    const int64_t init = INT64_MAX;
+    CK(upload(c, d_bad, &init, 8));
+    CK(hawk_pack_dev(st, d_ascii.as<uint8_t>(), b->total_slots, b->q.p, b->v.as<uint32_t>(), b->nz.as<uint32_t>(),
+                     d_bad.as<int64_t>()));
+    CKCUDA(cudaStreamSynchronize(st));  // d_ascii is released on return
+    b->edits_lazy = false;
+    b->sparse = false;
+    tr.tick("edits: all planes (texts + K1)");
+    return HAWK_OK;
+  }
+  const size_t nz_words = ((size_t)b->total_slots / HAWK_CHUNK + 31) / 32 + HAWK_SLACK_CHUNKS;
+  CKCUDA(cudaMemsetAsync(b->nz.p, 0, nz_words * 4, st));
+  CK(launch_edits_plain(st, b->ref_q.p, b->ref_v.as<uint32_t>(), b->ref_chunks, b->d_plain.as<int32_t>(), b->n_plain,
+                        b->d_slot_off.as<int64_t>(), b->q.p, b->v.as<uint32_t>()));
+  CK(launch_edit_windows(st, b->ref_q.p, b->var_off.as<int64_t>(), b->var_pos.as<int32_t>(), b->var_rl.as<int32_t>(),
+                         b->var_al.as<int32_t>(), b->var_ao.as<int64_t>(), b->edit_outpos.as<int32_t>(),
+                         b->var_pool.as<uint8_t>(), b->d_slot_off.as<int64_t>(), b->d_len.as<int32_t>(), b->n_hap,
+                         b->n_edits, b->q.p, b->v.as<uint32_t>(), b->nz.as<uint32_t>(), need));
+  b->edits_reach = need;
+  b->sparse = true;
+  b->sparse_reach = need;
+  tr.tick("edits: window planes launched");
+  return HAWK_OK;
+}
+
+extern "C" int hawk_ctx_set_edit_planes(hawk_ctx* c, int32_t mode) {
+  if (!c || mode < 0 || mode > 1) return hawk_fail(HAWK_EINVAL, "hawk_ctx_set_edit_planes: mode must be 0 or 1");
+  c->edit_planes = mode;
+  return HAWK_OK;
+}
+
 extern "C" int hawk_batch_layout(hawk_batch* b, int64_t* slot_off, int32_t* len) {
   if (!b) return hawk_fail(HAWK_EINVAL, "hawk_batch_layout: null batch");
   if (slot_off) memcpy(slot_off, b->slot_off.data(), (size_t)(b->n_hap + 1) * 8);
@@ -428,6 +534,7 @@ extern "C" int hawk_batch_repack_dev(hawk_batch* b, const uint8_t* d_ascii, int6
   cudaStream_t st = c->stream;
   if (bad_slot) *bad_slot = -1;
   if (b->total_slots == 0) return HAWK_OK;
+  b->edits_lazy = false;  // the planes now stand for the caller's texts
   DevBuf d_bad;
   int64_t init = INT64_MAX;
   CK(upload(c, d_bad, &init, 8));
@@ -504,6 +611,7 @@ extern "C" int hawk_batch_destroy(hawk_batch* b) {
 extern "C" int hawk_batch_export_nibbles(hawk_batch* b, int32_t hap, uint8_t* nibbles, uint8_t* lower) {
   if (!b || hap < 0 || hap >= b->n_hap || !nibbles)
     return hawk_fail(HAWK_EINVAL, "hawk_batch_export_nibbles: bad arguments");
+  CK(hawk_edits_ensure(b, HAWK_EDITS_DENSE));  // an edit-list batch: every plane, now
   if (b->sparse) return hawk_fail(HAWK_EINVAL, "hawk_batch_export_nibbles: the batch keeps planes only around variant bases");
   hawk_ctx* c = b->ctx;
   CKCUDA(cudaSetDevice(c->device));
@@ -758,7 +866,12 @@ static int run_scan(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const
 // chunks either side of a variant chunk whose planes the stages after the scan can read: a hit
 // needs a variant base inside its core, and its padded window reaches G + PAD before / C + PAD - 1
 // behind the PAM position, so no base further than G + C + PAD - 1 from a variant base is read
-static int fused_reach(const ScanConst& K) { return (31 + K.G + K.C + HAWK_GUIDESEQPAD - 1) >> 5; }
+// -- and never fewer than 2 chunks: a candidate chunk lies within one chunk of a variant chunk and
+// its matcher reads the case words of both of ITS neighbours
+static int fused_reach(const ScanConst& K) {
+  const int r = (31 + K.G + K.C + HAWK_GUIDESEQPAD - 1) >> 5;
+  return r < 2 ? 2 : r;
+}
 
 // K1 + K2 fused (fused_kernels.cu): the texts are read once, planes are stored only where later
 // stages read them, hit entries come out per warp sub-range; one host round trip (hit totals,
@@ -907,6 +1020,7 @@ extern "C" int hawk_pam_search(hawk_ctx* c, hawk_batch* b, const hawk_params* pa
                                const int32_t* scan_start, const int32_t* scan_stop,
                                hawk_result** out) {
   CK(check_scan_args(c, b, params, scan_start, scan_stop, out));
+  CK(hawk_edits_ensure(b, HAWK_EDITS_DENSE));  // the raw PAM scan reads every chunk
   if (b->sparse) return hawk_fail(HAWK_EINVAL, "hawk_pam_search: the batch keeps planes only around variant bases; re-encode it");
   CKCUDA(cudaSetDevice(c->device));
   hawk_result* r = new (std::nothrow) hawk_result();
@@ -1218,7 +1332,17 @@ int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, cons
   do {
     Trace tr;
     bool staged = true;
+    if (!fused_text && b->edits_lazy) {
+      // an edit-list batch builds its planes now: windows around the edits as far as this guide /
+      // PAM geometry reaches -- or all of them when a haplotype with edits is scanned like REF
+      // (every chunk), the search is unphased, or the windows are too wide for the fast form
+      int need = K.small && !unphased ? fused_reach(K) : HAWK_EDITS_DENSE;
+      for (int32_t h = 0; h < b->n_hap; ++h)
+        if (is_ref[h] && b->has_edits[h]) need = HAWK_EDITS_DENSE;
+      if ((rc = hawk_edits_ensure(b, need))) break;
+    }
     if (fused_text) {
+      b->edits_lazy = false;  // re-encoded from the caller's texts
       // The fused kernel is flat over the slot space: it wins when the haplotypes are short (an
       // unphased cohort's ~200-base indel windows: the staged K2 spends a thread block per
       // haplotype) and currently loses ~0.2 ms per 5 G bases on long ones, where its extra
@@ -1234,7 +1358,7 @@ int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, cons
       } else {
         if ((rc = hawk_batch_repack_dev(b, fused_text, bad_slot))) break;
       }
-    } else if (b->sparse && (!K.small || ((31 + K.G + K.C + HAWK_GUIDESEQPAD - 1) >> 5) > b->sparse_reach)) {
+    } else if (b->sparse && (!K.small || fused_reach(K) > b->sparse_reach)) {
       rc = hawk_fail(HAWK_EINVAL, "hawk_search: this batch keeps planes only around variant bases "
                      "(hawk_encode_search_dev) and this guide / PAM geometry reaches further; re-encode it");
       break;

@@ -50,7 +50,7 @@ struct FusedArgs {
   int32_t n_hap;
   const HapScan* hs;
   ScanConst K;
-  int32_t reach;      // planes are kept for chunks within `reach` chunks of a variant chunk (1..3)
+  int32_t reach;      // planes are kept for chunks within `reach` chunks of a variant chunk (2..3)
   const uint64_t* seg_base;  // per sub-range: first entry slot, capacity
   const uint32_t* seg_cap;
   uint4* entries;       // {haplotype, chunk (haplotype-relative), hits strand 0, hits strand 1}
@@ -424,12 +424,13 @@ int launch_fused_scan(cudaStream_t st, const FusedLaunch& L) {
   A.bad = (unsigned long long*)L.bad;
   const unsigned blocks = (unsigned)((n_sub + FUSED_WARPS - 1) / FUSED_WARPS);
   const bool wide = ((uintptr_t)L.ascii & 31) == 0;
-  if (L.reach < 1 || L.reach > 3) return hawk_fail(HAWK_EINVAL, "fused scan: reach %d out of range", L.reach);
+  // >= 2: a candidate chunk's matcher reads the case words two chunks from the variant chunk
+  if (L.reach < 2 || L.reach > 3) return hawk_fail(HAWK_EINVAL, "fused scan: reach %d out of range", L.reach);
 #define HAWK_FUSED_LAUNCH(W, R) fused_scan_kernel<W, R><<<blocks, FUSED_WARPS * 32, 0, st>>>(A)
   if (wide) {
-    if (L.reach == 1) HAWK_FUSED_LAUNCH(true, 1); else if (L.reach == 2) HAWK_FUSED_LAUNCH(true, 2); else HAWK_FUSED_LAUNCH(true, 3);
+    if (L.reach == 2) HAWK_FUSED_LAUNCH(true, 2); else HAWK_FUSED_LAUNCH(true, 3);
   } else {
-    if (L.reach == 1) HAWK_FUSED_LAUNCH(false, 1); else if (L.reach == 2) HAWK_FUSED_LAUNCH(false, 2); else HAWK_FUSED_LAUNCH(false, 3);
+    if (L.reach == 2) HAWK_FUSED_LAUNCH(false, 2); else HAWK_FUSED_LAUNCH(false, 3);
   }
 #undef HAWK_FUSED_LAUNCH
   hawk_note_launch(1);

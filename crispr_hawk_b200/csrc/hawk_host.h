@@ -111,6 +111,9 @@ struct hawk_ctx {
   // hawk_encode_search_dev: 0 = K1 then the staged K2, 1 = the fused kernel whenever the guide
   // geometry allows, 2 = choose by haplotype shape (hawk_ctx_set_fused)
   int fused_mode = 2;
+  // hawk_batch_create_from_edits: 1 = planes only around the edits, built at the first search
+  // (edits_kernels.cu); 0 = materialise every text and run K1 (hawk_ctx_set_edit_planes)
+  int edit_planes = 1;
   // optional per-kernel timing (hawk_ctx_set_profiling)
   bool profiling = false;
   struct Span { cudaEvent_t a, b; int kind; };
@@ -190,6 +193,15 @@ struct hawk_batch {
   DevBuf var_off, var_pos, var_rl, var_al, var_ao, var_pool;
   int32_t var_pos_base = 0;
   bool has_variants = false;
+  // N1: a batch created from edit lists keeps the reference's planes and the edits, and builds
+  // its own planes on demand (hawk_edits_ensure): windows of `edits_reach` chunks around the
+  // edits for a search, or all of them (materialise + K1) for whoever reads whole haplotypes
+  bool edits_lazy = false;
+  int32_t edits_reach = 0;
+  DevBuf ref_text, ref_q, ref_v, edit_outpos, d_plain;
+  int64_t ref_len = 0, ref_chunks = 0, n_edits = 0;
+  int32_t n_plain = 0;
+  std::vector<uint8_t> has_edits;  // per haplotype
   // scan bounds attached to the batch (hawk_batch_set_scan): searches that pass NULL bounds use
   // these device-resident copies instead of uploading n_hap-sized arrays per call
   bool has_scan = false;
@@ -236,8 +248,12 @@ struct StreamLink {
   int32_t key_min;
 };
 
+// planes of an edit-list batch: `need` = chunks a search reaches from a variant chunk, or
+// HAWK_EDITS_DENSE for every chunk (no-op for other batches and when already satisfied)
+#define HAWK_EDITS_DENSE (1 << 20)
+int hawk_edits_ensure(hawk_batch* b, int need);
 int batch_create_impl(hawk_ctx* c, const uint8_t* ascii, bool ascii_on_device, const int64_t* slot_off,
-                      const int32_t* len, int32_t n_hap, hawk_batch** out, int64_t* bad_slot);
+                      const int32_t* len, int32_t n_hap, hawk_batch** out, int64_t* bad_slot, bool defer_planes = false);
 // `fused_text`: device-resident texts of the batch's layout; the batch is re-encoded from them
 // inside the search (fused K1 + K2 when the guide geometry allows, else K1 then the staged K2)
 int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, const int32_t* scan_start,

@@ -386,10 +386,11 @@ extern "C" int hawk_search_stream_edits(hawk_ctx* c, const uint8_t* ref_ascii, i
   std::vector<int64_t> pseudo(n_hap + 1);
   for (int32_t h = 0; h <= n_hap; ++h) pseudo[h] = (int64_t)h * ref_len;
   Plan P;
-  // fewer, larger groups than the text path: nothing bulky goes up, so a group only has to be
-  // small enough for its rows to leave while the next one is computed (measured: about 8 groups
-  // for 5 G haplotype-bp; more groups pay more stream synchronisations than they hide)
-  CK(make_plan(pseudo.data(), n_hap, is_ref, n_groups, 640ll << 20, P));
+  // fewer, larger groups than the text path: only edit lists go up and the planes are built around
+  // the edits alone (edits_kernels.cu), so the call is bound by the rows leaving; a group only has
+  // to be small enough for the first rows to leave early (measured, 5 G haplotype-bp: 2 - 4 groups
+  // without the window text, 4 - 8 with it; every group costs ~0.5 ms of host round trips)
+  CK(make_plan(pseudo.data(), n_hap, is_ref, n_groups, 1280ll << 20, P));
   if (P.ref_first && edit_off[1] != edit_off[0])
     return hawk_fail(HAWK_EINVAL, "hawk_search_stream_edits: the REF haplotype must have no edits");
 

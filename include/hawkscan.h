@@ -311,6 +311,15 @@ int hawk_encode_search_dev(hawk_ctx *ctx, hawk_batch *batch, const uint8_t *d_as
  * 1 = the fused kernel whenever the guide geometry allows; 2 (default) = by haplotype shape --
  * fused for unphased cohorts and short haplotypes, staged for long ones. Results are identical. */
 int hawk_ctx_set_fused(hawk_ctx *ctx, int32_t mode);
+/* How hawk_batch_create_from_edits (and hawk_search_stream_edits) obtain the planes:
+ * 1 (default) = only where a search reads them -- every chunk of a haplotype without edits, and
+ * the chunks within a search's reach of an edit, cut from the reference's own planes at the
+ * first hawk_search (O(edits) work; the haplotype texts are never written). Whole-haplotype
+ * readers (hawk_pam_search, hawk_batch_export_nibbles, a search that marks a haplotype with
+ * edits as REF, unphased or long-guide searches) make the batch build every plane first, on
+ * their own. 0 = always materialise every text and run K1 (O(haplotype bases)). A reference with
+ * lower-case or non-IUPAC characters takes the second way whatever the mode. Same results. */
+int hawk_ctx_set_edit_planes(hawk_ctx *ctx, int32_t mode);
 
 /* The context's cudaStream_t (so callers can time with events on the stream the kernels
  * run on) and optional per-kernel timing: with profiling on, every K1 / K2 launch of the
