@@ -28,6 +28,13 @@ def both_ways(wl):
     tables_equal(staged, fused)
     for s in (0, 1):
         assert np.array_equal(hs[s], hf[s])
+    # the library's own choice by haplotype shape
+    r = wl.step_resident()
+    auto, ha = r.table(), [r.hits(0), r.hits(1)]
+    r.close()
+    tables_equal(staged, auto)
+    for s in (0, 1):
+        assert np.array_equal(hs[s], ha[s])
     # and again: a sparse batch re-encodes cleanly, the staged path works after a fused one
     r = wl.step_resident(fused=True)
     tables_equal(staged, r.table())
@@ -106,3 +113,4 @@ def test_fused_reports_a_bad_character():
     assert e.value.code == _cabi.HAWK_EIUPAC and e.value.bad_slot == slot
     wl.ascii_dev[slot] = keep
     wl.step_resident(fused=True).close()
+

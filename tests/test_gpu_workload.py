@@ -149,6 +149,7 @@ def test_dense_hits_force_the_exact_retry():
                           snv_frac=0.7, ins_frac=0.15, max_indel=6)  # fmt: skip
     wl, table = _run_against_oracle(c, "N", 20, False)
     assert len(table["hap"]) > 2 * 150_000 - 200  # every REF position, both strands
+    wl.batch.repack(wl.ascii_dev.data_ptr())  # the raw scan reads every chunk: dense planes
     raw = _cabi.pam_search(wl.ctx, wl.batch, wl.params, wl.a, wl.b)
     assert raw.n_hits[0] == raw.n_hits[1] == wl.scanned_bp
     raw.close()

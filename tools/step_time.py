@@ -16,7 +16,7 @@ c = synth.config_cohort(name, scale)
 W = UnphasedWorkload if k.get("unphased") else Workload
 wl = W(c, k["pam"], k["guidelen"], k["right"])
 wl.prepare_resident()
-for fused in (False, True, False, True):
+for fused in (False, True, None, False, None):
     for _ in range(3):
         wl.step_resident(fused=fused).close()
     torch.cuda.synchronize()
