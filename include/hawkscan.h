@@ -142,7 +142,14 @@ int hawk_batch_set_scan(hawk_batch *batch, const int32_t *scan_start, const int3
  * emission order (haplotype, strand, position, expansion), already filtered by
  * is_pamhit_in_range (:395-420), the REF-core filter (:468-471),
  * is_pamhit_valid + resolve_guide (unphased, :216-257, :372-392) and
- * remove_redundant_guides (:340-369). */
+ * remove_redundant_guides (:340-369).
+ * REF: at most one haplotype may be flagged is_ref (more: HAWK_EDUPREF up front -- the reference
+ * aborts as soon as two REF guides share a (start, strand), which two REF haplotypes always
+ * produce), and it should be haplotype 0, where every haplotype list the reference builds has
+ * it (haplotypes.py reconstructs REF first). With REF elsewhere the rows are still exact, but
+ * bucket ids are taken over the KEPT rows: a key whose first guide in emission order is a
+ * redundant ALT guide that remove_redundant_guides drops sorts by its first kept guide instead
+ * of that dropped one (group_guides_position :306-337 orders keys before filtering). */
 int hawk_search(hawk_ctx *ctx, hawk_batch *batch, const hawk_params *params,
                 const int32_t *scan_start, const int32_t *scan_stop, const uint8_t *is_ref,
                 hawk_result **result);
