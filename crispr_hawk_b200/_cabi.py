@@ -26,6 +26,7 @@ HAWK_ECAPACITY = -5
 HAWK_EALLELES = -6
 HAWK_EDUPREF = -7
 HAWK_EASSERT = -8
+HAWK_ECFD = -9
 
 
 class HawkLibraryError(RuntimeError):
@@ -139,6 +140,7 @@ SIGNATURES = {
     "hawk_result_annotate": (C.c_int, [_P, _P, _U8P, _I32P, _I32P, _I64P, _I64P]),
     "hawk_result_fetch_variants": (C.c_int, [_P, _I32P]),
     "hawk_result_collapse": (C.c_int, [_P, _U8P, C.c_int32, _U32P, _U8P, _I32P]),
+    "hawk_result_cfdon": (C.c_int, [_P, _U8P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), _I64P]),
     "hawk_table_text_stride": (C.c_int32, [C.c_int32, C.c_int32]),
     "hawk_stream_plan": (C.c_int32, [_I64P, C.c_int32, _U8P, C.c_int32, _I32P, _I32P, C.c_int32]),
     "hawk_search_stream": (
@@ -507,6 +509,20 @@ class Result:
         check(self.lib.hawk_result_collapse(self.handle, ptr(r, C.c_uint8), len(r), ptr(perm, C.c_uint32), ptr(head, C.c_uint8),
                                             C.byref(col)), "hawk_result_collapse")  # fmt: skip
         return perm, head, bool(col.value)
+
+    def cfdon(self, is_ref, mm, pam2):
+        """hawk_result_cfdon: float64 CFDon score per row (NaN: no REF guide at the row's key)."""
+        r = np.ascontiguousarray(is_ref, dtype=np.uint8)
+        mm = np.ascontiguousarray(mm, dtype=np.float64).reshape(320)
+        p2 = np.ascontiguousarray(pam2, dtype=np.float64).reshape(16)
+        out, bad = np.empty(self.n_guides, np.float64), C.c_int64(-1)
+        rc = self.lib.hawk_result_cfdon(self.handle, ptr(r, C.c_uint8), len(r), ptr(mm, C.c_double), ptr(p2, C.c_double),
+                                        ptr(out, C.c_double), C.byref(bad))  # fmt: skip
+        if rc != HAWK_OK:
+            err = HawkLibraryError(self.lib.hawk_last_error().decode(), rc)
+            err.bad_row = bad.value
+            raise err
+        return out
 
     def device_columns(self):
         """Borrowed device addresses {column: int} of the table (hawk_result_device_columns)."""

@@ -107,6 +107,9 @@ def _columns(guides, debug: bool):
             return None
         link["cols"] = annotate_table(link["table"], link["res"], link["batch"], link["haplotypes"], link["right"], debug=debug)
         link["groups"] = report_groups(link["table"], link["res"], link["haplotypes"])  # for the report's row collapse
+        from . import scoring
+
+        link["cfdon"] = scoring.cfdon_column(link, debug)  # N4, for scoring.cfdon_score (None: not applicable)
         link["res"].close()  # the table has served its purpose: release the device memory
         link["res"] = None
     return link["cols"], link["order"]

@@ -55,6 +55,7 @@ extern "C" const char* hawk_strerror(int code) {
     case HAWK_EALLELES: return "ambiguity code without variant alleles";
     case HAWK_EDUPREF: return "duplicate REF guide";
     case HAWK_EASSERT: return "the reference asserts on this input";
+    case HAWK_ECFD: return "CFD score tables hold no entry for this guide";
     default: return "unknown error";
   }
 }

@@ -751,6 +751,51 @@ HAWK_HD void annot_gc_counts(const ScanConst& K, int s, const uint8_t* src, int3
   *den_out = den;
 }
 
+// ---- N4: CFDon of one guide row against the REF guide of its (start, strand) key ----------------
+// scores/cfdscore/cfdscore.py:53-95 (compute_cfd) as called by scores/crisprhawk_scores.py:65-87
+// (cfdon): score = 1.0, times mm[i][wildtype[i]][guide[i]] for every i < min(G, 20) where the
+// upper-cased letters differ (key "r<W>:d<revcomp(S)>,<i+1>" of the reference's table, T read as
+// U), times pam2[last two PAM letters], multiplied in that order in double precision -- the same
+// IEEE operations as the Python loop. Both texts are the ones reverse_guides leaves (strand 1:
+// reverse complement), guide and PAM laid out by `right`. mm: 20 x 4 x 4 (A, C, G, T/U), pam2:
+// 4 x 4; a NaN entry stands for a key the reference's dict does not hold. Returns false where the
+// reference raises KeyError (a mismatch on a letter other than A, C, G, T; a PAM shorter than two
+// letters or with such a letter; a missing table entry).
+HAWK_HD int acgt_code(uint8_t c) {
+  switch (ascii_to_upper(c)) {
+    case 'A': return 0;
+    case 'C': return 1;
+    case 'G': return 2;
+    case 'T': case 'U': return 3;
+    default: return -1;
+  }
+}
+
+HAWK_HD bool cfdon_row(const uint8_t* ref_text, const uint8_t* row_text, int W, int G, int P, int right, int s,
+                       const double* mm, const double* pam2, double* out) {
+  const int g0 = HAWK_GUIDESEQPAD + (right ? P : 0), p0 = HAWK_GUIDESEQPAD + (right ? 0 : G);
+  double score = 1.0;
+  const int n = G < 20 ? G : 20;
+  for (int i = 0; i < n; ++i) {
+    const uint8_t w = ascii_to_upper(annot_text_byte(ref_text, W, s, g0 + i));
+    const uint8_t g = ascii_to_upper(annot_text_byte(row_text, W, s, g0 + i));
+    if (w == g) continue;
+    const int cw = acgt_code(w), cg = acgt_code(g);
+    if (cw < 0 || cg < 0) return false;
+    const double f = mm[(i * 4 + cw) * 4 + cg];
+    if (f != f) return false;
+    score *= f;
+  }
+  if (P < 2) return false;
+  const int c0 = acgt_code(annot_text_byte(row_text, W, s, p0 + P - 2));
+  const int c1 = acgt_code(annot_text_byte(row_text, W, s, p0 + P - 1));
+  if (c0 < 0 || c1 < 0) return false;
+  const double f = pam2[c0 * 4 + c1];
+  if (f != f) return false;
+  *out = score * f;
+  return true;
+}
+
 // polish_guide_variants (annotation.py:246-281) for one row: walks the core's G + P bases,
 // genomic coordinate through the run-length posmap (segment pointer advanced incrementally),
 // variant at that coordinate by a monotone walk of the haplotype's sorted table, then

@@ -8,6 +8,7 @@
 // (look-back, scans, merge, hashing) is replaced by trivial serial code here and
 // is only exercised by the GPU tests. libhawkscan.so never links or loads this.
 #include <stdint.h>
+#include <limits>
 #include <string.h>
 
 #include <algorithm>
@@ -274,6 +275,24 @@ int64_t hawkcheck_annotate(const int64_t* seg_off, const int32_t* seg_rel, const
     annot_gc_counts(K, strand[r], src, &gc_num[r], &gc_den[r]);
   }
   return would_assert ? -1 : out;
+}
+
+// N4: cfdon_row over a whole table (the loop of cfdon_kernel); returns the first row where the
+// reference would raise KeyError, or -1
+int64_t hawkcheck_cfdon(const int32_t* hap, const uint8_t* strand, const uint32_t* bucket, const uint8_t* text,
+                        int32_t text_stride, int32_t W, int32_t G, int32_t P, int32_t right, const uint8_t* is_ref,
+                        const double* mm, const double* pam2, int64_t n, double* out) {
+  int64_t bad = -1;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint32_t b = bucket[i];
+    double v = std::numeric_limits<double>::quiet_NaN();
+    if (is_ref[hap[b]] &&
+        !hawk::cfdon_row(text + (int64_t)b * text_stride, text + i * (int64_t)text_stride, W, G, P, right, strand[i], mm, pam2, &v) &&
+        bad < 0)
+      bad = i;
+    out[i] = v;
+  }
+  return bad;
 }
 
 }  // extern "C"

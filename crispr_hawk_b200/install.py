@@ -14,7 +14,8 @@ _saved = {}
 
 def install(module: Optional[object] = None, annotation_module: Optional[object] = None, annotation: bool = True,
             haplotypes_module: Optional[object] = None, haplotypes: bool = True,
-            reports_module: Optional[object] = None, reports: bool = True):
+            reports_module: Optional[object] = None, reports: bool = True,
+            scoring_module: Optional[object] = None, scoring: bool = True):
     """Rebind in `crisprhawk.crisprhawk` (or the given module object). Returns it.
 
     With `annotation` (N2) the four per-guide loops `annotation.annotate_guides` runs right
@@ -24,9 +25,12 @@ def install(module: Optional[object] = None, annotation_module: Optional[object]
     every other list to the reference's own functions. With `reports` (N2, second half)
     `reports._process_data` and `reports._collapse_report_entries` (reports.py:476-531, 958-1008)
     are rebound the same way: the row collapse uses the groups the device computed over the
-    resident table instead of a pandas groupby."""
+    resident table instead of a pandas groupby. With `scoring` (N4) `scoring.cfdon_score`
+    (scoring.py:352-387) is rebound: the scores come from `hawk_result_cfdon`, computed with the
+    reference's own factor tables while the table is on the device."""
     from . import _cabi
     from . import report_rows as rep
+    from . import scoring as sco
     from . import annotation as ann
     from . import haplotypes as hapmod
 
@@ -67,14 +71,42 @@ def install(module: Optional[object] = None, annotation_module: Optional[object]
                 if _saved[rmod][n] is not None:
                     rep._reference[n] = _saved[rmod][n]
                     setattr(rmod, n, getattr(rep, n))
+    if scoring:
+        smod = scoring_module
+        if smod is None and module is None:
+            try:
+                smod = importlib.import_module("crisprhawk.scoring")
+            except Exception:
+                smod = None  # the scorers' own dependencies are missing: nothing to rebind
+        if smod is not None and smod not in _saved:
+            _saved[smod] = {n: getattr(smod, n, None) for n in sco.SEAM}
+            if _saved[smod]["cfdon_score"] is not None:
+                sco._reference["cfdon_score"] = _saved[smod]["cfdon_score"]
+                smod.cfdon_score = sco.cfdon_score
+            try:
+                pmod = importlib.import_module("crisprhawk.pam")
+                sco._reference["cas9_systems"] = (pmod.SPCAS9, pmod.XCAS9)
+            except Exception:
+                pass
     return drv
 
 
 def uninstall(module: Optional[object] = None, annotation_module: Optional[object] = None,
-              haplotypes_module: Optional[object] = None, reports_module: Optional[object] = None) -> None:
+              haplotypes_module: Optional[object] = None, reports_module: Optional[object] = None,
+              scoring_module: Optional[object] = None) -> None:
     from . import annotation as ann
     from . import haplotypes as hapmod
     from . import report_rows as rep
+    from . import scoring as sco
+
+    smod = scoring_module
+    if smod is None and module is None:
+        smod = __import__("sys").modules.get("crisprhawk.scoring")
+    if smod is not None:
+        for name, fn in _saved.pop(smod, {}).items():
+            if fn is not None:
+                setattr(smod, name, fn)
+        sco._reference.clear()
 
     rmod = reports_module
     if rmod is None and module is None:

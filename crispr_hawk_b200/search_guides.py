@@ -258,7 +258,7 @@ def search(pam, region, haplotypes, haplotypes_bits, guidelen: int, right: bool,
     if not unphased:
         # N2 seam: the device-resident table travels with the list, so the mirrors of
         # annotation.py's per-guide loops (crispr_hawk_b200.annotation) can run on it
-        link = dict(table=table, res=res, batch=res.batch_ref, haplotypes=haplotypes, right=bool(right), order=order)
+        link = dict(table=table, res=res, batch=res.batch_ref, haplotypes=haplotypes, right=bool(right), order=order, pam=pam)
         LIVE_TABLES.add(link, res.device_bytes() + getattr(res.batch_ref, "device_bytes", lambda: 0)())
         return GuideList(len(order), make, link)
     res.close()

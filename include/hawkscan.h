@@ -57,7 +57,8 @@ enum {
   HAWK_ECAPACITY = -5,/* caller-provided output capacity too small (dev layer) */
   HAWK_EALLELES = -6, /* ambiguity code without variant_alleles entry (KeyError, search_guides.py:207-213) */
   HAWK_EDUPREF = -7,  /* two REF guides at one (start, strand) (search_guides.py:328-334) */
-  HAWK_EASSERT = -8   /* input on which the reference itself fails an assert (annotation.py:191) */
+  HAWK_EASSERT = -8,  /* input on which the reference itself fails an assert (annotation.py:191) */
+  HAWK_ECFD = -9      /* CFDon: a letter or key the score tables do not hold (KeyError, cfdscore.py:89-94) */
 };
 
 /* mode flags of hawk_params.flags */
@@ -286,6 +287,17 @@ int hawk_batch_set_variants(hawk_batch *batch, const int64_t *var_off, const int
 int hawk_result_annotate(hawk_result *result, hawk_batch *batch, uint8_t *rc_text, int32_t *gc_num,
                          int32_t *gc_den, int64_t *gv_off, int64_t *gv_total);
 int hawk_result_fetch_variants(hawk_result *result, int32_t *gv_idx /* gv_total */);
+
+/* N4 (next row): CFDon of every guide row against the REF guide of its (start, strand) key
+ * (scoring.py:303-387 cfdon_score + group_guides_position, scores/crisprhawk_scores.py:65-87,
+ * scores/cfdscore/cfdscore.py:53-95 compute_cfd) on the table of a phased / variant-free
+ * hawk_search whose REF, if any, is haplotype 0. mm[(i * 4 + w) * 4 + g], i < 20, w / g in
+ * A, C, G, T(U): the factor of the reference's key "r<w>:d<revcomp(g)>,<i + 1>"; pam2[a * 4 + b]:
+ * the factor of the PAM's last two letters; NaN = key absent from the reference's dict. The
+ * product runs in the reference's order in double precision (bit-identical floats). scores[row] =
+ * NaN where the key has no REF guide. HAWK_ECFD (+ *bad_row) where the reference raises KeyError. */
+int hawk_result_cfdon(hawk_result *result, const uint8_t *is_ref, int32_t n_hap, const double *mm /* 320 */,
+                      const double *pam2 /* 16 */, double *scores /* n_guides */, int64_t *bad_row);
 
 /* N2, the row collapse of the report (reports._collapse_report_entries, reports.py:958-1008, for
  * the score-free column set): rows of a phased / variant-free hawk_search result that agree in

@@ -110,6 +110,9 @@ class FakeResult:
         head = np.array([k == 0 or keys[perm[k]] != keys[perm[k - 1]] for k in range(self.n_guides)], dtype=np.uint8)
         return perm, head, False
 
+    def cfdon(self, is_ref, mm, pam2):
+        return hostcheck.cfdon_flat(self.tab, self.params, is_ref, mm, pam2)
+
     def close(self):
         self.closed, self.handle = True, None
 

@@ -140,3 +140,30 @@ def annotate_flat(table, params, seg, vt):
     if total < 0:
         raise AssertionError("the reference's _find_insertion_stop assert would fire")
     return {"rc_text": rc_text[:, :w], "gc_num": num, "gc_den": den, "gv_off": off, "gv_idx": idx[:total], "vt": vt}
+
+
+def cfdon_flat(table, params, is_ref, mm, pam2):
+    """hawk_result_cfdon on the CPU: the kernels' own cfdon_row over the table."""
+    from crispr_hawk_b200 import _cabi
+
+    L = lib()
+    L.hawkcheck_cfdon.restype = C.c_int64
+    n = len(table["hap"])
+    w = params.guide_len + params.pam_len + 20
+    stride = (w + 15) // 16 * 16
+    text = np.zeros((max(n, 1), stride), np.uint8)
+    if n:
+        text[:n, :w] = table["text"][:, :w]
+    out = np.zeros(max(n, 1), np.float64)
+    bad = L.hawkcheck_cfdon(
+        _p(np.ascontiguousarray(table["hap"], np.int32)), _p(np.ascontiguousarray(table["strand"], np.uint8)),
+        _p(np.ascontiguousarray(table["bucket"], np.uint32)), _p(text), C.c_int32(stride), C.c_int32(w),
+        C.c_int32(params.guide_len), C.c_int32(params.pam_len), C.c_int32(params.right),
+        _p(np.ascontiguousarray(is_ref, np.uint8)), _p(np.ascontiguousarray(mm, np.float64).reshape(320)),
+        _p(np.ascontiguousarray(pam2, np.float64).reshape(16)), C.c_int64(n), _p(out),
+    )  # fmt: skip
+    if bad >= 0:
+        err = _cabi.HawkLibraryError(f"hawk_result_cfdon: row {bad}", _cabi.HAWK_ECFD)
+        err.bad_row = bad
+        raise err
+    return out[:n]

@@ -268,3 +268,118 @@ def test_installed_report_collapse_equals_the_reference(case, monkeypatch):
     finally:
         hawk.uninstall()
     assert R._collapse_report_entries.__module__ == "crisprhawk.reports"
+
+
+# --------------------------------------------------------------------------- N4: CFDon
+def load_scoring():
+    """The genuine `crisprhawk.scoring` (cfdon_score, group_guides_position) and
+    `crisprhawk.scores.crisprhawk_scores.cfdon` / `cfdscore.compute_cfd`, with the learned scorers'
+    packages (Azimuth, RS3, DeepCpf1, Elevation, PLM-CRISPR, CRISPRon, sgDesigner: matplotlib,
+    rs3, model files -- out of scope) replaced by empty stubs."""
+    import importlib
+    import os
+
+    refshim.load()
+    import crisprhawk
+
+    base = os.path.join(os.path.dirname(crisprhawk.__file__), "scores")
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    cur = sys.modules.get("crisprhawk.scoring")
+    if cur is not None and getattr(cur, "__file__", None):
+        return cur, sys.modules["crisprhawk.scores.crisprhawk_scores"]
+    pkg = stub("crisprhawk.scores")
+    pkg.__path__ = [base]
+    for sub in ("azimuth", "deepCpf1", "elevation", "elevation.cmds", "plm_crispr", "crispron", "sgdesigner"):
+        stub("crisprhawk.scores." + sub).__path__ = [os.path.join(base, *sub.split("."))]
+    stub("crisprhawk.scores.azimuth.model_comparison", predict=None)
+    stub("rs3")
+    stub("rs3.seq", predict_seq=None)
+    stub("crisprhawk.scores.deepCpf1.seqdeepcpf1", SeqDeepCpf1=None, preprocess=None, load_deepcpf1_weights=None,
+         compute_deepcpf1=None)  # fmt: skip
+    stub("crisprhawk.scores.elevation.cmds.predict", Predict=None)
+    stub("crisprhawk.scores.plm_crispr.plm_crispr", compute_plm_crispr_score=None)
+    stub("crisprhawk.scores.crispron.crispron", compute_crispron_score=None)
+    stub("crisprhawk.scores.sgdesigner.sgdesigner", compute_sgdesigner_score=None)
+    cs = importlib.import_module("crisprhawk.scores.crisprhawk_scores")
+    for n in dir(cs):
+        if not n.startswith("_"):
+            setattr(pkg, n, getattr(cs, n))
+    sys.modules.pop("crisprhawk.scoring", None)  # a stub of it may be there (load_driver)
+    scoring = importlib.import_module("crisprhawk.scoring")
+    return scoring, cs
+
+
+def synthetic_cfd_dicts(seed, drop=None):
+    """Factor tables with the reference's keys (cfdscore.py:89-94) and seeded values in (0, 1]."""
+    import random
+
+    rnd = random.Random(seed)
+    rc = {"A": "T", "C": "G", "G": "C", "U": "A"}
+    mm = {f"r{w}:d{rc[g]},{i + 1}": rnd.random() for i in range(20) for w in "ACGU" for g in "ACGU" if w != g}
+    pam = {a + b: rnd.random() for a in "ACGT" for b in "ACGT"}
+    pam["GG"] = 1.0
+    for k in drop or ():
+        mm.pop(k, None), pam.pop(k, None)
+    return mm, pam
+
+
+CFD_CASES = [CASES[0]] + [make_case(130 + k, phased=True, pam=p, guidelen=g, right=False, bed_len=1200, n_sites=50, n_samples=6,
+                                    indel_frac=0.3) for k, (p, g) in enumerate([("NGG", 20), ("NRG", 20), ("NGG", 23), ("NGG", 18)])]  # fmt: skip
+
+
+def run_cfdon(drv, scoring, case):
+    region, _, guides = run_driver(drv, case)
+    out = scoring.cfdon_score(guides, 0, True)
+    return [(g.start, g.strand, g.guide, g.pam, g.hapid, g.cfdon_score) for g in out], guides, out
+
+
+@pytest.mark.parametrize("case", CFD_CASES, ids=[c.name for c in CFD_CASES])
+def test_installed_cfdon_equals_the_reference(case, monkeypatch):
+    """The genuine `cfdon_score` -> `cfdon` -> `compute_cfd` with seeded factor tables in place of
+    the model files, plain and with the package installed (scores then come from
+    hawk_result_cfdon, computed while the table was on the device)."""
+    scoring, cs = load_scoring()
+    drv = load_driver()
+    tables = synthetic_cfd_dicts(7)
+    monkeypatch.setattr(cs, "load_mismatch_pam_scores", lambda debug: tables)
+    monkeypatch.setattr(sys.modules["crisprhawk.scoring"], "cfdon_score", scoring.cfdon_score)
+    want, _, _ = run_cfdon(drv, scoring, case)
+    assert any(w[-1] not in ("NA", "1.0") for w in want) and any(w[-1] == "NA" for w in want)
+    fake_backend.activate(monkeypatch)
+    hawk.install()
+    try:
+        assert scoring.cfdon_score.__module__ == "crispr_hawk_b200.scoring"
+        got, guides, out = run_cfdon(drv, scoring, case)
+        assert out is guides and guides.hawk.get("cfdon") is not None  # the device column was used
+        assert got == want
+    finally:
+        hawk.uninstall()
+    assert scoring.cfdon_score.__module__ == "crisprhawk.scoring"
+
+
+def test_cfdon_key_errors_surface_like_the_reference(monkeypatch):
+    """A factor the tables do not hold: the reference's KeyError is wrapped by `cfdon_score` into
+    CrisprHawkCfdScoreError (scoring.py:370-379); so is the device's HAWK_ECFD."""
+    scoring, cs = load_scoring()
+    drv = load_driver()
+    case = CFD_CASES[1]
+    full = synthetic_cfd_dicts(7)
+    tables = synthetic_cfd_dicts(7, drop=[k for k in full[0] if k.endswith(",5")])
+    monkeypatch.setattr(cs, "load_mismatch_pam_scores", lambda debug: tables)
+    from crisprhawk.crisprhawk_error import CrisprHawkCfdScoreError
+
+    with pytest.raises(CrisprHawkCfdScoreError):
+        run_cfdon(drv, scoring, case)
+    fake_backend.activate(monkeypatch)
+    hawk.install()
+    try:
+        with pytest.raises(CrisprHawkCfdScoreError):
+            run_cfdon(drv, scoring, case)
+    finally:
+        hawk.uninstall()
