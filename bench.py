@@ -710,6 +710,15 @@ def run_product_arm(args, rank, world, local_rank):
             "cpu_port": "oracle/annot_oracle.py (pure Python, like the reference) on a random sample of non-REF rows, "
                         "each also compared with the device result",
         }}  # fmt: skip
+        next_rows["N2_collapse"] = {
+            "what": "hawk_result_collapse: the groups of reports._collapse_report_entries over the whole table (row keys, two "
+                    "radix sorts, head flags; permutation + flags copied to the host inside the timed call)",
+            "rows": m["rows"], "groups": m["collapse_groups"], "ms": m["collapse_ms"], "hash_collision": m["collapse_collision"]}
+        if "cfdon_ms" in m:
+            next_rows["N4_cfdon"] = {
+                "what": "hawk_result_cfdon: CFDon of every row against the REF guide of its (start, strand) key, float64 scores "
+                        "copied to the host inside the timed call; stand-in factor tables",
+                "rows": m["rows"], "rows_with_ref_guide": m["cfdon_scored"], "ms": m["cfdon_ms"]}
 
     # ---- the Python side of the seam (rank 0, N = 1 only): what a user of the drop-in sees ----
     if rank == 0 and world == 1 and not args.no_e2e and not unphased:
