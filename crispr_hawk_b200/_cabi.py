@@ -501,21 +501,25 @@ class Result:
         return {"rc_text": rc.reshape(n, ts)[:, :w] if want_text else None, "gc_num": num, "gc_den": den,
                 "gv_off": off, "gv_idx": idx}  # fmt: skip
 
-    def collapse(self, is_ref):
+    def collapse(self, is_ref, buffers=None):
         """hawk_result_collapse: (perm, head, collision) -- rows ordered by (start, stop, group),
-        head[k] = 1 where a report row (group) starts."""
+        head[k] = 1 where a report row (group) starts. `buffers`: optional dict of preallocated
+        (e.g. pinned) arrays `perm` (uint32) and `head` (uint8) with at least n rows."""
         r = np.ascontiguousarray(is_ref, dtype=np.uint8)
-        perm, head, col = np.empty(self.n_guides, np.uint32), np.empty(self.n_guides, np.uint8), C.c_int32(0)
+        n, col = self.n_guides, C.c_int32(0)
+        perm = buffers["perm"][:n] if buffers else np.empty(n, np.uint32)
+        head = buffers["head"][:n] if buffers else np.empty(n, np.uint8)
         check(self.lib.hawk_result_collapse(self.handle, ptr(r, C.c_uint8), len(r), ptr(perm, C.c_uint32), ptr(head, C.c_uint8),
                                             C.byref(col)), "hawk_result_collapse")  # fmt: skip
         return perm, head, bool(col.value)
 
-    def cfdon(self, is_ref, mm, pam2):
-        """hawk_result_cfdon: float64 CFDon score per row (NaN: no REF guide at the row's key)."""
+    def cfdon(self, is_ref, mm, pam2, out=None):
+        """hawk_result_cfdon: float64 CFDon score per row (NaN: no REF guide at the row's key).
+        `out`: optional preallocated (e.g. pinned) float64 array with at least n rows."""
         r = np.ascontiguousarray(is_ref, dtype=np.uint8)
         mm = np.ascontiguousarray(mm, dtype=np.float64).reshape(320)
         p2 = np.ascontiguousarray(pam2, dtype=np.float64).reshape(16)
-        out, bad = np.empty(self.n_guides, np.float64), C.c_int64(-1)
+        out, bad = (out[: self.n_guides] if out is not None else np.empty(self.n_guides, np.float64)), C.c_int64(-1)
         rc = self.lib.hawk_result_cfdon(self.handle, ptr(r, C.c_uint8), len(r), ptr(mm, C.c_double), ptr(p2, C.c_double),
                                         ptr(out, C.c_double), C.byref(bad))  # fmt: skip
         if rc != HAWK_OK:

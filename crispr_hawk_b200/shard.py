@@ -260,6 +260,9 @@ def merge_tables_device(res, ctx, hap_offset: int, rank: int, world: int, device
     temporary = session is None
     session = session or MergeSession(ctx, rank, world, device, group)
     base = session.ensure(nbytes.value)
+    import time
+
+    t_push = time.perf_counter()
     pushed = C.c_int64()
     _cabi.check(lib.hawk_result_push(res.handle, n_ref, int(hap_offset) if rank > 0 else 0, 0, base, total, at,
                                      1 if with_text else 0, C.byref(pushed)), "hawk_result_push")  # fmt: skip
@@ -267,6 +270,7 @@ def merge_tables_device(res, ctx, hap_offset: int, rank: int, world: int, device
     _cabi.check(lib.hawk_ctx_sync(ctx.handle), "hawk_ctx_sync")
     if world > 1:
         dist.barrier(group=group)  # every rank's rows are in rank 0's memory
+    push_ms = 1e3 * (time.perf_counter() - t_push)
     if temporary and world > 1:
         # no session to keep: the peers unmap now, rank 0's table owns the buffer from here on
         if rank > 0:
@@ -285,6 +289,9 @@ def merge_tables_device(res, ctx, hap_offset: int, rank: int, world: int, device
                         else torch.empty((0, ts), dtype=torch.uint8, device=device))  # fmt: skip
     merged = MergedTable(session, cols)
     merged.received_bytes = (total - sizes[0]) * (17 + (ts if with_text else 0))
+    merged.push_ms = push_ms  # hawk_result_push on every rank + the barrier, as rank 0 saw it
+    merged.first_seen_ms = 0.0
+    t_fs = time.perf_counter()
     if total:
         if getattr(session, "_key_table", None) is None or session._key_table.numel() < 2 * int(key_span) + 1:
             session._key_table = torch.empty(2 * int(key_span) + 1, dtype=torch.int32, device=device)
@@ -295,4 +302,5 @@ def merge_tables_device(res, ctx, hap_offset: int, rank: int, world: int, device
                                     C.c_void_p(base.value + off[5])),
             "hawk_first_seen_dev",
         )  # fmt: skip
+        merged.first_seen_ms = 1e3 * (time.perf_counter() - t_fs)  # hawk_first_seen_dev synchronises its stream
     return merged

@@ -209,7 +209,8 @@ class Workload:
                 best = dt if best is None else min(best, dt)
             return best, val
 
-        out["collapse_ms"], (perm, head, collision) = best_of(lambda: res.collapse(self.d.is_ref))
+        cbufs = {"perm": pin(n, torch.int32).view(np.uint32), "head": pin(n, torch.uint8), "cfd": pin(n, torch.float64)}
+        out["collapse_ms"], (perm, head, collision) = best_of(lambda: res.collapse(self.d.is_ref, cbufs))
         out["collapse_groups"], out["collapse_collision"] = int(head.sum()), bool(collision)
         if len(self.fwd) >= 2 and not self.right:
             import random
@@ -220,7 +221,7 @@ class Workload:
             mm = {f"r{w}:d{g},{i + 1}": rnd.random() for i in range(20) for w in "ACGU" for g in "ACGT"}
             pam = {a + b: rnd.random() for a in "ACGT" for b in "ACGT"}
             mm_t, pam_t = scoring.cfd_tables(mm, pam)
-            out["cfdon_ms"], col = best_of(lambda: res.cfdon(self.d.is_ref, mm_t, pam_t))
+            out["cfdon_ms"], col = best_of(lambda: res.cfdon(self.d.is_ref, mm_t, pam_t, cbufs["cfd"]))
             out["cfdon_scored"] = int((~np.isnan(col)).sum())
         if oracle is not None and n:
             if getattr(self, "_edits_out2", None) is None or len(self._edits_out2["hap"]) < n:
