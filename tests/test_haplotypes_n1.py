@@ -101,3 +101,68 @@ def test_bad_edits_are_rejected():
         hawk.build_phased(ref, 1000, [[], [HN.Edit(1010, "T", "A")]])
     with pytest.raises(_cabi.HawkLibraryError):  # overlapping edits
         hawk.build_phased(ref, 1000, [[HN.Edit(1008, "ACGT", "A"), HN.Edit(1010, "G", "T")]])
+
+
+# --------------------------------------------------------------------------- plan on arrays
+def random_records(seed, n_samples=9, n_sites=120, L=4000, dup=True):
+    import types
+
+    rng = np.random.default_rng(seed)
+    ref = "".join("ACGT"[i] for i in rng.integers(0, 4, L))
+    start = 7000
+    names = [f"S{i}" for i in range(n_samples)]
+    pos = np.sort(rng.choice(np.arange(20, L - 40, 12), n_sites, replace=False))
+    recs = []
+    for p in pos.tolist():
+        kind = rng.random()
+        if kind < 0.6:
+            r, a = ref[p], "ACGT"[("ACGT".index(ref[p]) + int(rng.integers(1, 4))) % 4]
+        elif kind < 0.8:
+            r, a = ref[p], ref[p] + "".join("ACGT"[i] for i in rng.integers(0, 4, int(rng.integers(1, 6))))
+        else:
+            r, a = ref[p : p + int(rng.integers(2, 7))], ref[p]
+        c0 = {n for n in names if rng.random() < 0.3}
+        c1 = {n for n in names if rng.random() < 0.3} if rng.random() < 0.7 else set(c0)
+        vt = "snp" if len(r) == 1 and len(a) == 1 else "indel"
+        recs.append(types.SimpleNamespace(position=start + p, ref=r, alt=[a], afs=[round(float(rng.random()), 3)],
+                                          samples=[(c0, c1)], vtype=[vt], id=[f"chr1-{start + p}-{r}/{a}"]))  # fmt: skip
+        if dup and rng.random() < 0.05:  # the same record twice (carriers differ)
+            recs.append(types.SimpleNamespace(position=start + p, ref=r, alt=[a], afs=[0.5], samples=[({names[0]}, set())],
+                                              vtype=[vt], id=[f"chr1-{start + p}-{r}/{a}"]))  # fmt: skip
+    return ref, start, names, recs
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_plan_on_arrays_equals_plan_on_objects(seed):
+    """plan_phased_arrays (one pass over the records, numpy per chromosome copy) against
+    plan_phased (Python per variant and copy): same haplotypes, order, strings and dicts."""
+    ref, start, names, recs = random_records(seed, dup=False)
+    slow = HN.plan_phased(ref, start, names, recs)
+    T, fast = HN.plan_phased_arrays(ref, start, names, recs)
+    assert len(slow) == len(fast) > 3
+    for a, b in zip(slow, fast):
+        e = b["e_idx"]
+        assert [(x.pos, len(x.ref), len(x.alt)) for x in a["edits"]] == list(zip(T.pos[e].tolist(), T.reflen[e].tolist(), T.altlen[e].tolist()))
+        assert [x.alt.upper() for x in a["edits"]] == [bytes(T.pool[o : o + n]).decode() for o, n in zip(T.altoff[e].tolist(), T.altlen[e].tolist())]
+        assert (a["samples"], a["variants"], a["afs"]) == (b["samples"], b["variants"], b["afs"])
+        assert list(a["afs"]) == list(b["afs"])  # insertion order too
+
+
+def test_unusual_inputs_leave_the_array_plan():
+    import types
+
+    ref, start, names, recs = random_records(3)
+    with pytest.raises(HN._Unusual):  # duplicate records on one copy overlap: plan_phased's business
+        HN.plan_phased_arrays(ref, start, names, recs + [types.SimpleNamespace(
+            position=recs[0].position, ref=recs[0].ref, alt=recs[0].alt, afs=[0.1], samples=recs[0].samples, vtype=recs[0].vtype, id=recs[0].id)])
+    ref2, start2, names2, recs2 = random_records(4, dup=False)
+    bad = recs2[5]
+    bad.ref = ("A" if bad.ref[0] != "A" else "C") + bad.ref[1:]
+    with pytest.raises(HN._Unusual):  # REF allele does not match the reference text
+        HN.plan_phased_arrays(ref2, start2, names2, recs2)
+    with pytest.raises(ValueError):  # ... and plan_phased raises the reference's message
+        HN.plan_phased(ref2, start2, names2, recs2)
+    ref3, start3, names3, recs3 = random_records(5, dup=False)
+    recs3[2].ref, recs3[2].alt = ref3[recs3[2].position - start3 : recs3[2].position - start3 + 2], ["TT"]
+    with pytest.raises(HN._Unusual):  # complex substitution
+        HN.plan_phased_arrays(ref3, start3, names3, recs3)
