@@ -409,6 +409,7 @@ extern "C" int hawk_batch_create_from_edits(hawk_ctx* c, const uint8_t* ref_asci
     b->ref_chunks = ref_chunks;
     b->n_edits = n_edits;
     b->has_edits.resize(n_hap);
+    b->h_edit_off.assign(edit_off, edit_off + n_hap + 1);
     std::vector<int32_t> plain;
     for (int32_t h = 0; h < n_hap; ++h) {
       b->has_edits[h] = edit_off[h + 1] > edit_off[h];
@@ -612,18 +613,44 @@ extern "C" int hawk_batch_destroy(hawk_batch* b) {
 extern "C" int hawk_batch_export_nibbles(hawk_batch* b, int32_t hap, uint8_t* nibbles, uint8_t* lower) {
   if (!b || hap < 0 || hap >= b->n_hap || !nibbles)
     return hawk_fail(HAWK_EINVAL, "hawk_batch_export_nibbles: bad arguments");
-  CK(hawk_edits_ensure(b, HAWK_EDITS_DENSE));  // an edit-list batch: every plane, now
-  if (b->sparse) return hawk_fail(HAWK_EINVAL, "hawk_batch_export_nibbles: the batch keeps planes only around variant bases");
   hawk_ctx* c = b->ctx;
   CKCUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   int32_t L = b->len[hap];
   if (L == 0) return HAWK_OK;
-  DevBuf dn, dl;
+  DevBuf dn, dl, t_ascii, t_q, t_v, t_nz, t_so, t_bad;
+  const void* q = b->q.p;
+  const uint32_t* v = b->v.as<uint32_t>();
+  int64_t chunk0 = b->slot_off[hap] >> 5;
+  if (b->edits_lazy) {
+    // an edit-list batch holds planes around the edits only: this ONE haplotype is materialised and
+    // packed into scratch (synth_kernels.cu + K1, ~len bytes), the batch itself stays as it is
+    const int32_t one_len = L;
+    int64_t so[2], total = 0;
+    CK(hawk_layout(&one_len, 1, so, &total));
+    CK(t_ascii.alloc(c, (size_t)total));
+    CK(upload(c, t_so, so, 16));
+    CK(hawk_materialize_range(st, b->ref_text.as<uint8_t>(), b->ref_len, b->var_off.as<int64_t>() + hap,
+                              b->var_pos.as<int32_t>(), b->var_rl.as<int32_t>(), b->var_al.as<int32_t>(), b->var_ao.as<int64_t>(),
+                              b->edit_outpos.as<int32_t>(), b->var_pool.as<uint8_t>(), t_so.as<int64_t>(),
+                              b->d_len.as<int32_t>() + hap, 1, total, b->h_edit_off[hap], b->h_edit_off[hap + 1], L,
+                              t_ascii.as<uint8_t>()));
+    const size_t n_chunks = (size_t)total / HAWK_CHUNK;
+    CK(t_q.alloc(c, n_chunks * 16));
+    CK(t_v.alloc(c, n_chunks * 4));
+    CK(t_nz.alloc(c, (n_chunks + 31) / 32 * 4 + 16));
+    const int64_t init = INT64_MAX;
+    CK(upload(c, t_bad, &init, 8));
+    CK(hawk_pack_dev(st, t_ascii.as<uint8_t>(), total, t_q.p, t_v.as<uint32_t>(), t_nz.as<uint32_t>(), t_bad.as<int64_t>()));
+    q = t_q.p;
+    v = t_v.as<uint32_t>();
+    chunk0 = so[0] >> 5;
+  } else if (b->sparse) {
+    return hawk_fail(HAWK_EINVAL, "hawk_batch_export_nibbles: the batch keeps planes only around variant bases");
+  }
   CK(dn.alloc(c, L));
   if (lower) CK(dl.alloc(c, L));
-  CK(launch_export_nibbles(st, b->q.p, b->v.as<uint32_t>(), b->slot_off[hap] >> 5, L,
-                           dn.as<uint8_t>(), lower ? dl.as<uint8_t>() : nullptr));
+  CK(launch_export_nibbles(st, q, v, chunk0, L, dn.as<uint8_t>(), lower ? dl.as<uint8_t>() : nullptr));
   CKCUDA(cudaMemcpyAsync(nibbles, dn.p, L, cudaMemcpyDeviceToHost, st));
   if (lower) CKCUDA(cudaMemcpyAsync(lower, dl.p, L, cudaMemcpyDeviceToHost, st));
   CKCUDA(cudaStreamSynchronize(st));

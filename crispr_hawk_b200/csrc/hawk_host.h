@@ -202,6 +202,7 @@ struct hawk_batch {
   int64_t ref_len = 0, ref_chunks = 0, n_edits = 0;
   int32_t n_plain = 0;
   std::vector<uint8_t> has_edits;  // per haplotype
+  std::vector<int64_t> h_edit_off; // n_hap + 1
   // scan bounds attached to the batch (hawk_batch_set_scan): searches that pass NULL bounds use
   // these device-resident copies instead of uploading n_hap-sized arrays per call
   bool has_scan = false;
@@ -252,6 +253,11 @@ struct StreamLink {
 // HAWK_EDITS_DENSE for every chunk (no-op for other batches and when already satisfied)
 #define HAWK_EDITS_DENSE (1 << 20)
 int hawk_edits_ensure(hawk_batch* b, int need);
+int hawk_materialize_range(cudaStream_t stream, const uint8_t* d_ref, int64_t ref_len, const int64_t* d_edit_off,
+                           const int32_t* d_edit_pos, const int32_t* d_edit_reflen, const int32_t* d_edit_altlen,
+                           const int64_t* d_edit_altoff, const int32_t* d_edit_outpos, const uint8_t* d_alt_pool,
+                           const int64_t* d_slot_off, const int32_t* d_len, int32_t n_hap, int64_t total_slots,
+                           int64_t e_lo, int64_t e_hi, int32_t max_len, uint8_t* d_ascii_out);
 int batch_create_impl(hawk_ctx* c, const uint8_t* ascii, bool ascii_on_device, const int64_t* slot_off,
                       const int32_t* len, int32_t n_hap, hawk_batch** out, int64_t* bad_slot, bool defer_planes = false);
 // `fused_text`: device-resident texts of the batch's layout; the batch is re-encoded from them

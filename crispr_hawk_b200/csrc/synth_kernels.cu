@@ -122,9 +122,9 @@ __global__ void __launch_bounds__(256) materialize_kernel(const __grid_constant_
 // Pass 2, one thread per edit: the chunks its ALT text touches, byte by byte. Two edits in
 // one chunk both write the same bytes.
 __global__ void __launch_bounds__(128) materialize_edits_kernel(const __grid_constant__ MaterializeArgs A,
-                                                                int64_t n_edits) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_edits) return;
+                                                                int64_t e_lo, int64_t e_hi) {
+  const int64_t e = e_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= e_hi) return;
   int32_t lo = 0, hi = A.n_hap;  // haplotype of edit e
   while (hi - lo > 1) {
     const int32_t m = (lo + hi) >> 1;
@@ -262,13 +262,13 @@ int launch_derive(cudaStream_t st, int32_t n_hap, const int64_t* edit_off, const
 
 using namespace hawk;
 
-extern "C" int hawk_materialize_dev(void* stream, const uint8_t* d_ref, int64_t ref_len,
-                                    const int64_t* d_edit_off, const int32_t* d_edit_pos,
-                                    const int32_t* d_edit_reflen, const int32_t* d_edit_altlen,
-                                    const int64_t* d_edit_altoff, const int32_t* d_edit_outpos,
-                                    const uint8_t* d_alt_pool, const int64_t* d_slot_off,
-                                    const int32_t* d_len, int32_t n_hap, int64_t total_slots,
-                                    int64_t n_edits, int32_t max_len, uint8_t* d_ascii_out) {
+// edits [e_lo, e_hi) must be those of the n_hap haplotypes d_edit_off describes (the whole table:
+// 0 .. n_edits; one haplotype of a larger table: its own range, with d_edit_off / d_len pointing at it)
+int hawk_materialize_range(cudaStream_t stream, const uint8_t* d_ref, int64_t ref_len, const int64_t* d_edit_off,
+                           const int32_t* d_edit_pos, const int32_t* d_edit_reflen, const int32_t* d_edit_altlen,
+                           const int64_t* d_edit_altoff, const int32_t* d_edit_outpos, const uint8_t* d_alt_pool,
+                           const int64_t* d_slot_off, const int32_t* d_len, int32_t n_hap, int64_t total_slots,
+                           int64_t e_lo, int64_t e_hi, int32_t max_len, uint8_t* d_ascii_out) {
   if (n_hap <= 0 || total_slots <= 0) return HAWK_OK;
   if ((uintptr_t)d_ascii_out & 15) return hawk_fail(HAWK_EINVAL, "hawk_materialize_dev: output must be 16-byte aligned");
   MaterializeArgs A{d_ref, ref_len, d_edit_off, d_edit_pos, d_edit_reflen, d_edit_altlen, d_edit_altoff,
@@ -276,11 +276,23 @@ extern "C" int hawk_materialize_dev(void* stream, const uint8_t* d_ref, int64_t 
   // grid row = haplotype: its leading gap + its padded slots (+ the trailing gap of the last one)
   const int64_t row_chunks = (((int64_t)max_len + HAWK_SLOT_ALIGN - 1) / HAWK_SLOT_ALIGN * HAWK_SLOT_ALIGN + 2 * HAWK_SLOT_GAP) / 32;
   dim3 grid((unsigned)((row_chunks + 255) / 256), (unsigned)(n_hap < 65535 ? n_hap : 65535));
-  materialize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
+  materialize_kernel<<<grid, 256, 0, stream>>>(A);
   hawk_note_launch(1);
-  if (n_edits > 0) {
-    materialize_edits_kernel<<<(unsigned)((n_edits + 127) / 128), 128, 0, (cudaStream_t)stream>>>(A, n_edits);
+  if (e_hi > e_lo) {
+    materialize_edits_kernel<<<(unsigned)((e_hi - e_lo + 127) / 128), 128, 0, stream>>>(A, e_lo, e_hi);
     hawk_note_launch(1);
   }
   return hawk_check_cuda(cudaGetLastError(), "materialize kernels launch");
+}
+
+extern "C" int hawk_materialize_dev(void* stream, const uint8_t* d_ref, int64_t ref_len,
+                                    const int64_t* d_edit_off, const int32_t* d_edit_pos,
+                                    const int32_t* d_edit_reflen, const int32_t* d_edit_altlen,
+                                    const int64_t* d_edit_altoff, const int32_t* d_edit_outpos,
+                                    const uint8_t* d_alt_pool, const int64_t* d_slot_off,
+                                    const int32_t* d_len, int32_t n_hap, int64_t total_slots,
+                                    int64_t n_edits, int32_t max_len, uint8_t* d_ascii_out) {
+  return hawk_materialize_range((cudaStream_t)stream, d_ref, ref_len, d_edit_off, d_edit_pos, d_edit_reflen, d_edit_altlen,
+                                d_edit_altoff, d_edit_outpos, d_alt_pool, d_slot_off, d_len, n_hap, total_slots, 0, n_edits,
+                                max_len, d_ascii_out);
 }
