@@ -16,14 +16,14 @@ namespace hawk {
 
 __global__ void cfdon_kernel(const int32_t* __restrict__ hap, const uint8_t* __restrict__ strand,
                              const uint32_t* __restrict__ bucket, const uint8_t* __restrict__ text, int32_t text_stride,
-                             int W, int G, int P, int right, const uint8_t* __restrict__ is_ref,
+                             int W, int G, int P, int right, const uint8_t* __restrict__ is_ref, int32_t n_hap,
                              const double* __restrict__ mm, const double* __restrict__ pam2, int64_t n,
                              double* __restrict__ out, unsigned long long* __restrict__ bad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t b = bucket[i];
   double v = __longlong_as_double(0x7FF8000000000000ll);  // no REF guide at this key: NaN (crisprhawk_scores.py:81-82)
-  if (is_ref[hap[b]]) {
+  if ((int64_t)b < n && (uint32_t)hap[b] < (uint32_t)n_hap && is_ref[hap[b]]) {
     if (!cfdon_row(text + (int64_t)b * text_stride, text + i * (int64_t)text_stride, W, G, P, right, strand[i], mm, pam2, &v))
       atomicMin(bad, (unsigned long long)i);
   }
@@ -58,7 +58,7 @@ extern "C" int hawk_result_cfdon(hawk_result* r, const uint8_t* is_ref, int32_t 
   CK(upload(c, d_bad, &none, 8));
   cfdon_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
       r->hap.as<int32_t>(), r->strand.as<uint8_t>(), r->bucket.as<uint32_t>(), r->text.as<uint8_t>(), r->text_stride, r->window,
-      r->params.guide_len, r->params.pam_len, r->params.right, d_ref.as<uint8_t>(), d_mm.as<double>(), d_pam.as<double>(), n,
+      r->params.guide_len, r->params.pam_len, r->params.right, d_ref.as<uint8_t>(), n_hap, d_mm.as<double>(), d_pam.as<double>(), n,
       d_out.as<double>(), d_bad.as<unsigned long long>());
   hawk_note_launch(1);
   CK(hawk_check_cuda(cudaGetLastError(), "cfdon_kernel launch"));

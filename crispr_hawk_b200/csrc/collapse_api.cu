@@ -34,13 +34,14 @@ __device__ __forceinline__ uint64_t mix_u64(uint64_t x) {
 __global__ void collapse_key_kernel(const int32_t* __restrict__ hap, const uint8_t* __restrict__ strand,
                                     const int32_t* __restrict__ start, const int32_t* __restrict__ stop,
                                     const uint8_t* __restrict__ text, int32_t text_stride, int32_t core_len,
-                                    const uint8_t* __restrict__ is_ref, int64_t n, uint64_t* __restrict__ k_hi,
+                                    const uint8_t* __restrict__ is_ref, int32_t n_hap, int64_t n, uint64_t* __restrict__ k_hi,
                                     uint64_t* __restrict__ k_lo, uint32_t* __restrict__ idx) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   k_hi[i] = ((uint64_t)(uint32_t)start[i] << 32) | (uint32_t)stop[i];
   const uint8_t* core = text + i * (int64_t)text_stride + HAWK_GUIDESEQPAD;
-  uint64_t h = mix_u64(0x9E3779B97F4A7C15ull ^ ((uint64_t)strand[i] << 1) ^ (uint64_t)is_ref[hap[i]]);
+  const uint32_t hp = (uint32_t)hap[i];  // a haplotype index the caller's is_ref does not cover counts as not REF
+  uint64_t h = mix_u64(0x9E3779B97F4A7C15ull ^ ((uint64_t)strand[i] << 1) ^ (uint64_t)(hp < (uint32_t)n_hap ? is_ref[hp] : 0));
   for (int j = 0; j < core_len; j += 8) {
     uint64_t w = 0;
     for (int k = 0; k < 8 && j + k < core_len; ++k) w |= (uint64_t)core[j + k] << (8 * k);
@@ -53,8 +54,8 @@ __global__ void collapse_key_kernel(const int32_t* __restrict__ hap, const uint8
 __global__ void collapse_head_kernel(const uint32_t* __restrict__ perm, const uint64_t* __restrict__ k_hi,
                                      const uint64_t* __restrict__ k_lo, const int32_t* __restrict__ hap,
                                      const uint8_t* __restrict__ strand, const uint8_t* __restrict__ text,
-                                     int32_t text_stride, int32_t core_len, const uint8_t* __restrict__ is_ref, int64_t n,
-                                     uint8_t* __restrict__ head, int* __restrict__ collision) {
+                                     int32_t text_stride, int32_t core_len, const uint8_t* __restrict__ is_ref, int32_t n_hap,
+                                     int64_t n, uint8_t* __restrict__ head, int* __restrict__ collision) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   if (k == 0) {
@@ -67,7 +68,9 @@ __global__ void collapse_head_kernel(const uint32_t* __restrict__ perm, const ui
     return;
   }
   const uint32_t a = perm[k], b = perm[k - 1];
-  bool same = strand[a] == strand[b] && is_ref[hap[a]] == is_ref[hap[b]];
+  const uint32_t ha = (uint32_t)hap[a], hb = (uint32_t)hap[b];
+  bool same = strand[a] == strand[b] &&
+              (ha < (uint32_t)n_hap ? is_ref[ha] : 0) == (hb < (uint32_t)n_hap ? is_ref[hb] : 0);
   const uint8_t* ca = text + (int64_t)a * text_stride + HAWK_GUIDESEQPAD;
   const uint8_t* cb = text + (int64_t)b * text_stride + HAWK_GUIDESEQPAD;
   for (int j = 0; j < core_len && same; ++j) same = ca[j] == cb[j];
@@ -104,7 +107,7 @@ extern "C" int hawk_result_collapse(hawk_result* r, const uint8_t* is_ref, int32
   const unsigned blocks = (unsigned)((n + 255) / 256);
   collapse_key_kernel<<<blocks, 256, 0, st>>>(r->hap.as<int32_t>(), r->strand.as<uint8_t>(), r->start.as<int32_t>(),
                                               r->stop.as<int32_t>(), r->text.as<uint8_t>(), r->text_stride, core_len,
-                                              d_ref.as<uint8_t>(), n, khi[0].as<uint64_t>(), klo[0].as<uint64_t>(),
+                                              d_ref.as<uint8_t>(), n_hap, n, khi[0].as<uint64_t>(), klo[0].as<uint64_t>(),
                                               idx[0].as<uint32_t>());
   hawk_note_launch(1);
   CK(hawk_check_cuda(cudaGetLastError(), "collapse_key_kernel launch"));
@@ -128,7 +131,7 @@ extern "C" int hawk_result_collapse(hawk_result* r, const uint8_t* is_ref, int32
   hawk_collapse_gather(st, idx[0].as<uint32_t>(), klo[0].as<uint64_t>(), klo[1].as<uint64_t>(), n);
   collapse_head_kernel<<<blocks, 256, 0, st>>>(idx[0].as<uint32_t>(), khi[0].as<uint64_t>(), klo[1].as<uint64_t>(),
                                                r->hap.as<int32_t>(), r->strand.as<uint8_t>(), r->text.as<uint8_t>(),
-                                               r->text_stride, core_len, d_ref.as<uint8_t>(), n, d_head.as<uint8_t>(),
+                                               r->text_stride, core_len, d_ref.as<uint8_t>(), n_hap, n, d_head.as<uint8_t>(),
                                                d_col.as<int>());
   hawk_note_launch(1);
   CK(hawk_check_cuda(cudaGetLastError(), "collapse_head_kernel launch"));
