@@ -169,3 +169,24 @@ def test_sacas9_and_short_guides():
                           snv_frac=0.7, ins_frac=0.15, max_indel=10)  # fmt: skip
     for pam, G, right in (("NNGRRT", 21, False), ("TTN", 23, True), ("NGG", 1, False), ("G", 5, True)):
         _run_against_oracle(c, pam, G, right)
+
+
+def test_full_size_edit_lists_give_the_table_of_the_texts():
+    """BASELINE config 2 at full size (5,009 x 1 Mb): the search from edit lists -- planes built
+    only around the 4.2 M edits, texts never written (hawk_search_stream_edits) -- returns the
+    table of the search over the resident texts, every column of all 14.66 M rows."""
+    k = synth.CONFIGS["c2"]
+    wl = Workload(synth.config_cohort("c2"), k["pam"], k["guidelen"], k["right"])
+    res = wl.step_resident()
+    want = res.table()
+    res.close()
+    got, h2d, d2h = wl.step_edits()
+    assert len(got["hap"]) == len(want["hap"]) > 1e7
+    for kcol in COLS + ("bucket",):
+        assert np.array_equal(got[kcol], want[kcol]), kcol
+    assert np.array_equal(got["text"], want["text"])
+    assert h2d < 0.05 * wl.d.total_slots  # edit lists, not texts, crossed PCIe (the first call runs twice: it sizes its buffers)
+    slim, _, d2h_slim = wl.step_edits(want_text=False)
+    for kcol in COLS + ("bucket",):
+        assert np.array_equal(slim[kcol], want[kcol]), kcol
+    assert d2h_slim < 0.35 * d2h
