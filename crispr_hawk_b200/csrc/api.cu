@@ -330,7 +330,7 @@ extern "C" int hawk_batch_create_from_edits(hawk_ctx* c, const uint8_t* ref_asci
   Trace tr;
   const int64_t n_edits = n_hap ? edit_off[n_hap] : 0;
   const size_t ne = (size_t)(n_edits > 0 ? n_edits : 1), nh = (size_t)(n_hap > 0 ? n_hap : 1);
-  DevBuf d_ref, d_eoff, d_pos, d_rl, d_al, d_ao, d_op, d_pool, d_so, d_len, d_segcnt, d_bad, d_ascii;
+  DevBuf d_ref, d_eoff, d_pos, d_rl, d_al, d_ao, d_op, d_eh, d_pool, d_so, d_len, d_segcnt, d_bad, d_ascii;
   // the reference text with readable slack behind it (block copies read whole aligned words)
   CK(d_ref.alloc(c, (size_t)ref_len + 32));
   CKCUDA(cudaMemsetAsync(d_ref.as<uint8_t>() + ref_len, 0, 32, st));
@@ -345,6 +345,7 @@ extern "C" int hawk_batch_create_from_edits(hawk_ctx* c, const uint8_t* ref_asci
   CK(upload(c, d_ao, n_edits ? (const void*)edit_altoff : (const void*)&zero64, ne * 8));
   CK(upload(c, d_pool, alt_pool_len > 0 ? alt_pool : &zero8, (size_t)(alt_pool_len > 0 ? alt_pool_len : 1)));
   CK(d_op.alloc(c, ne * 4));
+  CK(d_eh.alloc(c, ne * 4));
   CK(d_len.alloc(c, nh * 4));
   CK(d_segcnt.alloc(c, nh * 4));
   const int32_t int_max = INT32_MAX;
@@ -352,7 +353,7 @@ extern "C" int hawk_batch_create_from_edits(hawk_ctx* c, const uint8_t* ref_asci
   // pass 0 on the device: validation, output positions, lengths, segment counts
   CK(launch_derive(st, n_hap, d_eoff.as<int64_t>(), d_pos.as<int32_t>(), d_rl.as<int32_t>(), d_al.as<int32_t>(),
                    d_ao.as<int64_t>(), ref_len, alt_pool_len, region_start, d_op.as<int32_t>(), d_len.as<int32_t>(),
-                   d_segcnt.as<int32_t>(), d_bad.as<int32_t>(), nullptr, nullptr, nullptr, nullptr, 0));
+                   d_segcnt.as<int32_t>(), d_bad.as<int32_t>(), nullptr, nullptr, nullptr, nullptr, 0, d_eh.as<int32_t>()));
   // the reference's own planes (the windows around the edits are cut from them) and the ALT pool
   // check; anything unusual -- a non-IUPAC character, lower-case (soft-masked) reference bases,
   // which every haplotype would inherit as variant bases -- goes the long way round (texts + K1)
@@ -425,6 +426,7 @@ extern "C" int hawk_batch_create_from_edits(hawk_ctx* c, const uint8_t* ref_asci
     b->ref_q.move_from(d_refq);
     b->ref_v.move_from(d_refv);
     b->edit_outpos.move_from(d_op);
+    b->edit_hap.move_from(d_eh);
   } else {
     CK(d_ascii.alloc(c, (size_t)total));
     CK(hawk_materialize_dev(st, d_ref.as<uint8_t>(), ref_len, d_eoff.as<int64_t>(), d_pos.as<int32_t>(),
@@ -506,8 +508,8 @@ int hawk_edits_ensure(hawk_batch* b, int need) {
                         b->d_slot_off.as<int64_t>(), b->q.p, b->v.as<uint32_t>()));
   CK(launch_edit_windows(st, b->ref_q.p, b->var_off.as<int64_t>(), b->var_pos.as<int32_t>(), b->var_rl.as<int32_t>(),
                          b->var_al.as<int32_t>(), b->var_ao.as<int64_t>(), b->edit_outpos.as<int32_t>(),
-                         b->var_pool.as<uint8_t>(), b->d_slot_off.as<int64_t>(), b->d_len.as<int32_t>(), b->n_hap,
-                         b->n_edits, b->q.p, b->v.as<uint32_t>(), b->nz.as<uint32_t>(), need));
+                         b->edit_hap.as<int32_t>(), b->var_pool.as<uint8_t>(), b->d_slot_off.as<int64_t>(),
+                         b->d_len.as<int32_t>(), b->n_hap, b->n_edits, b->q.p, b->v.as<uint32_t>(), b->nz.as<uint32_t>(), need));
   b->edits_reach = need;
   b->sparse = true;
   b->sparse_reach = need;

@@ -58,6 +58,7 @@ struct EditWindowArgs {
   const int32_t* altlen;
   const int64_t* altoff;
   const int32_t* outpos;
+  const int32_t* edit_hap;  // haplotype of every edit (derive_kernel, pass 0)
   const uint8_t* pool;
   const int64_t* slot_off;
   const int32_t* len;
@@ -69,22 +70,17 @@ struct EditWindowArgs {
   int32_t reach;  // chunks either side of an edit's own chunks
 };
 
-// One thread per (edit, k): chunk first - reach + k of the edit's window (and every 2 reach + 2
-// chunks after it, for ALT texts longer than a chunk). A chunk two windows share belongs to the
+// One thread per (edit, k): chunk first - reach + k of the edit's window (and every 2 reach + 1
+// chunks after it, for ALT texts that span more than one chunk). A chunk two windows share belongs to the
 // earlier edit. The reference holds no lower-case base here (the caller checked), so case bits
 // come from ALT text only.
 __global__ void __launch_bounds__(128) edit_windows_kernel(const __grid_constant__ EditWindowArgs A) {
-  const int KW = 2 * A.reach + 2;
+  const int KW = 2 * A.reach + 1;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t e = idx / KW;
   const int k = (int)(idx - e * KW);
   if (e >= A.n_edits) return;
-  int32_t lo = 0, hi = A.n_hap;  // haplotype of edit e
-  while (hi - lo > 1) {
-    const int32_t m = (lo + hi) >> 1;
-    if (__ldg(&A.edit_off[m]) <= e) lo = m; else hi = m;
-  }
-  const int32_t h = lo;
+  const int32_t h = __ldg(&A.edit_hap[e]);
   const int64_t e0 = A.edit_off[h], e1 = A.edit_off[h + 1];
   const int32_t L = A.len[h];
   const int64_t chunk0 = A.slot_off[h] >> 5;
@@ -156,13 +152,13 @@ int launch_edits_plain(cudaStream_t st, const void* ref_q, const uint32_t* ref_v
 }
 
 int launch_edit_windows(cudaStream_t st, const void* ref_q, const int64_t* edit_off, const int32_t* pos, const int32_t* reflen,
-                        const int32_t* altlen, const int64_t* altoff, const int32_t* outpos, const uint8_t* pool,
-                        const int64_t* slot_off, const int32_t* len, int32_t n_hap, int64_t n_edits, void* q, uint32_t* v,
-                        uint32_t* nz, int32_t reach) {
+                        const int32_t* altlen, const int64_t* altoff, const int32_t* outpos, const int32_t* edit_hap,
+                        const uint8_t* pool, const int64_t* slot_off, const int32_t* len, int32_t n_hap, int64_t n_edits,
+                        void* q, uint32_t* v, uint32_t* nz, int32_t reach) {
   if (n_edits <= 0 || n_hap <= 0) return HAWK_OK;
-  EditWindowArgs A{(const uint4*)ref_q, edit_off, pos, reflen, altlen, altoff, outpos, pool, slot_off, len, n_hap, n_edits,
-                   (uint4*)q, v, nz, reach};
-  const int64_t threads = n_edits * (2 * reach + 2);
+  EditWindowArgs A{(const uint4*)ref_q, edit_off, pos, reflen, altlen, altoff, outpos, edit_hap, pool, slot_off, len, n_hap,
+                   n_edits, (uint4*)q, v, nz, reach};
+  const int64_t threads = n_edits * (2 * reach + 1);
   edit_windows_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(A);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "edit_windows_kernel launch");

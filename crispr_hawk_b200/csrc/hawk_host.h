@@ -198,7 +198,7 @@ struct hawk_batch {
   // edits for a search, or all of them (materialise + K1) for whoever reads whole haplotypes
   bool edits_lazy = false;
   int32_t edits_reach = 0;
-  DevBuf ref_text, ref_q, ref_v, edit_outpos, d_plain;
+  DevBuf ref_text, ref_q, ref_v, edit_outpos, edit_hap, d_plain;
   int64_t ref_len = 0, ref_chunks = 0, n_edits = 0;
   int32_t n_plain = 0;
   std::vector<uint8_t> has_edits;  // per haplotype

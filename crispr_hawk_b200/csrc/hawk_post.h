@@ -127,16 +127,17 @@ int launch_resolve_write(cudaStream_t st, const BatchView& B, const ScanConst& K
 int launch_derive(cudaStream_t st, int32_t n_hap, const int64_t* edit_off, const int32_t* pos, const int32_t* reflen,
                   const int32_t* altlen, const int64_t* altoff, int64_t ref_len, int64_t alt_pool_len,
                   int32_t region_start, int32_t* outpos, int32_t* len, int32_t* seg_count, int32_t* bad,
-                  const int64_t* seg_off, int32_t* seg_rel, int32_t* seg_gen, uint8_t* seg_step, int pass);
+                  const int64_t* seg_off, int32_t* seg_rel, int32_t* seg_gen, uint8_t* seg_step, int pass,
+                  int32_t* edit_hap = nullptr);
 
 // edits_kernels.cu: planes of edit-list haplotypes, only where a search reads them
 int launch_pool_check(cudaStream_t st, const uint8_t* pool, int64_t n, unsigned long long* bad);
 int launch_edits_plain(cudaStream_t st, const void* ref_q, const uint32_t* ref_v, int64_t ref_chunks, const int32_t* plain,
                        int32_t n_plain, const int64_t* slot_off, void* q, uint32_t* v);
 int launch_edit_windows(cudaStream_t st, const void* ref_q, const int64_t* edit_off, const int32_t* pos, const int32_t* reflen,
-                        const int32_t* altlen, const int64_t* altoff, const int32_t* outpos, const uint8_t* pool,
-                        const int64_t* slot_off, const int32_t* len, int32_t n_hap, int64_t n_edits, void* q, uint32_t* v,
-                        uint32_t* nz, int32_t reach);
+                        const int32_t* altlen, const int64_t* altoff, const int32_t* outpos, const int32_t* edit_hap,
+                        const uint8_t* pool, const int64_t* slot_off, const int32_t* len, int32_t n_hap, int64_t n_edits,
+                        void* q, uint32_t* v, uint32_t* nz, int32_t reach);
 
 int64_t scan_tiles(int64_t n);
 int exclusive_scan_u8(cudaStream_t st, const uint8_t* in, int64_t n, uint64_t* out, uint64_t* tile_sums);

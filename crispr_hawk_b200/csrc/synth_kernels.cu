@@ -157,6 +157,7 @@ struct DeriveArgs {
   int64_t ref_len, alt_pool_len;
   int32_t region_start;
   int32_t* outpos;      // pass 0
+  int32_t* edit_hap;    // pass 0, optional: haplotype of every edit
   int32_t* len;         // pass 0
   int32_t* seg_count;   // pass 0
   int32_t* bad;         // pass 0: smallest haplotype index with an invalid edit list, else INT_MAX
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(256) derive_kernel(const __grid_constant__ Der
       const int64_t op = (int64_t)p + carry_shift + (s_shift[tid] - d);
       if (pass == 0) {
         A.outpos[e] = (int32_t)op;
+        if (A.edit_hap) A.edit_hap[e] = h;
       } else if (ns) {
         const int64_t s = A.seg_off[h] + carry_segs + (s_segs[tid] - ns);
         const int32_t anchor = A.region_start + p;
@@ -249,10 +251,11 @@ __global__ void __launch_bounds__(256) derive_kernel(const __grid_constant__ Der
 int launch_derive(cudaStream_t st, int32_t n_hap, const int64_t* edit_off, const int32_t* pos, const int32_t* reflen,
                   const int32_t* altlen, const int64_t* altoff, int64_t ref_len, int64_t alt_pool_len,
                   int32_t region_start, int32_t* outpos, int32_t* len, int32_t* seg_count, int32_t* bad,
-                  const int64_t* seg_off, int32_t* seg_rel, int32_t* seg_gen, uint8_t* seg_step, int pass) {
+                  const int64_t* seg_off, int32_t* seg_rel, int32_t* seg_gen, uint8_t* seg_step, int pass,
+                  int32_t* edit_hap) {
   if (n_hap <= 0) return HAWK_OK;
-  DeriveArgs A{edit_off, pos, reflen, altlen, altoff, ref_len, alt_pool_len, region_start, outpos, len, seg_count, bad,
-               seg_off, seg_rel, seg_gen, seg_step};
+  DeriveArgs A{edit_off, pos, reflen, altlen, altoff, ref_len, alt_pool_len, region_start, outpos, edit_hap, len, seg_count,
+               bad, seg_off, seg_rel, seg_gen, seg_step};
   derive_kernel<<<(unsigned)n_hap, 256, 0, st>>>(A, pass);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "derive_kernel launch");
