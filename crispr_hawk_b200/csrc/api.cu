@@ -1227,7 +1227,7 @@ static int search_unphased(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const
     CK(start[s].alloc(c, (size_t)n_hits[s] * 4));
     CK(stop[s].alloc(c, (size_t)n_hits[s] * 4));
     CK(cnt[s].alloc(c, (size_t)n_hits[s] * 4));
-    CK(rpivot[s].alloc(c, (size_t)n_hits[s] * 4));
+    CK(rpivot[s].alloc(c, (size_t)n_hits[s] * 8));  // two words per hit (resolve_kernels.cu: ResStrand)
     CK(blk_sum[s].alloc(c, (size_t)(n_blk[s] + 1) * 8));
     CK(blk_base[s].alloc(c, (size_t)(n_blk[s] + 1) * 8));
   }

@@ -55,7 +55,9 @@ struct ResStrand {
   int32_t* start;
   int32_t* stop;
   uint32_t* cnt;      // kept rows per hit
-  int32_t* rpivot;    // REF partner's core start (REF-relative) when some string can equal it, else -1
+  int32_t* rpivot;    // two words per hit: [REF partner's core start (REF-relative) when some string can equal
+                      // it, else -1 | the variant_alleles site of the first ambiguous column relative to the
+                      // haplotype's first site, else -1 -- so that the second pass need not search for it again]
   uint64_t* blk_sum;
 };
 
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(RES_T) resolve_count_kernel(const __grid_const
         if (diff & ~ab & keep) equal = 0;
       }
     }
-    int64_t site = -1;
+    int64_t site = -1, first_site = -1;
     for (int w = 0; w < 3 && total; ++w) {
       uint32_t bits = amb[w];
       while (bits) {
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(RES_T) resolve_count_kernel(const __grid_const
           total = 0;
           break;
         }
+        if (first_site < 0) first_site = site;
         total *= cnt;
         if (total > HAWK_MAX_EXPANSION) {
           atomicExch(A.err, HAWK_ECAPACITY);
@@ -211,7 +214,8 @@ __global__ void __launch_bounds__(RES_T) resolve_count_kernel(const __grid_const
     if (total == 0) equal = 0;
     kept = total - equal;
     S.cnt[i] = (uint32_t)kept;
-    S.rpivot[i] = equal ? rpivot : -1;
+    S.rpivot[2 * i] = equal ? rpivot : -1;
+    S.rpivot[2 * i + 1] = first_site < 0 ? -1 : (int32_t)(first_site - B.va_off[h]);
   }
   uint64_t x = kept;
 #pragma unroll
@@ -428,11 +432,12 @@ __global__ void __launch_bounds__(RES_T) resolve_write_kernel(const __grid_const
       base_txt[warp][lane][p] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
     }
     // ambiguous columns, first column first (= most significant digit of the product index)
-    rpivot = S.rpivot[i];
+    rpivot = S.rpivot[2 * i];
     rchunk0 = A.ref_h >= 0 ? (B.slot_off[A.ref_h] >> 5) : 0;
     uint64_t total = 1;
     int n_amb = 0;
-    int64_t site = -1;
+    const int32_t site_rel = S.rpivot[2 * i + 1];  // found by resolve_count: the walk starts there
+    int64_t site = site_rel < 0 ? -1 : B.va_off[h] + site_rel;
     for (int w = 0; w < 3; ++w) {
       uint32_t bits = amb[w];
       while (bits) {
