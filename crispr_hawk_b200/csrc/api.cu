@@ -777,7 +777,8 @@ static int64_t count_dense_subs(const hawk_batch* b, const uint8_t* is_ref) {
     if (!is_ref[h]) continue;
     const int64_t t0 = (b->slot_off[h] >> 5) - HAWK_SLOT_GAP / HAWK_CHUNK;
     const int64_t t1 = h + 1 < b->n_hap ? (b->slot_off[h + 1] >> 5) - HAWK_SLOT_GAP / HAWK_CHUNK : n_chunks;
-    int64_t s0 = t0 / FUSED_SUB, s1 = (t1 - 1) / FUSED_SUB;
+    const int32_t sub = fused_sub_size(n_chunks);
+    int64_t s0 = t0 / sub, s1 = (t1 - 1) / sub;
     if (s0 <= last) s0 = last + 1;
     if (s1 >= s0) {
       n_dense += s1 - s0 + 1;
@@ -956,7 +957,8 @@ static int run_scan_fused(hawk_ctx* c, hawk_batch* b, const uint8_t* d_ascii, co
     n_dense = all_dense ? n_sub : count_dense_subs(b, is_ref);
   }
   for (int s = 0; s < 2; ++s) CK(out.hits[s].alloc(c, 16));
-  const size_t total_cap = (size_t)(n_sub - n_dense) * (FUSED_SUB / 4) + (size_t)n_dense * FUSED_SUB;
+  const size_t sub_size = (size_t)fused_sub_size(n_chunks);
+  const size_t total_cap = (size_t)(n_sub - n_dense) * (sub_size / 4) + (size_t)n_dense * sub_size;
   DevBuf d_hs, d_cap, d_segbase, d_tiles, d_entries, d_cnt, d_base;
   CK(d_hs.alloc(c, (size_t)(n_hap > 0 ? n_hap : 1) * sizeof(HapScan)));
   CK(d_cap.alloc(c, (size_t)(n_sub + 1) * 4));

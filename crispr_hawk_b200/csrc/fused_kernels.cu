@@ -16,7 +16,7 @@
 // exact prefix offsets, like the staged expand_kernel.
 //
 // Work decomposition is FLAT over the slot space: warp w owns the chunks
-// [w * FUSED_SUB, (w + 1) * FUSED_SUB) whatever haplotypes they belong to (a per-warp cursor maps
+// [w * sub, (w + 1) * sub), sub = fused_sub_size(n_chunks), whatever haplotypes they belong to (a per-warp cursor maps
 // chunks to haplotypes), so 5,009 haplotypes of 1 Mb and 428,529 haplotypes of 200 bases cost the
 // same per base. A warp streams its sub-range 32 chunks (1 KB of text) per iteration, software-
 // pipelined by one iteration: iteration i is packed, then iteration i - 1 -- whose neighbours on
@@ -27,6 +27,7 @@
 // were stored a moment ago by this warp).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "hawk_core.h"
 #include "hawk_kernels.h"
@@ -51,6 +52,7 @@ struct FusedArgs {
   const HapScan* hs;
   ScanConst K;
   int32_t reach;      // planes are kept for chunks within `reach` chunks of a variant chunk (2..3)
+  int32_t sub;        // chunks per warp sub-range (fused_sub_size)
   const uint64_t* seg_base;  // per sub-range: first entry slot, capacity
   const uint32_t* seg_cap;
   uint4* entries;       // {haplotype, chunk (haplotype-relative), hits strand 0, hits strand 1}
@@ -92,16 +94,19 @@ struct HapCursor {
   int32_t is_ref;
 };
 
-template <bool WIDE, int REACH>
+// SUBC: the sub-range size as a compile-time constant (FUSED_SUB_MAX, the large-input case), or 0 =
+// take it from the arguments (small slot spaces)
+template <bool WIDE, int REACH, int SUBC>
 __global__ void __launch_bounds__(FUSED_WARPS * 32, 24 / FUSED_WARPS) fused_scan_kernel(const __grid_constant__ FusedArgs A) {
   __shared__ uint16_t q_off[FUSED_WARPS][64];  // candidate queue (ring): chunk offset in the sub-range
   __shared__ int32_t q_hap[FUSED_WARPS][64];   // ... and its haplotype
   const int lane = threadIdx.x & 31, warp = FUSED_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5);
   const int64_t sub = (int64_t)blockIdx.x * FUSED_WARPS + warp;
-  const int64_t s = sub * FUSED_SUB;
+  const int32_t SUB = SUBC ? SUBC : A.sub;
+  const int64_t s = sub * SUB;
   if (s >= A.n_chunks) return;  // uniform over the warp; no block-wide barrier below
-  const int32_t n = (int32_t)(s + FUSED_SUB < A.n_chunks ? FUSED_SUB : A.n_chunks - s);  // chunks owned
-  const int32_t n_avail = (int32_t)(A.n_chunks - s < FUSED_SUB + 32 ? A.n_chunks - s : FUSED_SUB + 32);  // + halo
+  const int32_t n = (int32_t)(s + SUB < A.n_chunks ? SUB : A.n_chunks - s);  // chunks owned
+  const int32_t n_avail = (int32_t)(A.n_chunks - s < SUB + 32 ? A.n_chunks - s : SUB + 32);  // + halo
   const int32_t n_iter = (n + 31) >> 5;
   const ScanConst& K = A.K;
   BatchView B{};
@@ -117,15 +122,15 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, 24 / FUSED_WARPS) fused_scan
     HapCursor cu;
     cu.h = h;
     const int64_t tn = territory(A.slot_off, A.n_hap, A.n_chunks, h + 1) - s;
-    cu.t_next = tn > (int64_t)(FUSED_SUB + 64) ? FUSED_SUB + 64 : (int32_t)tn;
+    cu.t_next = tn > (int64_t)(SUB + 64) ? SUB + 64 : (int32_t)tn;
     const HapScan* H = A.hs + h;
     const int64_t c0 = H->chunk0 - s;  // may be far below zero; the clamps keep the interval test exact
     const int32_t a = H->a, b = H->b;
     int64_t lo = c0 + (a >> 5), hi = b > a ? c0 + ((b + 31) >> 5) : lo;
     if (lo < -64) lo = -64;
     if (hi < -64) hi = -64;
-    if (lo > FUSED_SUB + 64) lo = FUSED_SUB + 64;
-    if (hi > FUSED_SUB + 64) hi = FUSED_SUB + 64;
+    if (lo > SUB + 64) lo = SUB + 64;
+    if (hi > SUB + 64) hi = SUB + 64;
     cu.c_lo = (int32_t)lo;
     cu.c_hi = (int32_t)hi;
     cu.is_ref = H->is_ref;
@@ -328,10 +333,11 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, 24 / FUSED_WARPS) fused_scan
 // (every chunk of REF is a candidate) or when every haplotype is dense (unphased cohorts), else a
 // quarter of them
 __global__ void fused_caps_kernel(const int64_t* __restrict__ slot_off, const uint8_t* __restrict__ is_ref, int32_t n_hap,
-                                  int64_t n_chunks, int64_t n_sub, int32_t all_dense, uint32_t* __restrict__ cap) {
+                                  int64_t n_chunks, int64_t n_sub, int32_t sub_size, int32_t all_dense,
+                                  uint32_t* __restrict__ cap) {
   const int64_t sub = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (sub >= n_sub) return;
-  const int64_t s = sub * FUSED_SUB, e = s + FUSED_SUB < n_chunks ? s + FUSED_SUB : n_chunks;
+  const int64_t s = sub * sub_size, e = s + sub_size < n_chunks ? s + sub_size : n_chunks;
   bool dense = all_dense != 0;
   if (!dense) {
     int32_t lo = 0, hi = n_hap;
@@ -342,7 +348,7 @@ __global__ void fused_caps_kernel(const int64_t* __restrict__ slot_off, const ui
     for (int32_t h = lo; h < n_hap && territory(slot_off, n_hap, n_chunks, h) < e; ++h)
       if (is_ref[h]) dense = true;
   }
-  cap[sub] = dense ? (uint32_t)FUSED_SUB : (uint32_t)(FUSED_SUB / 4);
+  cap[sub] = dense ? (uint32_t)sub_size : (uint32_t)(sub_size / 4);
 }
 
 // entries -> (hap << 32 | pos) records at exact offsets; one warp per sub-range
@@ -389,13 +395,25 @@ __global__ void __launch_bounds__(128) fused_expand_kernel(const uint4* __restri
   }
 }
 
-int64_t fused_sub_ranges(int64_t n_chunks) { return (n_chunks + FUSED_SUB - 1) / FUSED_SUB; }
+int32_t fused_sub_size(int64_t n_chunks) {
+  static const int waves = getenv("HAWK_FUSED_WAVES") ? atoi(getenv("HAWK_FUSED_WAVES")) : 4;
+  const int64_t want = n_chunks / ((int64_t)waves * 148 * 24);  // one warp per CTA, 24 CTAs per SM
+  int32_t sub = FUSED_SUB_MAX;
+  while (sub > 256 && sub > want) sub >>= 1;
+  return sub;
+}
+
+int64_t fused_sub_ranges(int64_t n_chunks) {
+  const int32_t sub = fused_sub_size(n_chunks);
+  return (n_chunks + sub - 1) / sub;
+}
 
 int launch_fused_caps(cudaStream_t st, const int64_t* slot_off, const uint8_t* is_ref, int32_t n_hap, int64_t n_chunks,
                       int32_t all_dense, uint32_t* cap) {
   const int64_t n_sub = fused_sub_ranges(n_chunks);
   if (n_sub <= 0) return HAWK_OK;
-  fused_caps_kernel<<<(unsigned)((n_sub + 127) / 128), 128, 0, st>>>(slot_off, is_ref, n_hap, n_chunks, n_sub, all_dense, cap);
+  fused_caps_kernel<<<(unsigned)((n_sub + 127) / 128), 128, 0, st>>>(slot_off, is_ref, n_hap, n_chunks, n_sub,
+                                                                    fused_sub_size(n_chunks), all_dense, cap);
   hawk_note_launch(1);
   return hawk_check_cuda(cudaGetLastError(), "fused_caps_kernel launch");
 }
@@ -414,6 +432,7 @@ int launch_fused_scan(cudaStream_t st, const FusedLaunch& L) {
   A.hs = L.hs;
   A.K = L.K;
   A.reach = L.reach;
+  A.sub = fused_sub_size(L.n_chunks);
   A.seg_base = L.seg_base;
   A.seg_cap = L.seg_cap;
   A.entries = (uint4*)L.entries;
@@ -426,7 +445,11 @@ int launch_fused_scan(cudaStream_t st, const FusedLaunch& L) {
   const bool wide = ((uintptr_t)L.ascii & 31) == 0;
   // >= 2: a candidate chunk's matcher reads the case words two chunks from the variant chunk
   if (L.reach < 2 || L.reach > 3) return hawk_fail(HAWK_EINVAL, "fused scan: reach %d out of range", L.reach);
-#define HAWK_FUSED_LAUNCH(W, R) fused_scan_kernel<W, R><<<blocks, FUSED_WARPS * 32, 0, st>>>(A)
+#define HAWK_FUSED_LAUNCH(W, R)                                                                   \
+  do {                                                                                            \
+    if (A.sub == FUSED_SUB_MAX) fused_scan_kernel<W, R, FUSED_SUB_MAX><<<blocks, FUSED_WARPS * 32, 0, st>>>(A); \
+    else fused_scan_kernel<W, R, 0><<<blocks, FUSED_WARPS * 32, 0, st>>>(A);                      \
+  } while (0)
   if (wide) {
     if (L.reach == 2) HAWK_FUSED_LAUNCH(true, 2); else HAWK_FUSED_LAUNCH(true, 3);
   } else {

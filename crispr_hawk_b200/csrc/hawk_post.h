@@ -79,7 +79,10 @@ int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* str
 
 // fused_kernels.cu: K1 + K2 in one pass over the texts (flat over the slot space)
 constexpr int FUSED_WARPS = 1;    // warps per CTA (one: the warp index is then provably uniform -> uniform datapath)
-constexpr int FUSED_SUB = 4096;   // chunks per warp sub-range (128 KB of text)
+constexpr int FUSED_SUB_MAX = 4096;  // chunks per warp sub-range (128 KB of text) for large slot spaces
+// ... and fewer (a power of two >= 256) for small ones, so that there are a few waves of warps to
+// run: 275 MB of text in 4,096-chunk sub-ranges would be 2,100 warps for 3,552 warp slots
+int32_t fused_sub_size(int64_t n_chunks);
 struct FusedLaunch {
   const uint8_t* ascii;
   int64_t n_chunks;
@@ -91,6 +94,7 @@ struct FusedLaunch {
   const HapScan* hs;
   ScanConst K;
   int32_t reach, store_all;
+  int32_t sub;  // fused_sub_size(n_chunks)
   const uint64_t* seg_base;
   const uint32_t* seg_cap;
   void* entries;
