@@ -718,6 +718,13 @@ def run_product_arm(args, rank, world, local_rank):
             "what": "hawk_result_collapse: the groups of reports._collapse_report_entries over the whole table (row keys, two "
                     "radix sorts, head flags; permutation + flags copied to the host inside the timed call)",
             "rows": m["rows"], "groups": m["collapse_groups"], "ms": m["collapse_ms"], "hash_collision": m["collapse_collision"]}
+        if "kmers_ms" in m:
+            next_rows["N4_features"] = {
+                "what": "hawk_result_featurize: the learned scorers' input strings of every row (scoring.py:50-84, lead 4) copied to "
+                        "pinned host memory inside the timed call; DeepCpf1's float32 one-hot tensor (seqdeepcpf1.py:71-92) written "
+                        "into a device tensor",
+                "rows": m["rows"], "kmers_ms": m["kmers_ms"], "kmers_bytes": m["kmers_bytes"], "kmers_all_acgt": m["kmers_all_acgt"],
+                "onehot_ms": m.get("onehot_ms"), "onehot_bytes": m.get("onehot_bytes"), "onehot_sum_ok": m.get("onehot_sum_ok")}
         if "cfdon_ms" in m:
             next_rows["N4_cfdon"] = {
                 "what": "hawk_result_cfdon: CFDon of every row against the REF guide of its (start, strand) key, float64 scores "

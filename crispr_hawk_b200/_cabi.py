@@ -27,6 +27,7 @@ HAWK_EALLELES = -6
 HAWK_EDUPREF = -7
 HAWK_EASSERT = -8
 HAWK_ECFD = -9
+HAWK_EFEATURE = -10
 
 
 class HawkLibraryError(RuntimeError):
@@ -141,6 +142,7 @@ SIGNATURES = {
     "hawk_result_fetch_variants": (C.c_int, [_P, _I32P]),
     "hawk_result_collapse": (C.c_int, [_P, _U8P, C.c_int32, _U32P, _U8P, _I32P]),
     "hawk_result_cfdon": (C.c_int, [_P, _U8P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), _I64P]),
+    "hawk_result_featurize": (C.c_int, [_P, C.c_int32, _U8P, _P, C.c_int32, _I64P]),
     "hawk_table_text_stride": (C.c_int32, [C.c_int32, C.c_int32]),
     "hawk_stream_plan": (C.c_int32, [_I64P, C.c_int32, _U8P, C.c_int32, _I32P, _I32P, C.c_int32]),
     "hawk_search_stream": (
@@ -527,6 +529,28 @@ class Result:
             err.bad_row = bad.value
             raise err
         return out
+
+    def featurize(self, lead: int = 4, kmers: bool = True, onehot: bool = False, onehot_device_ptr: int = 0,
+                  kmers_out=None):
+        """hawk_result_featurize: the learned scorers' inputs of every row (emission order).
+        Returns (kmers, onehot): `kmers` an (n, L) uint8 array of upper-case letters
+        (scoring.py:50-84; lead 4, or 0 for sgDesigner) or None; `onehot` the float32 (n, 4, L)
+        tensor of DeepCpf1's preprocess (seqdeepcpf1.py:71-92) as a numpy array, or None when not
+        requested / when `onehot_device_ptr` names device memory of n * 4 * L floats to fill."""
+        n, L = self.n_guides, self.window - 20 + lead + 3
+        k = None
+        if kmers:
+            k = kmers_out[: n * L] if kmers_out is not None else np.empty(n * L, np.uint8)
+        o = np.empty((n, 4, L), np.float32) if onehot and not onehot_device_ptr else None
+        optr = C.c_void_p(onehot_device_ptr) if onehot_device_ptr else (o.ctypes.data_as(_P) if o is not None else None)
+        bad = C.c_int64(-1)
+        rc = self.lib.hawk_result_featurize(self.handle, lead, ptr(k, C.c_uint8) if k is not None else None, optr,
+                                            1 if onehot_device_ptr else 0, C.byref(bad))  # fmt: skip
+        if rc != HAWK_OK:
+            err = HawkLibraryError(self.lib.hawk_last_error().decode(), rc)
+            err.bad_row = bad.value
+            raise err
+        return (k.reshape(n, L) if k is not None else None), o
 
     def device_columns(self):
         """Borrowed device addresses {column: int} of the table (hawk_result_device_columns)."""

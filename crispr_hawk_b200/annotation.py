@@ -110,6 +110,7 @@ def _columns(guides, debug: bool):
         from . import scoring
 
         link["cfdon"] = scoring.cfdon_column(link, debug)  # N4, for scoring.cfdon_score (None: not applicable)
+        link["kmers"] = scoring.kmer_columns(link)  # N4, the learned scorers' input strings (scoring.py:50-84)
         link["res"].close()  # the table has served its purpose: release the device memory
         link["res"] = None
     return link["cols"], link["order"]

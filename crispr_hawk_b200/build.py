@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libhawkscan.so")
 CHECK_LIB = os.path.join(PKG, "libhawkcheck.so")
 
-CUDA_SOURCES = ["scan_kernels.cu", "scan2_kernels.cu", "fused_kernels.cu", "post_kernels.cu", "resolve_kernels.cu", "table_kernels.cu", "synth_kernels.cu", "annot_kernels.cu", "api.cu", "stream_api.cu", "annot_api.cu", "merge_api.cu", "collapse_api.cu", "edits_kernels.cu", "cfdon_api.cu"]
+CUDA_SOURCES = ["scan_kernels.cu", "scan2_kernels.cu", "fused_kernels.cu", "post_kernels.cu", "resolve_kernels.cu", "table_kernels.cu", "synth_kernels.cu", "annot_kernels.cu", "api.cu", "stream_api.cu", "annot_api.cu", "merge_api.cu", "collapse_api.cu", "edits_kernels.cu", "cfdon_api.cu", "featurize_api.cu"]
 HEADERS = ["hawk_core.h", "hawk_kernels.h", "hawk_post.h", "hawk_host.h", "../../include/hawkscan.h"]
 
 

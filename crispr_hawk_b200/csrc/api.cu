@@ -56,6 +56,7 @@ extern "C" const char* hawk_strerror(int code) {
     case HAWK_EDUPREF: return "duplicate REF guide";
     case HAWK_EASSERT: return "the reference asserts on this input";
     case HAWK_ECFD: return "CFD score tables hold no entry for this guide";
+    case HAWK_EFEATURE: return "scorer input holds a letter other than A, C, G, T";
     default: return "unknown error";
   }
 }

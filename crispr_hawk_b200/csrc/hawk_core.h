@@ -796,6 +796,27 @@ HAWK_HD bool cfdon_row(const uint8_t* ref_text, const uint8_t* row_text, int W, 
   return true;
 }
 
+// ---- N4 (second half): the learned scorers' input window of one guide row ----------------------
+// scoring.py:50-84 (_extract_guide_sequences / _extract_guide_sequences_sgdesigner):
+// sequence[(PAD - lead) : (-PAD + 3)].upper() of the text reverse_guides leaves (strand 1: reverse
+// complement), lead = 4 (Azimuth, RS3, DeepCpf1, CRISPRon) or 0 (sgDesigner); G + P + lead + 3
+// letters. Byte j of that string:
+HAWK_HD int feature_len(int W, int lead) { return W - 2 * HAWK_GUIDESEQPAD + lead + 3; }
+HAWK_HD uint8_t feature_byte(const uint8_t* src, int W, int s, int lead, int j) {
+  return ascii_to_upper(annot_text_byte(src, W, s, HAWK_GUIDESEQPAD - lead + j));
+}
+// scores/deepCpf1/seqdeepcpf1.py:19, 71-92 (preprocess): channel of a letter in the one-hot
+// tensor, A 0, C 1, G 2, T 3; -1 where NTENCODING raises KeyError (U is not a key there)
+HAWK_HD int onehot_channel(uint8_t upper) {
+  switch (upper) {
+    case 'A': return 0;
+    case 'C': return 1;
+    case 'G': return 2;
+    case 'T': return 3;
+    default: return -1;
+  }
+}
+
 // polish_guide_variants (annotation.py:246-281) for one row: walks the core's G + P bases,
 // genomic coordinate through the run-length posmap (segment pointer advanced incrementally),
 // variant at that coordinate by a monotone walk of the haplotype's sorted table, then

@@ -295,4 +295,24 @@ int64_t hawkcheck_cfdon(const int32_t* hap, const uint8_t* strand, const uint32_
   return bad;
 }
 
+// N4, second half: feature_byte / onehot_channel over a whole table (the loops of
+// featurize_kernel); returns the first row with a letter outside A, C, G, T, or -1
+int64_t hawkcheck_featurize(const uint8_t* strand, const uint8_t* text, int32_t text_stride, int32_t W, int32_t lead,
+                            int64_t n, uint8_t* kmers, float* onehot) {
+  const int L = hawk::feature_len(W, lead);
+  int64_t bad = -1;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint8_t* src = text + i * (int64_t)text_stride;
+    for (int j = 0; j < L; ++j) {
+      const uint8_t u = hawk::feature_byte(src, W, strand[i], lead, j);
+      const int ch = hawk::onehot_channel(u);
+      if (kmers) kmers[i * L + j] = u;
+      if (onehot)
+        for (int k = 0; k < 4; ++k) onehot[(i * 4 + k) * L + j] = ch == k ? 1.0f : 0.0f;
+      if (ch < 0 && bad < 0) bad = i;
+    }
+  }
+  return bad;
+}
+
 }  // extern "C"

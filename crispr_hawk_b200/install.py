@@ -27,7 +27,9 @@ def install(module: Optional[object] = None, annotation_module: Optional[object]
     are rebound the same way: the row collapse uses the groups the device computed over the
     resident table instead of a pandas groupby. With `scoring` (N4) `scoring.cfdon_score`
     (scoring.py:352-387) is rebound: the scores come from `hawk_result_cfdon`, computed with the
-    reference's own factor tables while the table is on the device."""
+    reference's own factor tables while the table is on the device; so are
+    `scoring._extract_guide_sequences` / `_extract_guide_sequences_sgdesigner` (scoring.py:50-84),
+    the learned scorers' input strings, cut for the whole batch by `hawk_result_featurize`."""
     from . import _cabi
     from . import report_rows as rep
     from . import scoring as sco
@@ -80,9 +82,10 @@ def install(module: Optional[object] = None, annotation_module: Optional[object]
                 smod = None  # the scorers' own dependencies are missing: nothing to rebind
         if smod is not None and smod not in _saved:
             _saved[smod] = {n: getattr(smod, n, None) for n in sco.SEAM}
-            if _saved[smod]["cfdon_score"] is not None:
-                sco._reference["cfdon_score"] = _saved[smod]["cfdon_score"]
-                smod.cfdon_score = sco.cfdon_score
+            for n in sco.SEAM:
+                if _saved[smod][n] is not None:
+                    sco._reference[n] = _saved[smod][n]
+                    setattr(smod, n, getattr(sco, n))
             try:
                 pmod = importlib.import_module("crisprhawk.pam")
                 sco._reference["cas9_systems"] = (pmod.SPCAS9, pmod.XCAS9)

@@ -107,4 +107,59 @@ def cfdon_score(guides, verbosity: int, debug: bool):
     return _stage(guides, None, order, apply)
 
 
-SEAM = ("cfdon_score",)
+# --------------------------------------------------------------------------- scorer inputs (N4)
+# scoring.py:50-84: `_extract_guide_sequences` / `_extract_guide_sequences_sgdesigner` slice and
+# upper-case every guide's sequence in a Python loop before Azimuth, RS3, DeepCpf1, CRISPRon and
+# sgDesigner are called. On a list that came from this package's `search` the whole batch was cut
+# on the device (`hawk_result_featurize`) while the table was resident; the models stay the
+# reference's host code.
+def kmer_columns(link):
+    """{lead: (n, L) uint8} for lead 4 and 0, rows in emission order; None without a table."""
+    res = link.get("res")
+    if res is None or not hasattr(res, "featurize"):
+        return None
+    return {lead: res.featurize(lead=lead)[0] for lead in (4, 0)}
+
+
+def _sequences(guides, lead: int, name: str):
+    link = getattr(guides, "hawk", None)
+    cols = link.get("kmers") if link is not None else None
+    if cols is None or len(link["order"]) != len(guides):
+        fn = _reference.get(name)
+        if fn is None:
+            raise RuntimeError(f"crispr_hawk_b200.scoring.{name}: not a crispr_hawk_b200 guide list and no reference "
+                               "implementation installed (there is no CPU path here)")  # fmt: skip
+        return fn(guides)
+    k = cols[lead]
+    n, L = len(guides), k.shape[1]
+    flat = k[link["order"]].tobytes().decode("ascii")  # one conversion for the whole batch
+    return [flat[i * L : (i + 1) * L] for i in range(n)]
+
+
+def _extract_guide_sequences(guides):
+    """scoring.py:50-67."""
+    return _sequences(guides, 4, "_extract_guide_sequences")
+
+
+def _extract_guide_sequences_sgdesigner(guides):
+    """scoring.py:70-84."""
+    return _sequences(guides, 0, "_extract_guide_sequences_sgdesigner")
+
+
+def deepcpf1_input(res, device_ptr: int = 0):
+    """scores/deepCpf1/seqdeepcpf1.py:71-92 (`preprocess`) for every row of a resident table
+    (emission order): the float32 (n, 4, 34) one-hot tensor DeepCpf1 reads, as a numpy array, or
+    written into `device_ptr` (device memory of n * 4 * L floats, e.g. a torch tensor's
+    data_ptr()) when given. A letter other than A, C, G, T raises KeyError like the reference's
+    NTENCODING lookup."""
+    from . import _cabi
+
+    try:
+        return res.featurize(lead=4, kmers=False, onehot=True, onehot_device_ptr=device_ptr)[1]
+    except _cabi.HawkLibraryError as e:
+        if e.code == _cabi.HAWK_EFEATURE:
+            raise KeyError(str(e)) from e
+        raise
+
+
+SEAM = ("cfdon_score", "_extract_guide_sequences", "_extract_guide_sequences_sgdesigner")

@@ -223,6 +223,21 @@ class Workload:
             mm_t, pam_t = scoring.cfd_tables(mm, pam)
             out["cfdon_ms"], col = best_of(lambda: res.cfdon(self.d.is_ref, mm_t, pam_t, cbufs["cfd"]))
             out["cfdon_scored"] = int((~np.isnan(col)).sum())
+        # N4, second half: the learned scorers' input strings (host, pinned) and DeepCpf1's one-hot
+        # tensor written straight into a device tensor
+        L = res.window - 20 + 7
+        kbuf = pin(n * L, torch.uint8)
+        out["kmers_ms"], (k4, _) = best_of(lambda: res.featurize(lead=4, kmers_out=kbuf))
+        out["kmers_bytes"] = int(n * L)
+        acgt = np.zeros(256, bool)
+        acgt[list(b"ACGT")] = True
+        out["kmers_all_acgt"] = bool(acgt[k4].all()) if n else True
+        if n * 4 * L * 4 <= 24 << 30:
+            dev = torch.empty((max(n, 1), 4, L), dtype=torch.float32, device=self.device)
+            out["onehot_ms"], _ = best_of(lambda: res.featurize(lead=4, kmers=False, onehot=True, onehot_device_ptr=dev.data_ptr()))
+            out["onehot_bytes"] = int(n * 4 * L * 4)
+            out["onehot_sum_ok"] = bool(int(dev[:n].sum(dtype=torch.float64).item()) == n * L)
+            del dev
         if oracle is not None and n:
             if getattr(self, "_edits_out2", None) is None or len(self._edits_out2["hap"]) < n:
                 self._edits_out2 = _cabi.alloc_table(int(n * 1.05) + 1024, ts, pinned=True)

@@ -58,7 +58,8 @@ enum {
   HAWK_EALLELES = -6, /* ambiguity code without variant_alleles entry (KeyError, search_guides.py:207-213) */
   HAWK_EDUPREF = -7,  /* two REF guides at one (start, strand) (search_guides.py:328-334) */
   HAWK_EASSERT = -8,  /* input on which the reference itself fails an assert (annotation.py:191) */
-  HAWK_ECFD = -9      /* CFDon: a letter or key the score tables do not hold (KeyError, cfdscore.py:89-94) */
+  HAWK_ECFD = -9,     /* CFDon: a letter or key the score tables do not hold (KeyError, cfdscore.py:89-94) */
+  HAWK_EFEATURE = -10 /* one-hot input: a letter other than A, C, G, T (KeyError, scores/deepCpf1/seqdeepcpf1.py:19, 91) */
 };
 
 /* mode flags of hawk_params.flags */
@@ -298,6 +299,24 @@ int hawk_result_fetch_variants(hawk_result *result, int32_t *gv_idx /* gv_total 
  * NaN where the key has no REF guide. HAWK_ECFD (+ *bad_row) where the reference raises KeyError. */
 int hawk_result_cfdon(hawk_result *result, const uint8_t *is_ref, int32_t n_hap, const double *mm /* 320 */,
                       const double *pam2 /* 16 */, double *scores /* n_guides */, int64_t *bad_row);
+
+/* N4 (next row), second half: the learned scorers' inputs of every guide row, batched -- what the
+ * reference builds guide by guide in Python before it calls Azimuth / RS3 / DeepCpf1 / CRISPRon /
+ * sgDesigner (the models themselves stay its host code).
+ *   kmers  (host, n_guides x L bytes, row-major, may be NULL): scoring.py:50-84
+ *          _extract_guide_sequences (lead = 4) / _extract_guide_sequences_sgdesigner (lead = 0):
+ *          sequence[(PAD - lead) : (-PAD + 3)].upper() of the text annotation.reverse_guides leaves
+ *          (strand 1: IUPAC-aware reverse complement); L = G + P + lead + 3 (30 for SpCas9 NGG / 20,
+ *          34 for Cpf1 TTTV / 23).
+ *   onehot (n_guides x 4 x L float32, may be NULL; HOST memory, or DEVICE memory of the context's
+ *          device if onehot_on_device): scores/deepCpf1/seqdeepcpf1.py:71-92 preprocess, channels
+ *          A, C, G, T. A row with any other letter: HAWK_EFEATURE and *bad_row = the smallest such
+ *          row (the reference's NTENCODING lookup raises KeyError); checked only when onehot is
+ *          requested.
+ * Rows in emission order (row i of hawk_result_fetch). Works on any result that holds the window
+ * text column (phased, variant-free, unphased). */
+int hawk_result_featurize(hawk_result *result, int32_t lead, uint8_t *kmers, float *onehot,
+                          int32_t onehot_on_device, int64_t *bad_row);
 
 /* N2, the row collapse of the report (reports._collapse_report_entries, reports.py:958-1008, for
  * the score-free column set): rows of a phased / variant-free hawk_search result that agree in

@@ -113,6 +113,9 @@ class FakeResult:
     def cfdon(self, is_ref, mm, pam2):
         return hostcheck.cfdon_flat(self.tab, self.params, is_ref, mm, pam2)
 
+    def featurize(self, lead=4, kmers=True, onehot=False, onehot_device_ptr=0, kmers_out=None):
+        return hostcheck.featurize_flat(self.tab, self.params, lead, kmers, onehot)
+
     def close(self):
         self.closed, self.handle = True, None
 

@@ -167,3 +167,27 @@ def cfdon_flat(table, params, is_ref, mm, pam2):
         err.bad_row = bad
         raise err
     return out[:n]
+
+
+def featurize_flat(table, params, lead, kmers=True, onehot=False):
+    """hawk_result_featurize on the CPU: the kernels' own feature_byte / onehot_channel."""
+    from crispr_hawk_b200 import _cabi
+
+    L = lib()
+    L.hawkcheck_featurize.restype = C.c_int64
+    n = len(table["hap"])
+    w = params.guide_len + params.pam_len + 20
+    stride = (w + 15) // 16 * 16
+    text = np.zeros((max(n, 1), stride), np.uint8)
+    if n:
+        text[:n, :w] = table["text"][:, :w]
+    fl = w - 20 + lead + 3
+    k = np.zeros((max(n, 1), fl), np.uint8) if kmers else None
+    o = np.zeros((max(n, 1), 4, fl), np.float32) if onehot else None
+    bad = L.hawkcheck_featurize(_p(np.ascontiguousarray(table["strand"], np.uint8)), _p(text), C.c_int32(stride), C.c_int32(w),
+                                C.c_int32(lead), C.c_int64(n), _p(k) if kmers else None, _p(o) if onehot else None)  # fmt: skip
+    if onehot and bad >= 0:
+        err = _cabi.HawkLibraryError(f"hawk_result_featurize: row {bad}", _cabi.HAWK_EFEATURE)
+        err.bad_row = bad
+        raise err
+    return (k[:n] if kmers else None), (o[:n] if onehot else None)

@@ -190,3 +190,61 @@ def test_full_size_edit_lists_give_the_table_of_the_texts():
     for kcol in COLS + ("bucket",):
         assert np.array_equal(slim[kcol], want[kcol]), kcol
     assert d2h_slim < 0.35 * d2h
+
+
+@pytest.mark.parametrize("k", range(8))
+def test_c5_slices_match_c_oracle(k):
+    """BASELINE.json config 5 at the parity size SURVEY.md 8(d) names: 8 sub-regions of 20 kb x 32
+    haplotypes with config 5's variant model (one alternate allele per kb and haplotype, SNV /
+    insertion / deletion 90 / 5 / 5, indels up to 10 bases), every row against the C oracle."""
+    cfg = synth.CONFIGS["c5shard"]
+    c = synth.config_cohort("c5shard", 20_000 / cfg["bed_len"], seed_offset=100 + k, n_alt_hap=32)
+    assert c.n_hap == 33
+    _run_against_oracle(c, cfg["pam"], cfg["guidelen"], cfg["right"])
+
+
+def test_full_size_config5_block():
+    """BASELINE.json config 5, one rank's share at full size: a 50 Mb region x 626 haplotypes
+    (31.3 G haplotype-bp, ~97 M guide rows). Whole table: emission order, bucket ids = first row
+    of the (start, strand) key; REF rows per strand against a numpy restatement of the PAM test on
+    the reference text; REF + two random haplotypes row by row against the C oracle."""
+    cfg = synth.CONFIGS["c5shard"]
+    c = synth.config_cohort("c5shard")
+    wl = Workload(c, cfg["pam"], cfg["guidelen"], cfg["right"])
+    res = wl.step_resident()
+    table = res.table()
+    res.close()
+    assert wl.scanned_bp > 31.0e9
+    n = len(table["hap"])
+    assert n > 5e7
+    key = (table["hap"].astype(np.int64) << 33) | (table["strand"].astype(np.int64) << 32) | table["pos"].astype(np.int64)
+    assert np.all(np.diff(key) > 0)
+    del key
+    # bucket ids through a direct-address table (np.unique over 1e8 keys would take minutes)
+    k2 = table["start"].astype(np.int64) * 2 + table["strand"]
+    k2 -= k2.min()
+    first = np.full(int(k2.max()) + 1, n, np.int64)
+    order = np.arange(n - 1, -1, -1)
+    first[k2[order]] = order  # later writes win: the smallest row index of every key stays
+    assert np.array_equal(table["bucket"], first[k2])
+    del k2, first, order
+    # REF rows per strand == NGG / CCN occurrences whose PAM lies inside the BED interval
+    ref = c.ref
+    B = cfg["bed_len"]
+    lo, hi = 100, 100 + B - 3  # compute_scan_start_stop (search_guides.py:49-84) on REF
+    g = ref == ord("G")
+    cc = ref == ord("C")
+    fwd = int(np.count_nonzero(g[lo + 1 : hi + 1] & g[lo + 2 : hi + 2]))
+    rev = int(np.count_nonzero(cc[lo:hi] & cc[lo + 1 : hi + 1]))
+    ref_rows = table["hap"] == 0
+    assert int(np.count_nonzero(ref_rows & (table["strand"] == 0))) == fwd
+    assert int(np.count_nonzero(ref_rows & (table["strand"] == 1))) == rev
+    rng = np.random.default_rng(5)
+    subset = np.sort(np.concatenate(([0], rng.choice(np.arange(1, c.n_hap), 2, replace=False))))
+    want = oracle_table(wl, subset, threads=8)
+    okey = (want["hap"].astype(np.int64) << 33) | (want["strand"].astype(np.int64) << 32) | want["pos"].astype(np.int64)
+    oo = np.argsort(okey, kind="stable")
+    sel = np.flatnonzero(np.isin(table["hap"], subset))
+    got = {kcol: table[kcol][sel] for kcol in COLS + ("text",)}
+    got["hap"] = np.searchsorted(subset, got["hap"]).astype(np.int32)
+    assert_tables_equal(got, {kcol: want[kcol][oo] for kcol in COLS + ("text",)}, "c5 block subset")

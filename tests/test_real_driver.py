@@ -383,3 +383,34 @@ def test_cfdon_key_errors_surface_like_the_reference(monkeypatch):
             run_cfdon(drv, scoring, case)
     finally:
         hawk.uninstall()
+
+
+FEATURE_SEAM_CASES = [CASES[0], CASES[-3], CASES[-2], CASES[-1]]
+
+
+@pytest.mark.parametrize("case", FEATURE_SEAM_CASES, ids=[c.name for c in FEATURE_SEAM_CASES])
+def test_installed_scorer_inputs_equal_the_reference(case, monkeypatch):
+    """The genuine `scoring._extract_guide_sequences` / `_extract_guide_sequences_sgdesigner`
+    (scoring.py:50-84) on the annotated guides, plain and with the package installed (the strings
+    then come from hawk_result_featurize, cut while the table was on the device); a list the
+    package does not know goes to the reference's own functions."""
+    scoring, _ = load_scoring()
+    drv = load_driver()
+    monkeypatch.setattr(sys.modules["crisprhawk.scoring"], "cfdon_score", scoring.cfdon_score)
+    _, _, guides = run_driver(drv, case)
+    want4, want0 = scoring._extract_guide_sequences(guides), scoring._extract_guide_sequences_sgdesigner(guides)
+    assert len(want4) > 20 and len(want4[0]) == case.guidelen + len(case.pam) + 7
+    fake_backend.activate(monkeypatch)
+    hawk.install()
+    try:
+        assert scoring._extract_guide_sequences.__module__ == "crispr_hawk_b200.scoring"
+        _, _, got = run_driver(drv, case)
+        assert got.hawk.get("kmers") is not None and got.built == 0  # device columns, no Guide object needed
+        assert scoring._extract_guide_sequences(got) == want4
+        assert scoring._extract_guide_sequences_sgdesigner(got) == want0
+        assert got.built == 0
+        plain = list(got)  # not a list of this package: the reference's loop over the objects
+        assert scoring._extract_guide_sequences(plain) == want4
+    finally:
+        hawk.uninstall()
+    assert scoring._extract_guide_sequences.__module__ == "crisprhawk.scoring"
