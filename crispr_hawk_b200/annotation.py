@@ -26,6 +26,12 @@ def format_af(af: float) -> str:
     return f"{af:.6e}" if decimal_digits > 3 else str(round(af, 6))
 
 
+class AmbiguousVariants(ValueError):
+    """Two variants at one (normalised) position of a haplotype: the reference's result depends on
+    its set iteration order there (annotation.py:96, 129-160), so there is nothing to be bit-exact
+    with; the seam hands such a list to the reference's own functions."""
+
+
 def annotate_table(table: Dict[str, np.ndarray], res, batch, haplotypes, right: bool,
                    vt: Optional[marshal.VariantTable] = None, debug: bool = True) -> Dict[str, list]:  # fmt: skip
     """Columns of annotation.annotate_guides' first four steps for every row of `table`
@@ -36,6 +42,8 @@ def annotate_table(table: Dict[str, np.ndarray], res, batch, haplotypes, right: 
 
     if not getattr(batch, "has_variants", False):
         vt = vt or marshal.variant_table(haplotypes)
+        if vt.ambiguous:
+            raise AmbiguousVariants("a haplotype carries two variants at one position")
         batch.set_variants(vt)
     elif vt is None:
         vt = marshal.variant_table(haplotypes)
@@ -105,7 +113,13 @@ def _columns(guides, debug: bool):
     if "cols" not in link:
         if link.get("res") is None or not getattr(link["res"], "handle", None):
             return None
-        link["cols"] = annotate_table(link["table"], link["res"], link["batch"], link["haplotypes"], link["right"], debug=debug)
+        try:
+            link["cols"] = annotate_table(link["table"], link["res"], link["batch"], link["haplotypes"], link["right"], debug=debug)
+        except AmbiguousVariants:
+            link["cols"] = None  # sticky: every later step of this list goes to the reference too
+            link["res"].close()
+            link["res"] = None
+            return None
         link["groups"] = report_groups(link["table"], link["res"], link["haplotypes"])  # for the report's row collapse
         from . import scoring
 
@@ -113,6 +127,8 @@ def _columns(guides, debug: bool):
         link["kmers"] = scoring.kmer_columns(link)  # N4, the learned scorers' input strings (scoring.py:50-84)
         link["res"].close()  # the table has served its purpose: release the device memory
         link["res"] = None
+    if link["cols"] is None:
+        return None
     return link["cols"], link["order"]
 
 

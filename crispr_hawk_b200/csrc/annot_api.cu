@@ -25,6 +25,9 @@ extern "C" int hawk_batch_set_variants(hawk_batch* b, const int64_t* var_off, co
     for (int64_t j = var_off[h]; j < var_off[h + 1]; ++j) {
       if (j > var_off[h] && var_pos[j] < var_pos[j - 1])
         return hawk_fail(HAWK_EINVAL, "hawk_batch_set_variants: variants of haplotype %d are not sorted by position", h);
+      if (j > var_off[h] && var_pos[j] == var_pos[j - 1])
+        return hawk_fail(HAWK_EINVAL, "hawk_batch_set_variants: haplotype %d has two variants at position %d (the reference's "
+                         "own annotation depends on Python's set order there: annotate such a list with its functions)", h, var_pos[j]);
       if (var_reflen[j] < 1 || var_altlen[j] < 1 || var_altoff[j] < 0 || var_altoff[j] + var_altlen[j] > alt_pool_len)
         return hawk_fail(HAWK_EINVAL, "hawk_batch_set_variants: bad allele of variant %lld", (long long)j);
     }

@@ -181,9 +181,14 @@ def normalise_variant(ref: str, alt: str, pos: int):
 class VariantTable:
     """Per-haplotype variant lists for hawk_batch_set_variants, plus the ids in table order."""
 
-    def __init__(self, var_off, var_pos, var_reflen, var_altlen, var_altoff, alt_pool, ids):
+    def __init__(self, var_off, var_pos, var_reflen, var_altlen, var_altoff, alt_pool, ids, ambiguous=False):
         self.var_off, self.var_pos, self.var_reflen = var_off, var_pos, var_reflen
         self.var_altlen, self.var_altoff, self.alt_pool, self.ids = var_altlen, var_altoff, alt_pool, ids
+        # a haplotype with two variants at one normalised position: annotation._create_variants_map
+        # keeps whichever its set iteration yields last (annotation.py:96, 129-160), i.e. the
+        # reference's own answer depends on Python's hash order -- such lists are not annotated
+        # on the device (the seam hands them to the reference's functions)
+        self.ambiguous = ambiguous
 
 
 def variant_table(haps) -> VariantTable:
@@ -191,6 +196,7 @@ def variant_table(haps) -> VariantTable:
     variant.py:436-453) into the normalised, position-sorted table the device walks."""
     off, pos, rl, al, ao, pool, ids = [0], [], [], [], [], [], []
     n_pool = 0
+    ambiguous = False
     for h in haps:
         rows = []
         if h.variants and h.variants != "NA":
@@ -201,6 +207,7 @@ def variant_table(haps) -> VariantTable:
                 r2, a2, p2 = normalise_variant(ref, alt, int(parts[1]))
                 rows.append((p2, vid, len(r2), a2))
         rows.sort(key=lambda t: t[0])
+        ambiguous = ambiguous or any(rows[k][0] == rows[k - 1][0] for k in range(1, len(rows)))
         ids.append([t[1] for t in rows])
         for p2, _, r_len, a2 in rows:
             pos.append(p2)
@@ -213,5 +220,5 @@ def variant_table(haps) -> VariantTable:
     return VariantTable(
         np.asarray(off, np.int64), np.asarray(pos, np.int32), np.asarray(rl, np.int32), np.asarray(al, np.int32),
         np.asarray(ao, np.int64), np.frombuffer("".join(pool).encode("ascii"), np.uint8).copy() if pool else np.zeros(0, np.uint8),
-        ids,
+        ids, ambiguous,
     )  # fmt: skip

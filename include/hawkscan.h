@@ -279,7 +279,8 @@ int hawk_search_stream_edits(hawk_ctx *ctx, const uint8_t *ref_ascii, int64_t re
  * alt_pool[var_altoff .. + var_altlen). Batches made by hawk_batch_create_from_edits keep their
  * edit lists as this table (anchored edits are normalised already). At most one variant per
  * position and haplotype is what a phased VCF yields; with more the reference's own answer
- * depends on Python's set order (variants at one position are taken in table order here).
+ * depends on Python's set order, so hawk_batch_set_variants refuses such a table (HAWK_EINVAL)
+ * and the Python seam hands the list to the reference's own annotation functions.
  * Any output pointer may be NULL (gv_off = NULL skips the variant pass). Returns HAWK_EASSERT on
  * the input the reference's _find_insertion_stop asserts on. */
 int hawk_batch_set_variants(hawk_batch *batch, const int64_t *var_off, const int32_t *var_pos,

@@ -152,3 +152,24 @@ def test_guide_table_wire_format(case):
     assert gt.scorer_sequences(sgdesigner=True) == [w[2][10:-7].upper() for w in want]
     plain = hawk.GuideTable(table, haps, pam, case["guidelen"], case["right"])
     assert [g.sequence for g in plain] == [bytes(r).decode() for r in plain.sequences()]
+
+
+def test_two_variants_at_one_position_are_refused():
+    """hawk_batch_set_variants: two variants at one normalised position of a haplotype have no
+    well-defined annotation in the reference (set order); the library says so instead of picking."""
+    case = CASES[0]
+    region, haps = fixture_objects(case)
+    packed = hawk.encode_region(haps, 0, True)
+    vt = marshal.variant_table(haps)
+    assert not vt.ambiguous
+    packed.batch.set_variants(vt)
+    h = next(i for i in range(len(haps)) if vt.var_off[i + 1] > vt.var_off[i])
+    j = int(vt.var_off[h])
+    dup = marshal.VariantTable(vt.var_off.copy(), vt.var_pos.copy(), vt.var_reflen, vt.var_altlen, vt.var_altoff, vt.alt_pool, vt.ids)
+    dup.var_off[h + 1 :] += 1
+    for name in ("var_pos", "var_reflen", "var_altlen", "var_altoff"):
+        a = getattr(vt, name)
+        setattr(dup, name, np.concatenate((a[: j + 1], a[j : j + 1], a[j + 1 :])))
+    with pytest.raises(_cabi.HawkLibraryError) as ei:
+        packed.batch.set_variants(dup)
+    assert ei.value.code == _cabi.HAWK_EINVAL and "two variants" in str(ei.value)

@@ -28,7 +28,7 @@ def test_features_at_scale(name):
     res = wl.step_resident()
     table = res.table()
     n, W = len(table["hap"]), res.window
-    assert n > 100_000
+    assert n > 50_000
     k4, _ = res.featurize(lead=4)
     k0, _ = res.featurize(lead=0)
     L = W - 20 + 7

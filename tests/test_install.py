@@ -168,3 +168,47 @@ def test_live_device_tables_are_bounded():
     assert live.total == 80 and not keep[2].closed and not keep[3].closed
     live.add(links[4], 500)  # one table larger than the cap stays (the newest is never dropped)
     assert keep[2].closed and keep[3].closed and not keep[4].closed and len(live.links) == 1
+
+
+def test_two_variants_at_one_position_go_to_the_reference(monkeypatch):
+    """N2's guard: a haplotype with two variants at one normalised position (an SNV and an insertion
+    at the same anchor) has no well-defined annotation in the reference (its variant map keeps
+    whichever a Python set yields last, annotation.py:96, 129-160). The table builder flags it, the
+    device annotation refuses it, and the seam reports 'not mine' so the reference's functions run."""
+    from crispr_hawk_b200 import annotation, marshal
+
+    class H:
+        def __init__(self, variants):
+            self.variants = variants
+
+    plain = marshal.variant_table([H("NA"), H("chr1-100-A/G,chr1-140-AT/A"), H("chr1-100-A/G,chr1-101-C/CT")])
+    assert not plain.ambiguous
+    clash = marshal.variant_table([H("NA"), H("chr1-100-A/G,chr1-100-A/AT")])
+    assert clash.ambiguous and clash.var_pos.tolist() == [100, 100]
+
+    closed = []
+
+    class Res:
+        handle = object()
+
+        def close(self):
+            closed.append(True)
+
+    class Batch:
+        has_variants = False
+
+        def set_variants(self, vt):
+            raise AssertionError("an ambiguous table must not reach the device")
+
+    class L(list):
+        pass
+
+    guides = L()
+    guides.hawk = {"res": Res(), "batch": Batch(), "table": {"hap": []}, "haplotypes": [H("chr1-5-A/G,chr1-5-A/AT")], "right": False,
+                   "order": []}  # fmt: skip
+    assert annotation._columns(guides, True) is None and closed == [True]
+    assert guides.hawk["cols"] is None and guides.hawk["res"] is None
+    assert annotation._columns(guides, True) is None  # sticky
+    called = []
+    monkeypatch.setitem(annotation._reference, "gc_content", lambda g, v, d: called.append("ref") or g)
+    assert annotation.gc_content(guides, 0, True) is guides and called == ["ref"]
