@@ -1376,14 +1376,15 @@ int hawk_search_impl(hawk_ctx* c, hawk_batch* b, const hawk_params* params, cons
     }
     if (fused_text) {
       b->edits_lazy = false;  // re-encoded from the caller's texts
-      // The fused kernel is flat over the slot space: it wins when the haplotypes are short (an
-      // unphased cohort's ~200-base indel windows: the staged K2 spends a thread block per
-      // haplotype) and currently loses ~0.2 ms per 5 G bases on long ones, where its extra
-      // integer work per chunk outweighs the plane writes it saves (K1 is bound by the integer
-      // pipe, not by HBM -- DESIGN.md section 3).
-      const int64_t n_chunks_all = b->total_slots / HAWK_CHUNK;
-      const bool short_haps = K.unphased || (int64_t)b->n_hap * 2048 > n_chunks_all;
-      const bool use_fused = c->fused_mode == 1 || (c->fused_mode == 2 && short_haps);
+      // The fused kernel reads the texts once, keeps planes only where a later stage reads them and
+      // matches in the same pass; it is flat over the slot space, so short haplotypes (an unphased
+      // cohort's ~200-base indel windows: the staged K2 spends a thread block per haplotype) cost
+      // the same per base as long ones. Since its K1 became pack_chunk_v3 with the texts arriving
+      // through a cp.async ring it also wins on long haplotypes (config 2: 1.36 ms against
+      // 1.27 + 0.09 + 0.24 ms staged), so mode 2 takes it whenever the geometry has the fast form;
+      // mode 0 keeps the staged kernels (all planes stored) for callers who search the batch again
+      // with another geometry.
+      const bool use_fused = c->fused_mode != 0;
       if (K.small && use_fused && b->total_slots > 0) {
         bool fell_back = false;
         if ((rc = run_scan_fused(c, b, fused_text, params, scan_start, scan_stop, is_ref, in, so, bad_slot, &fell_back))) break;

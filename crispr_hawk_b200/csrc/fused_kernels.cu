@@ -97,9 +97,13 @@ struct HapCursor {
 // SUBC: the sub-range size as a compile-time constant (FUSED_SUB_MAX, the large-input case), or 0 =
 // take it from the arguments (small slot spaces)
 template <bool WIDE, int REACH, int SUBC>
-__global__ void __launch_bounds__(FUSED_WARPS * 32, 24 / FUSED_WARPS) fused_scan_kernel(const __grid_constant__ FusedArgs A) {
+__global__ void __launch_bounds__(FUSED_WARPS * 32, FUSED_CTAS_PER_SM / FUSED_WARPS) fused_scan_kernel(const __grid_constant__ FusedArgs A) {
   __shared__ uint16_t q_off[FUSED_WARPS][64];  // candidate queue (ring): chunk offset in the sub-range
   __shared__ int32_t q_hap[FUSED_WARPS][64];   // ... and its haplotype
+  __shared__ uint4 ring[FUSED_RING][64];       // texts in flight: FUSED_RING iterations x 1 KB (one warp per CTA)
+  static_assert(FUSED_WARPS == 1, "the text ring is per CTA");
+  unsigned ring_base = (unsigned)__cvta_generic_to_shared(&ring[0][0]) + 32u * (threadIdx.x & 31);
+  asm volatile("" : "+r"(ring_base));  // keep it in a register (it was re-derived every iteration)
   const int lane = threadIdx.x & 31, warp = FUSED_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5);
   const int64_t sub = (int64_t)blockIdx.x * FUSED_WARPS + warp;
   const int32_t SUB = SUBC ? SUBC : A.sub;
@@ -150,7 +154,6 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, 24 / FUSED_WARPS) fused_scan
   const uint32_t cap = A.seg_cap[sub];
   uint32_t n_ent = 0, n_h0 = 0, n_h1 = 0;
   uint32_t qhead = 0, qn = 0;
-  uint32_t nz_mine = 0;  // lane l: the nz word of iteration (32 m + l), stored 32 words at a time
 
   // match the oldest `take` (<= 32) queued candidates, append the ones with hits to the segment
   auto flush = [&](uint32_t take) {
@@ -197,19 +200,35 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, 24 / FUSED_WARPS) fused_scan
     qn -= take;
   };
 
-  // text of iteration `it` (chunk 32 it + lane of the sub-range; -1 and n_iter are the halo)
-  auto fetch = [&](int32_t it, Raw8& r) {
-    if (32 * it + 32 <= n_avail) {  // uniform; only the tail of the slot space fails it
-      load_raw<WIDE>(asc + 64 * it, r);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) r.w[k] = 0u;
-      if (32 * it + lane < n_avail) load_raw<WIDE>(asc + 64 * it, r);
-    }
+  // text of iteration `it` (chunk 32 it + lane of the sub-range; -1 and n_iter are the halo) on its
+  // way into ring slot (it + 1) mod FUSED_RING; lanes beyond the slot space get zeros. One commit
+  // group per call whatever the lane copies, so "all but the newest FUSED_RING - 1 groups have
+  // landed" means iteration `it` has.
+  // running state of the ring: the next iteration to request (its text pointer, the chunks left
+  // from its first chunk to the end of what this warp may read, its slot) and the slot to take
+  const uint4* src_next = asc;
+  int32_t left_next = n_avail;
+  unsigned slot_next = ring_base, slot_take = ring_base;
+  auto issue = [&]() {
+    const bool ok = lane < left_next;
+    const uint4* src = ok ? src_next : asc;
+    const int bytes = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot_next), "l"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot_next + 16u), "l"(src + 1), "r"(bytes) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    src_next += 64;
+    left_next -= 32;
+    slot_next = ring_base + ((slot_next - ring_base + 1024u) & (unsigned)(FUSED_RING * 1024 - 1));
+  };
+  auto take = [&](Raw8& r) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(FUSED_RING - 1) : "memory");
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "r"(slot_take) : "memory");
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "r"(slot_take + 16u) : "memory");
+    slot_take = ring_base + ((slot_take - ring_base + 1024u) & (unsigned)(FUSED_RING * 1024 - 1));
   };
   // ... -> planes; returns the "case word non-zero" ballot
   auto pack = [&](int32_t it, const Raw8& r, Planes5& o) -> uint32_t {
-    const PackedChunk k = pack_chunk_lean(r.w);
+    const PackedChunk k = pack_chunk_v3(r.w);
     o.a = k.a, o.c = k.c, o.g = k.g, o.t = k.t, o.v = k.v;
     if (k.invalid) {
       const int32_t cl = 32 * it + lane;
@@ -232,8 +251,7 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, 24 / FUSED_WARPS) fused_scan
   // finalise iteration j: P are its planes, nzp / nzc / nzn the ballots of iterations j - 1, j, j + 1
   auto finalise = [&](int32_t j, const Planes5& P, uint32_t nzp, uint32_t nzc, uint32_t nzn) {
     const int32_t cl0 = 32 * j;
-    if (lane == (j & 31)) nz_mine = nzc;
-    if ((j & 31) == 31) nzs[j - 31 + lane] = nz_mine;
+    if (lane == 0) nzs[j] = nzc;
     // variant chunk within one chunk (candidate) / within REACH chunks (planes are kept)
     const uint32_t near1 = nzc | __funnelshift_l(nzp, nzc, 1) | __funnelshift_r(nzc, nzn, 1);
     uint32_t keep_bits = near1;
@@ -298,27 +316,31 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, 24 / FUSED_WARPS) fused_scan
   Planes5 prev{0u, 0u, 0u, 0u, 0u}, now;
   Raw8 raw;
   uint32_t nz_pp = 0, nz_p = 0, nz_c;  // ballots of iterations i - 2, i - 1, i
-  if (s > 0) {  // leading halo
-    fetch(-1, raw);
+  // Software pipeline: the text of the next iteration is on its way into the warp's shared-memory
+  // ring (cp.async, 16 bytes x 2 per lane and iteration: no registers held while in flight),
+  // iteration i is packed, then iteration i - 1 (neighbours on both sides now known) is finalised.
+  // Iteration -1 is the leading, iteration n_iter the trailing halo. Deeper rings (4, 8 KB per
+  // warp) and requests of 2 - 8 KB at a time measured no better: profiles/README.md.
+  if (s > 0) {  // start one iteration early: the leading halo
+    src_next -= 64;
+    left_next += 32;
+  }
+  for (int k = 0; k < FUSED_RING - 1; ++k) issue();
+  if (s > 0) {
+    issue();
+    take(raw);
     nz_p = pack(-1, raw, now);
     store_edge(-1, now, 31);
   }
-  // Software pipeline: the text of iteration i + 1 is requested, iteration i is packed, then
-  // iteration i - 1 (neighbours on both sides now known) is finalised. Iteration n_iter is the
-  // trailing halo.
-  fetch(0, raw);
   for (int32_t i = 0; i <= n_iter; ++i) {
+    issue();
+    take(raw);
     nz_c = pack(i, raw, now);
-    fetch(i + 1, raw);
     if (i == n_iter) store_edge(i, now, 0);
     if (i > 0) finalise(i - 1, prev, nz_pp, nz_p, nz_c);
     prev = now;
     nz_pp = nz_p;
     nz_p = nz_c;
-  }
-  if (n_iter & 31) {  // nz words of the last, partial group of 32 iterations
-    const int32_t j0 = n_iter & ~31;
-    if (lane < (n_iter & 31)) nzs[j0 + lane] = nz_mine;
   }
   while (qn > 0) flush(qn < 32 ? qn : 32);
   if (lane == 0) {

@@ -37,6 +37,19 @@ int64_t hawkcheck_pack_lean_diff(const uint8_t* bytes, int64_t n_chunks) {
 }
 
 
+// the same for pack_chunk_v3
+int64_t hawkcheck_pack_v3_diff(const uint8_t* bytes, int64_t n_chunks) {
+  int64_t bad = 0;
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    uint32_t w[8];
+    memcpy(w, bytes + 32 * c, 32);
+    const hawk::PackedChunk x = hawk::pack_chunk(w), y = hawk::pack_chunk_v3(w);
+    if (x.invalid != y.invalid) ++bad;
+    else if (!x.invalid && (x.a != y.a || x.c != y.c || x.g != y.g || x.t != y.t || x.v != y.v)) ++bad;
+  }
+  return bad;
+}
+
 // K1 on the CPU: ascii slot space -> planes; returns first invalid slot or -1
 int64_t hawkcheck_pack(const uint8_t* ascii, int64_t total_slots, uint32_t* q /*4 per chunk*/,
                        uint32_t* v) {

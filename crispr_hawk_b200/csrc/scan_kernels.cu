@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint4* __restrict__ asc
     if (c < n_chunks) {
       uint32_t w[8];
       load_chunk_text<WIDE>(ascii, c, w);
-      const PackedChunk o = pack_chunk(w);
+      const PackedChunk o = pack_chunk_v3(w);
       q[c] = make_uint4(o.a, o.c, o.g, o.t);
       v[c] = o.v;
       vw = o.v;

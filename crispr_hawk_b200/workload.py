@@ -54,8 +54,20 @@ class Workload:
 
     def fused_auto(self) -> bool:
         """Whether hawk_encode_search_dev picks the fused K1 + K2 kernel for this workload
-        (api.cu: unphased cohorts and short haplotypes)."""
-        return bool(self.params.flags & _cabi.HAWK_F_UNPHASED) or self.d.n_hap_total() * 2048 > self.d.total_slots // 32
+        (api.cu: whenever the guide geometry has the fast form, G <= 32 and G + P <= 33)."""
+        return self.guidelen <= 32 and self.guidelen + len(self.fwd) <= 33
+
+    def fused_algorithmic_bytes(self, n_hits: int, reach: int = 2) -> float:
+        """What the fused kernel has to move: 1 B of text read per slot; 0.625 B of planes written
+        per slot it keeps -- every REF slot and the chunks within `reach` chunks of a variant base
+        (an upper bound: windows of neighbouring variants overlap), never more than all slots; one
+        16-byte entry per chunk with a hit (about one per two hit records)."""
+        if self.params.flags & _cabi.HAWK_F_UNPHASED:
+            kept = float(self.d.total_slots)  # IUPAC codes every few bases: every chunk is kept
+        else:
+            ref_slots = float(self.d.lens[self.d.is_ref.astype(bool)].sum())
+            kept = min(float(self.d.total_slots), ref_slots + float(self.d.variant_bases) * (2 * reach + 1) * 32)
+        return 1.0 * self.d.total_slots + 0.625 * kept + 16.0 * n_hits / 2
 
     def table_algorithmic_bytes(self, n_rows: int, n_hits: int) -> float:
         """Guide-table pipeline: rows written (25 B of columns + the padded text row), hit records
@@ -391,6 +403,7 @@ class UnphasedWorkload:
 
     table_algorithmic_bytes = Workload.table_algorithmic_bytes
     fused_auto = Workload.fused_auto
+    fused_algorithmic_bytes = Workload.fused_algorithmic_bytes
 
     def oracle_subset(self, hap_indices):
         """The flat arrays of a subset of haplotypes (oracle/c_oracle.search's inputs)."""

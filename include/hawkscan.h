@@ -347,8 +347,9 @@ int hawk_encode_search_dev(hawk_ctx *ctx, hawk_batch *batch, const uint8_t *d_as
                            const int32_t *scan_start, const int32_t *scan_stop, const uint8_t *is_ref,
                            hawk_result **result, int64_t *bad_slot);
 /* Which kernels hawk_encode_search_dev runs: 0 = K1, then the staged K2 (the batch stays dense);
- * 1 = the fused kernel whenever the guide geometry allows; 2 (default) = by haplotype shape --
- * fused for unphased cohorts and short haplotypes, staged for long ones. Results are identical. */
+ * 1 = the fused kernel whenever the guide geometry allows; 2 (default) = the library's choice,
+ * which is the same as 1 since the fused kernel became the faster one on every haplotype shape
+ * (it used to be: fused for unphased cohorts and short haplotypes only). Results are identical. */
 int hawk_ctx_set_fused(hawk_ctx *ctx, int32_t mode);
 /* How hawk_batch_create_from_edits (and hawk_search_stream_edits) obtain the planes:
  * 1 (default) = only where a search reads them -- every chunk of a haplotype without edits, and

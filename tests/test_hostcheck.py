@@ -135,9 +135,10 @@ def test_n2_row_logic_on_cpu_matches_reference_annotation(case, want):
         assert got == want[k], f"guide {k}"
 
 
-def test_lean_pack_equals_pack_on_every_byte():
-    """pack_chunk_lean (the fused kernel's K1) vs pack_chunk: all 256 byte values in every lane
-    position, random mixes of IUPAC letters / NUL / junk."""
+@pytest.mark.parametrize("fn", ["hawkcheck_pack_lean_diff", "hawkcheck_pack_v3_diff"])
+def test_lean_pack_equals_pack_on_every_byte(fn):
+    """pack_chunk_lean / pack_chunk_v3 (the kernels' K1) vs pack_chunk: all 256 byte values in every
+    lane position, random mixes of IUPAC letters / NUL / junk."""
     import ctypes as C
 
     import numpy as np
@@ -145,7 +146,7 @@ def test_lean_pack_equals_pack_on_every_byte():
     from tests import hostcheck
 
     lib = hostcheck.lib()
-    lib.hawkcheck_pack_lean_diff.restype = C.c_int64
+    getattr(lib, fn).restype = C.c_int64
     rng = np.random.default_rng(5)
     letters = np.frombuffer(b"ACGTRYSWKMBDHVNacgtryswkmbdhvn", np.uint8)
     parts = []
@@ -160,4 +161,4 @@ def test_lean_pack_equals_pack_on_every_byte():
     parts.append(rng.integers(0, 256, (4096, 32)).astype(np.uint8))
     parts.append(np.zeros((4, 32), np.uint8))
     buf = np.ascontiguousarray(np.concatenate(parts).reshape(-1))
-    assert lib.hawkcheck_pack_lean_diff(buf.ctypes.data_as(C.c_void_p), C.c_int64(len(buf) // 32)) == 0
+    assert getattr(lib, fn)(buf.ctypes.data_as(C.c_void_p), C.c_int64(len(buf) // 32)) == 0
