@@ -386,34 +386,42 @@ __global__ void __launch_bounds__(128) fused_expand_kernel(const uint4* __restri
   const uint4* seg = entries + seg_base[sub];
   const uint32_t n = cnt_ent[sub];
   uint64_t run0 = base0[sub], run1 = base1[sub];
-  for (uint32_t k0 = 0; k0 < n; k0 += 32) {
-    const uint32_t k = k0 + lane;
-    uint4 en = make_uint4(0u, 0u, 0u, 0u);
-    if (k < n) en = seg[k];
-    const uint32_t pk = (uint32_t)__popc(en.z) | ((uint32_t)__popc(en.w) << 16);
-    uint32_t incl = pk;
+  // 128 entries per pass: the four loads of a lane are in flight together (the kernel is a chain
+  // of dependent loads: one pass per 32 entries took 0.17 ms for 9.6 M entries, bound by latency)
+  for (uint32_t k0 = 0; k0 < n; k0 += 128) {
+    uint4 en[4];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-      if (lane >= d) incl += y;
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t k = k0 + 32u * u + lane;
+      en[u] = k < n ? seg[k] : make_uint4(0u, 0u, 0u, 0u);
     }
-    const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31), excl = incl - pk;
-    const uint64_t p0 = ((uint64_t)en.x << 32) | ((uint64_t)en.y << 5);
-    uint64_t a = run0 + (excl & 0xFFFFu), b = run1 + (excl >> 16);
-    uint32_t bits = en.z;
-    while (bits) {
-      const int jb = __ffs(bits) - 1;
-      bits &= bits - 1;
-      hits0[a++] = p0 + (uint32_t)jb;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t pk = (uint32_t)__popc(en[u].z) | ((uint32_t)__popc(en[u].w) << 16);
+      uint32_t incl = pk;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += y;
+      }
+      const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31), excl = incl - pk;
+      const uint64_t p0 = ((uint64_t)en[u].x << 32) | ((uint64_t)en[u].y << 5);
+      uint64_t a = run0 + (excl & 0xFFFFu), b = run1 + (excl >> 16);
+      uint32_t bits = en[u].z;
+      while (bits) {
+        const int jb = __ffs(bits) - 1;
+        bits &= bits - 1;
+        hits0[a++] = p0 + (uint32_t)jb;
+      }
+      bits = en[u].w;
+      while (bits) {
+        const int jb = __ffs(bits) - 1;
+        bits &= bits - 1;
+        hits1[b++] = p0 + (uint32_t)jb;
+      }
+      run0 += tot & 0xFFFFu;
+      run1 += tot >> 16;
     }
-    bits = en.w;
-    while (bits) {
-      const int jb = __ffs(bits) - 1;
-      bits &= bits - 1;
-      hits1[b++] = p0 + (uint32_t)jb;
-    }
-    run0 += tot & 0xFFFFu;
-    run1 += tot >> 16;
   }
 }
 
