@@ -526,8 +526,12 @@ def run_product_arm(args, rank, world, local_rank):
             "note": "K1 + K2 fused: texts read once, planes kept only around variant bases and for REF, PAM match in the same "
                     "pass. algorithmic_bytes = what this kernel must move; survey_formula_bytes = SURVEY 8(d) pack + scan "
                     "(the work it replaces: pack_kernel + cand_count + match_kernel)"})
+    if fused:
+        scan_bytes_k2 = 16.0 * hits_total / 2 + 8.0 * hits_total  # what is left outside the fused kernel: entries read, records written
+    else:
+        scan_bytes_k2 = scan_bytes
     kernels["scan_k2_total"] = {
-        "ms": scan_ms, "algorithmic_bytes": scan_bytes, "gbs": gbs(scan_bytes, scan_ms),
+        "ms": scan_ms, "algorithmic_bytes": scan_bytes_k2, "gbs": gbs(scan_bytes_k2, scan_ms),
         "note": ("fused path: the PAM match runs inside fused_scan_kernel (see pack_kernel); this entry is the segment "
                  "bookkeeping + fused_expand_kernel only" if fused else
                  "all K2 kernels (hapscan, block table, cand_count, match_kernel, expand_kernel, prefix sums); "
