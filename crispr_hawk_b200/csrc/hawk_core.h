@@ -273,6 +273,57 @@ HAWK_HD PackedChunk pack_chunk_v3(const uint32_t* words) {
   return o;
 }
 
+// ---- planes -> text: 32 window characters from plane bits (extract_guide_sequence, :134-160) ----
+// The way back of pack_chunk_v3. (1) The ASCII bit planes of the letters "?ACMGRSVTWYHKDBN"[nibble]
+// as boolean functions of the four nibble planes (Shannon expansion over T: three 3-input gates per
+// bit), bit 5 also set where the case plane is (lower-case = variant base). (2) The exchange
+// stages of the transpose are involutions and commute, and so are the byte transposes: running
+// them again turns the eight bit planes into the 32 characters. ~90 instructions for 32
+// characters; the per-character table walk it replaces (spread four plane bits to bytes, build a
+// permute selector, two table permutes, merge) took ~35 per 4.
+constexpr uint32_t letter_bit_table(int bit, int t) {
+  uint32_t m = 0;
+  const char letters[] = "?ACMGRSVTWYHKDBN";
+  for (int a = 0; a < 2; ++a)
+    for (int c = 0; c < 2; ++c)
+      for (int g = 0; g < 2; ++g)
+        if ((letters[a + 2 * c + 4 * g + 8 * t] >> bit) & 1) m |= 1u << (a * 4 + c * 2 + g);
+  return m;
+}
+
+template <int BIT>
+HAWK_HD uint32_t ascii_plane(uint32_t a, uint32_t c, uint32_t g, uint32_t t) {
+  return lop3<0xCA>(t, lop3<(int)letter_bit_table(BIT, 1)>(a, c, g), lop3<(int)letter_bit_table(BIT, 0)>(a, c, g));
+}
+
+// w[0..7]: characters 0..31 (little-endian words); `valid`: bit i set = character i exists, the
+// others come out as zero bytes
+HAWK_HD void planes_to_chars32(uint32_t pa, uint32_t pc, uint32_t pg, uint32_t pt, uint32_t pv, uint32_t valid,
+                               uint32_t* w) {
+  uint32_t b0 = ascii_plane<0>(pa, pc, pg, pt), b1 = ascii_plane<1>(pa, pc, pg, pt), b2 = ascii_plane<2>(pa, pc, pg, pt);
+  uint32_t b3 = ascii_plane<3>(pa, pc, pg, pt), b4 = ascii_plane<4>(pa, pc, pg, pt);
+  uint32_t b5 = ascii_plane<5>(pa, pc, pg, pt) | pv, b6 = ascii_plane<6>(pa, pc, pg, pt), b7 = 0u;
+  if (valid != 0xFFFFFFFFu) {
+    b0 &= valid, b1 &= valid, b2 &= valid, b3 &= valid, b4 &= valid, b5 &= valid, b6 &= valid;
+  }
+  bit_exchange<4, 0x0F0F0F0Fu>(b0, b4);
+  bit_exchange<4, 0x0F0F0F0Fu>(b1, b5);
+  bit_exchange<4, 0x0F0F0F0Fu>(b2, b6);
+  bit_exchange<4, 0x0F0F0F0Fu>(b3, b7);
+  bit_exchange<2, 0x33333333u>(b0, b2);
+  bit_exchange<2, 0x33333333u>(b1, b3);
+  bit_exchange<2, 0x33333333u>(b4, b6);
+  bit_exchange<2, 0x33333333u>(b5, b7);
+  bit_exchange<1, 0x55555555u>(b0, b1);
+  bit_exchange<1, 0x55555555u>(b2, b3);
+  bit_exchange<1, 0x55555555u>(b4, b5);
+  bit_exchange<1, 0x55555555u>(b6, b7);
+  transpose4x4_bytes(b0, b1, b2, b3);
+  transpose4x4_bytes(b4, b5, b6, b7);
+  w[0] = b0, w[2] = b1, w[4] = b2, w[6] = b3;
+  w[1] = b4, w[3] = b5, w[5] = b6, w[7] = b7;
+}
+
 // nibble -> IUPAC letter (inverse of the table above), upper-case
 HAWK_HD char nibble_letter(uint32_t n) {
   // "?ACMGRSVTWYHKDBN" as two 64-bit immediates (no local array, no stack frame)

@@ -50,6 +50,29 @@ int64_t hawkcheck_pack_v3_diff(const uint8_t* bytes, int64_t n_chunks) {
   return bad;
 }
 
+// planes_to_chars32 against the letters it must give back: pack_chunk on n_chunks * 32 valid bytes
+// (IUPAC letters of either case), then planes -> characters with the first `keep` of them valid;
+// returns the number of chunks that do not come back as the input (zero bytes past `keep`)
+int64_t hawkcheck_chars32_diff(const uint8_t* bytes, int64_t n_chunks, int32_t keep) {
+  int64_t bad = 0;
+  const uint32_t valid = keep >= 32 ? 0xFFFFFFFFu : ((1u << keep) - 1u);
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    uint32_t w[8], out[8];
+    memcpy(w, bytes + 32 * c, 32);
+    const hawk::PackedChunk x = hawk::pack_chunk(w);
+    hawk::planes_to_chars32(x.a, x.c, x.g, x.t, x.v, valid, out);
+    uint8_t got[32];
+    memcpy(got, out, 32);
+    for (int i = 0; i < 32; ++i) {
+      uint8_t want = bytes[32 * c + i];
+      if (want == 0) want = '?';  // an unused slot has nibble 0: the table's '?'
+      if (i >= keep) want = 0;
+      if (got[i] != want) { ++bad; break; }
+    }
+  }
+  return bad;
+}
+
 // K1 on the CPU: ascii slot space -> planes; returns first invalid slot or -1
 int64_t hawkcheck_pack(const uint8_t* ascii, int64_t total_slots, uint32_t* q /*4 per chunk*/,
                        uint32_t* v) {

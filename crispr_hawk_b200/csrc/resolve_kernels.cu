@@ -316,18 +316,6 @@ struct ResWriteArgs {
   int32_t key_min;
 };
 
-// four plane bits -> one bit per byte (table_kernels.cu has the same helpers)
-__device__ __forceinline__ uint32_t r_spread4(uint32_t x) { return (x * 0x00204081u) & 0x01010101u; }
-__device__ __forceinline__ uint32_t r_chars4(uint32_t pa, uint32_t pc, uint32_t pg, uint32_t pt, uint32_t pv, int i) {
-  const uint32_t lo3 = r_spread4((pa >> i) & 0xFu) | (r_spread4((pc >> i) & 0xFu) << 1) | (r_spread4((pg >> i) & 0xFu) << 2);
-  const uint32_t hi = r_spread4((pt >> i) & 0xFu);
-  uint32_t sel = (lo3 | (lo3 >> 4)) & 0x00FF00FFu;
-  sel = (sel | (sel >> 8)) & 0xFFFFu;
-  const uint32_t x0 = __byte_perm(0x4D43413Fu, 0x56535247u, sel), x1 = __byte_perm(0x48595754u, 0x4E42444Bu, sel);
-  const uint32_t m = hi * 0xFFu;
-  return ((x0 & ~m) | (x1 & m)) | (r_spread4((pv >> i) & 0xFu) << 5);
-}
-
 // Per-hit descriptor of the row-balanced writer, in shared memory: up to RES_DCOLS ambiguous
 // columns, each with <= 8 candidate characters.
 constexpr int RES_DCOLS = 8;
@@ -418,18 +406,12 @@ __global__ void __launch_bounds__(RES_T) resolve_write_kernel(const __grid_const
     if (W <= 64) amb[2] = 0;
     if (W <= 32) amb[1] = 0;
 #pragma unroll
-    for (int p = 0; p < N16; ++p) {
-      uint32_t wd[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int j0 = 16 * p + 4 * q;  // first window column of this word
-        uint32_t word = r_chars4(pa[j0 >> 5], pc[j0 >> 5], pg[j0 >> 5], pt[j0 >> 5], pv[j0 >> 5], j0 & 31);
-        const int left = W - j0;
-        if (left <= 0) word = 0;
-        else if (left < 4) word &= (1u << (8 * left)) - 1u;
-        wd[q] = word;
-      }
-      base_txt[warp][lane][p] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    for (int g = 0; 2 * g < N16; ++g) {  // 32 window columns at a time (planes_to_chars32, hawk_core.h)
+      const int left = W - 32 * g;
+      uint32_t wd[8];
+      planes_to_chars32(pa[g], pc[g], pg[g], pt[g], pv[g], left >= 32 ? 0xFFFFFFFFu : (left > 0 ? (1u << left) - 1u : 0u), wd);
+      base_txt[warp][lane][2 * g] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+      if (2 * g + 1 < N16) base_txt[warp][lane][2 * g + 1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
     }
     // ambiguous columns, first column first (= most significant digit of the product index)
     rpivot = S.rpivot[2 * i];

@@ -196,40 +196,6 @@ struct GatherFastArgs {  // both strands in one launch, blocks interleaved (see 
   RowMap rm;            // streamed search: global row numbering / haplotype indices
 };
 
-// four plane bits (one per character) -> one bit per byte: bit j lands at 8j (the 16 partial
-// products of the multiply fall on distinct bit positions, so nothing carries)
-__device__ __forceinline__ uint32_t spread4(uint32_t x) { return (x * 0x00204081u) & 0x01010101u; }
-
-// 4 window characters from the plane bits at bit offset i: the nibbles are spread to bytes,
-// turned into a byte-permute selector and looked up in the 16-letter table "?ACMGRSVTWYHKDBN"
-// held in four registers; lower-case = bit 5 from the case plane
-__device__ __forceinline__ uint32_t chars4(uint32_t pa, uint32_t pc, uint32_t pg, uint32_t pt, uint32_t pv, int i) {
-  const uint32_t lo3 = spread4((pa >> i) & 0xFu) | (spread4((pc >> i) & 0xFu) << 1) | (spread4((pg >> i) & 0xFu) << 2);
-  const uint32_t hi = spread4((pt >> i) & 0xFu);  // base T: table entries 8..15
-  uint32_t sel = (lo3 | (lo3 >> 4)) & 0x00FF00FFu;
-  sel = (sel | (sel >> 8)) & 0xFFFFu;
-  const uint32_t x0 = __byte_perm(0x4D43413Fu /* ?ACM */, 0x56535247u /* GRSV */, sel);
-  const uint32_t x1 = __byte_perm(0x48595754u /* TWYH */, 0x4E42444Bu /* KDBN */, sel);
-  const uint32_t m = hi * 0xFFu;
-  return ((x0 & ~m) | (x1 & m)) | (spread4((pv >> i) & 0xFu) << 5);
-}
-
-// 16 window characters starting at window offset j0 (plane bits i0 .. i0 + 15); bytes at or
-// beyond W are zero
-__device__ __forceinline__ uint4 window_chars(uint32_t pa, uint32_t pc, uint32_t pg, uint32_t pt, uint32_t pv,
-                                              int i0, int W, int j0) {
-  uint32_t w[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t word = chars4(pa, pc, pg, pt, pv, i0 + 4 * q);
-    const int left = W - (j0 + 4 * q);  // characters of this word inside the window
-    if (left <= 0) word = 0;
-    else if (left < 4) word &= (1u << (8 * left)) - 1u;
-    w[q] = word;
-  }
-  return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
 __global__ void __launch_bounds__(ROW_T) gather_fast_kernel(const __grid_constant__ GatherFastArgs A) {
   __shared__ uint32_t warp_cnt[ROW_T / 32];
   const int s = blockIdx.x & 1;
@@ -269,8 +235,11 @@ __global__ void __launch_bounds__(ROW_T) gather_fast_kernel(const __grid_constan
     const uint32_t v0 = A.B.v[chunk0 + (o >> 5)], v1 = A.B.v[chunk0 + (o >> 5) + 1];
     const uint32_t pa = funnel_r(q0.x, q1.x, sh), pc = funnel_r(q0.y, q1.y, sh), pg = funnel_r(q0.z, q1.z, sh),
                    pt = funnel_r(q0.w, q1.w, sh), pv = funnel_r(v0, v1, sh);
-    dst[j0 >> 4] = window_chars(pa, pc, pg, pt, pv, 0, W, j0);
-    if (j0 + 16 < A.text_stride) dst[(j0 >> 4) + 1] = window_chars(pa, pc, pg, pt, pv, 16, W, j0 + 16);
+    const int left = W - j0;  // > 0: the stride rounds W up to a multiple of 16
+    uint32_t w[8];
+    planes_to_chars32(pa, pc, pg, pt, pv, left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u), w);
+    dst[j0 >> 4] = make_uint4(w[0], w[1], w[2], w[3]);
+    if (j0 + 16 < A.text_stride) dst[(j0 >> 4) + 1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 

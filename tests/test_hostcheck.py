@@ -162,3 +162,27 @@ def test_lean_pack_equals_pack_on_every_byte(fn):
     parts.append(np.zeros((4, 32), np.uint8))
     buf = np.ascontiguousarray(np.concatenate(parts).reshape(-1))
     assert getattr(lib, fn)(buf.ctypes.data_as(C.c_void_p), C.c_int64(len(buf) // 32)) == 0
+
+
+def test_planes_to_chars_gives_the_letters_back():
+    """planes_to_chars32 (the text column of gather_fast): every IUPAC letter of either case and
+    the unused slot in every lane position, random mixes, every valid-prefix length."""
+    import ctypes as C
+
+    import numpy as np
+
+    from tests import hostcheck
+
+    lib = hostcheck.lib()
+    lib.hawkcheck_chars32_diff.restype = C.c_int64
+    rng = np.random.default_rng(9)
+    letters = np.frombuffer(b"ACGTRYSWKMBDHVNacgtryswkmbdhvn\0", np.uint8)
+    parts = []
+    for lane in range(32):
+        blk = letters[rng.integers(0, len(letters), (len(letters), 32))]
+        blk[:, lane] = letters
+        parts.append(blk)
+    parts.append(letters[rng.integers(0, len(letters), (4096, 32))])
+    buf = np.ascontiguousarray(np.concatenate(parts).reshape(-1))
+    for keep in list(range(0, 33)):
+        assert lib.hawkcheck_chars32_diff(buf.ctypes.data_as(C.c_void_p), C.c_int64(len(buf) // 32), C.c_int32(keep)) == 0, keep
