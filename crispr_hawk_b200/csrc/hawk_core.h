@@ -768,18 +768,24 @@ HAWK_HD RowCoords row_coords(const BatchView& B, const ScanConst& K, int32_t h, 
   RowCoords r;
   const StrandGeom& g = K.geom[s];
   r.pivot = pos + g.c0;
-  int64_t s0 = B.seg_off[h], s1 = B.seg_off[h + 1];
-  // last segment with seg_rel <= pivot, then walk forward to the one holding the stop index
+  // the haplotype's own segment arrays, indexed with 32-bit offsets (the search was a third of
+  // rows_fast's instructions when it ran on 64-bit global indices)
+  const int64_t s0 = B.seg_off[h];
+  const int32_t n = (int32_t)(B.seg_off[h + 1] - s0);
+  const int32_t* rel = B.seg_rel + s0;
+  const int32_t* gen = B.seg_gen + s0;
+  const uint8_t* step = B.seg_step + s0;
+  // last segment with rel <= pivot, then walk forward to the one holding the stop index
   // (a guide spans G + P bases: almost always the same segment or the next)
-  int64_t lo = s0, hi = s1;
+  int32_t lo = 0, hi = n;
   while (hi - lo > 1) {
-    int64_t mid = (lo + hi) >> 1;
-    if (B.seg_rel[mid] <= r.pivot) lo = mid; else hi = mid;
+    const int32_t mid = (lo + hi) >> 1;
+    if (rel[mid] <= r.pivot) lo = mid; else hi = mid;
   }
-  r.start = B.seg_gen[lo] + (B.seg_step[lo] ? (r.pivot - B.seg_rel[lo]) : 0);
+  r.start = gen[lo] + (step[lo] ? (r.pivot - rel[lo]) : 0);
   const int32_t j = pos + g.stop_off;
-  while (lo + 1 < s1 && B.seg_rel[lo + 1] <= j) ++lo;
-  r.stop = B.seg_gen[lo] + (B.seg_step[lo] ? (j - B.seg_rel[lo]) : 0);
+  while (lo + 1 < n && rel[lo + 1] <= j) ++lo;
+  r.stop = gen[lo] + (step[lo] ? (j - rel[lo]) : 0);
   return r;
 }
 
