@@ -24,11 +24,23 @@ def test_features_match_reference(case):
 def test_features_at_scale(name):
     k = synth.CONFIGS[name]
     c = synth.config_cohort(name, 0.1, n_alt_hap=1200)
-    wl = Workload(c, k["pam"], k["guidelen"], k["right"])
+    check_against_numpy(Workload(c, k["pam"], k["guidelen"], k["right"]), 50_000)
+
+
+@pytest.mark.parametrize("pam,G,right", [("NGG", 1, False), ("TTTV", 70, True), ("NGG", 125, False), ("NNGRRT", 33, True)])
+def test_features_other_geometries(pam, G, right):
+    """One-base guides, windows of several 16-byte text words, the longest window the library
+    takes (G + P = 128: 148 characters, 135-letter scorer strings)."""
+    c = synth.make_cohort(bed_len=60_000, n_alt_hap=9, n_sites=900, mean_alts_per_hap=150, seed=12,
+                          snv_frac=0.6, ins_frac=0.2, max_indel=8)  # fmt: skip
+    check_against_numpy(Workload(c, pam, G, right), 300)
+
+
+def check_against_numpy(wl, min_rows):
     res = wl.step_resident()
     table = res.table()
     n, W = len(table["hap"]), res.window
-    assert n > 50_000
+    assert n > min_rows
     k4, _ = res.featurize(lead=4)
     k0, _ = res.featurize(lead=0)
     L = W - 20 + 7
