@@ -54,11 +54,13 @@ HAWK_HD uint8_t iupac_entry(uint8_t ch) {
 }
 
 // ---- K1: 32 ASCII bytes -> bit-sliced planes, no table lookups ---------------------
-// (1) an 8x8 bit-matrix transpose per 8 bytes turns the characters into bit planes
-//     b0..b7 (bit i of plane k = bit k of character i);
+// (1) a bit-matrix transpose turns the characters into bit planes b0..b7 (bit i of plane k =
+//     bit k of character i);
 // (2) the letter's low five bits index 32-entry truth tables, one per output plane,
-//     evaluated for 32 characters at once with 3-input boolean ops (Shannon expansion
-//     over b4, b3; LOP3 on the GPU).
+//     evaluated for 32 characters at once with 3-input boolean ops (LOP3 on the GPU).
+// Two forms with the same results: pack_chunk, the plain one (an 8x8 transpose per 8 bytes by
+// delta swaps, exact tables by Shannon expansion over b4, b3) -- round 1's kernel code, kept as
+// the form the tests compare with --, and pack_chunk_v3 further down, which the kernels run.
 
 // 3-input boolean function selected by the 8-bit truth table IMM (index a<<2 | b<<1 | c)
 template <int IMM>
@@ -183,38 +185,8 @@ HAWK_HD void transpose4x4_bytes(uint32_t& w0, uint32_t& w1, uint32_t& w2, uint32
   w3 = byte_perm(t2, t3, 0x7632);
 }
 
-// pack_chunk with fewer ALU-pipe instructions (the pack is bound by that pipe, not by HBM):
-// the per-plane byte gathers become two 4x4 byte transposes (16 permutes instead of 24), the
-// planes are not masked by "is a letter" (a non-letter other than NUL sets `invalid`, and a
-// batch with an invalid byte is refused as a whole; NUL has letter number 0 -> zero planes),
-// the case word is bit 5 as it stands, and the validity word takes 7 boolean ops. Same result
-// as pack_chunk on every NUL / IUPAC byte, and the same `invalid` word on every input.
-HAWK_HD PackedChunk pack_chunk_lean(const uint32_t* words) {
-  uint32_t lo[4], hi[4];
-  HAWK_UNROLL
-  for (int g = 0; g < 4; ++g) {
-    lo[g] = words[2 * g];
-    hi[g] = words[2 * g + 1];
-    transpose8x8(lo[g], hi[g]);
-  }
-  transpose4x4_bytes(lo[0], lo[1], lo[2], lo[3]);  // -> bit planes 0..3 of the 32 characters
-  transpose4x4_bytes(hi[0], hi[1], hi[2], hi[3]);  // -> bit planes 4..7
-  PackedChunk o;
-  o.a = table5<letter_table(0)>(lo[0], lo[1], lo[2], lo[3], hi[0]);
-  o.c = table5<letter_table(1)>(lo[0], lo[1], lo[2], lo[3], hi[0]);
-  o.g = table5<letter_table(2)>(lo[0], lo[1], lo[2], lo[3], hi[0]);
-  o.t = table5<letter_table(3)>(lo[0], lo[1], lo[2], lo[3], hi[0]);
-  o.v = hi[1];
-  const uint32_t or_a = lop3<0xFE>(lo[0], lo[1], lo[2]), or_b = lop3<0xFE>(lo[3], hi[0], hi[1]);
-  const uint32_t or_7 = lop3<0xFE>(or_a, or_b, hi[2]);      // bits 0..6: any set
-  const uint32_t alpha = ~hi[3] & hi[2];                    // 0x40..0x7F
-  const uint32_t acg = lop3<0xFE>(o.a, o.c, o.g);
-  const uint32_t ok = lop3<0xA8>(acg, o.t, alpha);          // (acg | t) & alpha: an IUPAC letter
-  o.invalid = lop3<0x54>(or_7, hi[3], ok);                  // (or_7 | b7) & ~ok: not NUL, not a letter
-  return o;
-}
-
-// ---- pack_chunk_v3: the same planes with two thirds of the instructions ----------------------
+// ---- pack_chunk_v3: the same planes with two thirds of the instructions (what the kernels run;
+// pack_chunk above stays as the plain form the tests compare it with) --------------------------
 // (1) Transpose. Two 4x4 byte transposes first put characters {m, m + 8, m + 16, m + 24} into word m,
 //     so a bit's address is (word m = i mod 8, position 8 (i div 8) + j) for bit j of character i.
 //     The wanted address is (word j, position i): exchange word-index bit k with position bit k for

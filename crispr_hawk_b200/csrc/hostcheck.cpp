@@ -21,23 +21,9 @@ using namespace hawk;
 
 extern "C" {
 
-// pack_chunk_lean against pack_chunk on n_chunks * 32 arbitrary bytes: returns the number of
-// chunks whose `invalid` words differ, or -- on chunks without an invalid byte -- whose planes /
-// case word differ
-int64_t hawkcheck_pack_lean_diff(const uint8_t* bytes, int64_t n_chunks) {
-  int64_t bad = 0;
-  for (int64_t c = 0; c < n_chunks; ++c) {
-    uint32_t w[8];
-    memcpy(w, bytes + 32 * c, 32);
-    const hawk::PackedChunk x = hawk::pack_chunk(w), y = hawk::pack_chunk_lean(w);
-    if (x.invalid != y.invalid) ++bad;
-    else if (!x.invalid && (x.a != y.a || x.c != y.c || x.g != y.g || x.t != y.t || x.v != y.v)) ++bad;
-  }
-  return bad;
-}
-
-
-// the same for pack_chunk_v3
+// pack_chunk_v3 (what the kernels run) against pack_chunk on n_chunks * 32 arbitrary bytes: returns the
+// number of chunks whose `invalid` words differ, or -- on chunks without an invalid byte -- whose
+// planes / case word differ
 int64_t hawkcheck_pack_v3_diff(const uint8_t* bytes, int64_t n_chunks) {
   int64_t bad = 0;
   for (int64_t c = 0; c < n_chunks; ++c) {

@@ -135,9 +135,8 @@ def test_n2_row_logic_on_cpu_matches_reference_annotation(case, want):
         assert got == want[k], f"guide {k}"
 
 
-@pytest.mark.parametrize("fn", ["hawkcheck_pack_lean_diff", "hawkcheck_pack_v3_diff"])
-def test_lean_pack_equals_pack_on_every_byte(fn):
-    """pack_chunk_lean / pack_chunk_v3 (the kernels' K1) vs pack_chunk: all 256 byte values in every
+def test_v3_pack_equals_pack_on_every_byte(fn="hawkcheck_pack_v3_diff"):
+    """pack_chunk_v3 (the kernels' K1) vs pack_chunk: all 256 byte values in every
     lane position, random mixes of IUPAC letters / NUL / junk."""
     import ctypes as C
 
