@@ -89,6 +89,7 @@ def install(module: Optional[object] = None, annotation_module: Optional[object]
             try:
                 pmod = importlib.import_module("crisprhawk.pam")
                 sco._reference["cas9_systems"] = (pmod.SPCAS9, pmod.XCAS9)
+                sco._reference["cpf1_system"] = pmod.CPF1
             except Exception:
                 pass
     return drv

@@ -113,10 +113,19 @@ def cfdon_score(guides, verbosity: int, debug: bool):
 # sgDesigner are called. On a list that came from this package's `search` the whole batch was cut
 # on the device (`hawk_result_featurize`) while the table was resident; the models stay the
 # reference's host code.
+def scorer_systems():
+    """Cas systems whose guides `scoring.scoring_guides` feeds to a learned scorer
+    (scoring.py:845-857: SpCas9 / xCas9 -> Azimuth, RS3, CRISPRon, sgDesigner; Cpf1 -> DeepCpf1)."""
+    from . import pam as mirror
+
+    return tuple(cas9_systems()) + (_reference.get("cpf1_system", mirror.CPF1),)
+
+
 def kmer_columns(link):
-    """{lead: (n, L) uint8} for lead 4 and 0, rows in emission order; None without a table."""
-    res = link.get("res")
-    if res is None or not hasattr(res, "featurize"):
+    """{lead: (n, L) uint8} for lead 4 and 0, rows in emission order; None without a table or for
+    a PAM no scorer takes (the strings would never be asked for)."""
+    res, pam = link.get("res"), link.get("pam")
+    if res is None or not hasattr(res, "featurize") or getattr(pam, "cas_system", None) not in scorer_systems():
         return None
     return {lead: res.featurize(lead=lead)[0] for lead in (4, 0)}
 
