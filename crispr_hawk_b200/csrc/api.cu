@@ -692,6 +692,8 @@ extern "C" int hawk_batch_set_posmap(hawk_batch* b, const int64_t* seg_off, cons
   if (gmin < INT32_MIN || gmax > INT32_MAX) return hawk_fail(HAWK_EINVAL, "hawk_batch_set_posmap: coordinates exceed 32 bits");
   b->gmin = (int32_t)gmin;
   b->gmax = (int32_t)gmax;
+  b->seg_idx.release();  // the coarse index follows the segments: rebuilt at the next phased search
+  b->seg_idx_stride = 0;
   CK(upload(c, b->seg_off, seg_off, (size_t)(b->n_hap + 1) * 8));
   CK(upload(c, b->seg_rel, seg_rel, n * 4));
   CK(upload(c, b->seg_gen, seg_gen, n * 4));
@@ -1078,10 +1080,35 @@ extern "C" int hawk_pam_search(hawk_ctx* c, hawk_batch* b, const hawk_params* pa
 }
 
 // phased / variant-free pipeline downstream of the scan (table_kernels.cu)
-static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const BatchView& B, ScanOut& so,
+// Coarse index of the batch's posmap segments for rows_fast (one entry per haplotype and 4 kb of
+// its text), built once per batch; skipped where it would be large (haplotypes of very unequal
+// length: the stride follows the longest) -- row_coords then searches all segments as before.
+static int ensure_seg_index(hawk_ctx* c, hawk_batch* b) {
+  if (b->seg_idx_stride != 0 || b->n_hap <= 0) return HAWK_OK;
+  int32_t max_len = 0;
+  for (int32_t h = 0; h < b->n_hap; ++h) max_len = b->len[h] > max_len ? b->len[h] : max_len;
+  const int32_t stride = (max_len >> HAWK_SEG_IDX_SHIFT) + 2;
+  if ((int64_t)stride * b->n_hap > (64ll << 20)) {
+    b->seg_idx_stride = -1;
+    return HAWK_OK;
+  }
+  CK(b->seg_idx.alloc(c, (size_t)stride * b->n_hap * 4));
+  CK(launch_seg_index(c->stream, b->seg_off.as<int64_t>(), b->seg_rel.as<int32_t>(), b->n_hap, stride,
+                      b->seg_idx.as<int32_t>()));
+  b->seg_idx_stride = stride;
+  return HAWK_OK;
+}
+
+static int search_fast(hawk_ctx* c, hawk_batch* b, const ScanConst& K, const BatchView& B_in, ScanOut& so,
                        int32_t ref_h, const StreamLink* link, hawk_result* r) {
   cudaStream_t st = c->stream;
   Trace tr;
+  BatchView B = B_in;
+  CK(ensure_seg_index(c, b));
+  if (b->seg_idx_stride > 0) {
+    B.seg_idx = b->seg_idx.as<int32_t>();
+    B.seg_idx_stride = b->seg_idx_stride;
+  }
   const int64_t n_hits[2] = {so.n[0], so.n[1]};
   const uint64_t* recs[2] = {so.hits[0].as<uint64_t>(), so.hits[1].as<uint64_t>()};
   RefInfo ref{ref_h, 0, 0, 0};

@@ -539,6 +539,8 @@ HAWK_HD bool cores_equal(const Planes* q, int64_t chunk0_a, int64_t pos_a, int64
 
 namespace hawk {
 
+#define HAWK_SEG_IDX_SHIFT 12
+
 struct BatchView {
   const Planes* q;            // planes, one per chunk
   const uint32_t* v;          // case bits, one word per chunk
@@ -554,6 +556,10 @@ struct BatchView {
   const int32_t* seg_rel;
   const int32_t* seg_gen;
   const uint8_t* seg_step;
+  // coarse index of the segments (may be null): seg_idx[h * seg_idx_stride + k] = last segment of
+  // haplotype h (haplotype-local) that starts at or before relative index k << HAWK_SEG_IDX_SHIFT
+  const int32_t* seg_idx;
+  int32_t seg_idx_stride;
   // variant alleles (unphased only, may be null)
   const int64_t* va_off;
   const int32_t* va_idx;
@@ -736,6 +742,21 @@ struct RowCoords {
   int32_t start, stop;  // adjust_guide_position, :260-280
 };
 
+// entry k of haplotype h's coarse segment index: the last segment (haplotype-local) that starts at or
+// before relative index k << HAWK_SEG_IDX_SHIFT
+HAWK_HD int32_t seg_index_entry(const int64_t* seg_off, const int32_t* seg_rel, int32_t h, int32_t k) {
+  const int64_t s0 = seg_off[h];
+  const int32_t n = (int32_t)(seg_off[h + 1] - s0);
+  const int32_t* rel = seg_rel + s0;
+  const int64_t target = (int64_t)k << HAWK_SEG_IDX_SHIFT;
+  int32_t lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int32_t mid = (lo + hi) >> 1;
+    if (rel[mid] <= target) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 HAWK_HD RowCoords row_coords(const BatchView& B, const ScanConst& K, int32_t h, int32_t pos, int s) {
   RowCoords r;
   const StrandGeom& g = K.geom[s];
@@ -750,6 +771,13 @@ HAWK_HD RowCoords row_coords(const BatchView& B, const ScanConst& K, int32_t h, 
   // last segment with rel <= pivot, then walk forward to the one holding the stop index
   // (a guide spans G + P bases: almost always the same segment or the next)
   int32_t lo = 0, hi = n;
+  if (B.seg_idx) {  // one lookup narrows the search to the segments of the pivot's 4 kb bucket
+    int32_t k = r.pivot < 0 ? 0 : r.pivot >> HAWK_SEG_IDX_SHIFT;
+    if (k > B.seg_idx_stride - 2) k = B.seg_idx_stride - 2;
+    const int32_t* ix = B.seg_idx + (int64_t)h * B.seg_idx_stride + k;
+    lo = ix[0];
+    hi = ix[1] + 1;
+  }
   while (hi - lo > 1) {
     const int32_t mid = (lo + hi) >> 1;
     if (rel[mid] <= r.pivot) lo = mid; else hi = mid;

@@ -183,6 +183,8 @@ struct hawk_batch {
   std::vector<int32_t> len;
   DevBuf q, v, nz, d_slot_off, d_len;
   DevBuf seg_off, seg_rel, seg_gen, seg_step;
+  DevBuf seg_idx;              // coarse index of the segments (table_kernels.cu), built at the first phased search
+  int32_t seg_idx_stride = 0;  // 0: not built; -1: not worth building for this batch
   DevBuf va_off, va_idx, va_ent_off, va_ref;
   bool has_posmap = false, has_alleles = false;
   // planes are kept only around variant bases and for REF haplotypes (hawk_encode_search_dev):

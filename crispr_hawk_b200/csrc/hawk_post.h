@@ -64,6 +64,8 @@ int launch_rows_fast(cudaStream_t st, const BatchView& B, const ScanConst& K, co
                      const int64_t n[2], const RefInfo& ref, const uint32_t* const ref_bm[2], const int64_t* ref_range,
                      int32_t drop_ref, int32_t* const start[2], int32_t* const stop[2], uint8_t* const keep[2],
                      uint32_t* const blk_cnt[2]);
+int launch_seg_index(cudaStream_t st, const int64_t* seg_off, const int32_t* seg_rel, int32_t n_hap, int32_t stride,
+                     int32_t* idx);
 int launch_blk_prefix(cudaStream_t st, const uint32_t* const cnt[2], const int64_t n_blk[2], uint64_t* const base[2],
                       uint64_t* totals);
 int launch_hap_offsets(cudaStream_t st, const uint64_t* r0, const uint64_t* r1, int64_t n0, int64_t n1,

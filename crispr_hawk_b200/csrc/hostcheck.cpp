@@ -144,6 +144,19 @@ void* hawkcheck_search(const uint32_t* q, const uint32_t* v, const int64_t* slot
   ScanConst K = make_scan_const(*params, raw);
   const int W = K.C + 2 * HAWK_GUIDESEQPAD;
   T->window = W;
+  // the coarse segment index rows_fast uses on the device (api.cu ensure_seg_index), so that the
+  // CPU tests walk the indexed search of row_coords too
+  std::vector<int32_t> seg_idx;
+  if (seg_off && n_hap > 0) {
+    int32_t max_len = 0;
+    for (int32_t h = 0; h < n_hap; ++h) max_len = len[h] > max_len ? len[h] : max_len;
+    const int32_t stride = (max_len >> HAWK_SEG_IDX_SHIFT) + 2;
+    seg_idx.resize((size_t)stride * n_hap);
+    for (int32_t h = 0; h < n_hap; ++h)
+      for (int32_t k = 0; k < stride; ++k) seg_idx[(size_t)h * stride + k] = seg_index_entry(seg_off, seg_rel, h, k);
+    B.seg_idx = seg_idx.data();
+    B.seg_idx_stride = stride;
+  }
   scan_all(B, K, T->hits);
   if (raw) return T;
   int32_t ref_h = -1;

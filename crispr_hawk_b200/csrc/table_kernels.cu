@@ -38,6 +38,28 @@ __global__ void ref_bitmap_kernel(const uint64_t* __restrict__ recs0, const uint
   }
 }
 
+// ---------------------------------------------------------------- coarse posmap index
+// rows_fast finds a hit's posmap segment by binary search: ~8 dependent loads per hit on a
+// haplotype with a few hundred segments, the longest chain of the kernel. One thread per
+// (haplotype, 4 kb bucket) does that search once per batch; a hit then needs one lookup and a
+// search over the segments of its own bucket (usually one or two).
+__global__ void seg_index_kernel(const int64_t* __restrict__ seg_off, const int32_t* __restrict__ seg_rel, int32_t n_hap,
+                                 int32_t stride, int32_t* __restrict__ idx) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n_hap * stride) return;
+  const int32_t h = (int32_t)(t / stride), k = (int32_t)(t - (int64_t)h * stride);
+  idx[t] = seg_index_entry(seg_off, seg_rel, h, k);
+}
+
+int launch_seg_index(cudaStream_t st, const int64_t* seg_off, const int32_t* seg_rel, int32_t n_hap, int32_t stride,
+                     int32_t* idx) {
+  const int64_t n = (int64_t)n_hap * stride;
+  if (n <= 0) return HAWK_OK;
+  seg_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seg_off, seg_rel, n_hap, stride, idx);
+  hawk_note_launch(1);
+  return hawk_check_cuda(cudaGetLastError(), "seg_index_kernel launch");
+}
+
 // ---------------------------------------------------------------- rows
 // Both strands in one launch, blocks interleaved (even = strand 0, odd = strand 1): the two hit
 // streams are sorted by (haplotype, position) and about equally dense, so block k of either
