@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(128) fused_expand_kernel(const uint4* __restri
 
 int32_t fused_sub_size(int64_t n_chunks) {
   static const int waves = getenv("HAWK_FUSED_WAVES") ? atoi(getenv("HAWK_FUSED_WAVES")) : 4;
-  const int64_t want = n_chunks / ((int64_t)waves * 148 * 24);  // one warp per CTA, 24 CTAs per SM
+  const int64_t want = n_chunks / ((int64_t)waves * 148 * 24);  // one warp per CTA, ~24 resident CTAs per SM (the sizes below were tuned with this figure)
   int32_t sub = FUSED_SUB_MAX;
   while (sub > 256 && sub > want) sub >>= 1;
   return sub;

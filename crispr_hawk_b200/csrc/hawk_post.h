@@ -81,7 +81,7 @@ int launch_bucket_read(cudaStream_t st, const int32_t* start, const uint8_t* str
 
 // fused_kernels.cu: K1 + K2 in one pass over the texts (flat over the slot space)
 constexpr int FUSED_RING = 2;          // slots (1 KB of text each) of a warp's cp.async ring, power of two
-constexpr int FUSED_CTAS_PER_SM = 28;  // launch bound: 72 registers (32 -> 64 registers ran 7 % slower)
+constexpr int FUSED_CTAS_PER_SM = 28;  // launch bound (ptxas settles on 63 registers; a bound of 32 CTAs ran 7 % slower, 24 the same)
 constexpr int FUSED_WARPS = 1;    // warps per CTA (one: the warp index is then provably uniform -> uniform datapath)
 constexpr int FUSED_SUB_MAX = 4096;  // chunks per warp sub-range (128 KB of text) for large slot spaces
 // ... and fewer (a power of two >= 256) for small ones, so that there are a few waves of warps to
