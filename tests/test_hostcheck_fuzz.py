@@ -41,3 +41,27 @@ def test_kernel_core_on_cpu_matches_c_oracle(seed):
     for col in ("hap", "strand", "pos", "start", "stop"):
         assert np.array_equal(tab[col][order], want[col]), col
     assert np.array_equal(tab["text"][order], want["text"])
+
+
+@pytest.mark.parametrize("seed,pam,G,right", [(1, "NGG", 20, False), (2, "TTTV", 23, True)])
+def test_indexed_posmap_search_over_many_buckets(seed, pam, G, right):
+    """A region of 60 kb with indel-rich haplotypes: ~15 buckets of the coarse segment index
+    (4 kb each) and dozens of posmap segments per haplotype -- row_coords' indexed search
+    (hawk_core.h, the table the device builds in seg_index_kernel) against the C oracle's
+    coordinates for every row."""
+    c = synth.make_cohort(60_000, 6, 1500, 300.0, seed=7000 + seed, snv_frac=0.3, ins_frac=0.35, max_indel=9)
+    haps = synth.synth_haplotypes(c)
+    region = synth.SynthRegion(c)
+    d = synth.derive(c)
+    n_seg = np.diff(d.seg.seg_off)
+    assert n_seg[1:].min() > 50 and d.lens.max() >> 12 >= 14
+    tab = hostcheck.search(pam, region, haps, G, right, True, True)
+    order = np.argsort(tab["bucket"], kind="stable")
+    buf, off, lens = marshal.stage_ascii([h.sequence.sequence for h in haps])
+    fwd, rc = pam_patterns(pam)
+    a, b = synth.scan_bounds(c, len(fwd))
+    want = c_oracle.search(buf, off, lens, a, b, d.is_ref, d.seg, fwd, rc, G, right, threads=2)
+    assert len(order) == len(want["hap"]) > 1000
+    for col in ("hap", "strand", "pos", "start", "stop"):
+        assert np.array_equal(tab[col][order], want[col]), col
+    assert np.array_equal(tab["text"][order], want["text"])
