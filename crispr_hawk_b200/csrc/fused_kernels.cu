@@ -163,21 +163,19 @@ __global__ void __launch_bounds__(FUSED_WARPS * 32, FUSED_CTAS_PER_SM / FUSED_WA
     if ((uint32_t)lane < take) {
       const uint32_t slot = (qhead + lane) & 63u;
       h = q_hap[warp][slot];
+      // the case words and planes sit at the candidate's place in the slot space: their loads
+      // do not wait for the haplotype's scan geometry (one round trip through L2 instead of two)
+      const int64_t g = s + q_off[warp][slot];
       const HapScan H = A.hs[h];
-      c = (int32_t)(s + q_off[warp][slot] - H.chunk0);
+      const uint32_t* vp = A.v + g;
+      const uint32_t v0 = vp[-1], v1 = vp[0], v2 = vp[1];  // g >= 4: the slot space starts with a zero gap
+      const Planes cur = B.q[g], nxt = B.q[g + 1];
+      c = (int32_t)(g - H.chunk0);
       const bool use_v = !H.is_ref;
-      uint32_t w0 = 0, w1 = 0, w2 = 0;
-      bool go = true;
-      if (use_v) {
-        const uint32_t* vp = A.v + H.chunk0 + c;
-        w0 = vp[-1] & K.prev_mask;
-        w1 = vp[0];
-        w2 = vp[1] & K.next_mask;
-        go = (w0 | w1 | w2) != 0;
-      }
-      if (go) {
+      const uint32_t w0 = v0 & K.prev_mask, w1 = v1, w2 = v2 & K.next_mask;
+      if (!use_v || (w0 | w1 | w2) != 0) {
         uint32_t out[2], raw[2];
-        scan_chunk_small(B, K, H, c, w0, w1, w2, use_v, out, raw);
+        scan_chunk_small_pre(K, H, c, w0, w1, w2, use_v, cur, nxt, out, raw);
         m0 = out[0];
         m1 = out[1];
       }

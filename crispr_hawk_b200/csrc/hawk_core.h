@@ -652,6 +652,37 @@ HAWK_HD HapScan load_hap_scan(const BatchView& B, const ScanConst& K, int32_t h)
 // K.small form of scan_chunk below with the three case words of chunks c - 1, c, c + 1
 // handed in (the kernel queues them with the candidate); use_v = false for REF / pam_search
 // mode, where the case words play no role.
+// ... with the planes of chunks c and c + 1 handed in as well (the fused kernel loads them beside
+// the haplotype's scan geometry instead of after it)
+HAWK_HD void scan_chunk_small_pre(const ScanConst& K, const HapScan& H, int32_t c, uint32_t w0, uint32_t w1,
+                                  uint32_t w2, bool use_v, const Planes& cur, const Planes& nxt, uint32_t out[2],
+                                  uint32_t raw[2]) {
+  const int32_t p0 = c << 5;
+  out[0] = out[1] = raw[0] = raw[1] = 0;
+  uint32_t inscan = 0xFFFFFFFFu, cand[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+  if (c < H.c_in_lo || c >= H.c_in_hi) {  // boundary chunk of the scan / window intervals
+    inscan = interval_mask(H.a, H.b, p0);
+    if (!inscan) return;
+    cand[0] = interval_mask(H.lo[0], H.hi[0], p0);
+    cand[1] = interval_mask(H.lo[1], H.hi[1], p0);
+  }
+  if (use_v) {
+    dilate96(w0, w1, w2, K.C);
+    HAWK_UNROLL
+    for (int s = 0; s < 2; ++s) {
+      const uint32_t off = (uint32_t)(32 + K.geom[s].c0);
+      cand[s] &= (off == 32u) ? w1 : funnel_r(w0, w1, off);
+    }
+    if (!(cand[0] | cand[1])) return;
+  }
+  uint32_t m[2];
+  match_chunk2(cur, nxt, K.sel, K.P, m);
+  raw[0] = m[0] & inscan;
+  raw[1] = m[1] & inscan;
+  out[0] = m[0] & cand[0];
+  out[1] = m[1] & cand[1];
+}
+
 HAWK_HD void scan_chunk_small(const BatchView& B, const ScanConst& K, const HapScan& H, int32_t c, uint32_t w0,
                               uint32_t w1, uint32_t w2, bool use_v, uint32_t out[2], uint32_t raw[2]) {
   const int32_t p0 = c << 5;
