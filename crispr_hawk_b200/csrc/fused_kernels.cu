@@ -71,20 +71,6 @@ struct Raw8 {
   uint32_t w[8];
 };
 
-template <bool WIDE>
-__device__ __forceinline__ void load_raw(const uint4* __restrict__ p, Raw8& r) {
-  if (WIDE) {
-    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
-                   "=r"(r.w[7])
-                 : "l"(p));
-  } else {
-    const uint4 a = __ldg(p), b = __ldg(p + 1);
-    r.w[0] = a.x, r.w[1] = a.y, r.w[2] = a.z, r.w[3] = a.w;
-    r.w[4] = b.x, r.w[5] = b.y, r.w[6] = b.z, r.w[7] = b.w;
-  }
-}
-
 // haplotype whose territory holds the chunks being finalised, everything relative to the
 // sub-range start s (32-bit): warp-uniform
 struct HapCursor {
@@ -94,6 +80,9 @@ struct HapCursor {
   int32_t is_ref;
 };
 
+// WIDE (the texts are 32-byte aligned) chose a 256-bit load when the texts were prefetched into
+// registers; the cp.async ring copies 16 bytes at a time either way, so both values now compile to
+// the same code (kept so the kernel names in earlier profiles stay comparable).
 // SUBC: the sub-range size as a compile-time constant (FUSED_SUB_MAX, the large-input case), or 0 =
 // take it from the arguments (small slot spaces)
 template <bool WIDE, int REACH, int SUBC>
