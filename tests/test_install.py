@@ -212,3 +212,29 @@ def test_two_variants_at_one_position_go_to_the_reference(monkeypatch):
     called = []
     monkeypatch.setitem(annotation._reference, "gc_content", lambda g, v, d: called.append("ref") or g)
     assert annotation.gc_content(guides, 0, True) is guides and called == ["ref"]
+
+
+def test_scorer_strings_fall_back_when_the_list_changed(monkeypatch):
+    """scoring._extract_guide_sequences hands a list to the reference's own function when the device
+    columns do not describe it any more (a caller filtered the list) or were never computed."""
+    import numpy as np
+
+    from crispr_hawk_b200 import scoring
+
+    class L(list):
+        pass
+
+    calls = []
+    monkeypatch.setitem(scoring._reference, "_extract_guide_sequences", lambda g: calls.append(len(g)) or ["ref"] * len(g))
+    k4 = np.frombuffer(b"ACGTAC" * 3, np.uint8).reshape(3, 6)
+    guides = L(["g0", "g1", "g2"])
+    guides.hawk = {"kmers": {4: k4, 0: k4[:, 4:]}, "order": np.array([2, 0, 1])}
+    assert scoring._extract_guide_sequences(guides) == ["ACGTAC"] * 3 and calls == []
+    assert scoring._extract_guide_sequences_sgdesigner.__name__ == "_extract_guide_sequences_sgdesigner"
+    short = L(["g0", "g1"])
+    short.hawk = guides.hawk
+    assert scoring._extract_guide_sequences(short) == ["ref", "ref"] and calls == [2]
+    none = L(["g0"])
+    none.hawk = {"kmers": None, "order": np.array([0])}
+    assert scoring._extract_guide_sequences(none) == ["ref"] and calls == [2, 1]
+    assert scoring._extract_guide_sequences(["x", "y"]) == ["ref", "ref"]  # a plain list
