@@ -489,6 +489,7 @@ def run_product_arm(args, rank, world, local_rank):
     # inside a step, so this is ~= the wall time, which is reported beside it
     step_ms = dev_ms / args.steps
     t = torch.tensor([step_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    scanned_bp_rank = int(wl.scanned_bp)  # of the headline workload (`wl` is the config-5 block later on)
     tot = torch.tensor([wl.scanned_bp, n_guides], dtype=torch.int64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -784,7 +785,7 @@ def run_product_arm(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args, wl.scanned_bp, n_hap_rank),
+            "config": workload_config(args, scanned_bp_rank, n_hap_rank),
             "guides_per_step": total_guides, "hits_per_step_rank0": hits_total,
             "job_guides_in_timed_region": int(job_counts[0].item()),
             "device_ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
